@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""Benchmark of the Sayram-2D time-step hot path on B200 (see DESIGN.md "measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Metric (BASELINE.json): cell-updates/sec = cells advanced one full implicit time
+step (PPFV assembly + complete linear solve) per second, whole job.
+
+Workload of the headline line ("ensemble4096"): BASELINE config 4 - 4096
+independent (L, MLT) problems on the 80x80 grid of p_AlbertYoungLC.ini (member m:
+D scaled by a_m, 1/tau by b_m), sharded contiguously over the N ranks with no
+data-path collective ("scaling": "strong" - the total is fixed at 4096 members).
+A "step" is one time step of every member.  At N=1 the line also carries
+"grid1024": BASELINE config 3 (single 1024x1024 grid, synthetic full tensor +
+loss), the configuration the HBM-roofline target is quoted on.
+
+--impl reference times the reference's own CPU implementation (oracle/_ref: the
+unmodified Solver.cc etc. compiled against shim headers) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NB_TOTAL = 4096
+NX = NY = 80
+DT = 0.002
+METRIC = "cell_updates_per_sec"
+UNIT = "cell-updates/s"
+REF_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+LC_INI = os.path.join(ROOT, "data", "p_AlbertYoungLC.ini")
+
+# algorithmic HBM bytes per cell and launch (DESIGN.md "kernels"; fp64 = 8 B)
+BYTES_PER_CELL = {"assembly": 104, "p_update": 32, "spmv_v": 56, "s_update": 24, "spmv_t": 48, "xr_update": 56,
+                  "finish": 40, "other": 56}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def shard(n, rank, world):
+    """Contiguous member range of this rank (sayram2d_b200.shard is the tested copy)."""
+    from sayram2d_b200.shard import shard_range
+    return shard_range(n, rank, world)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        self.path = tempfile.mktemp(prefix="sy2d_clocks_", suffix=".csv")
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(index)], stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1])); smax.append(float(p[2]))
+                except ValueError:
+                    continue
+                for k, nm in enumerate(names):
+                    if p[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            busy = [s for s in sm if s > 0.5 * max(sm)] or sm
+            out.update(sm_mhz=statistics.median(busy), sm_max_mhz=max(smax), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ----------------------------------------------------------------------------- workloads
+def lc_fields():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "lc80.npz"))
+    return {k: g[k] for k in ("x_edges", "y_edges", "G", "Dxx", "Dxy", "Dyy", "inv_tau", "f_0")}
+
+
+def make_ensemble(lo, hi, device):
+    """BASELINE config 4 members [lo, hi): LC case fields as the reference computes them
+    (tests/golden/lc80.npz inputs), D scaled by a_m and 1/tau by b_m."""
+    import sayram2d_b200 as sy
+    from sayram2d_b200 import fields
+    g = lc_fields()
+    nb = hi - lo
+    a, b = fields.ensemble_scales(np.arange(lo, hi))
+    sc = lambda arr, s: arr[None] * s[:, None, None]
+    one = np.ones(nb)
+    eng = sy.Engine(g["x_edges"], g["y_edges"], DT, nbatch=nb, device=device)
+    eng.set_coeffs(sc(g["G"], one), sc(g["Dxx"], a), sc(g["Dxy"], a), sc(g["Dyy"], a), sc(g["inv_tau"], b))
+    _, bct, lines = fields.ay_init_and_bc(g["x_edges"], g["y_edges"], lc=True)
+    eng.set_bc(bct, *lines)
+    f0 = np.ascontiguousarray(sc(g["f_0"], one))
+    eng.set_f(f0)
+    return eng, f0
+
+
+def make_grid(n, device):
+    """BASELINE config 3: AY domain/BCs/G/f0 on an n x n grid with the synthetic tensor."""
+    import sayram2d_b200 as sy
+    from sayram2d_b200 import fields
+    xe, ye = fields.uniform_edges(n, n)
+    eng = sy.Engine(xe, ye, DT, nbatch=1, device=device)
+    Dxx, Dxy, Dyy, inv_tau = fields.synthetic_tensor(xe, ye)
+    eng.set_coeffs(fields.ay_G(xe, ye), Dxx, Dxy, Dyy, inv_tau)
+    f0, bct, lines = fields.ay_init_and_bc(xe, ye)
+    eng.set_bc(bct, *lines)
+    eng.set_f(f0)
+    return eng, f0
+
+
+def roofline_from_profile(prof, only=None):
+    peak, peak_src = measured_peak()
+    rows = {}
+    for name, p in prof.items():
+        if p["launches"] == 0 or p["ms"] <= 0:
+            continue
+        gbs = p["cells"] * BYTES_PER_CELL[name] / (p["ms"] * 1e-3) / 1e9
+        rows[name] = {"achieved": round(gbs, 1), "frac": round(gbs / peak, 4), "ms_total": round(p["ms"], 3),
+                      "launches": p["launches"], "us_per_launch": round(1e3 * p["ms"] / p["launches"], 2),
+                      "bytes_per_cell": BYTES_PER_CELL[name]}
+    cand = {k: v for k, v in rows.items() if only is None or k in only}
+    dom = max(cand, key=lambda k: cand[k]["ms_total"]) if cand else None
+    return rows, dom, peak, peak_src
+
+
+def profile_pass(eng, steps):
+    eng.set_profiling(True)
+    eng.step(steps)
+    prof = eng.profile()
+    eng.set_profiling(False)
+    return prof
+
+
+# ----------------------------------------------------------------------------- CPU reference
+def run_ref_driver(case, ini, steps, skip, extra=(), timeout=3600):
+    with tempfile.TemporaryDirectory() as work:
+        os.symlink(os.path.join(ROOT, "data", "D"), os.path.join(work, "D"))
+        cmd = [REF_DRIVER, "--case", case, "--ini", ini, "--out", os.path.join(work, "o"), "--steps", str(steps),
+               "--skip", str(skip), "--every", "1000000", *map(str, extra)]
+        res = subprocess.run(cmd, cwd=work, capture_output=True, text=True, timeout=timeout, check=True)
+        return json.loads(res.stdout.strip().splitlines()[-1])
+
+
+def spawn_ref_driver(case, ini, steps, skip, extra, work):
+    cmd = [REF_DRIVER, "--case", case, "--ini", ini, "--out", os.path.join(work, "o"), "--steps", str(steps),
+           "--skip", str(skip), "--every", "1000000", *map(str, extra)]
+    return subprocess.Popen(cmd, cwd=work, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+
+
+def cpu_baseline_ensemble(members=(0, 2047, 4095), steps=400):
+    """Bounded sample of the same workload: `members` of the ensemble, `steps` time steps
+    each, one after the other on ONE core (the reference is single-threaded: no `#pragma omp`
+    in its sources and Eigen's SparseLU is sequential - BASELINE.md section 2)."""
+    from sayram2d_b200 import fields
+    if not os.path.exists(REF_DRIVER):
+        return {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": "oracle/_ref/ref_driver missing"}
+    wall, cells = 0.0, 0
+    for m in members:
+        a, b = fields.ensemble_scales(m)
+        r = run_ref_driver("ENS", LC_INI, steps, 0, ("--member", repr(float(a)), repr(float(b))))
+        wall += r["loop_wall_s"]
+        cells += r["nx"] * r["ny"] * r["timed_steps"]
+    return {"value": cells / wall, "unit": UNIT, "cores": 1, "kind": "reference",
+            "sample": f"members {list(members)} x {steps} steps of the 4096-member ensemble, sequentially on 1 core "
+                      f"({wall:.1f} s of oracle/_ref/ref_driver = reference Solver.cc + shim LU)"}
+
+
+def cpu_baseline_grid(n, steps=1):
+    if not os.path.exists(REF_DRIVER):
+        return {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": "oracle/_ref/ref_driver missing"}
+    with tempfile.TemporaryDirectory() as d:
+        ini = os.path.join(d, "syn.ini")
+        open(ini, "w").write(f"[basic]\nrun_id = syn{n}\nnalpha0 = {n}\nnE = {n}\nalpha0min = 5\nalpha0max = 90\nEmin = 0.2\n"
+                             f"Emax = 5\nT = 1.0\nnsteps = 500\n[diagnostics]\nnplots = 10\n[diffusion_coefficients]\n"
+                             f"dID = AlbertYoung_chorus\n")
+        r = run_ref_driver("SYN", ini, steps, 0)
+    return {"value": r["nx"] * r["ny"] * r["timed_steps"] / r["loop_wall_s"], "unit": UNIT, "cores": 1, "kind": "reference",
+            "sample": f"{steps} time step(s) of the {n}x{n} grid ({r['loop_wall_s']:.1f} s; LU factor {r['lu_factor_s']:.1f} s, "
+                      f"nnz(L+U)={r['nnz_LU']})"}
+
+
+def reference_arm(args):
+    """The reference's CPU implementation on the same workload/metric, using every host core
+    it can: the path itself is single-threaded, but ensemble members are independent, so one
+    process per core each advances its own member.  A "step" = one time step of that sample."""
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "gpu_launches": 0,
+            "config": {"workload": "ensemble4096", "members": NB_TOTAL, "grid": [NX, NY], "dt": DT}}
+    if not os.path.exists(REF_DRIVER):
+        line["unavailable"] = "oracle/_ref/ref_driver not built (make -C oracle ref needs /root/reference)"
+        print(json.dumps(line), flush=True)
+        return
+    from sayram2d_b200 import fields
+    cores = os.cpu_count() or 1
+    procs = min(cores, 64)
+    members = [int(round(k * (NB_TOTAL - 1) / max(procs - 1, 1))) for k in range(procs)]
+    t0 = time.perf_counter()
+    with tempfile.TemporaryDirectory() as base:
+        ps = []
+        for k, m in enumerate(members):
+            work = os.path.join(base, f"w{k}")
+            os.makedirs(work)
+            os.symlink(os.path.join(ROOT, "data", "D"), os.path.join(work, "D"))
+            a, b = fields.ensemble_scales(m)
+            ps.append(spawn_ref_driver("ENS", LC_INI, args.warmup + args.steps, args.warmup,
+                                       ("--member", repr(float(a)), repr(float(b))), work))
+        outs = [json.loads(p.communicate()[0].strip().splitlines()[-1]) for p in ps]
+    wall = max(o["loop_wall_s"] for o in outs)
+    value = procs * NX * NY * args.steps / wall
+    line.update(value=value, ms_per_step=1e3 * wall / args.steps,
+                cpu_baseline={"value": value, "unit": UNIT, "cores": procs, "kind": "reference",
+                              "sample": f"{procs} of the 4096 members (one oracle/_ref/ref_driver process per core, "
+                                        f"{args.warmup}+{args.steps} steps each); total wall {time.perf_counter() - t0:.1f} s"},
+                e2e={"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- ours
+def ours(args):
+    import torch
+    import torch.distributed as dist
+    rank, local_rank, world = dist_env()
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo", rank=rank, world_size=world)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    lo, hi = shard(NB_TOTAL, rank, world)
+    eng, f0 = make_ensemble(lo, hi, local_rank)
+    nb = hi - lo
+    cells_total = NB_TOTAL * NX * NY
+
+    # ---- device-resident timing (value) ----
+    eng.step(args.warmup)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t0 = time.perf_counter()
+    st = eng.step(args.steps)
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_s = max_over_ranks(st["seconds_device"])
+    wall_s = max_over_ranks(wall)
+    iters = max_over_ranks(st["iters_total"]) / args.steps
+    launches = sum_over_ranks(st["kernel_launches"])
+    negatives = sum_over_ranks(st["negatives"])
+    value = cells_total * args.steps / dev_s
+
+    # ---- end-to-end through the public call with HOST buffers ----
+    pin_in = torch.empty((nb, NX, NY), dtype=torch.float64).pin_memory()
+    pin_out = torch.empty((nb, NX, NY), dtype=torch.float64).pin_memory()
+    pin_in.numpy()[...] = eng.get_f()
+    h_in, h_out = pin_in.numpy(), pin_out.numpy()
+    for _ in range(max(1, min(args.warmup, 3))):
+        eng.put_f(h_in); eng.step(1); eng.get_f(h_out); h_in[...] = h_out
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.put_f(h_in)          # H2D of this step's input f (pinned)
+        eng.step(1)              # Solver::update()
+        eng.get_f(h_out)         # D2H of the step's result (synchronises)
+        h_in, h_out = h_out, h_in
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    clocks = sampler.stop() if sampler else None
+    e2e = {"value": cells_total * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": cells_total * 8,
+           "d2h_bytes_per_step": cells_total * 8, "ms_per_step": 1e3 * e2e_s / args.steps}
+
+    # ---- per-kernel roofline (separate profiled pass, CUDA events around every launch) ----
+    prof = profile_pass(eng, 2)
+    rows, dom, peak, peak_src = roofline_from_profile(prof, only=("p_update", "spmv_v", "s_update", "spmv_t", "xr_update", "assembly"))
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "ensemble4096", "members": NB_TOTAL, "members_per_gpu": nb, "grid": [NX, NY], "dt": DT,
+                       "case": "Albert_Young_LC fields, D x a_m, 1/tau x b_m (SURVEY 8d config 4)", "parallelism": f"ensemble-shard x{world}",
+                       "solver": "BiCGSTAB on the f-scaled unit-diagonal system, max|r|<=1e-14",
+                       "l2": f"working set {nb * NX * NY * 8 * 19 / 1e6:.0f} MB per GPU > 126 MB L2: no flush needed"},
+            "iters_per_step": iters, "negatives": int(negatives), "wall_ms_per_step": 1e3 * wall_s / args.steps,
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+    if dom:
+        r = rows[dom]
+        line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": r["achieved"], "peak": peak, "unit": "GB/s",
+                            "frac": r["frac"], "traffic": None, "peak_source": peak_src, "kernels": rows}
+    eng.close()
+
+    if rank == 0 and world == 1:
+        if not args.no_grid1024:
+            line["grid1024"] = grid_object(1024, local_rank, args, torch)
+        line["cpu_baseline"] = cpu_baseline_ensemble() if not args.no_cpu else None
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def grid_object(n, device, args, torch):
+    """BASELINE config 3 on one GPU: cell-updates/s, iterations, and the roofline of the
+    assembly and SpMV kernels.  L2 is flushed (256 MB write) between timed steps."""
+    eng, f0 = make_grid(n, device)
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=f"cuda:{device}")
+    steps = max(2, min(args.steps, 5))
+    eng.step(max(1, min(args.warmup, 3)))
+    dev_s, iters = 0.0, 0
+    for _ in range(steps):
+        flush.zero_(); torch.cuda.synchronize()
+        st = eng.step(1)
+        dev_s += st["seconds_device"]; iters += st["iters_total"]
+    prof = profile_pass(eng, 1)
+    rows, dom, peak, peak_src = roofline_from_profile(prof)
+    out = {"workload": f"grid{n}", "value": n * n * steps / dev_s, "unit": UNIT, "steps": steps, "ms_per_step": 1e3 * dev_s / steps,
+           "iters_per_step": iters / steps, "negatives": st["negatives"], "resid_last": st["resid_last"],
+           "l2": "256 MB flush between timed steps; the 19-array working set (~160 MB) cycles through L2 within a step",
+           "roofline": {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src, "dominant": dom, "kernels": rows}}
+    eng.close()
+    if not args.no_cpu and not args.no_grid_cpu:
+        out["cpu_baseline"] = cpu_baseline_grid(n, 1)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-grid1024", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs")
+    ap.add_argument("--no-grid-cpu", action="store_true", help="skip the ~40 s CPU baseline of the 1024^2 grid")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,150 @@
+/*
+ * sayram2d.h - C ABI of the B200-native Sayram-2D time-step engine.
+ *
+ * The reference (xtaohub/Sayram-2D) has no FFI: its seam is the C++ class
+ * `Solver` (source/Solver.h:18-25) as used by source/main.cc:51,74,80,83.  This
+ * header is what a host-side `Solver` forwards to; sayram2d_b200/host/Solver.h
+ * is that forwarding class and keeps the reference's public API unchanged.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every array argument is CALLER-OWNED HOST
+ *    memory (the *_dev variants take device pointers) and is copied during the
+ *    call; nothing is retained.
+ *  - 2-D fields are (nx, ny) row-major with j (log E) fastest - the reference's
+ *    xtensor layout (source/common.h:28) - with an optional leading batch
+ *    dimension [nbatch][nx][ny] for ensembles of independent problems that
+ *    share one mesh and one set of boundary conditions.
+ *  - every function returns SY2D_OK (0) or a negative sy2d_status; the message
+ *    of the last failure is available from sy2d_last_error().  No exception
+ *    crosses this boundary.  A context is bound to one device and must be used
+ *    by one host thread at a time (the reference is single-threaded too).
+ *  - there is NO CPU fallback: sy2d_create fails when no CUDA device is usable.
+ */
+#ifndef SAYRAM2D_H_
+#define SAYRAM2D_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sy2d_ctx sy2d_ctx;
+
+typedef enum {
+  SY2D_OK = 0,
+  SY2D_ERR_INVALID = -1,       /* bad argument (sizes, NULL, non-increasing edges: Grid2D.h:44-67) */
+  SY2D_ERR_CUDA = -2,          /* CUDA runtime failure or no device */
+  SY2D_ERR_NOT_CONVERGED = -3, /* Krylov solve hit maxit (the reference's direct LU cannot fail this way) */
+  SY2D_ERR_STATE = -4,         /* call order: coefficients / BCs / f not set yet */
+  SY2D_ERR_BC = -5             /* Dirichlet side without data: "Dirichlet BC: missing value." (Solver.cc:393) */
+} sy2d_status;
+
+/* source/BCTypes.h:13,16 */
+enum { SY2D_XMIN = 0, SY2D_XMAX = 1, SY2D_YMIN = 2, SY2D_YMAX = 3 };
+enum { SY2D_DIRICHLET = 0, SY2D_ZEROFLUX = 1 };
+
+/* preconditioner inside the BiCGSTAB loop */
+enum { SY2D_PRECOND_JACOBI = 0, SY2D_PRECOND_XLINE = 1 };
+
+typedef struct {
+  double tol;        /* stop when max_K |r_K| <= tol on the scaled system (unknown ~ O(1)); default 1e-14 */
+  int maxit;         /* per linear solve; default 20000 */
+  int precond;       /* SY2D_PRECOND_*; default JACOBI (the unit-diagonal scaling itself) */
+  int predictor;     /* 1: column-scale by f^n * (f^n/f^{n-1}) instead of f^n; default 1 */
+  int check_every;   /* iterations between host convergence polls; default 16 */
+  int use_graph;     /* 1: replay the iteration chunk as a CUDA graph; default 1 */
+  int engine;        /* 0 auto, 1 lockstep multi-kernel, 2 one-CTA-per-problem persistent */
+  int reserved[5];
+} sy2d_options;
+
+typedef struct {
+  long long steps;            /* time steps taken by the call */
+  long long iters_total;      /* BiCGSTAB iterations summed over steps (max over the batch per step) */
+  int iters_last;             /* iterations of the last step (max over the batch) */
+  int restarts_total;         /* true-residual restarts */
+  double resid_last;          /* max over batch and cells of |rhs - A x| after the last solve (true residual) */
+  double fmin;                /* min f over batch and cells after the last step */
+  long long negatives;        /* number of cells with f < 0 after the last step */
+  double seconds_device;      /* CUDA-event time of the whole call on the context's stream */
+  long long kernel_launches;  /* kernels of this library launched by the call (graph nodes included) */
+} sy2d_stats;
+
+/* per-kernel device time of profiled sy2d_step calls (see sy2d_set_profiling) */
+enum {
+  SY2D_K_ASSEMBLY = 0, /* fused PPFV assembly                          */
+  SY2D_K_P_UPDATE,     /* p = r + beta (p - omega v)                   */
+  SY2D_K_SPMV_V,       /* v = A p, (rhat, v)                           */
+  SY2D_K_S_UPDATE,     /* s = r - alpha v                              */
+  SY2D_K_SPMV_T,       /* t = A s, (t,s), (t,t)                        */
+  SY2D_K_XR_UPDATE,    /* x, r update, (rhat, r), max|r|               */
+  SY2D_K_FINISH,       /* f = c (1 + d), statistics                    */
+  SY2D_K_OTHER,        /* true-residual check                          */
+  SY2D_K_COUNT
+};
+typedef struct {
+  double ms[SY2D_K_COUNT];          /* summed CUDA-event time per kernel */
+  long long launches[SY2D_K_COUNT];
+  double cells[SY2D_K_COUNT];       /* cells of still-active problems summed over those launches
+                                       (exact when check_every == 1, which profiling forces) */
+} sy2d_profile;
+
+/* Replaces Mesh(grid, dt) + Solver ctor allocation (Mesh.cc:17-65, Solver.cc:14-34). */
+int sy2d_create(sy2d_ctx** out, int device, int nx, int ny, int nbatch,
+                const double* x_edges /* nx+1 */, const double* y_edges /* ny+1 */, double dt);
+void sy2d_destroy(sy2d_ctx* ctx);
+const char* sy2d_last_error(const sy2d_ctx* ctx); /* ctx may be NULL: error of a failed sy2d_create */
+
+int sy2d_default_options(sy2d_options* opt);
+int sy2d_set_options(sy2d_ctx* ctx, const sy2d_options* opt);
+
+/* Replaces Equation::G/Dxx/Dxy/Dyy/inv_tau + Solver::update_Lambda (Equation.h:44-50,
+ * Solver.cc:57-65).  Each array is [nbatch][nx][ny]; inv_tau may be NULL (= 0, Equation.h:39-40).
+ * Call again whenever Equation::update(t) changed a field (Solver.cc:287-288). */
+int sy2d_set_coeffs(sy2d_ctx* ctx, const double* G, const double* Dxx, const double* Dxy,
+                    const double* Dyy, const double* inv_tau);
+/* Same with device pointers (no host round trip). */
+int sy2d_set_coeffs_dev(sy2d_ctx* ctx, const double* G, const double* Dxx, const double* Dxy,
+                        const double* Dyy, const double* inv_tau);
+
+/* Replaces Equation::bc_type + dirichlet_vertex_value + Solver::fill_vertex_from_bcs
+ * (Equation.h:52,60-65, Solver.cc:385-422).  bc_type[side] in SY2D_XMIN..YMAX order; the
+ * vertex lines xmin/xmax have ny+1 entries, ymin/ymax nx+1; a line may be NULL only for a
+ * ZeroFlux side (else SY2D_ERR_BC).  Shared by all batch members.  Call again when the
+ * Dirichlet data change with t. */
+int sy2d_set_bc(sy2d_ctx* ctx, const int bc_type[4], const double* xmin, const double* xmax,
+                const double* ymin, const double* ymax);
+
+/* Solver::init f_ = eq.init_f (Solver.cc:38-42); [nbatch][nx][ny]. Resets the step counter. */
+int sy2d_set_f(sy2d_ctx* ctx, const double* f);
+int sy2d_set_f_dev(sy2d_ctx* ctx, const double* f_dev);
+/* Overwrites f from the host WITHOUT resetting the step counter or the predictor state:
+ * the host-resident-f flavour of Solver::update() (f_ lives on the host in the reference). */
+int sy2d_put_f(sy2d_ctx* ctx, const double* f);
+/* Solver::f() (Solver.h:24). */
+int sy2d_get_f(sy2d_ctx* ctx, double* f_out);
+int sy2d_get_f_dev(sy2d_ctx* ctx, double* f_out_dev);
+
+/* Solver::update() x nsteps (Solver.cc:270-290) without leaving the device; stats may be NULL. */
+int sy2d_step(sy2d_ctx* ctx, int nsteps, sy2d_stats* stats);
+/* Solver::t() (Solver.h:23). */
+double sy2d_time(const sy2d_ctx* ctx);
+long long sy2d_step_count(const sy2d_ctx* ctx);
+
+/* Assembles M(f), R(f) for the CURRENT f exactly as Solver::assemble does (Solver.cc:167-202)
+ * and returns them unscaled: diags = [5][nbatch][nx][ny] in the order diag, W(i-1), E(i+1),
+ * S(j-1), N(j+1); rhs = [nbatch][nx][ny].  For parity tests; does not advance time. */
+int sy2d_dump_operator(sy2d_ctx* ctx, double* diags, double* rhs);
+/* vertex_f_ (Solver.cc:292-422) for the current f: [nbatch][nx+1][ny+1]. For parity tests. */
+int sy2d_dump_vertex_f(sy2d_ctx* ctx, double* vf);
+
+/* Per-kernel CUDA-event timing of subsequent sy2d_step calls (adds event overhead; off by default). */
+int sy2d_set_profiling(sy2d_ctx* ctx, int on);
+int sy2d_get_profile(sy2d_ctx* ctx, sy2d_profile* out);
+
+/* Build/device facts: "sm_100a;cuda=12.9;..." */
+const char* sy2d_build_info(void);
+int sy2d_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAYRAM2D_H_ */

@@ -542,14 +542,14 @@ def ensemble_member_scales(mth):
     return 0.1 * 100.0 ** ((mth % 64) / 63.0), (mth // 64) / 63.0
 
 
-def run(case, ini_path=None, table=None, nsteps=None, linear="splu", stretch=0.0, member=None, **overrides):
-    """main.cc:41-85: returns snapshots /f/0 ... /f/nplots (or every step if nsteps given)."""
+def run(case, ini_path=None, table=None, run_steps=None, linear="splu", stretch=0.0, member=None, **overrides):
+    """main.cc:41-85: returns snapshots /f/0 ... /f/nplots (or every step if run_steps given)."""
     p, m, eq = build_case(case, ini_path, table, stretch=stretch, member=member, **overrides)
     s = Solver(m, eq, linear=linear)
     snaps = [s.f.copy()]
-    total = p.nsteps if nsteps is None else nsteps
+    total = p.nsteps if run_steps is None else run_steps
     for tstep in range(1, total + 1):
         s.update()
-        if nsteps is not None or tstep % p.save_every_step == 0:
+        if run_steps is not None or tstep % p.save_every_step == 0:
             snaps.append(s.f.copy())
     return p, m, eq, snaps

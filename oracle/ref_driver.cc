@@ -8,7 +8,7 @@
 // construction order, same time loop) but writes .npy files and per-step timing.
 //
 //   ref_driver --case AY|LC|SYN|ENS --ini <file> --out <dir> [--steps N]
-//              [--every K] [--dump-op s1,s2,...] [--member a b] [--stretch s] [--cwd <dir>]
+//              [--every K] [--skip W] [--dump-op s1,s2,...] [--member a b] [--stretch s] [--cwd <dir>]
 //
 // SYN  = BASELINE config 3 (synthetic full tensor + loss strip on the AY domain);
 // ENS  = BASELINE config 4 member: LC case with D scaled by a, inv_tau by b.
@@ -125,7 +125,7 @@ void dump_operator(const std::string& prefix, const Mesh& m) {
 
 int main(int argc, char** argv) {
   std::string kase = "AY", ini = "p.ini", out = "ref_out", cwd;
-  long steps = -1, every = -1;
+  long steps = -1, every = -1, skip = 0;
   double ma = 1.0, mb = 1.0, stretch = 0.0;
   std::set<long> dump_ops;
   for (int k = 1; k < argc; ++k) {
@@ -137,6 +137,7 @@ int main(int argc, char** argv) {
     else if (a == "--cwd") cwd = next();
     else if (a == "--steps") steps = std::stol(next());
     else if (a == "--every") every = std::stol(next());
+    else if (a == "--skip") skip = std::stol(next());  // warm-up steps excluded from the timings
     else if (a == "--stretch") stretch = std::stod(next());
     else if (a == "--member") { ma = std::stod(next()); mb = std::stod(next()); }
     else if (a == "--dump-op") { std::stringstream ss(next()); std::string t; while (std::getline(ss, t, ',')) dump_ops.insert(std::stol(t)); }
@@ -175,7 +176,8 @@ int main(int argc, char** argv) {
   for (long tstep = 1; tstep <= nsteps; ++tstep) {
     const auto t0 = std::chrono::steady_clock::now();
     solver.update();  // main.cc:80
-    loop_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (tstep > skip) loop_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (tstep == skip) Eigen::shim::last_system().factor_seconds = Eigen::shim::last_system().solve_seconds = 0.0;
     if (dump_ops.count(tstep)) dump_operator(out + "/op" + std::to_string(tstep) + "_", m);
     if (tstep % save_every == 0) h5shim::write_npy(out + "/f_" + std::to_string(tstep / save_every) + ".npy", solver.f().data(), {m.nx(), m.ny()});
   }
@@ -191,10 +193,10 @@ int main(int argc, char** argv) {
     }
   const auto& ls = Eigen::shim::last_system();
   std::printf(
-      "{\"case\": \"%s\", \"nx\": %zu, \"ny\": %zu, \"dt\": %.17g, \"steps\": %ld, \"save_every\": %ld, \"setup_s\": %.6f, "
+      "{\"case\": \"%s\", \"nx\": %zu, \"ny\": %zu, \"dt\": %.17g, \"steps\": %ld, \"timed_steps\": %ld, \"save_every\": %ld, \"setup_s\": %.6f, "
       "\"loop_wall_s\": %.6f, \"loop_cpu_clock_s\": %.6f, \"lu_factor_s\": %.6f, \"lu_solve_s\": %.6f, \"nnz_LU\": %ld, "
       "\"t_end\": %.17g, \"fmin\": %.17g, \"fmax\": %.17g, \"negatives\": %ld}\n",
-      kase.c_str(), m.nx(), m.ny(), m.dt(), nsteps, save_every, setup_s, loop_s, cpu_s, ls.factor_seconds, ls.solve_seconds,
+      kase.c_str(), m.nx(), m.ny(), m.dt(), nsteps, nsteps - std::min(skip, nsteps), save_every, setup_s, loop_s, cpu_s, ls.factor_seconds, ls.solve_seconds,
       ls.nnz_LU, solver.t(), fmin, fmax, neg);
   delete eq;
   return 0;

@@ -1,0 +1,72 @@
+"""Builds the CUDA library and the C++ host binary in-tree (nvcc, sm_100a).
+
+    python -m sayram2d_b200.build [--force]
+
+nvcc cross-compiles without a GPU; the resulting files travel to the GPU box with
+the repo snapshot (they are git-ignored, not gpurun-ignored).
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+LIB = os.path.join(PKG, "lib", "libsayram2d_b200.so")
+BIN = os.path.join(PKG, "bin", "sayram2d")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+CUDA_SOURCES = [os.path.join(PKG, "csrc", "sy2d_api.cu")]
+CUDA_HEADERS = [os.path.join(PKG, "csrc", h) for h in ("sy2d_kernels.cuh", "sy2d_geometry.h")] + [
+    os.path.join(ROOT, "include", "sayram2d.h")]
+
+
+def _stale(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.exists(s) and os.path.getmtime(s) > t for s in sources)
+
+
+def _run(cmd):
+    print("+", " ".join(cmd), flush=True)
+    subprocess.run(cmd, check=True)
+
+
+def build_library(force=False):
+    if force or _stale(LIB, CUDA_SOURCES + CUDA_HEADERS):
+        os.makedirs(os.path.dirname(LIB), exist_ok=True)
+        _run([NVCC, "-O3", "-std=c++17", *ARCH, "-lineinfo", "-Xcompiler", "-fPIC", "-shared",
+              "-o", LIB, *CUDA_SOURCES])
+    return LIB
+
+
+def host_sources():
+    hdir = os.path.join(PKG, "host")
+    if not os.path.isdir(hdir):
+        return []
+    return sorted(os.path.join(hdir, f) for f in os.listdir(hdir) if f.endswith(".cc"))
+
+
+def build_host(force=False):
+    """C++ host layer (reference API) + main, linked against the CUDA library."""
+    srcs = host_sources()
+    if not srcs:
+        return None
+    hdir = os.path.join(PKG, "host")
+    deps = srcs + [os.path.join(hdir, f) for f in os.listdir(hdir) if f.endswith(".h")] + [LIB]
+    if force or _stale(BIN, deps):
+        os.makedirs(os.path.dirname(BIN), exist_ok=True)
+        _run(["/usr/bin/g++", "-O2", "-std=c++17", "-I" + hdir, "-I" + os.path.join(ROOT, "include"), *srcs,
+              "-L" + os.path.dirname(LIB), "-lsayram2d_b200", "-Wl,-rpath,$ORIGIN/../lib", "-o", BIN])
+    return BIN
+
+
+def build_all(force=False):
+    build_library(force)
+    build_host(force)
+
+
+if __name__ == "__main__":
+    build_all("--force" in sys.argv)

@@ -1,0 +1,540 @@
+// C-ABI implementation (include/sayram2d.h) of the B200-native Sayram-2D engine.
+// Host orchestration only: staging, launch order, convergence polling, CUDA
+// graphs.  All arithmetic of the hot path lives in sy2d_kernels.cuh.
+#include "../../include/sayram2d.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "sy2d_geometry.h"
+#include "sy2d_kernels.cuh"
+
+using namespace sy2d;
+
+namespace {
+thread_local std::string g_create_error;
+
+}  // namespace
+
+struct sy2d_ctx {
+  int device = 0, nx = 0, ny = 0, nbatch = 0;
+  size_t N = 0, total = 0;
+  double dt = 0.0;
+  long long istep = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  sy2d_options opt;
+  bool have_coeffs = false, have_bc = false, have_f = false;
+
+  // geometry
+  std::vector<double> h_xe, h_ye;
+  double *d_wxL = nullptr, *d_wxR = nullptr, *d_wyB = nullptr, *d_wyT = nullptr, *d_dx = nullptr, *d_dy = nullptr;
+  double *d_bc[4] = {nullptr, nullptr, nullptr, nullptr};
+  int bc[4] = {SY2D_ZEROFLUX, SY2D_ZEROFLUX, SY2D_ZEROFLUX, SY2D_ZEROFLUX};
+  // coefficients
+  double *tx = nullptr, *ty = nullptr, *cxy = nullptr, *U = nullptr, *Ud = nullptr;
+  // state
+  double *f = nullptr, *yprev = nullptr, *cs = nullptr;
+  // operator + Krylov vectors
+  double *wW = nullptr, *wE = nullptr, *wS = nullptr, *wN = nullptr, *rhs = nullptr;
+  double *x = nullptr, *r = nullptr, *p = nullptr, *v = nullptr, *s = nullptr, *t = nullptr;
+  Scal* scal = nullptr;
+  int* d_nactive = nullptr;
+  int* h_nactive = nullptr;  // pinned
+  StepStats* d_stats = nullptr;
+  StepStats* h_stats = nullptr;  // pinned
+  // staging buffer for host->device coefficient uploads (5 fields), allocated on demand
+  double* stage = nullptr;
+  size_t stage_elems = 0;
+  // iteration-chunk graph
+  cudaGraphExec_t chunk_exec = nullptr;
+  int chunk_iters = 0;
+  // profiling
+  bool profiling = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+  std::vector<int> ev_class;
+  size_t ev_used = 0;
+  sy2d_profile prof;
+  std::vector<double> ev_cells;
+  double cur_cells = 0.0;       // cells of active problems for the launches being recorded
+  long long launches = 0;       // kernels launched since the start of the current sy2d_step
+  cudaEvent_t ev_call0 = nullptr, ev_call1 = nullptr;
+};
+
+namespace {
+
+int fail(sy2d_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CU(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(c, SY2D_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+Geometry geometry(const sy2d_ctx* c) {
+  Geometry g;
+  g.wxL = c->d_wxL; g.wxR = c->d_wxR; g.wyB = c->d_wyB; g.wyT = c->d_wyT;
+  g.bc_xmin = c->d_bc[0]; g.bc_xmax = c->d_bc[1]; g.bc_ymin = c->d_bc[2]; g.bc_ymax = c->d_bc[3];
+  for (int k = 0; k < 4; ++k) g.bc[k] = c->bc[k];
+  g.nx = c->nx; g.ny = c->ny;
+  return g;
+}
+
+KrylovVecs krylov(const sy2d_ctx* c) {
+  KrylovVecs k;
+  k.wW = c->wW; k.wE = c->wE; k.wS = c->wS; k.wN = c->wN; k.rhs = c->rhs;
+  k.x = c->x; k.r = c->r; k.p = c->p; k.v = c->v; k.s = c->s; k.t = c->t;
+  k.scal = c->scal; k.n_active = c->d_nactive; k.tol = c->opt.tol; k.maxit = c->opt.maxit;
+  return k;
+}
+
+dim3 grid_of(const sy2d_ctx* c) { return dim3((unsigned)((c->N + kBlock - 1) / kBlock), (unsigned)c->nbatch, 1); }
+
+// RAII-less event bracket used only in profiling mode
+struct Prof {
+  sy2d_ctx* c;
+  int idx = -1;
+  Prof(sy2d_ctx* c_, int klass) : c(c_) {
+    if (!c->profiling) return;
+    if (c->ev_used == c->ev_pool.size()) {
+      cudaEvent_t a, b;
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      c->ev_pool.emplace_back(a, b);
+      c->ev_class.push_back(klass);
+      c->ev_cells.push_back(0.0);
+    }
+    idx = (int)c->ev_used++;
+    c->ev_class[idx] = klass;
+    c->ev_cells[idx] = c->cur_cells;
+    cudaEventRecord(c->ev_pool[idx].first, c->stream);
+  }
+  ~Prof() {
+    if (idx >= 0) cudaEventRecord(c->ev_pool[idx].second, c->stream);
+  }
+};
+
+void launch_iteration(sy2d_ctx* c) {
+  const dim3 g = grid_of(c);
+  const KrylovVecs k = krylov(c);
+  { Prof p(c, SY2D_K_P_UPDATE); k_p_update<<<g, kBlock, 0, c->stream>>>(k, c->N); }
+  { Prof p(c, SY2D_K_SPMV_V); k_spmv_v<<<g, kBlock, 0, c->stream>>>(k, c->N, c->ny); }
+  { Prof p(c, SY2D_K_S_UPDATE); k_s_update<<<g, kBlock, 0, c->stream>>>(k, c->N); }
+  { Prof p(c, SY2D_K_SPMV_T); k_spmv_t<<<g, kBlock, 0, c->stream>>>(k, c->N, c->ny); }
+  { Prof p(c, SY2D_K_XR_UPDATE); k_xr_update<<<g, kBlock, 0, c->stream>>>(k, c->N); }
+}
+constexpr int kKernelsPerIteration = 5;
+
+int build_chunk_graph(sy2d_ctx* c) {
+  if (c->chunk_exec && c->chunk_iters == c->opt.check_every) return SY2D_OK;
+  if (c->chunk_exec) { cudaGraphExecDestroy(c->chunk_exec); c->chunk_exec = nullptr; }
+  cudaGraph_t graph = nullptr;
+  CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+  for (int it = 0; it < c->opt.check_every; ++it) launch_iteration(c);
+  CU(cudaMemcpyAsync(c->h_nactive, c->d_nactive, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamEndCapture(c->stream, &graph));
+  CU(cudaGraphInstantiate(&c->chunk_exec, graph, 0));
+  cudaGraphDestroy(graph);
+  c->chunk_iters = c->opt.check_every;
+  return SY2D_OK;
+}
+
+int collect_profile(sy2d_ctx* c) {
+  if (!c->profiling) return SY2D_OK;
+  for (size_t k = 0; k < c->ev_used; ++k) {
+    float t = 0.f;
+    CU(cudaEventElapsedTime(&t, c->ev_pool[k].first, c->ev_pool[k].second));
+    c->prof.ms[c->ev_class[k]] += t;
+    c->prof.launches[c->ev_class[k]] += 1;
+    c->prof.cells[c->ev_class[k]] += c->ev_cells[k];
+  }
+  c->ev_used = 0;
+  return SY2D_OK;
+}
+
+template <class T>
+int dalloc(sy2d_ctx* c, T** p, size_t n) {
+  CU(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
+  return SY2D_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* sy2d_build_info(void) {
+  return "sayram2d_b200;arch=sm_100a;cuda="
+#define SY2D_STR2(x) #x
+#define SY2D_STR(x) SY2D_STR2(x)
+      SY2D_STR(CUDART_VERSION) ";fp64;engine=lockstep-bicgstab";
+}
+
+int sy2d_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int sy2d_default_options(sy2d_options* o) {
+  if (!o) return SY2D_ERR_INVALID;
+  std::memset(o, 0, sizeof *o);
+  o->tol = 1e-14;
+  o->maxit = 20000;
+  o->precond = SY2D_PRECOND_JACOBI;
+  o->predictor = 1;
+  o->check_every = 16;
+  o->use_graph = 1;
+  o->engine = 0;
+  return SY2D_OK;
+}
+
+const char* sy2d_last_error(const sy2d_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int sy2d_create(sy2d_ctx** out, int device, int nx, int ny, int nbatch, const double* xe, const double* ye, double dt) {
+  sy2d_ctx* c = nullptr;
+  if (!out) return fail(c, SY2D_ERR_INVALID, "sy2d_create: out is NULL");
+  *out = nullptr;
+  if (nx < 1 || ny < 1) return fail(c, SY2D_ERR_INVALID, "Grid2D: edges must have size >= 2.");
+  if (nbatch < 1 || nbatch > 65535) return fail(c, SY2D_ERR_INVALID, "sy2d_create: nbatch must be in [1, 65535]");
+  if (!xe || !ye) return fail(c, SY2D_ERR_INVALID, "sy2d_create: NULL edge array");
+  if (!(dt > 0.0)) return fail(c, SY2D_ERR_INVALID, "sy2d_create: dt must be positive");
+  for (int i = 0; i < nx; ++i)
+    if (!(xe[i + 1] > xe[i])) return fail(c, SY2D_ERR_INVALID, "Grid2D: x_edges must be strictly increasing at i=%d", i);
+  for (int j = 0; j < ny; ++j)
+    if (!(ye[j + 1] > ye[j])) return fail(c, SY2D_ERR_INVALID, "Grid2D: y_edges must be strictly increasing at j=%d", j);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(c, SY2D_ERR_CUDA, "sy2d_create: no CUDA device available (this library has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(c, SY2D_ERR_INVALID, "sy2d_create: device %d out of range (%d devices)", device, ndev);
+
+  sy2d_ctx* ctx = new sy2d_ctx;
+  ctx->device = device; ctx->nx = nx; ctx->ny = ny; ctx->nbatch = nbatch; ctx->dt = dt;
+  ctx->N = (size_t)nx * ny; ctx->total = ctx->N * nbatch;
+  sy2d_default_options(&ctx->opt);
+  std::memset(&ctx->prof, 0, sizeof ctx->prof);
+  ctx->h_xe.assign(xe, xe + nx + 1);
+  ctx->h_ye.assign(ye, ye + ny + 1);
+  c = ctx;
+  auto bail = [&](int code) { g_create_error = ctx->err; sy2d_destroy(ctx); return code; };
+#define CUB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(c, SY2D_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); return bail(SY2D_ERR_CUDA); } } while (0)
+  CUB(cudaSetDevice(device));
+  CUB(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  const HostGeometry hg = make_host_geometry(nx, ny, xe, ye);
+  const std::vector<double>&wxL = hg.wxL, &wxR = hg.wxR, &wyB = hg.wyB, &wyT = hg.wyT, &dx = hg.dx, &dy = hg.dy;
+  struct Up { double** dst; const std::vector<double>* src; } ups[] = {
+      {&ctx->d_wxL, &wxL}, {&ctx->d_wxR, &wxR}, {&ctx->d_wyB, &wyB}, {&ctx->d_wyT, &wyT}, {&ctx->d_dx, &dx}, {&ctx->d_dy, &dy}};
+  for (auto& u : ups) {
+    CUB(cudaMalloc(reinterpret_cast<void**>(u.dst), u.src->size() * sizeof(double)));
+    CUB(cudaMemcpy(*u.dst, u.src->data(), u.src->size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  for (int k = 0; k < 4; ++k) {
+    const size_t n = (k < 2 ? ny : nx) + 1;
+    CUB(cudaMalloc(reinterpret_cast<void**>(&ctx->d_bc[k]), n * sizeof(double)));
+    CUB(cudaMemset(ctx->d_bc[k], 0, n * sizeof(double)));
+  }
+  double** fields[] = {&ctx->tx, &ctx->ty, &ctx->cxy, &ctx->U, &ctx->Ud, &ctx->f, &ctx->yprev, &ctx->cs, &ctx->wW, &ctx->wE,
+                       &ctx->wS, &ctx->wN, &ctx->rhs, &ctx->x, &ctx->r, &ctx->p, &ctx->v, &ctx->s, &ctx->t};
+  for (double** fp : fields) CUB(cudaMalloc(reinterpret_cast<void**>(fp), ctx->total * sizeof(double)));
+  CUB(cudaMalloc(reinterpret_cast<void**>(&ctx->scal), nbatch * sizeof(Scal)));
+  CUB(cudaMemset(ctx->scal, 0, nbatch * sizeof(Scal)));
+  CUB(cudaMalloc(reinterpret_cast<void**>(&ctx->d_nactive), sizeof(int)));
+  CUB(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_nactive), sizeof(int)));
+  CUB(cudaMalloc(reinterpret_cast<void**>(&ctx->d_stats), sizeof(StepStats)));
+  CUB(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_stats), sizeof(StepStats)));
+  CUB(cudaEventCreate(&ctx->ev_call0));
+  CUB(cudaEventCreate(&ctx->ev_call1));
+#undef CUB
+  *out = ctx;
+  return SY2D_OK;
+}
+
+void sy2d_destroy(sy2d_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->chunk_exec) cudaGraphExecDestroy(c->chunk_exec);
+  double* bufs[] = {c->d_wxL, c->d_wxR, c->d_wyB, c->d_wyT, c->d_dx, c->d_dy, c->d_bc[0], c->d_bc[1], c->d_bc[2], c->d_bc[3],
+                    c->tx, c->ty, c->cxy, c->U, c->Ud, c->f, c->yprev, c->cs, c->wW, c->wE, c->wS, c->wN, c->rhs,
+                    c->x, c->r, c->p, c->v, c->s, c->t, c->stage};
+  for (double* b : bufs) if (b) cudaFree(b);
+  if (c->scal) cudaFree(c->scal);
+  if (c->d_nactive) cudaFree(c->d_nactive);
+  if (c->h_nactive) cudaFreeHost(c->h_nactive);
+  if (c->d_stats) cudaFree(c->d_stats);
+  if (c->h_stats) cudaFreeHost(c->h_stats);
+  for (auto& e : c->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  if (c->ev_call0) cudaEventDestroy(c->ev_call0);
+  if (c->ev_call1) cudaEventDestroy(c->ev_call1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int sy2d_set_options(sy2d_ctx* c, const sy2d_options* o) {
+  if (!c || !o) return SY2D_ERR_INVALID;
+  if (!(o->tol > 0.0) || o->maxit < 1 || o->check_every < 1)
+    return fail(c, SY2D_ERR_INVALID, "sy2d_set_options: tol, maxit and check_every must be positive");
+  if (o->precond != SY2D_PRECOND_JACOBI) return fail(c, SY2D_ERR_INVALID, "sy2d_set_options: unsupported preconditioner %d", o->precond);
+  c->opt = *o;
+  return SY2D_OK;
+}
+
+int sy2d_set_coeffs_dev(sy2d_ctx* c, const double* G, const double* Dxx, const double* Dxy, const double* Dyy, const double* inv_tau) {
+  if (!c) return SY2D_ERR_INVALID;
+  if (!G || !Dxx || !Dxy || !Dyy) return fail(c, SY2D_ERR_INVALID, "sy2d_set_coeffs: NULL field");
+  CU(cudaSetDevice(c->device));
+  k_prepare_coeffs<<<grid_of(c), kBlock, 0, c->stream>>>(G, Dxx, Dxy, Dyy, inv_tau, c->d_dx, c->d_dy, c->dt, c->nx, c->ny,
+                                                       c->tx, c->ty, c->cxy, c->U, c->Ud);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(c->stream));
+  c->have_coeffs = true;
+  return SY2D_OK;
+}
+
+int sy2d_set_coeffs(sy2d_ctx* c, const double* G, const double* Dxx, const double* Dxy, const double* Dyy, const double* inv_tau) {
+  if (!c) return SY2D_ERR_INVALID;
+  if (!G || !Dxx || !Dxy || !Dyy) return fail(c, SY2D_ERR_INVALID, "sy2d_set_coeffs: NULL field");
+  CU(cudaSetDevice(c->device));
+  // stage through the (not yet needed) Krylov vectors: x, r, p, v, s hold the five raw fields
+  double* dst[5] = {c->x, c->r, c->p, c->v, c->s};
+  const double* src[5] = {G, Dxx, Dxy, Dyy, inv_tau};
+  for (int k = 0; k < 5; ++k)
+    if (src[k]) CU(cudaMemcpyAsync(dst[k], src[k], c->total * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  return sy2d_set_coeffs_dev(c, dst[0], dst[1], dst[2], dst[3], inv_tau ? dst[4] : nullptr);
+}
+
+int sy2d_set_bc(sy2d_ctx* c, const int bc_type[4], const double* xmin, const double* xmax, const double* ymin, const double* ymax) {
+  if (!c || !bc_type) return SY2D_ERR_INVALID;
+  const double* lines[4] = {xmin, xmax, ymin, ymax};
+  for (int k = 0; k < 4; ++k) {
+    if (bc_type[k] != SY2D_DIRICHLET && bc_type[k] != SY2D_ZEROFLUX) return fail(c, SY2D_ERR_INVALID, "sy2d_set_bc: unknown BCType %d", bc_type[k]);
+    if (bc_type[k] == SY2D_DIRICHLET && !lines[k]) return fail(c, SY2D_ERR_BC, "Dirichlet BC: missing value.");
+  }
+  CU(cudaSetDevice(c->device));
+  for (int k = 0; k < 4; ++k) {
+    c->bc[k] = bc_type[k];
+    const size_t n = (k < 2 ? c->ny : c->nx) + 1;
+    if (lines[k]) CU(cudaMemcpyAsync(c->d_bc[k], lines[k], n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  c->have_bc = true;
+  return SY2D_OK;
+}
+
+static int reset_state(sy2d_ctx* c) {
+  // yprev = 1: the first step column-scales by f^n alone
+  k_fill<<<grid_of(c), kBlock, 0, c->stream>>>(c->yprev, c->N, 1.0);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(c->stream));
+  c->istep = 0;
+  return SY2D_OK;
+}
+
+int sy2d_set_f_dev(sy2d_ctx* c, const double* f) {
+  if (!c || !f) return SY2D_ERR_INVALID;
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpyAsync(c->f, f, c->total * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  c->have_f = true;
+  return reset_state(c);
+}
+
+int sy2d_set_f(sy2d_ctx* c, const double* f) {
+  if (!c || !f) return SY2D_ERR_INVALID;
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpyAsync(c->f, f, c->total * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  c->have_f = true;
+  return reset_state(c);
+}
+
+int sy2d_put_f(sy2d_ctx* c, const double* f) {
+  if (!c || !f) return SY2D_ERR_INVALID;
+  if (!c->have_f) return sy2d_set_f(c, f);
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpyAsync(c->f, f, c->total * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  return SY2D_OK;
+}
+
+int sy2d_get_f(sy2d_ctx* c, double* out) {
+  if (!c || !out) return SY2D_ERR_INVALID;
+  if (!c->have_f) return fail(c, SY2D_ERR_STATE, "sy2d_get_f: f not set");
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpyAsync(out, c->f, c->total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return SY2D_OK;
+}
+
+int sy2d_get_f_dev(sy2d_ctx* c, double* out) {
+  if (!c || !out) return SY2D_ERR_INVALID;
+  if (!c->have_f) return fail(c, SY2D_ERR_STATE, "sy2d_get_f: f not set");
+  CU(cudaSetDevice(c->device));
+  CU(cudaMemcpyAsync(out, c->f, c->total * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return SY2D_OK;
+}
+
+double sy2d_time(const sy2d_ctx* c) { return c ? (double)c->istep * c->dt : 0.0; }
+long long sy2d_step_count(const sy2d_ctx* c) { return c ? c->istep : 0; }
+
+static int ready(sy2d_ctx* c, const char* who) {
+  if (!c->have_coeffs) return fail(c, SY2D_ERR_STATE, "%s: coefficients not set (sy2d_set_coeffs)", who);
+  if (!c->have_bc) return fail(c, SY2D_ERR_STATE, "%s: boundary conditions not set (sy2d_set_bc)", who);
+  if (!c->have_f) return fail(c, SY2D_ERR_STATE, "%s: f not set (sy2d_set_f)", who);
+  return SY2D_OK;
+}
+
+int sy2d_step(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
+  if (!c || nsteps < 0) return SY2D_ERR_INVALID;
+  int rc = ready(c, "sy2d_step");
+  if (rc) return rc;
+  CU(cudaSetDevice(c->device));
+  const dim3 g = grid_of(c);
+  const Geometry geo = geometry(c);
+  const bool graph = c->opt.use_graph && !c->profiling;
+  const int check_every = c->profiling ? 1 : c->opt.check_every;  // profiling: no zero-work launches
+  c->launches = 0;
+  if (graph) { rc = build_chunk_graph(c); if (rc) return rc; }
+  sy2d_stats st;
+  std::memset(&st, 0, sizeof st);
+  CU(cudaEventRecord(c->ev_call0, c->stream));
+  for (int step = 0; step < nsteps; ++step) {
+    CU(cudaMemsetAsync(c->d_nactive, 0, sizeof(int), c->stream));
+    c->cur_cells = (double)c->total;
+    {
+      Prof p(c, SY2D_K_ASSEMBLY);
+      AssembleOut o;
+      std::memset(&o, 0, sizeof o);
+      o.wW = c->wW; o.wE = c->wE; o.wS = c->wS; o.wN = c->wN; o.rhs = c->rhs; o.cs = c->cs;
+      o.scal = c->scal; o.n_active = c->d_nactive; o.tol = c->opt.tol;
+      k_assemble<0><<<g, kBlock, 0, c->stream>>>(c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud, geo, o);
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(c->h_nactive, c->d_nactive, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->launches += 1;
+    int launched = 0;
+    while (*c->h_nactive > 0 && launched < c->opt.maxit + check_every) {
+      c->cur_cells = (double)*c->h_nactive * (double)c->N;
+      if (graph) {
+        CU(cudaGraphLaunch(c->chunk_exec, c->stream));
+      } else {
+        for (int it = 0; it < check_every; ++it) launch_iteration(c);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(c->h_nactive, c->d_nactive, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      }
+      CU(cudaStreamSynchronize(c->stream));
+      launched += check_every;
+      c->launches += (long long)check_every * kKernelsPerIteration;
+    }
+    c->cur_cells = (double)c->total;
+    // verification + finish
+    StepStats init;
+    init.fmin = 1.0e300; init.negatives = 0; init.resid_max = 0.0; init.it_max = 0; init.n_bad = 0;
+    *c->h_stats = init;
+    CU(cudaMemcpyAsync(c->d_stats, c->h_stats, sizeof(StepStats), cudaMemcpyHostToDevice, c->stream));
+    {
+      Prof p(c, SY2D_K_OTHER);
+      k_true_residual<<<g, kBlock, 0, c->stream>>>(krylov(c), c->N, c->ny, &c->d_stats->resid_max);
+    }
+    {
+      Prof p(c, SY2D_K_FINISH);
+      k_finish<<<g, kBlock, 0, c->stream>>>(c->x, c->cs, c->f, c->yprev, c->scal, c->N, c->opt.predictor, c->d_stats);
+    }
+    c->launches += 2;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(StepStats), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    rc = collect_profile(c);
+    if (rc) return rc;
+    c->istep += 1;
+    st.steps += 1;
+    st.iters_total += c->h_stats->it_max;
+    st.iters_last = c->h_stats->it_max;
+    st.resid_last = c->h_stats->resid_max;
+    st.fmin = c->h_stats->fmin;
+    st.negatives = (long long)c->h_stats->negatives;
+    st.kernel_launches = c->launches;
+    if (c->h_stats->n_bad > 0 || *c->h_nactive > 0) {
+      if (stats) *stats = st;
+      collect_profile(c);
+      return fail(c, SY2D_ERR_NOT_CONVERGED, "sy2d_step: BiCGSTAB did not converge at step %lld (%d problems, %d iterations, max|r|=%.3e)",
+                  c->istep, c->h_stats->n_bad, c->h_stats->it_max, c->h_stats->resid_max);
+    }
+  }
+  CU(cudaEventRecord(c->ev_call1, c->stream));
+  CU(cudaEventSynchronize(c->ev_call1));
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, c->ev_call0, c->ev_call1));
+  st.seconds_device = ms * 1e-3;
+  rc = collect_profile(c);
+  if (stats) *stats = st;
+  return rc;
+}
+
+int sy2d_dump_operator(sy2d_ctx* c, double* diags, double* rhs) {
+  if (!c || !diags || !rhs) return SY2D_ERR_INVALID;
+  int rc = ready(c, "sy2d_dump_operator");
+  if (rc) return rc;
+  CU(cudaSetDevice(c->device));
+  AssembleOut o;
+  std::memset(&o, 0, sizeof o);
+  // the Krylov vectors are free between steps: x,r,p,v,s,t receive diag,W,E,S,N,R
+  o.diag = c->x; o.oW = c->r; o.oE = c->p; o.oS = c->v; o.oN = c->s; o.R = c->t;
+  k_assemble<1><<<grid_of(c), kBlock, 0, c->stream>>>(c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud, geometry(c), o);
+  CU(cudaGetLastError());
+  double* src[5] = {c->x, c->r, c->p, c->v, c->s};
+  for (int k = 0; k < 5; ++k)
+    CU(cudaMemcpyAsync(diags + (size_t)k * c->total, src[k], c->total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(rhs, c->t, c->total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return SY2D_OK;
+}
+
+int sy2d_dump_vertex_f(sy2d_ctx* c, double* vf) {
+  if (!c || !vf) return SY2D_ERR_INVALID;
+  int rc = ready(c, "sy2d_dump_vertex_f");
+  if (rc) return rc;
+  CU(cudaSetDevice(c->device));
+  const size_t nv = (size_t)(c->nx + 1) * (c->ny + 1) * c->nbatch;
+  double* d_vf = nullptr;
+  CU(cudaMalloc(reinterpret_cast<void**>(&d_vf), nv * sizeof(double)));
+  AssembleOut o;
+  std::memset(&o, 0, sizeof o);
+  o.vf = d_vf;
+  k_assemble<2><<<grid_of(c), kBlock, 0, c->stream>>>(c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud, geometry(c), o);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(vf, d_vf, nv * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(d_vf);
+  if (e != cudaSuccess) return fail(c, SY2D_ERR_CUDA, "sy2d_dump_vertex_f: %s", cudaGetErrorString(e));
+  return SY2D_OK;
+}
+
+int sy2d_set_profiling(sy2d_ctx* c, int on) {
+  if (!c) return SY2D_ERR_INVALID;
+  c->profiling = on != 0;
+  c->ev_used = 0;
+  std::memset(&c->prof, 0, sizeof c->prof);
+  return SY2D_OK;
+}
+
+int sy2d_get_profile(sy2d_ctx* c, sy2d_profile* out) {
+  if (!c || !out) return SY2D_ERR_INVALID;
+  *out = c->prof;
+  return SY2D_OK;
+}
+
+}  // extern "C"

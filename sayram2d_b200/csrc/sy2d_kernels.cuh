@@ -1,0 +1,609 @@
+// Device kernels of the B200-native Sayram-2D time-step engine (sm_100a).
+//
+// Everything is IEEE fp64 and HBM/L2-bandwidth bound (no dense contraction => no
+// tensor cores).  Layout: every field is [nbatch][nx][ny], j (log E) fastest, the
+// reference's xtensor layout (source/common.h:28); a thread owns one cell and the
+// flattened in-problem index n = i*ny + j is the coalescing axis.
+//
+// Linear system solved per time step (see DESIGN.md "formulation"):
+//   reference:  M f^{n+1} = R                         (Solver.cc:270-278, direct LU)
+//   here:       A d = rhs,  f^{n+1} = c (1 + d)
+//     c   = f^n * yprev            column scale (yprev = predicted per-cell ratio, or 1)
+//     A   = D_r M diag(c),  D_r = 1/(M_KK c_K)   => unit diagonal, 4 stored off-diagonals
+//     rhs = D_r R - A 1            (residual of the guess "f^{n+1} = c")
+//   so the unknown is O(1e-2) relative change, and max|r| <= tol bounds the
+//   ELEMENTWISE relative error of f^{n+1}, which is what parity with the direct
+//   solve over 17-49 orders of magnitude in f needs.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sy2d {
+
+constexpr int kBlock = 256;
+constexpr double kEps = 2.220446049250313e-16;  // gEPS, source/common.h:38
+// The predicted per-cell ratio f^{n+1}/f^n is only trusted inside this range; outside it (fast
+// transients, e.g. loss-cone cells dropping 1000x per step) the unknown d would grow to O(100)
+// and cost accuracy, so the prediction is clamped and d stays O(1).
+constexpr double kPredMin = 0.5, kPredMax = 2.0;
+
+// Per-problem Krylov scalars, written only by the last block of a kernel to
+// finish that problem (threadfence reduction), read by every block of the NEXT
+// kernels => no intra-kernel races and no host round trip.
+struct Scal {
+  double rho, alpha, omega, beta;
+  double acc_rv, acc_ts, acc_tt, acc_rho;
+  unsigned long long acc_rmax;  // max |r| as raw bits (non-negative doubles order like integers)
+  double rmax;
+  unsigned int counter;
+  int it;
+  int state;  // 0 active, 1 converged, 2 maxit, 3 breakdown
+  int first;  // first iteration after (re)start: p = r, x = 0, r = rhs
+};
+
+struct Geometry {  // 1-D device arrays shared by the batch
+  const double* wxL;  // [nx+1] weight of cell i-1 at vertex i   (Solver.cc:340; 0 at i=0, 1 at i=nx)
+  const double* wxR;  // [nx+1] weight of cell i   at vertex i   (Solver.cc:341; 1 at i=0, 0 at i=nx)
+  const double* wyB;  // [ny+1]
+  const double* wyT;  // [ny+1]
+  const double* bc_xmin;  // [ny+1] Dirichlet vertex lines (Solver.cc:385-422)
+  const double* bc_xmax;
+  const double* bc_ymin;  // [nx+1]
+  const double* bc_ymax;
+  int bc[4];
+  int nx, ny;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block reductions for up to 3 sums and 1 max; result valid in thread 0.
+template <int NS>
+__device__ __forceinline__ void block_sums(double (&v)[NS], double* smem /* >= NS*32 */) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int k = 0; k < NS; ++k) v[k] = warp_sum(v[k]);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NS; ++k) smem[k * 32 + w] = v[k];
+  }
+  __syncthreads();
+  if (w == 0) {
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+      double x = lane < nw ? smem[k * 32 + lane] : 0.0;
+      v[k] = warp_sum(x);
+    }
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ double block_max(double v, double* smem /* >= 32 */) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  if (lane == 0) smem[w] = v;
+  __syncthreads();
+  if (w == 0) v = warp_max(lane < nw ? smem[lane] : 0.0);
+  __syncthreads();
+  return v;
+}
+
+// true in exactly one thread (thread 0 of the last block of this problem to get here)
+__device__ __forceinline__ bool last_block_done(Scal* sc, unsigned int nblocks) {
+  __threadfence();
+  const unsigned int prev = atomicAdd(&sc->counter, 1u);
+  if (prev == nblocks - 1) {
+    sc->counter = 0;
+    __threadfence();
+    return true;
+  }
+  return false;
+}
+
+__global__ void __launch_bounds__(kBlock) k_fill(double* __restrict__ a, size_t N, double value) {
+  const size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n < N) a[(size_t)blockIdx.y * N + n] = value;
+}
+
+// ---------------------------------------------------------------------------
+// Coefficient staging: Lambda = G*D (Solver.cc:57-65) folded with the face
+// geometry into the closed forms of SURVEY.md section 0:
+//   tx = Lxx*dy_j/dx_i, ty = Lyy*dx_i/dy_j, cxy = Lxy, U = G*dx*dy/dt (Solver.cc:193),
+//   Ud = U*(1 + dt/tau) (Solver.cc:195).
+// ---------------------------------------------------------------------------
+struct CellCoeffs { double tx, ty, cxy, U, Ud; };
+__host__ __device__ __forceinline__ CellCoeffs prepare_cell(double G, double Dxx, double Dxy, double Dyy, double inv_tau,
+                                                            double dxi, double dyj, double dt) {
+  CellCoeffs c;
+  const double lxx = Dxx * G, lxy = Dxy * G, lyy = Dyy * G;  // Solver.cc:61-62
+  c.tx = lxx * dyj / dxi;
+  c.ty = lyy * dxi / dyj;
+  c.cxy = lxy;
+  c.U = G * (dxi * dyj / dt);             // Solver.cc:193, Mesh.h:61-63
+  c.Ud = c.U * (1.0 + dt * inv_tau);      // Solver.cc:195
+  return c;
+}
+
+__global__ void __launch_bounds__(kBlock) k_prepare_coeffs(
+    const double* __restrict__ G, const double* __restrict__ Dxx, const double* __restrict__ Dxy,
+    const double* __restrict__ Dyy, const double* __restrict__ inv_tau, const double* __restrict__ dx,
+    const double* __restrict__ dy, double dt, int nx, int ny, double* __restrict__ tx, double* __restrict__ ty,
+    double* __restrict__ cxy, double* __restrict__ U, double* __restrict__ Ud) {
+  const size_t N = (size_t)nx * ny;
+  const size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const size_t g = (size_t)blockIdx.y * N + n;
+  const int i = (int)(n / ny), j = (int)(n - (size_t)i * ny);
+  const CellCoeffs c = prepare_cell(G[g], Dxx[g], Dxy[g], Dyy[g], inv_tau ? inv_tau[g] : 0.0, dx[i], dy[j], dt);
+  tx[g] = c.tx; ty[g] = c.ty; cxy[g] = c.cxy; U[g] = c.U; Ud[g] = c.Ud;
+}
+
+// vertex_f_(vi, vj) of Solver.cc:292-422 from the 2x2 cells around the vertex.
+// The padded weights make the interior bilinear formula (Solver.cc:346) reproduce
+// the edge lerp (:361-380) and the corner copy (:316-319); Dirichlet lines then
+// override in the reference's order XMIN, XMAX, YMIN, YMAX (later wins).
+__host__ __device__ __forceinline__ double vertex_value(const Geometry& g, int vi, int vj, double f00, double f10,
+                                                        double f01, double f11) {
+  if (vj == g.ny && g.bc[3] == 0) return g.bc_ymax[vi];
+  if (vj == 0 && g.bc[2] == 0) return g.bc_ymin[vi];
+  if (vi == g.nx && g.bc[1] == 0) return g.bc_xmax[vj];
+  if (vi == 0 && g.bc[0] == 0) return g.bc_xmin[vj];
+  const double wl = g.wxL[vi], wr = g.wxR[vi], wb = g.wyB[vj], wt = g.wyT[vj];
+  return wl * wb * f00 + wr * wb * f10 + wl * wt * f01 + wr * wt * f11;
+}
+
+// Nonlinear two-point flux of one interior face (Solver.cc:99-141, Solver.h:63-67).
+// K is the cell that owns the face as its west/south face (the reference's loop
+// cell), L its neighbour.  Returns A_K, A_L.
+__host__ __device__ __forceinline__ void face_pair(double asK, double sumK, double fK, double asL, double sumL,
+                                                   double fL, double& AK, double& AL) {
+  const double aK = fabs(asK), aL = fabs(asL);
+  const double denom = aK + aL + 2.0 * kEps;
+  const double muK = (aL + kEps) / denom;
+  const double muL = 1.0 - muK;
+  const double B = muL * asL - muK * asK;
+  const double Babs = fabs(B);
+  const double Bp = (Babs + B) / 2.0, Bm = (Babs - B) / 2.0;
+  // exactly one of Bp, Bm is non-zero and 0/(f+eps) == 0, so one division serves both
+  const double q = (B > 0.0 ? Bp : Bm) / ((B > 0.0 ? fK : fL) + kEps);
+  AK = muK * sumK + (B > 0.0 ? q : 0.0);
+  AL = muL * sumL + (B > 0.0 ? 0.0 : q);
+}
+
+// Dirichlet boundary face (Solver.cc:143-164): returns A_K, adds B^- to R.
+__host__ __device__ __forceinline__ double dirichlet_face(double asK, double sumK, double fK, double& R) {
+  const double B = -asK;
+  const double Babs = fabs(B);
+  const double Bp = (Babs + B) / 2.0, Bm = (Babs - B) / 2.0;
+  R += Bm;
+  return sumK + Bp / (fK + kEps);
+}
+
+struct Row {  // one row of the reference's M and R (unscaled)
+  double diag, oW, oE, oS, oN, R;
+  double f00, fW, fE, fS, fN;     // f of the cell and its face neighbours (clamped)
+  double vSW, vSE, vNW, vNE;      // vertex_f_ at the cell's four corners
+};
+
+// Row (i,j) of M(f), R(f): vertex values from the 3x3 block of f (never
+// materialised in HBM), one-sided weights of the four faces and of the matching
+// faces of the neighbours, nonlinear combination.  fp/tx/ty/cxy/U/Ud point at the
+// start of the problem.  Replaces Solver::update_vertex_f, a_sigma_func,
+// apply_inner_face_pair, apply_dirichlet_face, apply_boundary_faces and assemble
+// (Solver.cc:68-267, 292-422).  __host__ too so that tests/ can run the same
+// arithmetic on the CPU against the reference's (M,R) without a GPU.
+__host__ __device__ __forceinline__ void assemble_row(const double* __restrict__ fp, const double* __restrict__ tx,
+                                                      const double* __restrict__ ty, const double* __restrict__ cxy,
+                                                      const double* __restrict__ U, const double* __restrict__ Ud,
+                                                      const Geometry& g, int i, int j, Row& o) {
+  const int nx = g.nx, ny = g.ny;
+  const int im = i > 0 ? i - 1 : 0, ip = i < nx - 1 ? i + 1 : nx - 1;
+  const int jm = j > 0 ? j - 1 : 0, jp = j < ny - 1 ? j + 1 : ny - 1;
+  const size_t rm = (size_t)im * ny, r0 = (size_t)i * ny, rp = (size_t)ip * ny;
+  // 3x3 block of f, clamped at the domain boundary (clamped values only meet zero weights)
+  const double fmm = fp[rm + jm], fm0 = fp[rm + j], fmp = fp[rm + jp];
+  const double f0m = fp[r0 + jm], f00 = fp[r0 + j], f0p = fp[r0 + jp];
+  const double fpm = fp[rp + jm], fp0 = fp[rp + j], fpp = fp[rp + jp];
+  // vertices of cell (i,j): SW=(i,j) SE=(i+1,j) NW=(i,j+1) NE=(i+1,j+1)   (Mesh.cc:94-149)
+  const double vSW = vertex_value(g, i, j, fmm, f0m, fm0, f00);
+  const double vSE = vertex_value(g, i + 1, j, f0m, fpm, f00, fp0);
+  const double vNW = vertex_value(g, i, j + 1, fm0, f00, fmp, f0p);
+  const double vNE = vertex_value(g, i + 1, j + 1, f00, fp0, f0p, fpp);
+  o.vSW = vSW; o.vSE = vSE; o.vNW = vNW; o.vNE = vNE;
+  o.f00 = f00; o.fW = fm0; o.fE = fp0; o.fS = f0m; o.fN = f0p;
+  const size_t c0 = r0 + j;
+  const double txP = tx[c0], tyP = ty[c0], cP = cxy[c0];
+  // one-sided weights of cell P (closed form of Solver.cc:68-97)
+  const double aW_A = txP - cP, aW_B = txP + cP;  // W: A=NW, B=SW
+  const double aE_A = txP - cP, aE_B = txP + cP;  // E: A=SE, B=NE
+  const double aN_A = tyP + cP, aN_B = tyP - cP;  // N: A=NE, B=NW
+  const double aS_A = tyP + cP, aS_B = tyP - cP;  // S: A=SW, B=SE
+  const double asW = aW_A * vNW + aW_B * vSW;
+  const double asE = aE_A * vSE + aE_B * vNE;
+  const double asN = aN_A * vNE + aN_B * vNW;
+  const double asS = aS_A * vSW + aS_B * vSE;
+  double diag = 0.0, R = 0.0, oW = 0.0, oE = 0.0, oS = 0.0, oN = 0.0;
+  double AK, AL;
+  if (i > 0) {  // west face: K = P, L = (i-1,j) through its east face (A=SE_L=SW_P, B=NE_L=NW_P)
+    const size_t cl = c0 - ny;
+    const double t = tx[cl], c = cxy[cl];
+    const double lA = t - c, lB = t + c;
+    face_pair(asW, aW_A + aW_B, f00, lA * vSW + lB * vNW, lA + lB, fm0, AK, AL);
+    diag += AK;
+    oW = -AL;
+  } else if (g.bc[0] == 0) {
+    diag += dirichlet_face(asW, aW_A + aW_B, f00, R);
+  }
+  if (i < nx - 1) {  // east face: K = (i+1,j) through its west face (A=NW_K=NE_P, B=SW_K=SE_P), L = P
+    const size_t ck = c0 + ny;
+    const double t = tx[ck], c = cxy[ck];
+    const double kA = t - c, kB = t + c;
+    face_pair(kA * vNE + kB * vSE, kA + kB, fp0, asE, aE_A + aE_B, f00, AK, AL);
+    diag += AL;
+    oE = -AK;
+  } else if (g.bc[1] == 0) {
+    diag += dirichlet_face(asE, aE_A + aE_B, f00, R);
+  }
+  if (j > 0) {  // south face: K = P, L = (i,j-1) through its north face (A=NE_L=SE_P, B=NW_L=SW_P)
+    const size_t cl = c0 - 1;
+    const double t = ty[cl], c = cxy[cl];
+    const double lA = t + c, lB = t - c;
+    face_pair(asS, aS_A + aS_B, f00, lA * vSE + lB * vSW, lA + lB, f0m, AK, AL);
+    diag += AK;
+    oS = -AL;
+  } else if (g.bc[2] == 0) {
+    diag += dirichlet_face(asS, aS_A + aS_B, f00, R);
+  }
+  if (j < ny - 1) {  // north face: K = (i,j+1) through its south face (A=SW_K=NW_P, B=SE_K=NE_P), L = P
+    const size_t ck = c0 + 1;
+    const double t = ty[ck], c = cxy[ck];
+    const double kA = t + c, kB = t - c;
+    face_pair(kA * vNW + kB * vNE, kA + kB, f0p, asN, aN_A + aN_B, f00, AK, AL);
+    diag += AL;
+    oN = -AK;
+  } else if (g.bc[3] == 0) {
+    diag += dirichlet_face(asN, aN_A + aN_B, f00, R);
+  }
+  diag += Ud[c0];    // Solver.cc:195
+  R += U[c0] * f00;  // Solver.cc:197
+  o.diag = diag; o.oW = oW; o.oE = oE; o.oS = oS; o.oN = oN; o.R = R;
+}
+
+struct Scaled {  // row of the scaled unit-diagonal system A d = rhs
+  double wW, wE, wS, wN, rhs, cs;
+};
+
+// Column scale c = f*yprev (neighbours too), row scale 1/(M_KK c_K); rhs = D_r R - A 1.
+__host__ __device__ __forceinline__ void scale_row(const Row& r, double ypC, double ypW, double ypE, double ypS,
+                                                   double ypN, Scaled& s) {
+  const double cs0 = r.f00 * ypC;
+  const double dscale = 1.0 / (r.diag * cs0);
+  s.wW = r.oW * (r.fW * ypW) * dscale;
+  s.wE = r.oE * (r.fE * ypE) * dscale;
+  s.wS = r.oS * (r.fS * ypS) * dscale;
+  s.wN = r.oN * (r.fN * ypN) * dscale;
+  s.rhs = r.R * dscale - 1.0 - ((s.wW + s.wE) + (s.wS + s.wN));
+  s.cs = cs0;
+}
+
+struct AssembleOut {
+  // MODE 0 (solve): scaled unit-diagonal operator + Krylov start
+  double *wW, *wE, *wS, *wN, *rhs, *cs;
+  Scal* scal;
+  int* n_active;
+  double tol;
+  // MODE 1 (dump): the reference's unscaled M as 5 diagonals + R
+  double *diag, *oW, *oE, *oS, *oN, *R;
+  // MODE 2 (dump vertex_f): [nbatch][nx+1][ny+1]
+  double* vf;
+};
+
+// ---------------------------------------------------------------------------
+// Fused PPFV assembly, one thread per cell (see assemble_row / scale_row).
+// Algorithmic HBM bytes per cell (MODE 0): read f, yprev, tx, ty, cxy, U, Ud (56) +
+// write wW, wE, wS, wN, rhs, cs (48) = 104 B (96 B with predictor off).
+// ---------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(kBlock) k_assemble(const double* __restrict__ f, const double* __restrict__ yprev,
+                                                     const double* __restrict__ tx, const double* __restrict__ ty,
+                                                     const double* __restrict__ cxy, const double* __restrict__ U,
+                                                     const double* __restrict__ Ud, Geometry g, AssembleOut o) {
+  __shared__ double red[3 * 32];
+  const int nx = g.nx, ny = g.ny;
+  const size_t N = (size_t)nx * ny;
+  const size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t base = (size_t)blockIdx.y * N;
+  double rr = 0.0, rabs = 0.0;
+  if (n < N) {
+    const int i = (int)(n / ny), j = (int)(n - (size_t)i * ny);
+    Row row;
+    assemble_row(f + base, tx + base, ty + base, cxy + base, U + base, Ud + base, g, i, j, row);
+    const size_t c0 = base + n;
+    if (MODE == 2) {
+      double* vf = o.vf + (size_t)blockIdx.y * (nx + 1) * (ny + 1);
+      vf[(size_t)i * (ny + 1) + j] = row.vSW;
+      if (i == nx - 1) vf[(size_t)nx * (ny + 1) + j] = row.vSE;
+      if (j == ny - 1) vf[(size_t)i * (ny + 1) + ny] = row.vNW;
+      if (i == nx - 1 && j == ny - 1) vf[(size_t)nx * (ny + 1) + ny] = row.vNE;
+    } else if (MODE == 1) {
+      o.diag[c0] = row.diag; o.oW[c0] = row.oW; o.oE[c0] = row.oE; o.oS[c0] = row.oS; o.oN[c0] = row.oN; o.R[c0] = row.R;
+    } else {
+      const double* yp = yprev + base;
+      const size_t nW = i > 0 ? n - ny : n, nE = i < nx - 1 ? n + ny : n;
+      const size_t nS = j > 0 ? n - 1 : n, nN = j < ny - 1 ? n + 1 : n;
+      Scaled sc;
+      scale_row(row, yp[n], yp[nW], yp[nE], yp[nS], yp[nN], sc);
+      o.wW[c0] = sc.wW; o.wE[c0] = sc.wE; o.wS[c0] = sc.wS; o.wN[c0] = sc.wN;
+      o.rhs[c0] = sc.rhs;
+      o.cs[c0] = sc.cs;
+      rr = sc.rhs * sc.rhs;
+      rabs = fabs(sc.rhs);
+    }
+  }
+  if (MODE != 0) return;
+  // Krylov start: rho = (rhat, r0) = |rhs|^2, max-norm of the initial residual
+  double sums[1] = {rr};
+  block_sums<1>(sums, red);
+  const double bmax = block_max(rabs, red);
+  Scal* sc = o.scal + blockIdx.y;
+  if (threadIdx.x == 0) {
+    atomicAdd(&sc->acc_rho, sums[0]);
+    atomicMax(&sc->acc_rmax, (unsigned long long)__double_as_longlong(bmax));
+    if (last_block_done(sc, gridDim.x)) {
+      const double rmax = __longlong_as_double((long long)sc->acc_rmax);
+      sc->rho = sc->acc_rho;
+      sc->rmax = rmax;
+      sc->alpha = 1.0; sc->omega = 1.0; sc->beta = 0.0;
+      sc->acc_rv = 0.0; sc->acc_ts = 0.0; sc->acc_tt = 0.0; sc->acc_rho = 0.0; sc->acc_rmax = 0ull;
+      sc->it = 0;
+      sc->first = 1;
+      const int active_now = !(rmax <= o.tol);  // NaN counts as active => surfaces as an error later
+      sc->state = active_now ? 0 : 1;
+      if (active_now) atomicAdd(o.n_active, 1);
+    }
+  }
+}
+
+// y = A x for one cell of the unit-diagonal 5-point operator.  Out-of-range
+// neighbours are clamped to the cell itself: their weights are exactly zero.
+__host__ __device__ __forceinline__ double stencil_apply(const double* __restrict__ x, size_t n, size_t N, int ny, double xc,
+                                                double wW, double wE, double wS, double wN) {
+  const double xW = x[n >= (size_t)ny ? n - ny : n];
+  const double xE = x[n + ny < N ? n + ny : n];
+  const double xS = x[n > 0 ? n - 1 : n];
+  const double xN = x[n + 1 < N ? n + 1 : n];
+  return xc + ((wW * xW + wE * xE) + (wS * xS + wN * xN));
+}
+
+struct KrylovVecs {
+  const double *wW, *wE, *wS, *wN, *rhs;
+  double *x, *r, *p, *v, *s, *t;
+  Scal* scal;
+  int* n_active;
+  double tol;
+  int maxit;
+};
+
+// KA: p = r + beta (p - omega v)            (first iteration: p = rhs)      32 B/cell
+__global__ void __launch_bounds__(kBlock) k_p_update(KrylovVecs k, size_t N) {
+  const Scal* sc = k.scal + blockIdx.y;
+  if (sc->state != 0) return;
+  const size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const size_t g = (size_t)blockIdx.y * N + n;
+  if (sc->first) {
+    k.p[g] = k.rhs[g];
+  } else {
+    k.p[g] = k.r[g] + sc->beta * (k.p[g] - sc->omega * k.v[g]);
+  }
+}
+
+// KB: v = A p, acc (rhat, v); last block: alpha = rho / (rhat, v)            56 B/cell
+__global__ void __launch_bounds__(kBlock) k_spmv_v(KrylovVecs k, size_t N, int ny) {
+  __shared__ double red[32];
+  Scal* sc = k.scal + blockIdx.y;
+  if (sc->state != 0) return;
+  const size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t base = (size_t)blockIdx.y * N;
+  double dot = 0.0;
+  if (n < N) {
+    const size_t g = base + n;
+    const double* p = k.p + base;
+    const double v = stencil_apply(p, n, N, ny, p[n], k.wW[g], k.wE[g], k.wS[g], k.wN[g]);
+    k.v[g] = v;
+    dot = k.rhs[g] * v;
+  }
+  double sums[1] = {dot};
+  block_sums<1>(sums, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(&sc->acc_rv, sums[0]);
+    if (last_block_done(sc, gridDim.x)) {
+      const double rv = sc->acc_rv;
+      sc->acc_rv = 0.0;
+      sc->alpha = rv != 0.0 ? sc->rho / rv : 0.0;
+    }
+  }
+}
+
+// KC: s = r - alpha v                                                         24 B/cell
+__global__ void __launch_bounds__(kBlock) k_s_update(KrylovVecs k, size_t N) {
+  const Scal* sc = k.scal + blockIdx.y;
+  if (sc->state != 0) return;
+  const size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const size_t g = (size_t)blockIdx.y * N + n;
+  const double r = sc->first ? k.rhs[g] : k.r[g];
+  k.s[g] = r - sc->alpha * k.v[g];
+}
+
+// KD: t = A s, acc (t,s), (t,t); last block: omega = (t,s)/(t,t)             48 B/cell
+__global__ void __launch_bounds__(kBlock) k_spmv_t(KrylovVecs k, size_t N, int ny) {
+  __shared__ double red[2 * 32];
+  Scal* sc = k.scal + blockIdx.y;
+  if (sc->state != 0) return;
+  const size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t base = (size_t)blockIdx.y * N;
+  double ts = 0.0, tt = 0.0;
+  if (n < N) {
+    const size_t g = base + n;
+    const double* s = k.s + base;
+    const double sc0 = s[n];
+    const double t = stencil_apply(s, n, N, ny, sc0, k.wW[g], k.wE[g], k.wS[g], k.wN[g]);
+    k.t[g] = t;
+    ts = t * sc0;
+    tt = t * t;
+  }
+  double sums[2] = {ts, tt};
+  block_sums<2>(sums, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(&sc->acc_ts, sums[0]);
+    atomicAdd(&sc->acc_tt, sums[1]);
+    if (last_block_done(sc, gridDim.x)) {
+      const double a = sc->acc_ts, b = sc->acc_tt;
+      sc->acc_ts = 0.0;
+      sc->acc_tt = 0.0;
+      sc->omega = b > 0.0 ? a / b : 0.0;
+    }
+  }
+}
+
+// KE: x += alpha p + omega s; r = s - omega t; acc (rhat, r), max|r|;
+// last block: iteration bookkeeping, convergence, beta                        56 B/cell
+__global__ void __launch_bounds__(kBlock) k_xr_update(KrylovVecs k, size_t N) {
+  __shared__ double red[32];
+  Scal* sc = k.scal + blockIdx.y;
+  if (sc->state != 0) return;
+  const size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double dot = 0.0, rabs = 0.0;
+  if (n < N) {
+    const size_t g = (size_t)blockIdx.y * N + n;
+    const double alpha = sc->alpha, omega = sc->omega;
+    const double s = k.s[g];
+    const double x0 = sc->first ? 0.0 : k.x[g];
+    k.x[g] = x0 + (alpha * k.p[g] + omega * s);
+    const double r = s - omega * k.t[g];
+    k.r[g] = r;
+    dot = k.rhs[g] * r;
+    rabs = fabs(r);
+  }
+  double sums[1] = {dot};
+  block_sums<1>(sums, red);
+  const double bmax = block_max(rabs, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(&sc->acc_rho, sums[0]);
+    atomicMax(&sc->acc_rmax, (unsigned long long)__double_as_longlong(bmax));
+    if (last_block_done(sc, gridDim.x)) {
+      const double rho_new = sc->acc_rho;
+      const double rmax = __longlong_as_double((long long)sc->acc_rmax);
+      sc->acc_rho = 0.0;
+      sc->acc_rmax = 0ull;
+      sc->rmax = rmax;
+      sc->it += 1;
+      sc->first = 0;
+      int state = 0;
+      if (rmax <= k.tol) state = 1;
+      else if (!(rmax == rmax) || rho_new == 0.0 || sc->omega == 0.0) state = 3;  // NaN / breakdown
+      else if (sc->it >= k.maxit) state = 2;
+      sc->beta = (rho_new / sc->rho) * (sc->alpha / sc->omega);
+      sc->rho = rho_new;
+      if (state != 0) {
+        sc->state = state;
+        atomicSub(k.n_active, 1);
+      }
+    }
+  }
+}
+
+// True residual max|rhs - A x| per problem (verification of the recursive residual).
+__global__ void __launch_bounds__(kBlock) k_true_residual(KrylovVecs k, size_t N, int ny, double* out_max) {
+  __shared__ double red[32];
+  const Scal* sc = k.scal + blockIdx.y;
+  const size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t base = (size_t)blockIdx.y * N;
+  double rabs = 0.0;
+  if (n < N) {
+    const size_t g = base + n;
+    double ax = 0.0;
+    if (sc->it > 0) {
+      const double* x = k.x + base;
+      ax = stencil_apply(x, n, N, ny, x[n], k.wW[g], k.wE[g], k.wS[g], k.wN[g]);
+    }
+    rabs = fabs(k.rhs[g] - ax);
+  }
+  const double bmax = block_max(rabs, red);
+  if (threadIdx.x == 0)
+    atomicMax(reinterpret_cast<unsigned long long*>(out_max), (unsigned long long)__double_as_longlong(bmax));
+}
+
+struct StepStats {  // device-resident, copied back with the step result
+  double fmin;
+  unsigned long long negatives;
+  double resid_max;
+  int it_max;
+  int n_bad;  // problems that ended in state 2/3
+};
+
+// KF: f^{n+1} = c (1 + d); yprev = clamp(f^{n+1}/f^n); statistics.           40 B/cell
+__global__ void __launch_bounds__(kBlock) k_finish(const double* __restrict__ x, const double* __restrict__ cs,
+                                                   double* __restrict__ f, double* __restrict__ yprev,
+                                                   const Scal* __restrict__ scal, size_t N, int predictor,
+                                                   StepStats* st) {
+  const Scal* sc = scal + blockIdx.y;
+  const size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double fmin = 1.0e300;
+  int neg = 0;
+  if (n < N) {
+    const size_t g = (size_t)blockIdx.y * N + n;
+    const double d = sc->it > 0 ? x[g] : 0.0;
+    const double fold = f[g];
+    const double fnew = cs[g] * (1.0 + d);
+    f[g] = fnew;
+    if (predictor) {
+      double y = fnew / fold;
+      y = ::fmin(::fmax(y, kPredMin), kPredMax);
+      yprev[g] = (y == y) ? y : 1.0;
+    }
+    fmin = fnew;
+    neg = fnew < 0.0;
+  }
+  double mn = warp_min(fmin);
+  __shared__ double smin[32];
+  __shared__ int sneg[32];
+  int wn = __reduce_add_sync(0xffffffffu, neg);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (lane == 0) { smin[w] = mn; sneg[w] = wn; }
+  __syncthreads();
+  if (w == 0) {
+    mn = warp_min(lane < nw ? smin[lane] : 1.0e300);
+    wn = __reduce_add_sync(0xffffffffu, lane < nw ? sneg[lane] : 0);
+    if (lane == 0) {
+      if (wn) atomicAdd(&st->negatives, (unsigned long long)wn);
+      // atomic min on a double through CAS (values may be negative)
+      unsigned long long* addr = reinterpret_cast<unsigned long long*>(&st->fmin);
+      unsigned long long old = *addr;
+      while (mn < __longlong_as_double((long long)old)) {
+        const unsigned long long assumed = old;
+        old = atomicCAS(addr, assumed, (unsigned long long)__double_as_longlong(mn));
+        if (old == assumed) break;
+      }
+      if (blockIdx.x == 0) {
+        atomicMax(&st->it_max, sc->it);
+        if (sc->state >= 2) atomicAdd(&st->n_bad, 1);
+      }
+    }
+  }
+}
+
+}  // namespace sy2d

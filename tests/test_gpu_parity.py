@@ -1,0 +1,259 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes), against
+ (1) the golden fixtures produced by the reference's own sources,
+ (2) the oracle on seeded random inputs at sizes it finishes in seconds,
+ (3) size-independent properties at BASELINE.json's full sizes.
+Tolerances: the reference solves with a direct LU, this engine with BiCGSTAB to
+max|r| <= 1e-14 on the scaled system; north_star asks for max relative difference
+in f <= 1e-8 after the full run and zero negative cells."""
+import numpy as np
+import pytest
+
+from conftest import CASE_OF, bc_for, engine_from_golden, load_golden, max_rel
+
+import sayram2d_b200 as sy
+from sayram2d_b200 import fields
+
+pytestmark = pytest.mark.gpu
+
+PARITY = 1e-8  # north_star: max relative difference in f after the full run
+
+
+@pytest.mark.parametrize("tag", ["ay80", "lc80", "nu48x40", "syn64x48"])
+def test_operator_and_vertex_values_match_reference(tag):
+    import ppfv_oracle as O
+    g = load_golden(tag)
+    eng = engine_from_golden(g, CASE_OF[tag])
+    op = eng.dump_operator()
+    for k in ("diag", "W", "E", "S", "N", "R"):
+        ref = g["op1_" + k]
+        assert np.max(np.abs(op[k][0] - ref)) <= 5e-14 * np.max(np.abs(ref)), k
+    m = O.Mesh(g["x_edges"], g["y_edges"], g["meta"]["dt"])
+    bct, lines = bc_for(CASE_OF[tag], g["x_edges"], g["y_edges"])
+    eq = O.Equation(m); eq.bc = list(bct); eq.dirichlet_lines = lambda t: lines
+    ref_vf = O.fill_vertex_from_bcs(m, eq, O.fill_vertex_from_cells(m, g["f_0"]), 0.0)
+    assert np.max(np.abs(eng.dump_vertex_f()[0] - ref_vf)) <= 1e-15 * np.max(np.abs(ref_vf))
+    eng.close()
+
+
+@pytest.mark.parametrize("tag", ["ay80", "lc80"])
+def test_full_run_parity_with_reference(tag):
+    """data/p.ini and data/p_AlbertYoungLC.ini: 500 steps, snapshots at t = 0.1, 0.5, 1.0 day."""
+    g = load_golden(tag)
+    eng = engine_from_golden(g, CASE_OF[tag])
+    done = 0
+    for k, upto in ((1, 50), (5, 250), (10, 500)):
+        st = eng.step(upto - done)
+        done = upto
+        f = eng.get_f()[0]
+        assert st["negatives"] == 0 and (f < 0).sum() == 0
+        assert max_rel(f, g[f"f_{k}"]) < PARITY, (k, max_rel(f, g[f"f_{k}"]))
+        assert st["resid_last"] < 1e-12
+    assert abs(eng.time() - 1.0) < 1e-12 and eng.step_count() == 500
+    # the operator of step 250 was assembled from f at step 249; check step-250 operator by re-running
+    eng.close()
+
+
+def test_mid_run_operator_matches_reference():
+    g = load_golden("ay80")
+    eng = engine_from_golden(g, "AY")
+    eng.step(249)
+    op = eng.dump_operator()   # M(f^249), R(f^249) = what the reference factorises in its 250th update()
+    for k in ("diag", "W", "E", "S", "N", "R"):
+        ref = g["op250_" + k]
+        assert np.max(np.abs(op[k][0] - ref)) <= 1e-9 * np.max(np.abs(ref)), k
+    eng.close()
+
+
+@pytest.mark.parametrize("tag,nsteps,key", [("nu48x40", 20, "f_20"), ("syn64x48", 10, "f_10")])
+def test_short_runs_nonuniform_and_synthetic(tag, nsteps, key):
+    g = load_golden(tag)
+    eng = engine_from_golden(g, CASE_OF[tag])
+    eng.step(1)
+    assert max_rel(eng.get_f()[0], g["f_1"]) < 1e-10
+    eng.step(nsteps - 1)
+    assert max_rel(eng.get_f()[0], g[key]) < 1e-9
+    eng.close()
+
+
+def test_ensemble_members_match_reference():
+    """BASELINE config 4: members 0, 63, 2047, 4095 (+ fillers) batched in one context."""
+    lc = load_golden("lc80")
+    ens = load_golden("ens_members")
+    members = [0, 63, 2047, 4095, 1, 64, 2048, 777]
+    a, b = fields.ensemble_scales(np.array(members))
+    nb = len(members)
+    eng = sy.Engine(lc["x_edges"], lc["y_edges"], lc["meta"]["dt"], nbatch=nb)
+    sc = lambda arr, s: arr[None] * s[:, None, None]
+    one = np.ones(nb)
+    eng.set_coeffs(sc(lc["G"], one), sc(lc["Dxx"], a), sc(lc["Dxy"], a), sc(lc["Dyy"], a), sc(lc["inv_tau"], b))
+    bct, lines = bc_for("LC", lc["x_edges"], lc["y_edges"])
+    eng.set_bc(bct, *lines)
+    eng.set_f(sc(lc["f_0"], one))
+    eng.step(50)
+    f = eng.get_f()
+    for k, mth in enumerate(members[:4]):
+        assert max_rel(f[k], ens[f"f1_m{mth}"]) < PARITY, mth
+    eng.step(450)
+    f = eng.get_f()
+    for k, mth in enumerate(members[:4]):
+        assert max_rel(f[k], ens[f"f10_m{mth}"]) < PARITY, mth
+    assert (f < 0).sum() == 0
+    eng.close()
+
+
+def test_batch_members_are_independent_and_reproducible():
+    g = load_golden("lc80")
+    e1 = engine_from_golden(g, "LC", nbatch=1)
+    e3 = engine_from_golden(g, "LC", nbatch=3)
+    e1.step(5); e3.step(5)
+    f1, f3 = e1.get_f(), e3.get_f()
+    for k in range(3):
+        assert max_rel(f3[k], f1[0]) < 1e-11
+    e1.close(); e3.close()
+
+
+def test_graph_and_plain_launch_agree():
+    g = load_golden("ay80")
+    a = engine_from_golden(g, "AY", use_graph=1, check_every=8)
+    b = engine_from_golden(g, "AY", use_graph=0, check_every=3)
+    a.step(10); b.step(10)
+    assert max_rel(a.get_f(), b.get_f()) < 1e-11
+    a.close(); b.close()
+
+
+def test_grid_1024_matches_reference_subsample():
+    """BASELINE config 3 (1024x1024 synthetic tensor + loss), 3 steps, against the
+    reference build's f sub-sampled every 8 cells (tests/golden/make_golden.py)."""
+    g = load_golden("syn1024_sub")
+    n = 1024
+    xe, ye = fields.uniform_edges(n, n)
+    eng = sy.Engine(xe, ye, 0.002)
+    Dxx, Dxy, Dyy, inv_tau = fields.synthetic_tensor(xe, ye)
+    eng.set_coeffs(fields.ay_G(xe, ye), Dxx, Dxy, Dyy, inv_tau)
+    f0, bct, lines = fields.ay_init_and_bc(xe, ye)
+    eng.set_bc(bct, *lines)
+    eng.set_f(f0)
+    assert max_rel(f0[3::8, 5::8], g["f_0"]) < 1e-12
+    st = eng.step(1)
+    assert max_rel(eng.get_f()[0][3::8, 5::8], g["f_1"]) < PARITY
+    st = eng.step(2)
+    f = eng.get_f()[0]
+    assert max_rel(f[3::8, 5::8], g["f_3"]) < PARITY
+    assert st["negatives"] == 0 and (f < 0).sum() == 0 and st["resid_last"] < 1e-12
+    eng.close()
+
+
+# ---- seeded random inputs vs the oracle ---------------------------------------
+def _random_case(seed, nx, ny, bc):
+    import ppfv_oracle as O
+    rng = np.random.default_rng(seed)
+    xe = np.concatenate([[0.0], np.cumsum(rng.uniform(0.5, 1.5, nx))]) * 0.05
+    ye = np.concatenate([[0.0], np.cumsum(rng.uniform(0.5, 1.5, ny))]) * 0.05
+    m = O.Mesh(xe, ye, 0.01)
+    eq = O.Equation(m)
+    eq.G = rng.uniform(0.5, 2.0, (nx, ny))
+    eq.Dxx = rng.uniform(0.1, 3.0, (nx, ny))
+    eq.Dyy = rng.uniform(0.1, 3.0, (nx, ny))
+    eq.Dxy = rng.uniform(-0.9, 0.9, (nx, ny)) * np.sqrt(eq.Dxx * eq.Dyy)
+    eq.inv_tau = rng.uniform(0.0, 4.0, (nx, ny))
+    eq.bc = list(bc)
+    lines = [rng.uniform(0.1, 1.0, ny + 1), rng.uniform(0.1, 1.0, ny + 1), rng.uniform(0.1, 1.0, nx + 1), rng.uniform(0.1, 1.0, nx + 1)]
+    eq.dirichlet_lines = lambda t: lines
+    f = rng.uniform(0.1, 2.0, (nx, ny)) * 10.0 ** rng.uniform(-12, 0, (nx, ny))
+    eq.init_f = lambda: f
+    return m, eq, lines, f
+
+
+@pytest.mark.parametrize("seed,nx,ny,bc", [(1, 33, 21, (0, 0, 0, 0)), (2, 7, 50, (1, 1, 1, 1)), (3, 64, 64, (0, 1, 1, 0)),
+                                           (4, 1, 9, (0, 0, 1, 1)), (5, 9, 1, (1, 0, 0, 0)), (6, 2, 2, (0, 1, 0, 1))])
+def test_random_problems_match_oracle(seed, nx, ny, bc):
+    """Ragged, tiny and degenerate (single row/column) grids, every BC combination class."""
+    import ppfv_oracle as O
+    m, eq, lines, f = _random_case(seed, nx, ny, bc)
+    eng = sy.Engine(m.x_edges, m.y_edges, m.dt)
+    eng.set_coeffs(eq.G, eq.Dxx, eq.Dxy, eq.Dyy, eq.inv_tau)
+    eng.set_bc(bc, *[l if b == 0 else None for l, b in zip(lines, bc)])
+    eng.set_f(f)
+    s = O.Solver(m, eq, linear="banded")
+    op_ref = s.assemble()
+    op = eng.dump_operator()
+    for k in ("diag", "W", "E", "S", "N", "R"):
+        assert np.max(np.abs(op[k][0] - op_ref[k])) <= 1e-13 * max(np.max(np.abs(op_ref[k])), 1e-300), k
+    for _ in range(5):
+        s.update()
+    eng.step(5)
+    assert max_rel(eng.get_f()[0], s.f) < 1e-9
+    eng.close()
+
+
+# ---- properties at full size ---------------------------------------------------
+def test_constants_and_mass_with_zero_flux_at_full_size():
+    n = 1024
+    xe, ye = fields.uniform_edges(n, n)
+    Dxx, Dxy, Dyy, _ = fields.synthetic_tensor(xe, ye)
+    G = fields.ay_G(xe, ye)
+    eng = sy.Engine(xe, ye, 0.002)
+    eng.set_coeffs(G, Dxx, Dxy, Dyy, None)
+    eng.set_bc([1, 1, 1, 1])
+    eng.set_f(np.full((n, n), 0.37))
+    eng.step(2)
+    assert np.max(np.abs(eng.get_f() - 0.37)) < 1e-12          # constants are preserved
+    f0, _, _ = fields.ay_init_and_bc(xe, ye)
+    eng.set_f(f0)
+    vol = G * np.diff(xe)[:, None] * np.diff(ye)[None, :]
+    mass0 = (vol * f0).sum()
+    st = eng.step(2)
+    f = eng.get_f()[0]
+    assert abs((vol * f).sum() - mass0) < 1e-10 * mass0          # discrete mass is conserved
+    assert st["negatives"] == 0 and f.min() > 0
+    op = eng.dump_operator()                                      # M-matrix structure
+    assert (op["diag"] > 0).all() and all((op[k] <= 0).all() for k in "WESN") and (op["R"] >= 0).all()
+    eng.close()
+
+
+def test_ensemble_4096_members_positive_and_consistent():
+    """Full BASELINE config-4 batch for a few steps: positivity everywhere, and member
+    m equals the same member solved alone (no cross-talk inside the batch)."""
+    lc = load_golden("lc80")
+    nb = 4096
+    a, b = fields.ensemble_scales(np.arange(nb))
+    eng = sy.Engine(lc["x_edges"], lc["y_edges"], lc["meta"]["dt"], nbatch=nb)
+    sc = lambda arr, s: arr[None] * s[:, None, None]
+    one = np.ones(nb)
+    eng.set_coeffs(sc(lc["G"], one), sc(lc["Dxx"], a), sc(lc["Dxy"], a), sc(lc["Dyy"], a), sc(lc["inv_tau"], b))
+    bct, lines = bc_for("LC", lc["x_edges"], lc["y_edges"])
+    eng.set_bc(bct, *lines)
+    eng.set_f(sc(lc["f_0"], one))
+    st = eng.step(3)
+    f = eng.get_f()
+    assert st["negatives"] == 0 and f.min() > 0
+    for mth in (0, 1234, 4095):
+        solo = sy.Engine(lc["x_edges"], lc["y_edges"], lc["meta"]["dt"])
+        solo.set_coeffs(lc["G"], lc["Dxx"] * a[mth], lc["Dxy"] * a[mth], lc["Dyy"] * a[mth], lc["inv_tau"] * b[mth])
+        solo.set_bc(bct, *lines)
+        solo.set_f(lc["f_0"])
+        solo.step(3)
+        assert max_rel(f[mth], solo.get_f()[0]) < 1e-10
+        solo.close()
+    eng.close()
+
+
+# ---- error behaviour -----------------------------------------------------------
+def test_error_behaviour():
+    g = load_golden("ay80")
+    eng = sy.Engine(g["x_edges"], g["y_edges"], 0.002)
+    with pytest.raises(sy.Sy2dError) as e:
+        eng.step(1)
+    assert e.value.code == -4                                     # nothing staged yet
+    eng.set_coeffs(g["G"], g["Dxx"], g["Dxy"], g["Dyy"], None)
+    with pytest.raises(sy.Sy2dError) as e:
+        eng.set_bc([0, 1, 0, 0], None, None, None, None)
+    assert e.value.code == -5 and "Dirichlet BC: missing value." in str(e.value)   # Solver.cc:393
+    bct, lines = bc_for("AY", g["x_edges"], g["y_edges"])
+    eng.set_bc(bct, *lines)
+    eng.set_f(g["f_0"])
+    eng.set_options(maxit=3, check_every=1)
+    with pytest.raises(sy.Sy2dError) as e:
+        eng.step(1)
+    assert e.value.code == -3                                     # explicit non-convergence error
+    eng.close()
