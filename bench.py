@@ -44,7 +44,7 @@ LC_INI = os.path.join(ROOT, "data", "p_AlbertYoungLC.ini")
 
 # algorithmic HBM bytes per cell and launch (DESIGN.md "kernels"; fp64 = 8 B)
 BYTES_PER_CELL = {"assembly": 104, "p_update": 32, "spmv_v": 56, "s_update": 24, "spmv_t": 48, "xr_update": 56,
-                  "finish": 40, "other": 56}
+                  "finish": 40, "other": 56, "problem_steps": None}
 
 
 def measured_peak():
@@ -154,27 +154,37 @@ def make_grid(n, device):
     return eng, f0
 
 
-def roofline_from_profile(prof, only=None):
+def roofline_from_profile(prof, only=None, stats=None, cells_per_problem=None):
+    """achieved = algorithmic bytes / CUDA-event time per kernel.  The engine-2 kernel does whole
+    time steps: its bytes are (assembly 104 + finish 40) per cell-step + 216 per cell-iteration
+    + one 56 B/cell true-residual pass, with the iteration count it reported."""
     peak, peak_src = measured_peak()
     rows = {}
     for name, p in prof.items():
         if p["launches"] == 0 or p["ms"] <= 0:
             continue
+        if name == "problem_steps":
+            nbytes = p["cells"] * 144 + 216 * cells_per_problem * stats["iters_sum_all"] + 56 * p["cells"] / max(stats["steps"], 1)
+            gbs = nbytes / (p["ms"] * 1e-3) / 1e9
+            rows[name] = {"achieved": round(gbs, 1), "frac": round(gbs / peak, 4), "ms_total": round(p["ms"], 3),
+                          "launches": p["launches"], "bytes_total": nbytes,
+                          "mean_iters_per_step": stats["iters_sum_all"] * cells_per_problem / p["cells"]}
+            continue
         gbs = p["cells"] * BYTES_PER_CELL[name] / (p["ms"] * 1e-3) / 1e9
         rows[name] = {"achieved": round(gbs, 1), "frac": round(gbs / peak, 4), "ms_total": round(p["ms"], 3),
                       "launches": p["launches"], "us_per_launch": round(1e3 * p["ms"] / p["launches"], 2),
                       "bytes_per_cell": BYTES_PER_CELL[name]}
-    cand = {k: v for k, v in rows.items() if only is None or k in only}
+    cand = {k: v for k, v in rows.items() if only is None or k in only or k == "problem_steps"}
     dom = max(cand, key=lambda k: cand[k]["ms_total"]) if cand else None
     return rows, dom, peak, peak_src
 
 
 def profile_pass(eng, steps):
     eng.set_profiling(True)
-    eng.step(steps)
+    st = eng.step(steps)
     prof = eng.profile()
     eng.set_profiling(False)
-    return prof
+    return prof, st
 
 
 # ----------------------------------------------------------------------------- CPU reference
@@ -314,6 +324,7 @@ def ours(args):
     dev_s = max_over_ranks(st["seconds_device"])
     wall_s = max_over_ranks(wall)
     iters = max_over_ranks(st["iters_total"]) / args.steps
+    iters_mean = sum_over_ranks(st["iters_sum_all"]) / (NB_TOTAL * args.steps)
     launches = sum_over_ranks(st["kernel_launches"])
     negatives = sum_over_ranks(st["negatives"])
     value = cells_total * args.steps / dev_s
@@ -339,8 +350,9 @@ def ours(args):
            "d2h_bytes_per_step": cells_total * 8, "ms_per_step": 1e3 * e2e_s / args.steps}
 
     # ---- per-kernel roofline (separate profiled pass, CUDA events around every launch) ----
-    prof = profile_pass(eng, 2)
-    rows, dom, peak, peak_src = roofline_from_profile(prof, only=("p_update", "spmv_v", "s_update", "spmv_t", "xr_update", "assembly"))
+    prof, pst = profile_pass(eng, 2)
+    rows, dom, peak, peak_src = roofline_from_profile(prof, only=("p_update", "spmv_v", "s_update", "spmv_t", "xr_update", "assembly"),
+                                                      stats=pst, cells_per_problem=NX * NY)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
@@ -348,7 +360,7 @@ def ours(args):
                        "case": "Albert_Young_LC fields, D x a_m, 1/tau x b_m (SURVEY 8d config 4)", "parallelism": f"ensemble-shard x{world}",
                        "solver": "BiCGSTAB on the f-scaled unit-diagonal system, max|r|<=1e-14",
                        "l2": f"working set {nb * NX * NY * 8 * 19 / 1e6:.0f} MB per GPU > 126 MB L2: no flush needed"},
-            "iters_per_step": iters, "negatives": int(negatives), "wall_ms_per_step": 1e3 * wall_s / args.steps,
+            "iters_per_step": iters, "iters_per_step_mean": iters_mean, "engine": st["engine"], "negatives": int(negatives), "wall_ms_per_step": 1e3 * wall_s / args.steps,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
     if dom:
         r = rows[dom]
@@ -379,8 +391,8 @@ def grid_object(n, device, args, torch):
         flush.zero_(); torch.cuda.synchronize()
         st = eng.step(1)
         dev_s += st["seconds_device"]; iters += st["iters_total"]
-    prof = profile_pass(eng, 1)
-    rows, dom, peak, peak_src = roofline_from_profile(prof)
+    prof, pst = profile_pass(eng, 1)
+    rows, dom, peak, peak_src = roofline_from_profile(prof, stats=pst, cells_per_problem=n * n)
     out = {"workload": f"grid{n}", "value": n * n * steps / dev_s, "unit": UNIT, "steps": steps, "ms_per_step": 1e3 * dev_s / steps,
            "iters_per_step": iters / steps, "negatives": st["negatives"], "resid_last": st["resid_last"],
            "l2": "256 MB flush between timed steps; the 19-array working set (~160 MB) cycles through L2 within a step",

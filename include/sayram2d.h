@@ -52,7 +52,8 @@ typedef struct {
   int predictor;     /* 1: column-scale by f^n * (f^n/f^{n-1}) instead of f^n; default 1 */
   int check_every;   /* iterations between host convergence polls; default 16 */
   int use_graph;     /* 1: replay the iteration chunk as a CUDA graph; default 1 */
-  int engine;        /* 0 auto, 1 lockstep multi-kernel, 2 one-CTA-per-problem persistent */
+  int engine;        /* 0 auto (2 when nx*ny <= 16384, else 1), 1 lockstep multi-kernel,
+                        2 one persistent CTA per problem (whole time loop in one launch) */
   int reserved[5];
 } sy2d_options;
 
@@ -66,6 +67,10 @@ typedef struct {
   long long negatives;        /* number of cells with f < 0 after the last step */
   double seconds_device;      /* CUDA-event time of the whole call on the context's stream */
   long long kernel_launches;  /* kernels of this library launched by the call (graph nodes included) */
+  long long iters_sum_all;    /* iterations summed over steps AND batch members (mean = / (steps*nbatch));
+                                 lockstep engine: iters_total * nbatch (all members iterate together) */
+  int engine;                 /* engine that ran: 1 lockstep multi-kernel, 2 one CTA per problem */
+  int reserved;
 } sy2d_stats;
 
 /* per-kernel device time of profiled sy2d_step calls (see sy2d_set_profiling) */
@@ -78,6 +83,7 @@ enum {
   SY2D_K_XR_UPDATE,    /* x, r update, (rhat, r), max|r|               */
   SY2D_K_FINISH,       /* f = c (1 + d), statistics                    */
   SY2D_K_OTHER,        /* true-residual check                          */
+  SY2D_K_PROBLEM_STEPS,/* engine 2: whole time steps, one CTA per problem */
   SY2D_K_COUNT
 };
 typedef struct {

@@ -14,6 +14,7 @@
 
 #include "sy2d_geometry.h"
 #include "sy2d_kernels.cuh"
+#include "sy2d_problem_kernel.cuh"
 
 using namespace sy2d;
 
@@ -181,7 +182,7 @@ const char* sy2d_build_info(void) {
   return "sayram2d_b200;arch=sm_100a;cuda="
 #define SY2D_STR2(x) #x
 #define SY2D_STR(x) SY2D_STR2(x)
-      SY2D_STR(CUDART_VERSION) ";fp64;engine=lockstep-bicgstab";
+      SY2D_STR(CUDART_VERSION) ";fp64;engines=lockstep-bicgstab,cta-per-problem";
 }
 
 int sy2d_device_count(void) {
@@ -396,11 +397,67 @@ static int ready(sy2d_ctx* c, const char* who) {
   return SY2D_OK;
 }
 
+static int engine_of(const sy2d_ctx* c) {
+  if (c->opt.engine == 1 || c->opt.engine == 2) return c->opt.engine;
+  return c->N <= 16384 ? 2 : 1;
+}
+
+// Engine 2: the whole call (nsteps time steps of every problem) is ONE kernel launch.
+static int step_per_problem(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
+  sy2d_stats st;
+  std::memset(&st, 0, sizeof st);
+  st.engine = 2;
+  if (nsteps == 0) { if (stats) *stats = st; return SY2D_OK; }
+  StepStats init;
+  std::memset(&init, 0, sizeof init);
+  init.fmin = 1.0e300;
+  *c->h_stats = init;
+  CU(cudaEventRecord(c->ev_call0, c->stream));
+  CU(cudaMemcpyAsync(c->d_stats, c->h_stats, sizeof(StepStats), cudaMemcpyHostToDevice, c->stream));
+  ProblemArgs a;
+  a.tx = c->tx; a.ty = c->ty; a.cxy = c->cxy; a.U = c->U; a.Ud = c->Ud;
+  a.f = c->f; a.yprev = c->yprev; a.cs = c->cs;
+  a.wW = c->wW; a.wE = c->wE; a.wS = c->wS; a.wN = c->wN; a.rhs = c->rhs;
+  a.x = c->x; a.r = c->r; a.p = c->p; a.v = c->v; a.s = c->s; a.t = c->t;
+  a.scal = c->scal; a.stats = c->d_stats; a.g = geometry(c);
+  a.tol = c->opt.tol; a.maxit = c->opt.maxit; a.predictor = c->opt.predictor; a.nsteps = nsteps;
+  c->cur_cells = (double)c->total * nsteps;
+  {
+    Prof p(c, SY2D_K_PROBLEM_STEPS);
+    k_problem_steps<<<c->nbatch, kProblemThreads, 0, c->stream>>>(a);
+  }
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(StepStats), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaEventRecord(c->ev_call1, c->stream));
+  CU(cudaEventSynchronize(c->ev_call1));
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, c->ev_call0, c->ev_call1));
+  int rc = collect_profile(c);
+  if (rc) return rc;
+  const StepStats& h = *c->h_stats;
+  c->istep += nsteps;
+  st.steps = nsteps;
+  st.iters_total = h.it_total_max;
+  st.iters_last = h.it_max;
+  st.iters_sum_all = (long long)h.it_sum_all;
+  st.resid_last = h.resid_max;
+  st.fmin = h.fmin;
+  st.negatives = (long long)h.negatives;
+  st.seconds_device = ms * 1e-3;
+  st.kernel_launches = 1;
+  if (stats) *stats = st;
+  if (h.n_bad > 0)
+    return fail(c, SY2D_ERR_NOT_CONVERGED, "sy2d_step: BiCGSTAB did not converge (%d problems, up to %d iterations in a step)",
+                h.n_bad, h.it_max);
+  return SY2D_OK;
+}
+
 int sy2d_step(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
   if (!c || nsteps < 0) return SY2D_ERR_INVALID;
   int rc = ready(c, "sy2d_step");
   if (rc) return rc;
   CU(cudaSetDevice(c->device));
+  if (engine_of(c) == 2) return step_per_problem(c, nsteps, stats);
   const dim3 g = grid_of(c);
   const Geometry geo = geometry(c);
   const bool graph = c->opt.use_graph && !c->profiling;
@@ -409,6 +466,7 @@ int sy2d_step(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
   if (graph) { rc = build_chunk_graph(c); if (rc) return rc; }
   sy2d_stats st;
   std::memset(&st, 0, sizeof st);
+  st.engine = 1;
   CU(cudaEventRecord(c->ev_call0, c->stream));
   for (int step = 0; step < nsteps; ++step) {
     CU(cudaMemsetAsync(c->d_nactive, 0, sizeof(int), c->stream));
@@ -442,7 +500,8 @@ int sy2d_step(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
     c->cur_cells = (double)c->total;
     // verification + finish
     StepStats init;
-    init.fmin = 1.0e300; init.negatives = 0; init.resid_max = 0.0; init.it_max = 0; init.n_bad = 0;
+    std::memset(&init, 0, sizeof init);
+    init.fmin = 1.0e300;
     *c->h_stats = init;
     CU(cudaMemcpyAsync(c->d_stats, c->h_stats, sizeof(StepStats), cudaMemcpyHostToDevice, c->stream));
     {
@@ -462,6 +521,7 @@ int sy2d_step(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
     c->istep += 1;
     st.steps += 1;
     st.iters_total += c->h_stats->it_max;
+    st.iters_sum_all += (long long)c->h_stats->it_max * c->nbatch;
     st.iters_last = c->h_stats->it_max;
     st.resid_last = c->h_stats->resid_max;
     st.fmin = c->h_stats->fmin;

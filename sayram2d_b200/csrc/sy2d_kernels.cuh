@@ -553,6 +553,9 @@ struct StepStats {  // device-resident, copied back with the step result
   double resid_max;
   int it_max;
   int n_bad;  // problems that ended in state 2/3
+  int it_total_max;                // engine B: max over problems of iterations summed over the call's steps
+  int pad_;
+  unsigned long long it_sum_all;   // engine B: iterations summed over problems and steps
 };
 
 // KF: f^{n+1} = c (1 + d); yprev = clamp(f^{n+1}/f^n); statistics.           40 B/cell

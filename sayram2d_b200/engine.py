@@ -9,7 +9,7 @@ import numpy as np
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-K_NAMES = ("assembly", "p_update", "spmv_v", "s_update", "spmv_t", "xr_update", "finish", "other")
+K_NAMES = ("assembly", "p_update", "spmv_v", "s_update", "spmv_t", "xr_update", "finish", "other", "problem_steps")
 DIRICHLET, ZEROFLUX = 0, 1
 
 
@@ -27,7 +27,8 @@ class Options(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("steps", C.c_longlong), ("iters_total", C.c_longlong), ("iters_last", C.c_int),
                 ("restarts_total", C.c_int), ("resid_last", C.c_double), ("fmin", C.c_double),
-                ("negatives", C.c_longlong), ("seconds_device", C.c_double), ("kernel_launches", C.c_longlong)]
+                ("negatives", C.c_longlong), ("seconds_device", C.c_double), ("kernel_launches", C.c_longlong),
+                ("iters_sum_all", C.c_longlong), ("engine", C.c_int), ("reserved", C.c_int)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
