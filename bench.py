@@ -245,7 +245,7 @@ def reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "gpu_launches": 0,
-            "config": {"workload": "ensemble4096", "members": NB_TOTAL, "grid": [NX, NY], "dt": DT}}
+            "config": {"workload": f"ensemble{NB_TOTAL}", "members": NB_TOTAL, "grid": [NX, NY], "dt": DT}}
     if not os.path.exists(REF_DRIVER):
         line["unavailable"] = "oracle/_ref/ref_driver not built (make -C oracle ref needs /root/reference)"
         print(json.dumps(line), flush=True)
@@ -356,7 +356,7 @@ def ours(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "ensemble4096", "members": NB_TOTAL, "members_per_gpu": nb, "grid": [NX, NY], "dt": DT,
+            "config": {"workload": f"ensemble{NB_TOTAL}", "members": NB_TOTAL, "members_per_gpu": nb, "grid": [NX, NY], "dt": DT,
                        "case": "Albert_Young_LC fields, D x a_m, 1/tau x b_m (SURVEY 8d config 4)", "parallelism": f"ensemble-shard x{world}",
                        "solver": "BiCGSTAB on the f-scaled unit-diagonal system, max|r|<=1e-14",
                        "l2": f"working set {nb * NX * NY * 8 * 19 / 1e6:.0f} MB per GPU > 126 MB L2: no flush needed"},
@@ -404,16 +404,19 @@ def grid_object(n, device, args, torch):
 
 
 def main():
+    global NB_TOTAL
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-grid1024", action="store_true")
+    ap.add_argument("--members", type=int, default=NB_TOTAL, help="ensemble size (profiling runs use a smaller one)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs")
     ap.add_argument("--no-grid-cpu", action="store_true", help="skip the ~40 s CPU baseline of the 1024^2 grid")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    NB_TOTAL = args.members
     if args.impl == "reference":
         reference_arm(args)
     else:

@@ -42,11 +42,14 @@ def build_library(force=False):
     return LIB
 
 
+DROPIN = os.path.join(PKG, "dropin")  # Solver.{h,cc}: compile against these host classes OR the reference's
+
+
 def host_sources():
     hdir = os.path.join(PKG, "host")
     if not os.path.isdir(hdir):
         return []
-    return sorted(os.path.join(hdir, f) for f in os.listdir(hdir) if f.endswith(".cc"))
+    return sorted(os.path.join(hdir, f) for f in os.listdir(hdir) if f.endswith(".cc")) + [os.path.join(DROPIN, "Solver.cc")]
 
 
 def build_host(force=False):
@@ -55,10 +58,10 @@ def build_host(force=False):
     if not srcs:
         return None
     hdir = os.path.join(PKG, "host")
-    deps = srcs + [os.path.join(hdir, f) for f in os.listdir(hdir) if f.endswith(".h")] + [LIB]
+    deps = srcs + [os.path.join(hdir, f) for f in os.listdir(hdir) if f.endswith(".h")] + [LIB, os.path.join(DROPIN, "Solver.h")]
     if force or _stale(BIN, deps):
         os.makedirs(os.path.dirname(BIN), exist_ok=True)
-        _run(["/usr/bin/g++", "-O2", "-std=c++17", "-I" + hdir, "-I" + os.path.join(ROOT, "include"), *srcs,
+        _run(["/usr/bin/g++", "-O2", "-std=c++17", "-I" + hdir, "-I" + DROPIN, "-I" + os.path.join(ROOT, "include"), *srcs,
               "-L" + os.path.dirname(LIB), "-lsayram2d_b200", "-Wl,-rpath,$ORIGIN/../lib", "-o", BIN])
     return BIN
 

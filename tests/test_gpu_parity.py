@@ -270,3 +270,47 @@ def test_error_behaviour():
             eng.step(1)
         assert e.value.code == -3                                 # explicit non-convergence error
     eng.close()
+
+
+# ---- the C++ host layer end to end ------------------------------------------------
+def _run_binary(exe, args, tmp_path):
+    import os
+    import subprocess
+    from conftest import ROOT
+    if not os.path.exists(exe):
+        pytest.skip(f"{exe} not built")
+    if not os.path.exists(tmp_path / "D"):
+        os.symlink(os.path.join(ROOT, "data", "D"), tmp_path / "D")
+    res = subprocess.run([exe, *args], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout + res.stderr
+    return res.stdout
+
+
+@pytest.mark.parametrize("case,ini,tag,run_id", [("AY", "p.ini", "ay80", "AlbertYoung"), ("LC", "p_AlbertYoungLC.ini", "lc80", "AlbertYoungLC")])
+def test_standalone_host_binary_full_run(tmp_path, case, ini, tag, run_id):
+    """sayram2d_b200/bin/sayram2d = this repo's Parameters/Mesh/Equation/Solver + main on the ini files."""
+    import os
+    from conftest import ROOT
+    out = _run_binary(os.path.join(ROOT, "sayram2d_b200", "bin", "sayram2d"), [os.path.join(ROOT, "data", ini), "--case", case], tmp_path)
+    assert "CPU time used" in out and " 0 negative cells" in out
+    g = load_golden(tag)
+    d = tmp_path / "output" / run_id / f"{run_id}_data"
+    for k in (0, 1, 5, 10):
+        assert max_rel(np.load(d / f"f_{k}.npy"), g[f"f_{k}"]) < PARITY
+    assert np.allclose(np.load(d / "t.npy"), np.linspace(0, 1, 11)) and np.load(d / "alpha0.npy").shape == (80,)
+
+
+@pytest.mark.parametrize("case,ini,tag,run_id", [("AY", "p.ini", "ay80", "AlbertYoung"), ("LC", "p_AlbertYoungLC.ini", "lc80", "AlbertYoungLC")])
+def test_reference_main_with_gpu_solver_dropped_in(tmp_path, case, ini, tag, run_id):
+    """The reference's UNMODIFIED main.cc / Mesh.cc / Parameters.cc / Cases/*.cc linked with
+    sayram2d_b200/dropin/Solver.cc in place of its Solver.cc (oracle/Makefile target dropin)."""
+    import os
+    import shutil
+    from conftest import ROOT
+    shutil.copy(os.path.join(ROOT, "data", ini), tmp_path / ini)
+    out = _run_binary(os.path.join(ROOT, "oracle", "_ref", f"sayram-2d_{case}_dropin"), [ini], tmp_path)
+    assert "CPU time used" in out
+    g = load_golden(tag)
+    d = tmp_path / "output" / run_id / f"{run_id}_data.h5.d"
+    for k in (0, 1, 5, 10):
+        assert max_rel(np.load(d / f"f_{k}.npy"), g[f"f_{k}"]) < PARITY
