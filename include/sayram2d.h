@@ -43,12 +43,16 @@ enum { SY2D_XMIN = 0, SY2D_XMAX = 1, SY2D_YMIN = 2, SY2D_YMAX = 3 };
 enum { SY2D_DIRICHLET = 0, SY2D_ZEROFLUX = 1 };
 
 /* preconditioner inside the BiCGSTAB loop */
-enum { SY2D_PRECOND_JACOBI = 0, SY2D_PRECOND_XLINE = 1 };
+enum {
+  SY2D_PRECOND_AUTO = -1,  /* XLINE where the engine supports it (engine 2, nx <= 80, ny <= 128), else JACOBI */
+  SY2D_PRECOND_JACOBI = 0, /* the unit-diagonal scaling itself */
+  SY2D_PRECOND_XLINE = 1   /* right preconditioning by the tridiagonal along i (alpha0): ~4x fewer iterations */
+};
 
 typedef struct {
   double tol;        /* stop when max_K |r_K| <= tol on the scaled system (unknown ~ O(1)); default 1e-14 */
   int maxit;         /* per linear solve; default 20000 */
-  int precond;       /* SY2D_PRECOND_*; default JACOBI (the unit-diagonal scaling itself) */
+  int precond;       /* SY2D_PRECOND_*; default AUTO */
   int predictor;     /* 1: column-scale by f^n * (f^n/f^{n-1}) instead of f^n; default 1 */
   int check_every;   /* iterations between host convergence polls; default 16 */
   int use_graph;     /* 1: replay the iteration chunk as a CUDA graph; default 1 */
@@ -70,7 +74,7 @@ typedef struct {
   long long iters_sum_all;    /* iterations summed over steps AND batch members (mean = / (steps*nbatch));
                                  lockstep engine: iters_total * nbatch (all members iterate together) */
   int engine;                 /* engine that ran: 1 lockstep multi-kernel, 2 one CTA per problem */
-  int reserved;
+  int precond;                /* preconditioner that ran (SY2D_PRECOND_JACOBI or _XLINE) */
 } sy2d_stats;
 
 /* per-kernel device time of profiled sy2d_step calls (see sy2d_set_profiling) */

@@ -15,6 +15,7 @@
 #include "sy2d_geometry.h"
 #include "sy2d_kernels.cuh"
 #include "sy2d_problem_kernel.cuh"
+#include "sy2d_xline_kernel.cuh"
 
 using namespace sy2d;
 
@@ -50,9 +51,12 @@ struct sy2d_ctx {
   int* h_nactive = nullptr;  // pinned
   StepStats* d_stats = nullptr;
   StepStats* h_stats = nullptr;  // pinned
-  // staging buffer for host->device coefficient uploads (5 fields), allocated on demand
-  double* stage = nullptr;
+  double* stage = nullptr;      // unused staging pointer (kept for destroy)
   size_t stage_elems = 0;
+  // engine 2 / x-line: per-problem scratch in thread-private layout, allocated on first use
+  double* xl_scratch = nullptr;
+  int xl_R = 0, xl_NT = 0, xl_S = 0;
+  size_t xl_smem = 0;
   // iteration-chunk graph
   cudaGraphExec_t chunk_exec = nullptr;
   int chunk_iters = 0;
@@ -196,7 +200,7 @@ int sy2d_default_options(sy2d_options* o) {
   std::memset(o, 0, sizeof *o);
   o->tol = 1e-14;
   o->maxit = 20000;
-  o->precond = SY2D_PRECOND_JACOBI;
+  o->precond = SY2D_PRECOND_AUTO;
   o->predictor = 1;
   o->check_every = 16;
   o->use_graph = 1;
@@ -271,7 +275,7 @@ void sy2d_destroy(sy2d_ctx* c) {
   if (c->chunk_exec) cudaGraphExecDestroy(c->chunk_exec);
   double* bufs[] = {c->d_wxL, c->d_wxR, c->d_wyB, c->d_wyT, c->d_dx, c->d_dy, c->d_bc[0], c->d_bc[1], c->d_bc[2], c->d_bc[3],
                     c->tx, c->ty, c->cxy, c->U, c->Ud, c->f, c->yprev, c->cs, c->wW, c->wE, c->wS, c->wN, c->rhs,
-                    c->x, c->r, c->p, c->v, c->s, c->t, c->stage};
+                    c->x, c->r, c->p, c->v, c->s, c->t, c->stage, c->xl_scratch};
   for (double* b : bufs) if (b) cudaFree(b);
   if (c->scal) cudaFree(c->scal);
   if (c->d_nactive) cudaFree(c->d_nactive);
@@ -289,7 +293,8 @@ int sy2d_set_options(sy2d_ctx* c, const sy2d_options* o) {
   if (!c || !o) return SY2D_ERR_INVALID;
   if (!(o->tol > 0.0) || o->maxit < 1 || o->check_every < 1)
     return fail(c, SY2D_ERR_INVALID, "sy2d_set_options: tol, maxit and check_every must be positive");
-  if (o->precond != SY2D_PRECOND_JACOBI) return fail(c, SY2D_ERR_INVALID, "sy2d_set_options: unsupported preconditioner %d", o->precond);
+  if (o->precond < SY2D_PRECOND_AUTO || o->precond > SY2D_PRECOND_XLINE)
+    return fail(c, SY2D_ERR_INVALID, "sy2d_set_options: unknown preconditioner %d", o->precond);
   c->opt = *o;
   return SY2D_OK;
 }
@@ -397,9 +402,46 @@ static int ready(sy2d_ctx* c, const char* who) {
   return SY2D_OK;
 }
 
+}  // extern "C"
+
 static int engine_of(const sy2d_ctx* c) {
   if (c->opt.engine == 1 || c->opt.engine == 2) return c->opt.engine;
   return c->N <= 16384 ? 2 : 1;
+}
+
+// Shape of the x-line kernel for this grid: R rows per thread (template instance), NT threads.
+// Returns false when the grid does not fit (too many rows per lane, too wide, or too much shared memory).
+static bool xline_shape(const sy2d_ctx* c, int* R, int* NT, int* S, size_t* smem) {
+  const int need = (c->nx + kXlineNCH - 1) / kXlineNCH;
+  const int choices[4] = {4, 6, 8, 10};
+  int r = 0;
+  for (int q : choices) if (q >= need) { r = q; break; }
+  if (r == 0) return false;
+  const int ny_pad = (c->ny + kXlineCPW - 1) / kXlineCPW * kXlineCPW;
+  const int nt = ny_pad * kXlineNCH;
+  if (nt > 1024) return false;
+  const size_t bytes = ((size_t)c->nx * (c->ny + 1) + 3 * (size_t)r * nt + 128) * sizeof(double);
+  if (bytes > 232448) return false;
+  *R = r; *NT = nt; *S = r * nt; *smem = bytes;
+  return true;
+}
+
+template <int R, int MAXT>
+static cudaError_t launch_xline(const XlineArgs& xa, int nbatch, size_t smem, cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(k_problem_xline<R, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_problem_xline<R, MAXT><<<nbatch, xa.NT, smem, stream>>>(xa);
+  return cudaGetLastError();
+}
+
+static cudaError_t dispatch_xline(const XlineArgs& xa, int R, int nbatch, size_t smem, cudaStream_t stream) {
+  const bool small = xa.NT <= 640;
+  switch (R) {
+    case 4: return small ? launch_xline<4, 640>(xa, nbatch, smem, stream) : launch_xline<4, 1024>(xa, nbatch, smem, stream);
+    case 6: return small ? launch_xline<6, 640>(xa, nbatch, smem, stream) : launch_xline<6, 1024>(xa, nbatch, smem, stream);
+    case 8: return small ? launch_xline<8, 640>(xa, nbatch, smem, stream) : launch_xline<8, 1024>(xa, nbatch, smem, stream);
+    default: return small ? launch_xline<10, 640>(xa, nbatch, smem, stream) : launch_xline<10, 1024>(xa, nbatch, smem, stream);
+  }
 }
 
 // Engine 2: the whole call (nsteps time steps of every problem) is ONE kernel launch.
@@ -422,7 +464,24 @@ static int step_per_problem(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
   a.scal = c->scal; a.stats = c->d_stats; a.g = geometry(c);
   a.tol = c->opt.tol; a.maxit = c->opt.maxit; a.predictor = c->opt.predictor; a.nsteps = nsteps;
   c->cur_cells = (double)c->total * nsteps;
-  {
+  int R = 0, NT = 0, S = 0;
+  size_t smem = 0;
+  const bool xline = c->opt.precond != SY2D_PRECOND_JACOBI && xline_shape(c, &R, &NT, &S, &smem);
+  if (c->opt.precond == SY2D_PRECOND_XLINE && !xline)
+    return fail(c, SY2D_ERR_INVALID, "sy2d_step: the x-line preconditioner needs nx <= 80, ny <= 128 and engine 2");
+  st.precond = xline ? SY2D_PRECOND_XLINE : SY2D_PRECOND_JACOBI;
+  if (xline) {
+    if (!c->xl_scratch || c->xl_S != S) {
+      if (c->xl_scratch) cudaFree(c->xl_scratch);
+      c->xl_scratch = nullptr;
+      CU(cudaMalloc(reinterpret_cast<void**>(&c->xl_scratch), (size_t)c->nbatch * 5 * S * sizeof(double)));
+      c->xl_S = S;
+    }
+    XlineArgs xa;
+    xa.a = a; xa.scratch = c->xl_scratch; xa.NT = NT; xa.S = S;
+    Prof p(c, SY2D_K_PROBLEM_STEPS);
+    CU(dispatch_xline(xa, R, c->nbatch, smem, c->stream));
+  } else {
     Prof p(c, SY2D_K_PROBLEM_STEPS);
     k_problem_steps<<<c->nbatch, kProblemThreads, 0, c->stream>>>(a);
   }
@@ -451,6 +510,8 @@ static int step_per_problem(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
                 h.n_bad, h.it_max);
   return SY2D_OK;
 }
+
+extern "C" {
 
 int sy2d_step(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
   if (!c || nsteps < 0) return SY2D_ERR_INVALID;

@@ -298,6 +298,18 @@ __host__ __device__ __forceinline__ void scale_row(const Row& r, double ypC, dou
   s.cs = cs0;
 }
 
+// LU of the x-line tridiagonal T = tridiag(wW, 1, wE) along i (one column j):
+//   d_0 = 1,  l_i = wW_i / d_{i-1},  d_i = 1 - l_i * wE_{i-1}
+// T is an M-matrix (A with its S/N couplings dropped), so the pivots stay positive.
+struct XlineFactor { double l, d, dinv; };
+__host__ __device__ __forceinline__ XlineFactor xline_factor(double wW_i, double wE_prev, double d_prev, bool first_row) {
+  XlineFactor f;
+  f.l = first_row ? 0.0 : wW_i / d_prev;
+  f.d = 1.0 - f.l * wE_prev;
+  f.dinv = 1.0 / f.d;
+  return f;
+}
+
 struct AssembleOut {
   // MODE 0 (solve): scaled unit-diagonal operator + Krylov start
   double *wW, *wE, *wS, *wN, *rhs, *cs;

@@ -28,7 +28,7 @@ class Stats(C.Structure):
     _fields_ = [("steps", C.c_longlong), ("iters_total", C.c_longlong), ("iters_last", C.c_int),
                 ("restarts_total", C.c_int), ("resid_last", C.c_double), ("fmin", C.c_double),
                 ("negatives", C.c_longlong), ("seconds_device", C.c_double), ("kernel_launches", C.c_longlong),
-                ("iters_sum_all", C.c_longlong), ("engine", C.c_int), ("reserved", C.c_int)]
+                ("iters_sum_all", C.c_longlong), ("engine", C.c_int), ("precond", C.c_int)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

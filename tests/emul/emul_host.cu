@@ -152,4 +152,93 @@ int emul_step(void* h, double* f, double* yprev, double tol, int maxit, int pred
   return rmax <= tol ? it : -it;
 }
 
+// Same step with the x-line (tridiagonal along i) right preconditioner, as engine 2's
+// k_problem_xline runs it:  T = tridiag(wW, 1, wE) per column j,  phat = T^-1 p,
+// v = A phat = p + wS phat_S + wN phat_N  (because T phat = p),  likewise for s.
+int emul_step_xline(void* h, double* f, double* yprev, double tol, int maxit, int predictor, double* resid_out) {
+  Emul* e = static_cast<Emul*>(h);
+  const Geometry g = e->geo();
+  const int nx = e->nx, ny = e->ny;
+  const size_t N = (size_t)nx * ny;
+  std::vector<double> wW(N), wE(N), wS(N), wN(N), rhs(N), cs(N), x(N, 0.0), r(N), p(N), v(N), t(N), hat(N), l(N), dinv(N), ee(N);
+  double rho = 0.0, rmax = 0.0;
+  for (int i = 0; i < nx; ++i)
+    for (int j = 0; j < ny; ++j) {
+      Row row;
+      assemble_row(f, e->tx.data(), e->ty.data(), e->cxy.data(), e->U.data(), e->Ud.data(), g, i, j, row);
+      const size_t n = (size_t)i * ny + j;
+      const size_t nW = i > 0 ? n - ny : n, nE = i < nx - 1 ? n + ny : n, nS = j > 0 ? n - 1 : n, nN = j < ny - 1 ? n + 1 : n;
+      Scaled sc;
+      scale_row(row, yprev[n], yprev[nW], yprev[nE], yprev[nS], yprev[nN], sc);
+      wW[n] = sc.wW; wE[n] = sc.wE; wS[n] = sc.wS; wN[n] = sc.wN; rhs[n] = sc.rhs; cs[n] = sc.cs;
+      rho += sc.rhs * sc.rhs;
+      rmax = std::fmax(rmax, std::fabs(sc.rhs));
+    }
+  for (int j = 0; j < ny; ++j) {  // LU of T per column: d_0 = 1, l_i = wW_i/d_{i-1}, d_i = 1 - l_i wE_{i-1}
+    double dprev = 1.0;
+    for (int i = 0; i < nx; ++i) {
+      const size_t n = (size_t)i * ny + j;
+      const XlineFactor fc = xline_factor(wW[n], i > 0 ? wE[n - ny] : 0.0, dprev, i == 0);
+      l[n] = fc.l; dinv[n] = fc.dinv; ee[n] = wE[n] * fc.dinv;
+      dprev = fc.d;
+    }
+  }
+  auto tsolve = [&](const std::vector<double>& b, std::vector<double>& y) {
+    for (int j = 0; j < ny; ++j) {
+      double carry = 0.0;
+      for (int i = 0; i < nx; ++i) { const size_t n = (size_t)i * ny + j; carry = b[n] - l[n] * carry; y[n] = carry; }
+      carry = 0.0;
+      for (int i = nx - 1; i >= 0; --i) { const size_t n = (size_t)i * ny + j; carry = y[n] * dinv[n] - ee[n] * carry; y[n] = carry; }
+    }
+  };
+  auto sn_apply = [&](const std::vector<double>& c, const std::vector<double>& yh, size_t n) {
+    const double yS = yh[n > 0 ? n - 1 : n], yN = yh[n + 1 < N ? n + 1 : n];
+    return c[n] + (wS[n] * yS + wN[n] * yN);
+  };
+  int it = 0;
+  double alpha = 1.0, omega = 1.0, beta = 0.0;
+  bool first = true;
+  r = rhs;
+  while (!(rmax <= tol) && it < maxit) {
+    for (size_t n = 0; n < N; ++n) p[n] = first ? r[n] : r[n] + beta * (p[n] - omega * v[n]);
+    tsolve(p, hat);
+    double rv = 0.0;
+    for (size_t n = 0; n < N; ++n) { v[n] = sn_apply(p, hat, n); rv += rhs[n] * v[n]; }
+    alpha = rv != 0.0 ? rho / rv : 0.0;
+    for (size_t n = 0; n < N; ++n) { r[n] = r[n] - alpha * v[n]; x[n] += alpha * hat[n]; }  // r now holds s
+    tsolve(r, hat);
+    double ts = 0.0, tt = 0.0;
+    for (size_t n = 0; n < N; ++n) { t[n] = sn_apply(r, hat, n); ts += t[n] * r[n]; tt += t[n] * t[n]; }
+    omega = tt > 0.0 ? ts / tt : 0.0;
+    double rho_new = 0.0;
+    rmax = 0.0;
+    for (size_t n = 0; n < N; ++n) {
+      x[n] += omega * hat[n];
+      r[n] = r[n] - omega * t[n];
+      rho_new += rhs[n] * r[n];
+      rmax = std::fmax(rmax, std::fabs(r[n]));
+    }
+    beta = (rho_new / rho) * (alpha / omega);
+    rho = rho_new;
+    first = false;
+    ++it;
+  }
+  double res = 0.0;  // true residual with the FULL operator (all four neighbours)
+  for (size_t n = 0; n < N; ++n) {
+    const double ax = it > 0 ? stencil_apply(x.data(), n, N, ny, x[n], wW[n], wE[n], wS[n], wN[n]) : 0.0;
+    res = std::fmax(res, std::fabs(rhs[n] - ax));
+  }
+  if (resid_out) *resid_out = res;
+  for (size_t n = 0; n < N; ++n) {
+    const double fold = f[n], fnew = cs[n] * (1.0 + (it > 0 ? x[n] : 0.0));
+    f[n] = fnew;
+    if (predictor) {
+      double y = fnew / fold;
+      y = std::fmin(std::fmax(y, kPredMin), kPredMax);
+      yprev[n] = (y == y) ? y : 1.0;
+    }
+  }
+  return rmax <= tol ? it : -it;
+}
+
 }  // extern "C"

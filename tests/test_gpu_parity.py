@@ -35,13 +35,17 @@ def test_operator_and_vertex_values_match_reference(tag):
     eng.close()
 
 
-@pytest.mark.parametrize("engine", [1, 2])
+ENGINES = [(1, 0), (2, 0), (2, 1)]  # (engine, precond): lockstep; CTA per problem with Jacobi / x-line
+
+
+@pytest.mark.parametrize("engine,precond", ENGINES)
 @pytest.mark.parametrize("tag", ["ay80", "lc80"])
-def test_full_run_parity_with_reference(tag, engine):
+def test_full_run_parity_with_reference(tag, engine, precond):
     """data/p.ini and data/p_AlbertYoungLC.ini: 500 steps, snapshots at t = 0.1, 0.5, 1.0 day,
-    with both engines (1 = lockstep multi-kernel, 2 = one persistent CTA per problem)."""
+    with every engine (1 = lockstep multi-kernel, 2 = one persistent CTA per problem, the latter
+    with the Jacobi scaling only or with the x-line preconditioner)."""
     g = load_golden(tag)
-    eng = engine_from_golden(g, CASE_OF[tag], engine=engine)
+    eng = engine_from_golden(g, CASE_OF[tag], engine=engine, precond=precond)
     done = 0
     for k, upto in ((1, 50), (5, 250), (10, 500)):
         st = eng.step(upto - done)
@@ -49,7 +53,7 @@ def test_full_run_parity_with_reference(tag, engine):
         f = eng.get_f()[0]
         assert st["negatives"] == 0 and (f < 0).sum() == 0
         assert max_rel(f, g[f"f_{k}"]) < PARITY, (k, max_rel(f, g[f"f_{k}"]))
-        assert st["resid_last"] < 1e-12 and st["engine"] == engine
+        assert st["resid_last"] < 1e-12 and st["engine"] == engine and st["precond"] == precond
     assert abs(eng.time() - 1.0) < 1e-12 and eng.step_count() == 500
     # the operator of step 250 was assembled from f at step 249; check step-250 operator by re-running
     eng.close()
@@ -66,11 +70,11 @@ def test_mid_run_operator_matches_reference():
     eng.close()
 
 
-@pytest.mark.parametrize("engine", [1, 2])
+@pytest.mark.parametrize("engine,precond", ENGINES)
 @pytest.mark.parametrize("tag,nsteps,key", [("nu48x40", 20, "f_20"), ("syn64x48", 10, "f_10")])
-def test_short_runs_nonuniform_and_synthetic(tag, nsteps, key, engine):
+def test_short_runs_nonuniform_and_synthetic(tag, nsteps, key, engine, precond):
     g = load_golden(tag)
-    eng = engine_from_golden(g, CASE_OF[tag], engine=engine)
+    eng = engine_from_golden(g, CASE_OF[tag], engine=engine, precond=precond)
     eng.step(1)
     assert max_rel(eng.get_f()[0], g["f_1"]) < 1e-10
     eng.step(nsteps - 1)
@@ -104,11 +108,11 @@ def test_ensemble_members_match_reference():
     eng.close()
 
 
-@pytest.mark.parametrize("engine", [1, 2])
-def test_batch_members_are_independent_and_reproducible(engine):
+@pytest.mark.parametrize("engine,precond", ENGINES)
+def test_batch_members_are_independent_and_reproducible(engine, precond):
     g = load_golden("lc80")
-    e1 = engine_from_golden(g, "LC", nbatch=1, engine=engine)
-    e3 = engine_from_golden(g, "LC", nbatch=3, engine=engine)
+    e1 = engine_from_golden(g, "LC", nbatch=1, engine=engine, precond=precond)
+    e3 = engine_from_golden(g, "LC", nbatch=3, engine=engine, precond=precond)
     e1.step(5); e3.step(5)
     f1, f3 = e1.get_f(), e3.get_f()
     for k in range(3):
@@ -120,10 +124,12 @@ def test_graph_and_plain_launch_agree():
     g = load_golden("ay80")
     a = engine_from_golden(g, "AY", engine=1, use_graph=1, check_every=8)
     b = engine_from_golden(g, "AY", engine=1, use_graph=0, check_every=3)
-    c = engine_from_golden(g, "AY", engine=2)
-    a.step(10); b.step(10); c.step(10)
+    c = engine_from_golden(g, "AY", engine=2, precond=0)
+    d = engine_from_golden(g, "AY", engine=2, precond=1)
+    a.step(10); b.step(10); c.step(10); st = d.step(10)
     assert max_rel(a.get_f(), b.get_f()) < 1e-11 and max_rel(c.get_f(), b.get_f()) < 1e-11
-    a.close(); b.close(); c.close()
+    assert max_rel(d.get_f(), b.get_f()) < 1e-11 and st["iters_total"] < 0.5 * c.last_stats["iters_total"]
+    a.close(); b.close(); c.close(); d.close()
 
 
 def test_grid_1024_matches_reference_subsample():
@@ -174,13 +180,13 @@ def _random_case(seed, nx, ny, bc):
 
 @pytest.mark.parametrize("seed,nx,ny,bc", [(1, 33, 21, (0, 0, 0, 0)), (2, 7, 50, (1, 1, 1, 1)), (3, 64, 64, (0, 1, 1, 0)),
                                            (4, 1, 9, (0, 0, 1, 1)), (5, 9, 1, (1, 0, 0, 0)), (6, 2, 2, (0, 1, 0, 1))])
-@pytest.mark.parametrize("engine", [1, 2])
-def test_random_problems_match_oracle(seed, nx, ny, bc, engine):
+@pytest.mark.parametrize("engine,precond", ENGINES)
+def test_random_problems_match_oracle(seed, nx, ny, bc, engine, precond):
     """Ragged, tiny and degenerate (single row/column) grids, every BC combination class."""
     import ppfv_oracle as O
     m, eq, lines, f = _random_case(seed, nx, ny, bc)
     eng = sy.Engine(m.x_edges, m.y_edges, m.dt)
-    eng.set_options(engine=engine)
+    eng.set_options(engine=engine, precond=precond)
     eng.set_coeffs(eq.G, eq.Dxx, eq.Dxy, eq.Dyy, eq.inv_tau)
     eng.set_bc(bc, *[l if b == 0 else None for l, b in zip(lines, bc)])
     eng.set_f(f)
