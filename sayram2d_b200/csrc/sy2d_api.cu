@@ -411,7 +411,7 @@ static int engine_of(const sy2d_ctx* c) {
 
 // Shape of the x-line kernel for this grid: R rows per thread (template instance), NT threads.
 // Returns false when the grid does not fit (too many rows per lane, too wide, or too much shared memory).
-static bool xline_shape(const sy2d_ctx* c, int* R, int* NT, int* S, size_t* smem) {
+static bool xline_shape(const sy2d_ctx* c, int* R, int* NT, int* S, int* HS, size_t* smem) {
   const int need = (c->nx + kXlineNCH - 1) / kXlineNCH;
   const int choices[4] = {4, 6, 8, 10};
   int r = 0;
@@ -420,27 +420,32 @@ static bool xline_shape(const sy2d_ctx* c, int* R, int* NT, int* S, size_t* smem
   const int ny_pad = (c->ny + kXlineCPW - 1) / kXlineCPW * kXlineCPW;
   const int nt = ny_pad * kXlineNCH;
   if (nt > 1024) return false;
-  const size_t bytes = ((size_t)c->nx * (c->ny + 1) + 3 * (size_t)r * nt + 128) * sizeof(double);
+  int hs = c->ny;  // smallest stride >= ny with r*hs = 4 (mod 16): conflict-free hat accesses (not solvable for r = 8)
+  for (int t = c->ny; t < c->ny + 16; ++t)
+    if ((r * t) % 16 == 4) { hs = t; break; }
+  if (hs == c->ny && (r * hs) % 16 != 4) hs = c->ny + 1;
+  const size_t bytes = ((size_t)c->nx * hs + 3 * (size_t)r * nt + 128) * sizeof(double);
   if (bytes > 232448) return false;
-  *R = r; *NT = nt; *S = r * nt; *smem = bytes;
+  *R = r; *NT = nt; *S = r * nt; *HS = hs; *smem = bytes;
   return true;
 }
 
-template <int R, int MAXT>
+template <int R, int MAXT, int NTC>
 static cudaError_t launch_xline(const XlineArgs& xa, int nbatch, size_t smem, cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(k_problem_xline<R, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(k_problem_xline<R, MAXT, NTC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_problem_xline<R, MAXT><<<nbatch, xa.NT, smem, stream>>>(xa);
+  k_problem_xline<R, MAXT, NTC><<<nbatch, xa.NT, smem, stream>>>(xa);
   return cudaGetLastError();
 }
 
 static cudaError_t dispatch_xline(const XlineArgs& xa, int R, int nbatch, size_t smem, cudaStream_t stream) {
+  if (R == 10 && xa.NT == 640) return launch_xline<10, 640, 640>(xa, nbatch, smem, stream);  // 80 x 80: the production shape
   const bool small = xa.NT <= 640;
   switch (R) {
-    case 4: return small ? launch_xline<4, 640>(xa, nbatch, smem, stream) : launch_xline<4, 1024>(xa, nbatch, smem, stream);
-    case 6: return small ? launch_xline<6, 640>(xa, nbatch, smem, stream) : launch_xline<6, 1024>(xa, nbatch, smem, stream);
-    case 8: return small ? launch_xline<8, 640>(xa, nbatch, smem, stream) : launch_xline<8, 1024>(xa, nbatch, smem, stream);
-    default: return small ? launch_xline<10, 640>(xa, nbatch, smem, stream) : launch_xline<10, 1024>(xa, nbatch, smem, stream);
+    case 4: return small ? launch_xline<4, 640, 0>(xa, nbatch, smem, stream) : launch_xline<4, 1024, 0>(xa, nbatch, smem, stream);
+    case 6: return small ? launch_xline<6, 640, 0>(xa, nbatch, smem, stream) : launch_xline<6, 1024, 0>(xa, nbatch, smem, stream);
+    case 8: return small ? launch_xline<8, 640, 0>(xa, nbatch, smem, stream) : launch_xline<8, 1024, 0>(xa, nbatch, smem, stream);
+    default: return small ? launch_xline<10, 640, 0>(xa, nbatch, smem, stream) : launch_xline<10, 1024, 0>(xa, nbatch, smem, stream);
   }
 }
 
@@ -464,9 +469,9 @@ static int step_per_problem(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
   a.scal = c->scal; a.stats = c->d_stats; a.g = geometry(c);
   a.tol = c->opt.tol; a.maxit = c->opt.maxit; a.predictor = c->opt.predictor; a.nsteps = nsteps;
   c->cur_cells = (double)c->total * nsteps;
-  int R = 0, NT = 0, S = 0;
+  int R = 0, NT = 0, S = 0, HS = 0;
   size_t smem = 0;
-  const bool xline = c->opt.precond != SY2D_PRECOND_JACOBI && xline_shape(c, &R, &NT, &S, &smem);
+  const bool xline = c->opt.precond != SY2D_PRECOND_JACOBI && xline_shape(c, &R, &NT, &S, &HS, &smem);
   if (c->opt.precond == SY2D_PRECOND_XLINE && !xline)
     return fail(c, SY2D_ERR_INVALID, "sy2d_step: the x-line preconditioner needs nx <= 80, ny <= 128 and engine 2");
   st.precond = xline ? SY2D_PRECOND_XLINE : SY2D_PRECOND_JACOBI;
@@ -478,7 +483,7 @@ static int step_per_problem(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
       c->xl_S = S;
     }
     XlineArgs xa;
-    xa.a = a; xa.scratch = c->xl_scratch; xa.NT = NT; xa.S = S;
+    xa.a = a; xa.scratch = c->xl_scratch; xa.NT = NT; xa.S = S; xa.hs = HS;
     Prof p(c, SY2D_K_PROBLEM_STEPS);
     CU(dispatch_xline(xa, R, c->nbatch, smem, c->stream));
   } else {

@@ -9,6 +9,9 @@
 // accuracy of f - exactly those of the unpreconditioned engine; iterations drop ~4x
 // (80x80 AY: 59 -> 14.5 per step).
 //
+// Bank conflicts: lane (k, jj) touches hat[(k*R + m)*hs + j]; with R*hs = 4 (mod 16) the eight
+// lanes of a column land 8 words apart and a warp covers all 32 banks exactly once.
+//
 // Thread layout: a warp owns CPW = 32/NCH columns j; the NCH lanes of a column own R consecutive
 // rows each (lane = jj*NCH + k, rows k*R .. k*R+R-1).  A Thomas sweep is then a chain over the
 // NCH lanes of a column, handed from lane to lane with a warp shuffle: no block barrier inside a
@@ -33,6 +36,7 @@ struct XlineArgs {
   double* scratch;   // [nbatch][5][S]
   int NT;            // threads per CTA = ny_pad * NCH
   int S;             // R * NT
+  int hs;            // row stride of hat in shared memory (>= ny)
 };
 
 template <int NV>
@@ -69,18 +73,22 @@ __device__ __noinline__ Scaled assemble_scaled_cell(const double* f, const doubl
   return sc;
 }
 
-template <int R, int MAXT>
+// NTC > 0 fixes the CTA size at compile time (the 80-column production shape: 640 threads), so
+// that every thread-private slot m*NT + tid is base + immediate and costs no address registers.
+template <int R, int MAXT, int NTC>
 __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
   constexpr int NCH = kXlineNCH;
   extern __shared__ double sm[];
   const ProblemArgs& a = xa.a;
-  const int nx = a.g.nx, ny = a.g.ny, N = nx * ny, NT = xa.NT, S = xa.S;
+  const int nx = a.g.nx, ny = a.g.ny, N = nx * ny;
+  const int NT = NTC > 0 ? NTC : xa.NT;
+  const int S = R * NT;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int k = lane % NCH, jj = lane / NCH;
   const int j = w * kXlineCPW + jj;
   const bool col_ok = j < ny;
   const int i0 = k * R;
-  const int hs = ny + 1;  // hat row stride
+  const int hs = xa.hs;   // hat row stride, chosen on the host so that the NCH lanes of a column hit distinct banks
   double* hat = sm;
   double* l_s = hat + nx * hs;
   double* di_s = l_s + S;
@@ -123,7 +131,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
     // LU of T down each column: chain over the NCH lanes of the column
     {
       double dlast = 1.0, wElast = 0.0;
-#pragma unroll
+#pragma unroll 1
       for (int c = 0; c < NCH; ++c) {
         const double din = __shfl_up_sync(full, dlast, 1, NCH);
         const double win = __shfl_up_sync(full, wElast, 1, NCH);
@@ -149,29 +157,54 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
     it = 0;
     state = (rmax <= a.tol) ? 1 : 0;
 
-    // one Thomas solve of the owned rows: z <- T^-1 b  (b in registers)
+    // One Thomas solve of the owned rows, z <- T^-1 b (b in registers), as a partitioned solve:
+    // every lane runs the recurrence over its R rows with carry-in 0 and tracks the product of
+    // the multipliers, i.e. its chunk as an affine map  carry_out = A + B * carry_in.  The maps
+    // of the NCH lanes of a column are composed with a 3-step shuffle scan, and a second pass adds
+    // (product up to row m) * carry_in.  All lanes work concurrently - no serial hand-off.
     auto tsolve = [&](const double (&b)[R]) {
-      double carry_out = 0.0;
+      double A = 0.0, B = 1.0;
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        const double cin = __shfl_up_sync(full, carry_out, 1, NCH);
-        if (k == c) {
-          double carry = k == 0 ? 0.0 : cin;
-#pragma unroll
-          for (int m = 0; m < R; ++m) { carry = b[m] - l_s[m * NT + tid] * carry; z[m] = carry; }
-          carry_out = carry;
-        }
+      for (int m = 0; m < R; ++m) {
+        const double lm = l_s[m * NT + tid];
+        A = b[m] - lm * A;
+        z[m] = A;
+        B = -lm * B;
       }
-      carry_out = 0.0;
 #pragma unroll
-      for (int c = NCH - 1; c >= 0; --c) {
-        const double cin = __shfl_down_sync(full, carry_out, 1, NCH);
-        if (k == c) {
-          double carry = k == NCH - 1 ? 0.0 : cin;
+      for (int d = 1; d < NCH; d <<= 1) {
+        const double Au = __shfl_up_sync(full, A, d, NCH), Bu = __shfl_up_sync(full, B, d, NCH);
+        if (k >= d) { A = A + B * Au; B = B * Bu; }
+      }
+      double cin = __shfl_up_sync(full, A, 1, NCH);
+      if (k == 0) cin = 0.0;
+      double P = 1.0;
 #pragma unroll
-          for (int m = R - 1; m >= 0; --m) { carry = z[m] * di_s[m * NT + tid] - e_s[m * NT + tid] * carry; z[m] = carry; }
-          carry_out = carry;
-        }
+      for (int m = 0; m < R; ++m) {
+        P = -l_s[m * NT + tid] * P;
+        z[m] += P * cin;
+      }
+      // backward: y_m = z_m / d_m - (wE_m / d_m) y_{m+1}
+      A = 0.0; B = 1.0;
+#pragma unroll
+      for (int m = R - 1; m >= 0; --m) {
+        const double em = e_s[m * NT + tid];
+        A = z[m] * di_s[m * NT + tid] - em * A;
+        z[m] = A;
+        B = -em * B;
+      }
+#pragma unroll
+      for (int d = 1; d < NCH; d <<= 1) {
+        const double Ad = __shfl_down_sync(full, A, d, NCH), Bd = __shfl_down_sync(full, B, d, NCH);
+        if (k + d < NCH) { A = A + B * Ad; B = B * Bd; }
+      }
+      cin = __shfl_down_sync(full, A, 1, NCH);
+      if (k == NCH - 1) cin = 0.0;
+      P = 1.0;
+#pragma unroll
+      for (int m = R - 1; m >= 0; --m) {
+        P = -e_s[m * NT + tid] * P;
+        z[m] += P * cin;
       }
     };
     // publish z into hat (natural layout) for the S/N neighbours
