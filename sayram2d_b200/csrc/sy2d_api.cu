@@ -5,6 +5,7 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -54,6 +55,10 @@ struct sy2d_ctx {
   double* stage = nullptr;      // unused staging pointer (kept for destroy)
   size_t stage_elems = 0;
   // engine 2 / x-line: per-problem scratch in thread-private layout, allocated on first use
+  int* d_order = nullptr;       // engine 2 scheduling: problems sorted by last call's cost, longest first
+  int* d_cost = nullptr;
+  std::vector<int> h_cost, h_order;
+  bool have_order = false;
   double* xl_scratch = nullptr;
   int xl_R = 0, xl_NT = 0, xl_S = 0;
   size_t xl_smem = 0;
@@ -135,8 +140,17 @@ struct Prof {
 };
 
 void launch_iteration(sy2d_ctx* c) {
-  const dim3 g = grid_of(c);
   const KrylovVecs k = krylov(c);
+  if (c->ny % 2 == 0) {  // two cells per thread, 16-byte accesses
+    const dim3 g2((unsigned)((c->N / 2 + kBlock - 1) / kBlock), (unsigned)c->nbatch, 1);
+    { Prof p(c, SY2D_K_P_UPDATE); k_p_update2<<<g2, kBlock, 0, c->stream>>>(k, c->N); }
+    { Prof p(c, SY2D_K_SPMV_V); k_spmv_v2<<<g2, kBlock, 0, c->stream>>>(k, c->N, c->ny); }
+    { Prof p(c, SY2D_K_S_UPDATE); k_s_update2<<<g2, kBlock, 0, c->stream>>>(k, c->N); }
+    { Prof p(c, SY2D_K_SPMV_T); k_spmv_t2<<<g2, kBlock, 0, c->stream>>>(k, c->N, c->ny); }
+    { Prof p(c, SY2D_K_XR_UPDATE); k_xr_update2<<<g2, kBlock, 0, c->stream>>>(k, c->N); }
+    return;
+  }
+  const dim3 g = grid_of(c);
   { Prof p(c, SY2D_K_P_UPDATE); k_p_update<<<g, kBlock, 0, c->stream>>>(k, c->N); }
   { Prof p(c, SY2D_K_SPMV_V); k_spmv_v<<<g, kBlock, 0, c->stream>>>(k, c->N, c->ny); }
   { Prof p(c, SY2D_K_S_UPDATE); k_s_update<<<g, kBlock, 0, c->stream>>>(k, c->N); }
@@ -278,6 +292,8 @@ void sy2d_destroy(sy2d_ctx* c) {
                     c->x, c->r, c->p, c->v, c->s, c->t, c->stage, c->xl_scratch};
   for (double* b : bufs) if (b) cudaFree(b);
   if (c->scal) cudaFree(c->scal);
+  if (c->d_order) cudaFree(c->d_order);
+  if (c->d_cost) cudaFree(c->d_cost);
   if (c->d_nactive) cudaFree(c->d_nactive);
   if (c->h_nactive) cudaFreeHost(c->h_nactive);
   if (c->d_stats) cudaFree(c->d_stats);
@@ -468,6 +484,14 @@ static int step_per_problem(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
   a.x = c->x; a.r = c->r; a.p = c->p; a.v = c->v; a.s = c->s; a.t = c->t;
   a.scal = c->scal; a.stats = c->d_stats; a.g = geometry(c);
   a.tol = c->opt.tol; a.maxit = c->opt.maxit; a.predictor = c->opt.predictor; a.nsteps = nsteps;
+  if (!c->d_order) {
+    CU(cudaMalloc(reinterpret_cast<void**>(&c->d_order), c->nbatch * sizeof(int)));
+    CU(cudaMalloc(reinterpret_cast<void**>(&c->d_cost), c->nbatch * sizeof(int)));
+    c->h_cost.assign(c->nbatch, 0);
+    c->h_order.resize(c->nbatch);
+  }
+  a.order = c->have_order ? c->d_order : nullptr;
+  a.cost = c->d_cost;
   c->cur_cells = (double)c->total * nsteps;
   int R = 0, NT = 0, S = 0, HS = 0;
   size_t smem = 0;
@@ -493,9 +517,16 @@ static int step_per_problem(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(StepStats), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaEventRecord(c->ev_call1, c->stream));
-  CU(cudaEventSynchronize(c->ev_call1));
+  if (c->nbatch > 1) CU(cudaMemcpyAsync(c->h_cost.data(), c->d_cost, c->nbatch * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
   float ms = 0.f;
   CU(cudaEventElapsedTime(&ms, c->ev_call0, c->ev_call1));
+  if (c->nbatch > 1) {  // order for the next call: most expensive problems first
+    for (int b = 0; b < c->nbatch; ++b) c->h_order[b] = b;
+    std::stable_sort(c->h_order.begin(), c->h_order.end(), [&](int x, int y) { return c->h_cost[x] > c->h_cost[y]; });
+    CU(cudaMemcpyAsync(c->d_order, c->h_order.data(), c->nbatch * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    c->have_order = true;
+  }
   int rc = collect_profile(c);
   if (rc) return rc;
   const StepStats& h = *c->h_stats;

@@ -408,6 +408,28 @@ struct KrylovVecs {
   int maxit;
 };
 
+// End-of-iteration bookkeeping done by the last block of a problem: iteration count,
+// convergence / breakdown / maxit, beta for the next p update.
+__device__ __forceinline__ void xr_finish_iteration(Scal* sc, const KrylovVecs& k) {
+  const double rho_new = sc->acc_rho;
+  const double rmax = __longlong_as_double((long long)sc->acc_rmax);
+  sc->acc_rho = 0.0;
+  sc->acc_rmax = 0ull;
+  sc->rmax = rmax;
+  sc->it += 1;
+  sc->first = 0;
+  int state = 0;
+  if (rmax <= k.tol) state = 1;
+  else if (!(rmax == rmax) || rho_new == 0.0 || sc->omega == 0.0) state = 3;  // NaN / breakdown
+  else if (sc->it >= k.maxit) state = 2;
+  sc->beta = (rho_new / sc->rho) * (sc->alpha / sc->omega);
+  sc->rho = rho_new;
+  if (state != 0) {
+    sc->state = state;
+    atomicSub(k.n_active, 1);
+  }
+}
+
 // KA: p = r + beta (p - omega v)            (first iteration: p = rhs)      32 B/cell
 __global__ void __launch_bounds__(kBlock) k_p_update(KrylovVecs k, size_t N) {
   const Scal* sc = k.scal + blockIdx.y;
@@ -516,25 +538,140 @@ __global__ void __launch_bounds__(kBlock) k_xr_update(KrylovVecs k, size_t N) {
   if (threadIdx.x == 0) {
     atomicAdd(&sc->acc_rho, sums[0]);
     atomicMax(&sc->acc_rmax, (unsigned long long)__double_as_longlong(bmax));
+    if (last_block_done(sc, gridDim.x)) xr_finish_iteration(sc, k);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Two-cells-per-thread variants of the five Krylov kernels (ny even): every array access is a
+// 16-byte ld/st.global.v2.f64, the two cells share their inner S/N neighbours in registers, and
+// the grid is half as large (half the block reductions and atomics).  Same arithmetic per cell.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+__device__ __forceinline__ void st2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
+
+__global__ void __launch_bounds__(kBlock) k_p_update2(KrylovVecs k, size_t N) {
+  const Scal* sc = k.scal + blockIdx.y;
+  if (sc->state != 0) return;
+  const size_t n = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
+  if (n >= N) return;
+  const size_t g = (size_t)blockIdx.y * N + n;
+  if (sc->first) {
+    const double2 r = ld2(k.rhs + g);
+    st2(k.p + g, r.x, r.y);
+  } else {
+    const double beta = sc->beta, omega = sc->omega;
+    const double2 r = ld2(k.r + g), p = ld2(k.p + g), v = ld2(k.v + g);
+    st2(k.p + g, r.x + beta * (p.x - omega * v.x), r.y + beta * (p.y - omega * v.y));
+  }
+}
+
+// y = A x for cells n, n+1 (n even, ny even => both in the same row)
+__device__ __forceinline__ void stencil_apply2(const double* __restrict__ x, size_t n, size_t N, int ny, double2 xc, double2 wW,
+                                               double2 wE, double2 wS, double2 wN, double& y0, double& y1) {
+  const double2 xW = ld2(x + (n >= (size_t)ny ? n - ny : n));
+  const double2 xE = ld2(x + (n + ny < N ? n + ny : n));
+  const double xS = x[n > 0 ? n - 1 : n];
+  const double xN = x[n + 2 < N ? n + 2 : n + 1];
+  y0 = xc.x + ((wW.x * xW.x + wE.x * xE.x) + (wS.x * xS + wN.x * xc.y));
+  y1 = xc.y + ((wW.y * xW.y + wE.y * xE.y) + (wS.y * xc.x + wN.y * xN));
+}
+
+__global__ void __launch_bounds__(kBlock) k_spmv_v2(KrylovVecs k, size_t N, int ny) {
+  __shared__ double red[32];
+  Scal* sc = k.scal + blockIdx.y;
+  if (sc->state != 0) return;
+  const size_t n = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
+  const size_t base = (size_t)blockIdx.y * N;
+  double dot = 0.0;
+  if (n < N) {
+    const size_t g = base + n;
+    const double* p = k.p + base;
+    double v0, v1;
+    stencil_apply2(p, n, N, ny, ld2(p + n), ld2(k.wW + g), ld2(k.wE + g), ld2(k.wS + g), ld2(k.wN + g), v0, v1);
+    st2(k.v + g, v0, v1);
+    const double2 rh = ld2(k.rhs + g);
+    dot = rh.x * v0 + rh.y * v1;
+  }
+  double sums[1] = {dot};
+  block_sums<1>(sums, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(&sc->acc_rv, sums[0]);
     if (last_block_done(sc, gridDim.x)) {
-      const double rho_new = sc->acc_rho;
-      const double rmax = __longlong_as_double((long long)sc->acc_rmax);
-      sc->acc_rho = 0.0;
-      sc->acc_rmax = 0ull;
-      sc->rmax = rmax;
-      sc->it += 1;
-      sc->first = 0;
-      int state = 0;
-      if (rmax <= k.tol) state = 1;
-      else if (!(rmax == rmax) || rho_new == 0.0 || sc->omega == 0.0) state = 3;  // NaN / breakdown
-      else if (sc->it >= k.maxit) state = 2;
-      sc->beta = (rho_new / sc->rho) * (sc->alpha / sc->omega);
-      sc->rho = rho_new;
-      if (state != 0) {
-        sc->state = state;
-        atomicSub(k.n_active, 1);
-      }
+      const double rv = sc->acc_rv;
+      sc->acc_rv = 0.0;
+      sc->alpha = rv != 0.0 ? sc->rho / rv : 0.0;
     }
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_s_update2(KrylovVecs k, size_t N) {
+  const Scal* sc = k.scal + blockIdx.y;
+  if (sc->state != 0) return;
+  const size_t n = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
+  if (n >= N) return;
+  const size_t g = (size_t)blockIdx.y * N + n;
+  const double alpha = sc->alpha;
+  const double2 r = ld2((sc->first ? k.rhs : k.r) + g), v = ld2(k.v + g);
+  st2(k.s + g, r.x - alpha * v.x, r.y - alpha * v.y);
+}
+
+__global__ void __launch_bounds__(kBlock) k_spmv_t2(KrylovVecs k, size_t N, int ny) {
+  __shared__ double red[2 * 32];
+  Scal* sc = k.scal + blockIdx.y;
+  if (sc->state != 0) return;
+  const size_t n = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
+  const size_t base = (size_t)blockIdx.y * N;
+  double ts = 0.0, tt = 0.0;
+  if (n < N) {
+    const size_t g = base + n;
+    const double* s = k.s + base;
+    const double2 sc0 = ld2(s + n);
+    double t0, t1;
+    stencil_apply2(s, n, N, ny, sc0, ld2(k.wW + g), ld2(k.wE + g), ld2(k.wS + g), ld2(k.wN + g), t0, t1);
+    st2(k.t + g, t0, t1);
+    ts = t0 * sc0.x + t1 * sc0.y;
+    tt = t0 * t0 + t1 * t1;
+  }
+  double sums[2] = {ts, tt};
+  block_sums<2>(sums, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(&sc->acc_ts, sums[0]);
+    atomicAdd(&sc->acc_tt, sums[1]);
+    if (last_block_done(sc, gridDim.x)) {
+      const double a = sc->acc_ts, b = sc->acc_tt;
+      sc->acc_ts = 0.0;
+      sc->acc_tt = 0.0;
+      sc->omega = b > 0.0 ? a / b : 0.0;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_xr_update2(KrylovVecs k, size_t N) {
+  __shared__ double red[32];
+  Scal* sc = k.scal + blockIdx.y;
+  if (sc->state != 0) return;
+  const size_t n = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
+  double dot = 0.0, rabs = 0.0;
+  if (n < N) {
+    const size_t g = (size_t)blockIdx.y * N + n;
+    const double alpha = sc->alpha, omega = sc->omega;
+    const double2 s = ld2(k.s + g), p = ld2(k.p + g), t = ld2(k.t + g), rh = ld2(k.rhs + g);
+    double2 x = make_double2(0.0, 0.0);
+    if (!sc->first) x = ld2(k.x + g);
+    st2(k.x + g, x.x + (alpha * p.x + omega * s.x), x.y + (alpha * p.y + omega * s.y));
+    const double r0 = s.x - omega * t.x, r1 = s.y - omega * t.y;
+    st2(k.r + g, r0, r1);
+    dot = rh.x * r0 + rh.y * r1;
+    rabs = fmax(fabs(r0), fabs(r1));
+  }
+  double sums[1] = {dot};
+  block_sums<1>(sums, red);
+  const double bmax = block_max(rabs, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(&sc->acc_rho, sums[0]);
+    atomicMax(&sc->acc_rmax, (unsigned long long)__double_as_longlong(bmax));
+    if (last_block_done(sc, gridDim.x)) xr_finish_iteration(sc, k);
   }
 }
 

@@ -26,6 +26,12 @@ struct ProblemArgs {
   Geometry g;
   double tol;
   int maxit, predictor, nsteps;
+  // Scheduling: CTA b works on problem order[b]; the host sorts problems by the iterations they
+  // needed in the previous call (longest first), so the last wave is filled with cheap problems
+  // (longest-processing-time list scheduling: matters when nbatch is only a few waves, e.g. 512
+  // members per GPU on 148 SMs).  cost[problem] receives this call's iteration total.
+  const int* order;
+  int* cost;
 };
 
 constexpr int kProblemThreads = 1024;
@@ -54,7 +60,8 @@ __global__ void __launch_bounds__(kProblemThreads, 1) k_problem_steps(ProblemArg
   __shared__ double red[4 * 32];
   const int nx = a.g.nx, ny = a.g.ny;
   const int N = nx * ny;
-  const size_t base = (size_t)blockIdx.x * N;
+  const int prob = a.order ? a.order[blockIdx.x] : blockIdx.x;
+  const size_t base = (size_t)prob * N;
   const int tid = threadIdx.x;
   const double* __restrict__ tx = a.tx + base;
   const double* __restrict__ ty = a.ty + base;
@@ -181,7 +188,8 @@ __global__ void __launch_bounds__(kProblemThreads, 1) k_problem_steps(ProblemArg
     if (state >= 2) break;
   }
   if (tid == 0) {
-    Scal* sc = a.scal + blockIdx.x;
+    Scal* sc = a.scal + prob;
+    if (a.cost) a.cost[prob] = it_total;
     sc->it = it;
     sc->state = state;
     sc->rmax = rmax;

@@ -94,7 +94,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
   double* di_s = l_s + S;
   double* e_s = di_s + S;
   double* red = e_s + S;
-  const size_t base = (size_t)blockIdx.x * N;
+  const int prob = a.order ? a.order[blockIdx.x] : blockIdx.x;
+  const size_t base = (size_t)prob * N;
   const double* __restrict__ tx = a.tx + base;
   const double* __restrict__ ty = a.ty + base;
   const double* __restrict__ cxy = a.cxy + base;
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
   const double* __restrict__ Ud = a.Ud + base;
   double* f = a.f + base;
   double* yprev = a.yprev + base;
-  double* scr = xa.scratch + (size_t)blockIdx.x * 5 * S;
+  double* scr = xa.scratch + (size_t)prob * 5 * S;
   double* wS_g = scr; double* wN_g = scr + S; double* v_g = scr + 2 * S; double* x_g = scr + 3 * S; double* rhs_g = scr + 4 * S;
   const unsigned full = 0xffffffffu;
 
@@ -358,7 +359,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
     if (state >= 2) break;
   }
   if (tid == 0) {
-    Scal* sc = a.scal + blockIdx.x;
+    Scal* sc = a.scal + prob;
+    if (a.cost) a.cost[prob] = it_total;
     sc->it = it;
     sc->state = state;
     sc->rmax = rmax;
