@@ -574,7 +574,13 @@ int sy2d_step(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
       std::memset(&o, 0, sizeof o);
       o.wW = c->wW; o.wE = c->wE; o.wS = c->wS; o.wN = c->wN; o.rhs = c->rhs; o.cs = c->cs;
       o.scal = c->scal; o.n_active = c->d_nactive; o.tol = c->opt.tol;
-      k_assemble<0><<<g, kBlock, 0, c->stream>>>(c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud, geo, o);
+      if (c->nx >= 2 * kTI && c->ny >= kTJ && c->opt.reserved[0] == 0) {  // reserved[0] = 1 forces the per-cell kernel (tests)
+        const int tiles_i = (c->nx + kTI - 1) / kTI, tiles_j = (c->ny + kTJ - 1) / kTJ;
+        k_assemble_tiled<<<dim3((unsigned)(tiles_i * tiles_j), (unsigned)c->nbatch, 1), kTI * kTJ, 0, c->stream>>>(
+            c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud, geo, o, tiles_j);
+      } else {
+        k_assemble<0><<<g, kBlock, 0, c->stream>>>(c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud, geo, o);
+      }
     }
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(c->h_nactive, c->d_nactive, sizeof(int), cudaMemcpyDeviceToHost, c->stream));

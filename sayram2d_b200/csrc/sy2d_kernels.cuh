@@ -388,6 +388,147 @@ __global__ void __launch_bounds__(kBlock) k_assemble(const double* __restrict__ 
   }
 }
 
+// ---------------------------------------------------------------------------
+// Tiled PPFV assembly for large grids (engine 1): a CTA of 256 threads owns a tile of
+// TI x TJ = 8 x 32 cells.  Shared-memory stages, each computed ONCE per tile:
+//   1. f and c = f*yprev with a one-cell halo                       (10 x 34)
+//   2. the vertex values of the tile                                 (9 x 33)
+//   3. the nonlinear two-point fluxes of the west faces (9 x 32) and south faces (8 x 33):
+//      A_K, A_L per face (face_pair), so every interior face is evaluated once per tile
+//      instead of once per adjacent cell
+//   4. the operator row of every cell, gathered from its four faces, scaled, written coalesced.
+// Per cell: ~1.1 vertex, ~2.2 face evaluations and 5 divisions instead of 4, 4 and 9 in the
+// one-thread-per-cell kernel, 16.6 KB of shared memory per CTA.  Same arithmetic per face, so the
+// rows are bit-identical to k_assemble<0>.
+// ---------------------------------------------------------------------------
+constexpr int kTI = 8, kTJ = 32;
+
+__global__ void __launch_bounds__(kTI * kTJ) k_assemble_tiled(const double* __restrict__ f, const double* __restrict__ yprev,
+                                                              const double* __restrict__ tx, const double* __restrict__ ty,
+                                                              const double* __restrict__ cxy, const double* __restrict__ U,
+                                                              const double* __restrict__ Ud, Geometry g, AssembleOut o, int tiles_j) {
+  __shared__ double fs[kTI + 2][kTJ + 2], cs_[kTI + 2][kTJ + 2], vs[kTI + 1][kTJ + 1];
+  __shared__ double WK[kTI + 1][kTJ], WL[kTI + 1][kTJ], SK[kTI][kTJ + 1], SL[kTI][kTJ + 1];
+  __shared__ double red[3 * 32];
+  const int nx = g.nx, ny = g.ny;
+  const size_t N = (size_t)nx * ny;
+  const size_t base = (size_t)blockIdx.y * N;
+  const int tile_i = blockIdx.x / tiles_j, tile_j = blockIdx.x - tile_i * tiles_j;
+  const int I0 = tile_i * kTI, J0 = tile_j * kTJ;
+  const int tid = threadIdx.x;
+  const double* fp = f + base;
+  const double* yp = yprev + base;
+  const double* txp = tx + base;
+  const double* typ = ty + base;
+  const double* cp = cxy + base;
+  // 1. f and c with halo (indices clamped at the domain boundary: clamped values only meet zero weights)
+  for (int e = tid; e < (kTI + 2) * (kTJ + 2); e += kTI * kTJ) {
+    const int a = e / (kTJ + 2), b = e - a * (kTJ + 2);
+    int i = I0 + a - 1, j = J0 + b - 1;
+    i = i < 0 ? 0 : (i > nx - 1 ? nx - 1 : i);
+    j = j < 0 ? 0 : (j > ny - 1 ? ny - 1 : j);
+    const double fv = fp[(size_t)i * ny + j];
+    fs[a][b] = fv;
+    cs_[a][b] = fv * yp[(size_t)i * ny + j];
+  }
+  __syncthreads();
+  // 2. vertices (I0 + a, J0 + b)
+  for (int e = tid; e < (kTI + 1) * (kTJ + 1); e += kTI * kTJ) {
+    const int a = e / (kTJ + 1), b = e - a * (kTJ + 1);
+    const int vi = I0 + a, vj = J0 + b;
+    double v = 0.0;
+    if (vi <= nx && vj <= ny) v = vertex_value(g, vi, vj, fs[a][b], fs[a + 1][b], fs[a][b + 1], fs[a + 1][b + 1]);
+    vs[a][b] = v;
+  }
+  __syncthreads();
+  // 3a. west faces of cells (I0 + a, J0 + b), a = 0..TI: K = (i, j), L = (i-1, j)
+  for (int e = tid; e < (kTI + 1) * kTJ; e += kTI * kTJ) {
+    const int a = e / kTJ, b = e - a * kTJ;
+    const int i = I0 + a, j = J0 + b;
+    double AK = 0.0, AL = 0.0;
+    if (i >= 1 && i <= nx - 1 && j < ny) {
+      const size_t ck = (size_t)i * ny + j, cl = ck - ny;
+      const double tK = txp[ck], cK = cp[ck], tL = txp[cl], cL = cp[cl];
+      const double vSW = vs[a][b], vNW = vs[a][b + 1];
+      const double kA = tK - cK, kB = tK + cK;   // W face of K: A = NW, B = SW
+      const double lA = tL - cL, lB = tL + cL;   // E face of L: A = SE_L = SW_K, B = NE_L = NW_K
+      face_pair(kA * vNW + kB * vSW, kA + kB, fs[a + 1][b + 1], lA * vSW + lB * vNW, lA + lB, fs[a][b + 1], AK, AL);
+    }
+    WK[a][b] = AK;
+    WL[a][b] = AL;
+  }
+  // 3b. south faces of cells (I0 + a, J0 + b), b = 0..TJ: K = (i, j), L = (i, j-1)
+  for (int e = tid; e < kTI * (kTJ + 1); e += kTI * kTJ) {
+    const int a = e / (kTJ + 1), b = e - a * (kTJ + 1);
+    const int i = I0 + a, j = J0 + b;
+    double AK = 0.0, AL = 0.0;
+    if (j >= 1 && j <= ny - 1 && i < nx) {
+      const size_t ck = (size_t)i * ny + j, cl = ck - 1;
+      const double tK = typ[ck], cK = cp[ck], tL = typ[cl], cL = cp[cl];
+      const double vSW = vs[a][b], vSE = vs[a + 1][b];
+      const double kA = tK + cK, kB = tK - cK;   // S face of K: A = SW, B = SE
+      const double lA = tL + cL, lB = tL - cL;   // N face of L: A = NE_L = SE_K, B = NW_L = SW_K
+      face_pair(kA * vSW + kB * vSE, kA + kB, fs[a + 1][b + 1], lA * vSE + lB * vSW, lA + lB, fs[a + 1][b], AK, AL);
+    }
+    SK[a][b] = AK;
+    SL[a][b] = AL;
+  }
+  __syncthreads();
+  // 4. rows
+  const int a = tid / kTJ, b = tid - a * kTJ;
+  const int i = I0 + a, j = J0 + b;
+  double rr = 0.0, rabs = 0.0;
+  if (i < nx && j < ny) {
+    const size_t n = (size_t)i * ny + j, c0 = base + n;
+    const double f00 = fs[a + 1][b + 1];
+    double diag = 0.0, R = 0.0, oW = 0.0, oE = 0.0, oS = 0.0, oN = 0.0;
+    if (i > 0) { diag += WK[a][b]; oW = -WL[a][b]; }
+    if (i < nx - 1) { diag += WL[a + 1][b]; oE = -WK[a + 1][b]; }
+    if (j > 0) { diag += SK[a][b]; oS = -SL[a][b]; }
+    if (j < ny - 1) { diag += SL[a][b + 1]; oN = -SK[a][b + 1]; }
+    if (i == 0 || i == nx - 1 || j == 0 || j == ny - 1) {  // Dirichlet boundary faces (Solver.cc:143-164, 204-267)
+      const double txP = txp[n], tyP = typ[n], cP = cp[n];
+      const double vSW = vs[a][b], vSE = vs[a + 1][b], vNW = vs[a][b + 1], vNE = vs[a + 1][b + 1];
+      if (i == 0 && g.bc[0] == 0) diag += dirichlet_face((txP - cP) * vNW + (txP + cP) * vSW, (txP - cP) + (txP + cP), f00, R);
+      if (i == nx - 1 && g.bc[1] == 0) diag += dirichlet_face((txP - cP) * vSE + (txP + cP) * vNE, (txP - cP) + (txP + cP), f00, R);
+      if (j == 0 && g.bc[2] == 0) diag += dirichlet_face((tyP + cP) * vSW + (tyP - cP) * vSE, (tyP + cP) + (tyP - cP), f00, R);
+      if (j == ny - 1 && g.bc[3] == 0) diag += dirichlet_face((tyP + cP) * vNE + (tyP - cP) * vNW, (tyP + cP) + (tyP - cP), f00, R);
+    }
+    diag += Ud[c0];
+    R += U[c0] * f00;
+    const double cs0 = cs_[a + 1][b + 1];
+    const double dscale = 1.0 / (diag * cs0);
+    const double wW = oW * cs_[a][b + 1] * dscale, wE = oE * cs_[a + 2][b + 1] * dscale;
+    const double wS = oS * cs_[a + 1][b] * dscale, wN = oN * cs_[a + 1][b + 2] * dscale;
+    const double rhs = R * dscale - 1.0 - ((wW + wE) + (wS + wN));
+    o.wW[c0] = wW; o.wE[c0] = wE; o.wS[c0] = wS; o.wN[c0] = wN;
+    o.rhs[c0] = rhs;
+    o.cs[c0] = cs0;
+    rr = rhs * rhs;
+    rabs = fabs(rhs);
+  }
+  double sums[1] = {rr};
+  block_sums<1>(sums, red);
+  const double bmax = block_max(rabs, red);
+  Scal* sc = o.scal + blockIdx.y;
+  if (threadIdx.x == 0) {
+    atomicAdd(&sc->acc_rho, sums[0]);
+    atomicMax(&sc->acc_rmax, (unsigned long long)__double_as_longlong(bmax));
+    if (last_block_done(sc, gridDim.x)) {
+      const double rmax = __longlong_as_double((long long)sc->acc_rmax);
+      sc->rho = sc->acc_rho;
+      sc->rmax = rmax;
+      sc->alpha = 1.0; sc->omega = 1.0; sc->beta = 0.0;
+      sc->acc_rv = 0.0; sc->acc_ts = 0.0; sc->acc_tt = 0.0; sc->acc_rho = 0.0; sc->acc_rmax = 0ull;
+      sc->it = 0;
+      sc->first = 1;
+      const int active_now = !(rmax <= o.tol);
+      sc->state = active_now ? 0 : 1;
+      if (active_now) atomicAdd(o.n_active, 1);
+    }
+  }
+}
+
 // y = A x for one cell of the unit-diagonal 5-point operator.  Out-of-range
 // neighbours are clamped to the cell itself: their weights are exactly zero.
 __host__ __device__ __forceinline__ double stencil_apply(const double* __restrict__ x, size_t n, size_t N, int ny, double xc,

@@ -320,3 +320,17 @@ def test_reference_main_with_gpu_solver_dropped_in(tmp_path, case, ini, tag, run
     d = tmp_path / "output" / run_id / f"{run_id}_data.h5.d"
     for k in (0, 1, 5, 10):
         assert max_rel(np.load(d / f"f_{k}.npy"), g[f"f_{k}"]) < PARITY
+
+
+@pytest.mark.parametrize("tag", ["nu48x40", "syn64x48", "lc80"])
+def test_tiled_assembly_equals_per_cell_assembly(tag):
+    """Engine 1 assembles with the shared-memory tile kernel (faces evaluated once per tile);
+    forcing the one-thread-per-cell kernel must give the same f (ragged tiles: 40 = 32 + 8 columns)."""
+    g = load_golden(tag)
+    a = engine_from_golden(g, CASE_OF[tag], engine=1)
+    b = engine_from_golden(g, CASE_OF[tag], engine=1)
+    o = b.options(); o.engine = 1; o.reserved[0] = 1
+    b._check(b.lib.sy2d_set_options(b._ctx, o)); b._opt = o
+    a.step(6); b.step(6)
+    assert max_rel(a.get_f(), b.get_f()) < 1e-12
+    a.close(); b.close()
