@@ -371,6 +371,7 @@ def ours(args):
     if rank == 0 and world == 1:
         if not args.no_grid1024:
             line["grid1024"] = grid_object(1024, local_rank, args, torch)
+            line["grid4096"] = big_grid_object(4096, local_rank)
         line["cpu_baseline"] = cpu_baseline_ensemble() if not args.no_cpu else None
     if rank == 0:
         print(json.dumps(line), flush=True)
@@ -397,9 +398,34 @@ def grid_object(n, device, args, torch):
            "iters_per_step": iters / steps, "negatives": st["negatives"], "resid_last": st["resid_last"],
            "l2": "256 MB flush between timed steps; the 19-array working set (~160 MB) cycles through L2 within a step",
            "roofline": {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src, "dominant": dom, "kernels": rows}}
+    out["roofline"]["sustained"] = sustained_kernels(eng, n * n, peak)
     eng.close()
     if not args.no_cpu and not args.no_grid_cpu:
         out["cpu_baseline"] = cpu_baseline_grid(n, 1)
+    return out
+
+
+def sustained_kernels(eng, cells, peak, reps=20):
+    """Back-to-back launches of one kernel between two CUDA events (sy2d_bench_kernel): the
+    kernel's sustained rate without per-launch event gaps."""
+    rows = {}
+    for name in ("assembly", "p_update", "spmv_v", "s_update", "spmv_t", "xr_update"):
+        ms = eng.bench_kernel(name, reps)
+        gbs = cells * BYTES_PER_CELL[name] / (ms * 1e-3) / 1e9
+        rows[name] = {"us_per_launch": round(1e3 * ms, 2), "achieved": round(gbs, 1), "frac": round(gbs / peak, 4),
+                      "bytes_per_cell": BYTES_PER_CELL[name]}
+    return rows
+
+
+def big_grid_object(n, device):
+    """DRAM-bound kernel rates: the same kernels on an n x n grid whose per-kernel inputs
+    (n = 4096: 0.8-1.7 GB) are far larger than the 126 MB L2."""
+    eng, f0 = make_grid(n, device)
+    eng.set_options(engine=1)
+    peak, peak_src = measured_peak()
+    out = {"workload": f"grid{n}", "l2": f"per-kernel inputs {n * n * 48 / 1e6:.0f}-{n * n * 104 / 1e6:.0f} MB >> 126 MB L2: DRAM-bound, no flush needed",
+           "peak": peak, "unit": "GB/s", "peak_source": peak_src, "sustained": sustained_kernels(eng, n * n, peak, reps=10)}
+    eng.close()
     return out
 
 

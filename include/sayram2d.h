@@ -150,6 +150,12 @@ int sy2d_dump_vertex_f(sy2d_ctx* ctx, double* vf);
 int sy2d_set_profiling(sy2d_ctx* ctx, int on);
 int sy2d_get_profile(sy2d_ctx* ctx, sy2d_profile* out);
 
+/* Sustained time of ONE kernel of the lockstep engine: the operator is assembled from the current f,
+ * the Krylov vectors are primed, then kernel `which` (SY2D_K_ASSEMBLY, _P_UPDATE, _SPMV_V, _S_UPDATE,
+ * _SPMV_T, _XR_UPDATE) is launched `reps` times back to back between two CUDA events on the context's
+ * stream; *ms_per_launch is the average.  Solver state (f, step count) is left untouched. */
+int sy2d_bench_kernel(sy2d_ctx* ctx, int which, int reps, double* ms_per_launch);
+
 /* Build/device facts: "sm_100a;cuda=12.9;..." */
 const char* sy2d_build_info(void);
 int sy2d_device_count(void);

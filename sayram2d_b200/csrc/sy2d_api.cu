@@ -110,6 +110,7 @@ KrylovVecs krylov(const sy2d_ctx* c) {
   k.wW = c->wW; k.wE = c->wE; k.wS = c->wS; k.wN = c->wN; k.rhs = c->rhs;
   k.x = c->x; k.r = c->r; k.p = c->p; k.v = c->v; k.s = c->s; k.t = c->t;
   k.scal = c->scal; k.n_active = c->d_nactive; k.tol = c->opt.tol; k.maxit = c->opt.maxit;
+  k.freeze_state = 0;
   return k;
 }
 
@@ -683,6 +684,64 @@ int sy2d_dump_vertex_f(sy2d_ctx* c, double* vf) {
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   cudaFree(d_vf);
   if (e != cudaSuccess) return fail(c, SY2D_ERR_CUDA, "sy2d_dump_vertex_f: %s", cudaGetErrorString(e));
+  return SY2D_OK;
+}
+
+int sy2d_bench_kernel(sy2d_ctx* c, int which, int reps, double* ms_per_launch) {
+  if (!c || !ms_per_launch || reps < 1) return SY2D_ERR_INVALID;
+  int rc = ready(c, "sy2d_bench_kernel");
+  if (rc) return rc;
+  CU(cudaSetDevice(c->device));
+  const Geometry geo = geometry(c);
+  KrylovVecs k = krylov(c);
+  k.freeze_state = 1;
+  const dim3 g = grid_of(c);
+  const bool vec2 = c->ny % 2 == 0;
+  const dim3 g2((unsigned)((c->N / 2 + kBlock - 1) / kBlock), (unsigned)c->nbatch, 1);
+  const bool tiled = c->nx >= 2 * kTI && c->ny >= kTJ;
+  const int tiles_i = (c->nx + kTI - 1) / kTI, tiles_j = (c->ny + kTJ - 1) / kTJ;
+  AssembleOut o;
+  std::memset(&o, 0, sizeof o);
+  o.wW = c->wW; o.wE = c->wE; o.wS = c->wS; o.wN = c->wN; o.rhs = c->rhs; o.cs = c->cs;
+  o.scal = c->scal; o.n_active = c->d_nactive; o.tol = -1.0;  // tol < 0: every problem stays active
+  auto assemble = [&]() {
+    if (tiled)
+      k_assemble_tiled<<<dim3((unsigned)(tiles_i * tiles_j), (unsigned)c->nbatch, 1), kTI * kTJ, 0, c->stream>>>(
+          c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud, geo, o, tiles_j);
+    else
+      k_assemble<0><<<g, kBlock, 0, c->stream>>>(c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud, geo, o);
+  };
+  auto launch = [&](int w) {
+    switch (w) {
+      case SY2D_K_ASSEMBLY: assemble(); break;
+      case SY2D_K_P_UPDATE: if (vec2) k_p_update2<<<g2, kBlock, 0, c->stream>>>(k, c->N); else k_p_update<<<g, kBlock, 0, c->stream>>>(k, c->N); break;
+      case SY2D_K_SPMV_V: if (vec2) k_spmv_v2<<<g2, kBlock, 0, c->stream>>>(k, c->N, c->ny); else k_spmv_v<<<g, kBlock, 0, c->stream>>>(k, c->N, c->ny); break;
+      case SY2D_K_S_UPDATE: if (vec2) k_s_update2<<<g2, kBlock, 0, c->stream>>>(k, c->N); else k_s_update<<<g, kBlock, 0, c->stream>>>(k, c->N); break;
+      case SY2D_K_SPMV_T: if (vec2) k_spmv_t2<<<g2, kBlock, 0, c->stream>>>(k, c->N, c->ny); else k_spmv_t<<<g, kBlock, 0, c->stream>>>(k, c->N, c->ny); break;
+      default: if (vec2) k_xr_update2<<<g2, kBlock, 0, c->stream>>>(k, c->N); else k_xr_update<<<g, kBlock, 0, c->stream>>>(k, c->N); break;
+    }
+  };
+  if (which < SY2D_K_ASSEMBLY || which > SY2D_K_XR_UPDATE) return fail(c, SY2D_ERR_INVALID, "sy2d_bench_kernel: unknown kernel %d", which);
+  // prime: operator + one full iteration so that every vector holds finite data
+  CU(cudaMemsetAsync(c->d_nactive, 0, sizeof(int), c->stream));
+  CU(cudaMemsetAsync(c->scal, 0, c->nbatch * sizeof(Scal), c->stream));
+  assemble();
+  for (int w = SY2D_K_P_UPDATE; w <= SY2D_K_XR_UPDATE; ++w) launch(w);
+  launch(SY2D_K_P_UPDATE);
+  launch(SY2D_K_SPMV_V);
+  launch(SY2D_K_S_UPDATE);
+  launch(which);  // warm-up of the kernel under test
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(c->ev_call0, c->stream));
+  for (int r = 0; r < reps; ++r) launch(which);
+  CU(cudaEventRecord(c->ev_call1, c->stream));
+  CU(cudaEventSynchronize(c->ev_call1));
+  CU(cudaGetLastError());
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, c->ev_call0, c->ev_call1));
+  *ms_per_launch = (double)ms / reps;
+  CU(cudaMemsetAsync(c->scal, 0, c->nbatch * sizeof(Scal), c->stream));
+  CU(cudaStreamSynchronize(c->stream));
   return SY2D_OK;
 }
 

@@ -547,6 +547,7 @@ struct KrylovVecs {
   int* n_active;
   double tol;
   int maxit;
+  int freeze_state;  // sy2d_bench_kernel: keep every problem active whatever the residual does
 };
 
 // End-of-iteration bookkeeping done by the last block of a problem: iteration count,
@@ -565,7 +566,7 @@ __device__ __forceinline__ void xr_finish_iteration(Scal* sc, const KrylovVecs& 
   else if (sc->it >= k.maxit) state = 2;
   sc->beta = (rho_new / sc->rho) * (sc->alpha / sc->omega);
   sc->rho = rho_new;
-  if (state != 0) {
+  if (state != 0 && !k.freeze_state) {
     sc->state = state;
     atomicSub(k.n_active, 1);
   }

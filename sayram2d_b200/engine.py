@@ -75,6 +75,7 @@ def load_library():
         "sy2d_dump_vertex_f": (C.c_int, [vp, dp]),
         "sy2d_set_profiling": (C.c_int, [vp, C.c_int]),
         "sy2d_get_profile": (C.c_int, [vp, C.POINTER(Profile)]),
+        "sy2d_bench_kernel": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_double)]),
         "sy2d_build_info": (C.c_char_p, []),
         "sy2d_device_count": (C.c_int, []),
     }
@@ -214,6 +215,12 @@ class Engine:
         p = Profile()
         self._check(self.lib.sy2d_get_profile(self._ctx, C.byref(p)))
         return {n: {"ms": p.ms[k], "launches": p.launches[k], "cells": p.cells[k]} for k, n in enumerate(K_NAMES)}
+
+    def bench_kernel(self, name, reps=20):
+        """Sustained ms per launch of one lockstep-engine kernel (back-to-back launches)."""
+        ms = C.c_double()
+        self._check(self.lib.sy2d_bench_kernel(self._ctx, K_NAMES.index(name), int(reps), C.byref(ms)))
+        return ms.value
 
     def build_info(self):
         return self.lib.sy2d_build_info().decode()
