@@ -31,6 +31,7 @@ struct sy2d_ctx {
   double dt = 0.0;
   long long istep = 0;
   cudaStream_t stream = nullptr;
+  int sm_count = 148;
   std::string err;
   sy2d_options opt;
   bool have_coeffs = false, have_bc = false, have_f = false;
@@ -116,6 +117,14 @@ KrylovVecs krylov(const sy2d_ctx* c) {
 
 dim3 grid_of(const sy2d_ctx* c) { return dim3((unsigned)((c->N + kBlock - 1) / kBlock), (unsigned)c->nbatch, 1); }
 
+// Grid-stride kernels: at most ~16 resident CTAs per SM over the whole batch, so that a problem
+// costs a few hundred block-level atomics per reduction instead of one per 256 cells.
+unsigned capped_blocks(const sy2d_ctx* c, size_t work_items_per_problem, int threads) {
+  const size_t need = (work_items_per_problem + threads - 1) / threads;
+  const size_t cap = std::max<size_t>(1, (size_t)c->sm_count * 16 / (size_t)c->nbatch);
+  return (unsigned)std::min(need, cap);
+}
+
 // RAII-less event bracket used only in profiling mode
 struct Prof {
   sy2d_ctx* c;
@@ -143,7 +152,7 @@ struct Prof {
 void launch_iteration(sy2d_ctx* c) {
   const KrylovVecs k = krylov(c);
   if (c->ny % 2 == 0) {  // two cells per thread, 16-byte accesses
-    const dim3 g2((unsigned)((c->N / 2 + kBlock - 1) / kBlock), (unsigned)c->nbatch, 1);
+    const dim3 g2(capped_blocks(c, c->N / 2, kBlock), (unsigned)c->nbatch, 1);
     { Prof p(c, SY2D_K_P_UPDATE); k_p_update2<<<g2, kBlock, 0, c->stream>>>(k, c->N); }
     { Prof p(c, SY2D_K_SPMV_V); k_spmv_v2<<<g2, kBlock, 0, c->stream>>>(k, c->N, c->ny); }
     { Prof p(c, SY2D_K_S_UPDATE); k_s_update2<<<g2, kBlock, 0, c->stream>>>(k, c->N); }
@@ -254,6 +263,7 @@ int sy2d_create(sy2d_ctx** out, int device, int nx, int ny, int nbatch, const do
 #define CUB(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(c, SY2D_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); return bail(SY2D_ERR_CUDA); } } while (0)
   CUB(cudaSetDevice(device));
   CUB(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CUB(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
   const HostGeometry hg = make_host_geometry(nx, ny, xe, ye);
   const std::vector<double>&wxL = hg.wxL, &wxR = hg.wxR, &wyB = hg.wyB, &wyT = hg.wyT, &dx = hg.dx, &dy = hg.dy;
   struct Up { double** dst; const std::vector<double>* src; } ups[] = {
@@ -577,7 +587,7 @@ int sy2d_step(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
       o.scal = c->scal; o.n_active = c->d_nactive; o.tol = c->opt.tol;
       if (c->nx >= 2 * kTI && c->ny >= kTJ && c->opt.reserved[0] == 0) {  // reserved[0] = 1 forces the per-cell kernel (tests)
         const int tiles_i = (c->nx + kTI - 1) / kTI, tiles_j = (c->ny + kTJ - 1) / kTJ;
-        k_assemble_tiled<<<dim3((unsigned)(tiles_i * tiles_j), (unsigned)c->nbatch, 1), kTI * kTJ, 0, c->stream>>>(
+        k_assemble_tiled<<<dim3(capped_blocks(c, (size_t)tiles_i * tiles_j, 1), (unsigned)c->nbatch, 1), kTI * kTJ, 0, c->stream>>>(
             c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud, geo, o, tiles_j);
       } else {
         k_assemble<0><<<g, kBlock, 0, c->stream>>>(c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud, geo, o);
@@ -697,7 +707,7 @@ int sy2d_bench_kernel(sy2d_ctx* c, int which, int reps, double* ms_per_launch) {
   k.freeze_state = 1;
   const dim3 g = grid_of(c);
   const bool vec2 = c->ny % 2 == 0;
-  const dim3 g2((unsigned)((c->N / 2 + kBlock - 1) / kBlock), (unsigned)c->nbatch, 1);
+  const dim3 g2(capped_blocks(c, c->N / 2, kBlock), (unsigned)c->nbatch, 1);
   const bool tiled = c->nx >= 2 * kTI && c->ny >= kTJ;
   const int tiles_i = (c->nx + kTI - 1) / kTI, tiles_j = (c->ny + kTJ - 1) / kTJ;
   AssembleOut o;
@@ -706,7 +716,7 @@ int sy2d_bench_kernel(sy2d_ctx* c, int which, int reps, double* ms_per_launch) {
   o.scal = c->scal; o.n_active = c->d_nactive; o.tol = -1.0;  // tol < 0: every problem stays active
   auto assemble = [&]() {
     if (tiled)
-      k_assemble_tiled<<<dim3((unsigned)(tiles_i * tiles_j), (unsigned)c->nbatch, 1), kTI * kTJ, 0, c->stream>>>(
+      k_assemble_tiled<<<dim3(capped_blocks(c, (size_t)tiles_i * tiles_j, 1), (unsigned)c->nbatch, 1), kTI * kTJ, 0, c->stream>>>(
           c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud, geo, o, tiles_j);
     else
       k_assemble<0><<<g, kBlock, 0, c->stream>>>(c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud, geo, o);

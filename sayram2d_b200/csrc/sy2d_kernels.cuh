@@ -413,14 +413,17 @@ __global__ void __launch_bounds__(kTI * kTJ) k_assemble_tiled(const double* __re
   const int nx = g.nx, ny = g.ny;
   const size_t N = (size_t)nx * ny;
   const size_t base = (size_t)blockIdx.y * N;
-  const int tile_i = blockIdx.x / tiles_j, tile_j = blockIdx.x - tile_i * tiles_j;
-  const int I0 = tile_i * kTI, J0 = tile_j * kTJ;
   const int tid = threadIdx.x;
+  const int ntiles = tiles_j * ((nx + kTI - 1) / kTI);
+  double rr = 0.0, rabs = 0.0;
   const double* fp = f + base;
   const double* yp = yprev + base;
   const double* txp = tx + base;
   const double* typ = ty + base;
   const double* cp = cxy + base;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {  // a CTA walks over several tiles: few atomics per problem
+  const int tile_i = tile / tiles_j, tile_j = tile - tile_i * tiles_j;
+  const int I0 = tile_i * kTI, J0 = tile_j * kTJ;
   // 1. f and c with halo (indices clamped at the domain boundary: clamped values only meet zero weights)
   for (int e = tid; e < (kTI + 2) * (kTJ + 2); e += kTI * kTJ) {
     const int a = e / (kTJ + 2), b = e - a * (kTJ + 2);
@@ -477,7 +480,6 @@ __global__ void __launch_bounds__(kTI * kTJ) k_assemble_tiled(const double* __re
   // 4. rows
   const int a = tid / kTJ, b = tid - a * kTJ;
   const int i = I0 + a, j = J0 + b;
-  double rr = 0.0, rabs = 0.0;
   if (i < nx && j < ny) {
     const size_t n = (size_t)i * ny + j, c0 = base + n;
     const double f00 = fs[a + 1][b + 1];
@@ -504,8 +506,10 @@ __global__ void __launch_bounds__(kTI * kTJ) k_assemble_tiled(const double* __re
     o.wW[c0] = wW; o.wE[c0] = wE; o.wS[c0] = wS; o.wN[c0] = wN;
     o.rhs[c0] = rhs;
     o.cs[c0] = cs0;
-    rr = rhs * rhs;
-    rabs = fabs(rhs);
+    rr += rhs * rhs;
+    rabs = fmax(rabs, fabs(rhs));
+  }
+  __syncthreads();  // the tile's shared arrays are rewritten by the next tile
   }
   double sums[1] = {rr};
   block_sums<1>(sums, red);
@@ -695,16 +699,18 @@ __device__ __forceinline__ void st2(double* p, double a, double b) { *reinterpre
 __global__ void __launch_bounds__(kBlock) k_p_update2(KrylovVecs k, size_t N) {
   const Scal* sc = k.scal + blockIdx.y;
   if (sc->state != 0) return;
-  const size_t n = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
-  if (n >= N) return;
-  const size_t g = (size_t)blockIdx.y * N + n;
-  if (sc->first) {
-    const double2 r = ld2(k.rhs + g);
-    st2(k.p + g, r.x, r.y);
-  } else {
-    const double beta = sc->beta, omega = sc->omega;
-    const double2 r = ld2(k.r + g), p = ld2(k.p + g), v = ld2(k.v + g);
-    st2(k.p + g, r.x + beta * (p.x - omega * v.x), r.y + beta * (p.y - omega * v.y));
+  const size_t stride = 2 * (size_t)gridDim.x * blockDim.x;
+  const bool first = sc->first;
+  const double beta = sc->beta, omega = sc->omega;
+  for (size_t n = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); n < N; n += stride) {
+    const size_t g = (size_t)blockIdx.y * N + n;
+    if (first) {
+      const double2 r = ld2(k.rhs + g);
+      st2(k.p + g, r.x, r.y);
+    } else {
+      const double2 r = ld2(k.r + g), p = ld2(k.p + g), v = ld2(k.v + g);
+      st2(k.p + g, r.x + beta * (p.x - omega * v.x), r.y + beta * (p.y - omega * v.y));
+    }
   }
 }
 
@@ -723,17 +729,17 @@ __global__ void __launch_bounds__(kBlock) k_spmv_v2(KrylovVecs k, size_t N, int 
   __shared__ double red[32];
   Scal* sc = k.scal + blockIdx.y;
   if (sc->state != 0) return;
-  const size_t n = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
+  const size_t stride = 2 * (size_t)gridDim.x * blockDim.x;
   const size_t base = (size_t)blockIdx.y * N;
   double dot = 0.0;
-  if (n < N) {
+  for (size_t n = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); n < N; n += stride) {
     const size_t g = base + n;
     const double* p = k.p + base;
     double v0, v1;
     stencil_apply2(p, n, N, ny, ld2(p + n), ld2(k.wW + g), ld2(k.wE + g), ld2(k.wS + g), ld2(k.wN + g), v0, v1);
     st2(k.v + g, v0, v1);
     const double2 rh = ld2(k.rhs + g);
-    dot = rh.x * v0 + rh.y * v1;
+    dot += rh.x * v0 + rh.y * v1;
   }
   double sums[1] = {dot};
   block_sums<1>(sums, red);
@@ -750,30 +756,32 @@ __global__ void __launch_bounds__(kBlock) k_spmv_v2(KrylovVecs k, size_t N, int 
 __global__ void __launch_bounds__(kBlock) k_s_update2(KrylovVecs k, size_t N) {
   const Scal* sc = k.scal + blockIdx.y;
   if (sc->state != 0) return;
-  const size_t n = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
-  if (n >= N) return;
-  const size_t g = (size_t)blockIdx.y * N + n;
+  const size_t stride = 2 * (size_t)gridDim.x * blockDim.x;
   const double alpha = sc->alpha;
-  const double2 r = ld2((sc->first ? k.rhs : k.r) + g), v = ld2(k.v + g);
-  st2(k.s + g, r.x - alpha * v.x, r.y - alpha * v.y);
+  const double* rsrc = sc->first ? k.rhs : k.r;
+  for (size_t n = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); n < N; n += stride) {
+    const size_t g = (size_t)blockIdx.y * N + n;
+    const double2 r = ld2(rsrc + g), v = ld2(k.v + g);
+    st2(k.s + g, r.x - alpha * v.x, r.y - alpha * v.y);
+  }
 }
 
 __global__ void __launch_bounds__(kBlock) k_spmv_t2(KrylovVecs k, size_t N, int ny) {
   __shared__ double red[2 * 32];
   Scal* sc = k.scal + blockIdx.y;
   if (sc->state != 0) return;
-  const size_t n = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
+  const size_t stride = 2 * (size_t)gridDim.x * blockDim.x;
   const size_t base = (size_t)blockIdx.y * N;
   double ts = 0.0, tt = 0.0;
-  if (n < N) {
+  for (size_t n = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); n < N; n += stride) {
     const size_t g = base + n;
     const double* s = k.s + base;
     const double2 sc0 = ld2(s + n);
     double t0, t1;
     stencil_apply2(s, n, N, ny, sc0, ld2(k.wW + g), ld2(k.wE + g), ld2(k.wS + g), ld2(k.wN + g), t0, t1);
     st2(k.t + g, t0, t1);
-    ts = t0 * sc0.x + t1 * sc0.y;
-    tt = t0 * t0 + t1 * t1;
+    ts += t0 * sc0.x + t1 * sc0.y;
+    tt += t0 * t0 + t1 * t1;
   }
   double sums[2] = {ts, tt};
   block_sums<2>(sums, red);
@@ -793,19 +801,20 @@ __global__ void __launch_bounds__(kBlock) k_xr_update2(KrylovVecs k, size_t N) {
   __shared__ double red[32];
   Scal* sc = k.scal + blockIdx.y;
   if (sc->state != 0) return;
-  const size_t n = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
+  const size_t stride = 2 * (size_t)gridDim.x * blockDim.x;
   double dot = 0.0, rabs = 0.0;
-  if (n < N) {
+  const double alpha = sc->alpha, omega = sc->omega;
+  const bool first = sc->first;
+  for (size_t n = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); n < N; n += stride) {
     const size_t g = (size_t)blockIdx.y * N + n;
-    const double alpha = sc->alpha, omega = sc->omega;
     const double2 s = ld2(k.s + g), p = ld2(k.p + g), t = ld2(k.t + g), rh = ld2(k.rhs + g);
     double2 x = make_double2(0.0, 0.0);
-    if (!sc->first) x = ld2(k.x + g);
+    if (!first) x = ld2(k.x + g);
     st2(k.x + g, x.x + (alpha * p.x + omega * s.x), x.y + (alpha * p.y + omega * s.y));
     const double r0 = s.x - omega * t.x, r1 = s.y - omega * t.y;
     st2(k.r + g, r0, r1);
-    dot = rh.x * r0 + rh.y * r1;
-    rabs = fmax(fabs(r0), fabs(r1));
+    dot += rh.x * r0 + rh.y * r1;
+    rabs = fmax(rabs, fmax(fabs(r0), fabs(r1)));
   }
   double sums[1] = {dot};
   block_sums<1>(sums, red);
