@@ -156,6 +156,19 @@ int sy2d_get_profile(sy2d_ctx* ctx, sy2d_profile* out);
  * stream; *ms_per_launch is the average.  Solver state (f, step count) is left untouched. */
 int sy2d_bench_kernel(sy2d_ctx* ctx, int which, int reps, double* ms_per_launch);
 
+/* ---- one large grid split into row slabs over the GPUs of a node (BASELINE config 5) ----
+ * Rank r holds rows [i_lo, i_hi) of the nx_global x ny grid (contiguous split along i, the slow axis,
+ * so a halo line is ny contiguous doubles).  Per BiCGSTAB iteration: two one-line halo exchanges
+ * (ncclSend/Recv with both neighbours) and three all-gathers of 5 doubles that every rank reduces in
+ * rank order.  NCCL is loaded with dlopen; rank 0 calls sy2d_nccl_unique_id and the host distributes
+ * the 128 bytes (bench.py / the tests use torch.distributed for that).  On a slab context the field
+ * arguments of sy2d_set_coeffs / set_f / put_f / get_f are the OWNED rows [i_hi - i_lo][ny]; the
+ * boundary lines of sy2d_set_bc stay global.  stats.fmin / negatives cover the owned rows only. */
+int sy2d_nccl_unique_id(void* id_out /* 128 bytes */);
+int sy2d_create_slab(sy2d_ctx** out, int device, int nx_global, int ny, int rank, int nranks, const void* nccl_id,
+                     const double* x_edges /* nx_global+1 */, const double* y_edges /* ny+1 */, double dt);
+int sy2d_slab_rows(const sy2d_ctx* ctx, int* i_lo, int* i_hi);
+
 /* Build/device facts: "sm_100a;cuda=12.9;..." */
 const char* sy2d_build_info(void);
 int sy2d_device_count(void);

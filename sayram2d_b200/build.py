@@ -18,7 +18,8 @@ BIN = os.path.join(PKG, "bin", "sayram2d")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CUDA_SOURCES = [os.path.join(PKG, "csrc", "sy2d_api.cu")]
-CUDA_HEADERS = [os.path.join(PKG, "csrc", h) for h in ("sy2d_kernels.cuh", "sy2d_geometry.h")] + [
+CUDA_HEADERS = [os.path.join(PKG, "csrc", h) for h in ("sy2d_kernels.cuh", "sy2d_geometry.h", "sy2d_problem_kernel.cuh",
+                                                        "sy2d_xline_kernel.cuh")] + [
     os.path.join(ROOT, "include", "sayram2d.h")]
 
 
@@ -38,7 +39,7 @@ def build_library(force=False):
     if force or _stale(LIB, CUDA_SOURCES + CUDA_HEADERS):
         os.makedirs(os.path.dirname(LIB), exist_ok=True)
         _run([NVCC, "-O3", "-std=c++17", *ARCH, "-lineinfo", "-Xcompiler", "-fPIC", "-shared",
-              "-o", LIB, *CUDA_SOURCES])
+              "-o", LIB, *CUDA_SOURCES, "-ldl"])
     return LIB
 
 

@@ -56,6 +56,12 @@ struct sy2d_ctx {
   double* stage = nullptr;      // unused staging pointer (kept for destroy)
   size_t stage_elems = 0;
   // engine 2 / x-line: per-problem scratch in thread-private layout, allocated on first use
+  // row-slab mode (sy2d_create_slab): this context holds rows [i_lo, i_hi) of an nx_glob x ny grid in
+  // local arrays of nx = (i_hi - i_lo) + 2 rows (one halo row on each side)
+  bool slab = false;
+  int rank = 0, nranks = 1, nx_glob = 0, i_lo = 0, i_hi = 0;
+  void* comm = nullptr;          // ncclComm_t
+  double* d_gather = nullptr;    // [nranks][5]
   int* d_order = nullptr;       // engine 2 scheduling: problems sorted by last call's cost, longest first
   int* d_cost = nullptr;
   std::vector<int> h_cost, h_order;
@@ -102,7 +108,7 @@ Geometry geometry(const sy2d_ctx* c) {
   g.wxL = c->d_wxL; g.wxR = c->d_wxR; g.wyB = c->d_wyB; g.wyT = c->d_wyT;
   g.bc_xmin = c->d_bc[0]; g.bc_xmax = c->d_bc[1]; g.bc_ymin = c->d_bc[2]; g.bc_ymax = c->d_bc[3];
   for (int k = 0; k < 4; ++k) g.bc[k] = c->bc[k];
-  g.nx = c->nx; g.ny = c->ny;
+  g.nx = c->slab ? c->nx_glob : c->nx; g.ny = c->ny;
   return g;
 }
 
@@ -112,6 +118,8 @@ KrylovVecs krylov(const sy2d_ctx* c) {
   k.x = c->x; k.r = c->r; k.p = c->p; k.v = c->v; k.s = c->s; k.t = c->t;
   k.scal = c->scal; k.n_active = c->d_nactive; k.tol = c->opt.tol; k.maxit = c->opt.maxit;
   k.freeze_state = 0;
+  k.n_begin = 0; k.n_end = c->N; k.defer = 0;
+  if (c->slab) { k.n_begin = (size_t)c->ny; k.n_end = (size_t)(c->nx - 1) * c->ny; k.defer = 1; }
   return k;
 }
 
@@ -196,12 +204,186 @@ int collect_profile(sy2d_ctx* c) {
   return SY2D_OK;
 }
 
+int step_slab(sy2d_ctx* c, int nsteps, sy2d_stats* stats);
+int slab_halo_exchange(sy2d_ctx* c, double* a);
+void slab_comm_destroy(sy2d_ctx* c);
+double* own_ptr(const sy2d_ctx* c, double* a);
+size_t own_elems(const sy2d_ctx* c);
+
 template <class T>
 int dalloc(sy2d_ctx* c, T** p, size_t n) {
   CU(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
   return SY2D_OK;
 }
 
+}  // namespace
+
+
+// ---------------------------------------------------------------------------------------------
+// Row-slab mode: NCCL through dlopen (the library does not link libnccl; a process that never
+// creates a slab context never needs it, and a process that already loaded NCCL - e.g. through
+// torch - reuses that copy).
+// ---------------------------------------------------------------------------------------------
+#include <dlfcn.h>
+#include <nccl.h>
+
+namespace {
+struct NcclApi {
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclAllGather) AllGather = nullptr;
+  decltype(&ncclSend) Send = nullptr;
+  decltype(&ncclRecv) Recv = nullptr;
+  decltype(&ncclGroupStart) GroupStart = nullptr;
+  decltype(&ncclGroupEnd) GroupEnd = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  bool ok = false;
+  std::string why;
+};
+
+NcclApi& nccl() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api;
+  tried = true;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) { api.why = std::string("cannot load libnccl.so.2: ") + dlerror(); return api; }
+#define SY2D_NCCL_SYM(name) api.name = reinterpret_cast<decltype(api.name)>(dlsym(h, "nccl" #name)); if (!api.name) { api.why = "missing symbol nccl" #name; return api; }
+  SY2D_NCCL_SYM(GetUniqueId) SY2D_NCCL_SYM(CommInitRank) SY2D_NCCL_SYM(CommDestroy) SY2D_NCCL_SYM(AllGather)
+  SY2D_NCCL_SYM(Send) SY2D_NCCL_SYM(Recv) SY2D_NCCL_SYM(GroupStart) SY2D_NCCL_SYM(GroupEnd) SY2D_NCCL_SYM(GetErrorString)
+#undef SY2D_NCCL_SYM
+  api.ok = true;
+  return api;
+}
+
+#define NC(call)                                                                                             \
+  do {                                                                                                       \
+    ncclResult_t r_ = (call);                                                                                \
+    if (r_ != ncclSuccess) return fail(c, SY2D_ERR_CUDA, "NCCL: %s failed: %s", #call, nccl().GetErrorString(r_)); \
+  } while (0)
+
+double* own_ptr(const sy2d_ctx* c, double* a) { return c->slab ? a + c->ny : a; }
+size_t own_elems(const sy2d_ctx* c) { return c->slab ? (size_t)(c->nx - 2) * c->ny : c->total; }
+
+void slab_comm_destroy(sy2d_ctx* c) {
+  if (c->comm && nccl().ok) nccl().CommDestroy(static_cast<ncclComm_t>(c->comm));
+  c->comm = nullptr;
+}
+
+// One line (ny doubles) to each neighbour: my first owned row -> bottom halo of rank-1, my last owned
+// row -> top halo of rank+1.  Contiguous 8*ny bytes over NVLink.
+int slab_halo_exchange(sy2d_ctx* c, double* a) {
+  ncclComm_t comm = static_cast<ncclComm_t>(c->comm);
+  const size_t ny = (size_t)c->ny;
+  const int rows = c->nx - 2;
+  NC(nccl().GroupStart());
+  if (c->rank > 0) {
+    NC(nccl().Send(a + ny, ny, ncclDouble, c->rank - 1, comm, c->stream));
+    NC(nccl().Recv(a, ny, ncclDouble, c->rank - 1, comm, c->stream));
+  }
+  if (c->rank < c->nranks - 1) {
+    NC(nccl().Send(a + (size_t)rows * ny, ny, ncclDouble, c->rank + 1, comm, c->stream));
+    NC(nccl().Recv(a + (size_t)(rows + 1) * ny, ny, ncclDouble, c->rank + 1, comm, c->stream));
+  }
+  NC(nccl().GroupEnd());
+  return SY2D_OK;
+}
+
+// accumulators of every rank -> scalars on every rank (identical summation order everywhere)
+int slab_reduce(sy2d_ctx* c, int phase, const KrylovVecs& k) {
+  ncclComm_t comm = static_cast<ncclComm_t>(c->comm);
+  NC(nccl().AllGather(&c->scal->acc_rv, c->d_gather, 5, ncclDouble, comm, c->stream));
+  k_slab_scalars<<<1, 32, 0, c->stream>>>(phase, c->scal, c->d_gather, c->nranks, k);
+  CU(cudaGetLastError());
+  return SY2D_OK;
+}
+
+int step_slab(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
+  if (c->ny % 2) return fail(c, SY2D_ERR_INVALID, "slab mode needs an even ny");
+  const Geometry geo = geometry(c);
+  const KrylovVecs k = krylov(c);
+  const int rows = c->nx - 2;
+  const size_t own = (size_t)rows * c->ny;
+  const dim3 g2(capped_blocks(c, own / 2, kBlock), 1, 1);
+  const int tiles_i = (rows + kTI - 1) / kTI, tiles_j = (c->ny + kTJ - 1) / kTJ;
+  sy2d_stats st;
+  std::memset(&st, 0, sizeof st);
+  st.engine = 1;
+  CU(cudaEventRecord(c->ev_call0, c->stream));
+  for (int step = 0; step < nsteps; ++step) {
+    int rc = slab_halo_exchange(c, c->f);
+    if (!rc) rc = slab_halo_exchange(c, c->yprev);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(c->d_nactive, 0, sizeof(int), c->stream));
+    AssembleOut o;
+    std::memset(&o, 0, sizeof o);
+    o.wW = c->wW; o.wE = c->wE; o.wS = c->wS; o.wN = c->wN; o.rhs = c->rhs; o.cs = c->cs;
+    o.scal = c->scal; o.n_active = c->d_nactive; o.tol = c->opt.tol; o.local_rows = c->nx;
+    k_assemble_tiled<<<dim3(capped_blocks(c, (size_t)tiles_i * tiles_j, 1), 1, 1), kTI * kTJ, 0, c->stream>>>(
+        c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud, geo, o, tiles_j, c->i_lo - 1, 1, rows + 1, 1);
+    CU(cudaGetLastError());
+    rc = slab_reduce(c, 0, k);
+    if (rc) return rc;
+    c->launches += 2;
+    CU(cudaMemcpyAsync(c->h_nactive, c->d_nactive, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    int done_its = 0;
+    while (*c->h_nactive > 0 && done_its < c->opt.maxit + c->opt.check_every) {
+      for (int it = 0; it < c->opt.check_every; ++it) {
+        k_p_update2<<<g2, kBlock, 0, c->stream>>>(k, c->N);
+        if ((rc = slab_halo_exchange(c, c->p))) return rc;
+        k_spmv_v2<<<g2, kBlock, 0, c->stream>>>(k, c->N, c->ny);
+        if ((rc = slab_reduce(c, 1, k))) return rc;
+        k_s_update2<<<g2, kBlock, 0, c->stream>>>(k, c->N);
+        if ((rc = slab_halo_exchange(c, c->s))) return rc;
+        k_spmv_t2<<<g2, kBlock, 0, c->stream>>>(k, c->N, c->ny);
+        if ((rc = slab_reduce(c, 2, k))) return rc;
+        k_xr_update2<<<g2, kBlock, 0, c->stream>>>(k, c->N);
+        if ((rc = slab_reduce(c, 3, k))) return rc;
+      }
+      CU(cudaGetLastError());
+      CU(cudaMemcpyAsync(c->h_nactive, c->d_nactive, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      done_its += c->opt.check_every;
+      c->launches += (long long)c->opt.check_every * 8;
+    }
+    StepStats init;
+    std::memset(&init, 0, sizeof init);
+    init.fmin = 1.0e300;
+    *c->h_stats = init;
+    CU(cudaMemcpyAsync(c->d_stats, c->h_stats, sizeof(StepStats), cudaMemcpyHostToDevice, c->stream));
+    const dim3 gf((unsigned)((own + kBlock - 1) / kBlock), 1, 1);
+    k_finish<<<gf, kBlock, 0, c->stream>>>(c->x + c->ny, c->cs + c->ny, c->f + c->ny, c->yprev + c->ny, c->scal, own, c->opt.predictor, c->d_stats);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(StepStats), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->istep += 1;
+    st.steps += 1;
+    st.iters_total += c->h_stats->it_max;
+    st.iters_sum_all += c->h_stats->it_max;
+    st.iters_last = c->h_stats->it_max;
+    st.fmin = c->h_stats->fmin;                      // of this rank's rows
+    st.negatives = (long long)c->h_stats->negatives;  // of this rank's rows
+    st.kernel_launches = c->launches;
+    Scal hs;
+    CU(cudaMemcpy(&hs, c->scal, sizeof(Scal), cudaMemcpyDeviceToHost));
+    st.resid_last = hs.rmax;                         // recursive residual (global max-norm)
+    if ((c->h_stats->n_bad > 0 || *c->h_nactive > 0) && !c->opt.reserved[1]) {  // reserved[1]: fixed iteration budget (bench)
+      if (stats) *stats = st;
+      return fail(c, SY2D_ERR_NOT_CONVERGED, "sy2d_step (slab): BiCGSTAB did not converge at step %lld (%d iterations, max|r|=%.3e)",
+                  c->istep, c->h_stats->it_max, hs.rmax);
+    }
+  }
+  CU(cudaEventRecord(c->ev_call1, c->stream));
+  CU(cudaEventSynchronize(c->ev_call1));
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, c->ev_call0, c->ev_call1));
+  st.seconds_device = ms * 1e-3;
+  if (stats) *stats = st;
+  return SY2D_OK;
+}
 }  // namespace
 
 extern "C" {
@@ -234,7 +416,11 @@ int sy2d_default_options(sy2d_options* o) {
 
 const char* sy2d_last_error(const sy2d_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
 
-int sy2d_create(sy2d_ctx** out, int device, int nx, int ny, int nbatch, const double* xe, const double* ye, double dt) {
+}  // extern "C"
+
+// nx: rows of the global grid.  Slab contexts (nranks > 1) store rows [i_lo, i_hi) plus two halo rows.
+static int create_impl(sy2d_ctx** out, int device, int nx, int ny, int nbatch, const double* xe, const double* ye, double dt,
+                       int rank, int nranks) {
   sy2d_ctx* c = nullptr;
   if (!out) return fail(c, SY2D_ERR_INVALID, "sy2d_create: out is NULL");
   *out = nullptr;
@@ -253,7 +439,14 @@ int sy2d_create(sy2d_ctx** out, int device, int nx, int ny, int nbatch, const do
 
   sy2d_ctx* ctx = new sy2d_ctx;
   ctx->device = device; ctx->nx = nx; ctx->ny = ny; ctx->nbatch = nbatch; ctx->dt = dt;
-  ctx->N = (size_t)nx * ny; ctx->total = ctx->N * nbatch;
+  if (nranks > 1) {
+    const int base_rows = nx / nranks, extra = nx % nranks;
+    ctx->slab = true; ctx->rank = rank; ctx->nranks = nranks; ctx->nx_glob = nx;
+    ctx->i_lo = rank * base_rows + std::min(rank, extra);
+    ctx->i_hi = ctx->i_lo + base_rows + (rank < extra ? 1 : 0);
+    ctx->nx = ctx->i_hi - ctx->i_lo + 2;  // local rows incl. the two halo rows
+  }
+  ctx->N = (size_t)ctx->nx * ny; ctx->total = ctx->N * nbatch;
   sy2d_default_options(&ctx->opt);
   std::memset(&ctx->prof, 0, sizeof ctx->prof);
   ctx->h_xe.assign(xe, xe + nx + 1);
@@ -279,7 +472,10 @@ int sy2d_create(sy2d_ctx** out, int device, int nx, int ny, int nbatch, const do
   }
   double** fields[] = {&ctx->tx, &ctx->ty, &ctx->cxy, &ctx->U, &ctx->Ud, &ctx->f, &ctx->yprev, &ctx->cs, &ctx->wW, &ctx->wE,
                        &ctx->wS, &ctx->wN, &ctx->rhs, &ctx->x, &ctx->r, &ctx->p, &ctx->v, &ctx->s, &ctx->t};
-  for (double** fp : fields) CUB(cudaMalloc(reinterpret_cast<void**>(fp), ctx->total * sizeof(double)));
+  for (double** fp : fields) {
+    CUB(cudaMalloc(reinterpret_cast<void**>(fp), ctx->total * sizeof(double)));
+    if (ctx->slab) CUB(cudaMemset(*fp, 0, ctx->total * sizeof(double)));  // halo rows outside the domain stay finite
+  }
   CUB(cudaMalloc(reinterpret_cast<void**>(&ctx->scal), nbatch * sizeof(Scal)));
   CUB(cudaMemset(ctx->scal, 0, nbatch * sizeof(Scal)));
   CUB(cudaMalloc(reinterpret_cast<void**>(&ctx->d_nactive), sizeof(int)));
@@ -291,6 +487,12 @@ int sy2d_create(sy2d_ctx** out, int device, int nx, int ny, int nbatch, const do
 #undef CUB
   *out = ctx;
   return SY2D_OK;
+}
+
+extern "C" {
+
+int sy2d_create(sy2d_ctx** out, int device, int nx, int ny, int nbatch, const double* xe, const double* ye, double dt) {
+  return create_impl(out, device, nx, ny, nbatch, xe, ye, dt, 0, 1);
 }
 
 void sy2d_destroy(sy2d_ctx* c) {
@@ -305,6 +507,8 @@ void sy2d_destroy(sy2d_ctx* c) {
   if (c->scal) cudaFree(c->scal);
   if (c->d_order) cudaFree(c->d_order);
   if (c->d_cost) cudaFree(c->d_cost);
+  if (c->d_gather) cudaFree(c->d_gather);
+  slab_comm_destroy(c);
   if (c->d_nactive) cudaFree(c->d_nactive);
   if (c->h_nactive) cudaFreeHost(c->h_nactive);
   if (c->d_stats) cudaFree(c->d_stats);
@@ -330,9 +534,20 @@ int sy2d_set_coeffs_dev(sy2d_ctx* c, const double* G, const double* Dxx, const d
   if (!c) return SY2D_ERR_INVALID;
   if (!G || !Dxx || !Dxy || !Dyy) return fail(c, SY2D_ERR_INVALID, "sy2d_set_coeffs: NULL field");
   CU(cudaSetDevice(c->device));
-  k_prepare_coeffs<<<grid_of(c), kBlock, 0, c->stream>>>(G, Dxx, Dxy, Dyy, inv_tau, c->d_dx, c->d_dy, c->dt, c->nx, c->ny,
-                                                       c->tx, c->ty, c->cxy, c->U, c->Ud);
-  CU(cudaGetLastError());
+  if (c->slab) {  // inputs are the owned rows [i_lo, i_hi); outputs go to local rows 1..; dx is indexed globally
+    const int rows = c->nx - 2, off = c->ny;
+    const dim3 g((unsigned)(((size_t)rows * c->ny + kBlock - 1) / kBlock), 1, 1);
+    k_prepare_coeffs<<<g, kBlock, 0, c->stream>>>(G, Dxx, Dxy, Dyy, inv_tau, c->d_dx + c->i_lo, c->d_dy, c->dt, rows, c->ny,
+                                                  c->tx + off, c->ty + off, c->cxy + off, c->U + off, c->Ud + off);
+    CU(cudaGetLastError());
+    int rc = slab_halo_exchange(c, c->tx);
+    if (!rc) rc = slab_halo_exchange(c, c->cxy);
+    if (rc) return rc;
+  } else {
+    k_prepare_coeffs<<<grid_of(c), kBlock, 0, c->stream>>>(G, Dxx, Dxy, Dyy, inv_tau, c->d_dx, c->d_dy, c->dt, c->nx, c->ny,
+                                                         c->tx, c->ty, c->cxy, c->U, c->Ud);
+    CU(cudaGetLastError());
+  }
   CU(cudaStreamSynchronize(c->stream));
   c->have_coeffs = true;
   return SY2D_OK;
@@ -346,7 +561,7 @@ int sy2d_set_coeffs(sy2d_ctx* c, const double* G, const double* Dxx, const doubl
   double* dst[5] = {c->x, c->r, c->p, c->v, c->s};
   const double* src[5] = {G, Dxx, Dxy, Dyy, inv_tau};
   for (int k = 0; k < 5; ++k)
-    if (src[k]) CU(cudaMemcpyAsync(dst[k], src[k], c->total * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (src[k]) CU(cudaMemcpyAsync(dst[k], src[k], own_elems(c) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   return sy2d_set_coeffs_dev(c, dst[0], dst[1], dst[2], dst[3], inv_tau ? dst[4] : nullptr);
 }
 
@@ -360,7 +575,7 @@ int sy2d_set_bc(sy2d_ctx* c, const int bc_type[4], const double* xmin, const dou
   CU(cudaSetDevice(c->device));
   for (int k = 0; k < 4; ++k) {
     c->bc[k] = bc_type[k];
-    const size_t n = (k < 2 ? c->ny : c->nx) + 1;
+    const size_t n = (k < 2 ? c->ny : (c->slab ? c->nx_glob : c->nx)) + 1;
     if (lines[k]) CU(cudaMemcpyAsync(c->d_bc[k], lines[k], n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   }
   CU(cudaStreamSynchronize(c->stream));
@@ -380,7 +595,7 @@ static int reset_state(sy2d_ctx* c) {
 int sy2d_set_f_dev(sy2d_ctx* c, const double* f) {
   if (!c || !f) return SY2D_ERR_INVALID;
   CU(cudaSetDevice(c->device));
-  CU(cudaMemcpyAsync(c->f, f, c->total * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  CU(cudaMemcpyAsync(own_ptr(c, c->f), f, own_elems(c) * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
   c->have_f = true;
   return reset_state(c);
 }
@@ -388,7 +603,7 @@ int sy2d_set_f_dev(sy2d_ctx* c, const double* f) {
 int sy2d_set_f(sy2d_ctx* c, const double* f) {
   if (!c || !f) return SY2D_ERR_INVALID;
   CU(cudaSetDevice(c->device));
-  CU(cudaMemcpyAsync(c->f, f, c->total * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(own_ptr(c, c->f), f, own_elems(c) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   c->have_f = true;
   return reset_state(c);
 }
@@ -397,7 +612,7 @@ int sy2d_put_f(sy2d_ctx* c, const double* f) {
   if (!c || !f) return SY2D_ERR_INVALID;
   if (!c->have_f) return sy2d_set_f(c, f);
   CU(cudaSetDevice(c->device));
-  CU(cudaMemcpyAsync(c->f, f, c->total * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(own_ptr(c, c->f), f, own_elems(c) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   return SY2D_OK;
 }
 
@@ -405,7 +620,7 @@ int sy2d_get_f(sy2d_ctx* c, double* out) {
   if (!c || !out) return SY2D_ERR_INVALID;
   if (!c->have_f) return fail(c, SY2D_ERR_STATE, "sy2d_get_f: f not set");
   CU(cudaSetDevice(c->device));
-  CU(cudaMemcpyAsync(out, c->f, c->total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(out, own_ptr(c, c->f), own_elems(c) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return SY2D_OK;
 }
@@ -414,7 +629,7 @@ int sy2d_get_f_dev(sy2d_ctx* c, double* out) {
   if (!c || !out) return SY2D_ERR_INVALID;
   if (!c->have_f) return fail(c, SY2D_ERR_STATE, "sy2d_get_f: f not set");
   CU(cudaSetDevice(c->device));
-  CU(cudaMemcpyAsync(out, c->f, c->total * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  CU(cudaMemcpyAsync(out, own_ptr(c, c->f), own_elems(c) * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return SY2D_OK;
 }
@@ -432,6 +647,7 @@ static int ready(sy2d_ctx* c, const char* who) {
 }  // extern "C"
 
 static int engine_of(const sy2d_ctx* c) {
+  if (c->slab) return 1;
   if (c->opt.engine == 1 || c->opt.engine == 2) return c->opt.engine;
   return c->N <= 16384 ? 2 : 1;
 }
@@ -565,6 +781,7 @@ int sy2d_step(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
   int rc = ready(c, "sy2d_step");
   if (rc) return rc;
   CU(cudaSetDevice(c->device));
+  if (c->slab) return step_slab(c, nsteps, stats);
   if (engine_of(c) == 2) return step_per_problem(c, nsteps, stats);
   const dim3 g = grid_of(c);
   const Geometry geo = geometry(c);
@@ -584,11 +801,11 @@ int sy2d_step(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
       AssembleOut o;
       std::memset(&o, 0, sizeof o);
       o.wW = c->wW; o.wE = c->wE; o.wS = c->wS; o.wN = c->wN; o.rhs = c->rhs; o.cs = c->cs;
-      o.scal = c->scal; o.n_active = c->d_nactive; o.tol = c->opt.tol;
+      o.scal = c->scal; o.n_active = c->d_nactive; o.tol = c->opt.tol; o.local_rows = c->nx;
       if (c->nx >= 2 * kTI && c->ny >= kTJ && c->opt.reserved[0] == 0) {  // reserved[0] = 1 forces the per-cell kernel (tests)
         const int tiles_i = (c->nx + kTI - 1) / kTI, tiles_j = (c->ny + kTJ - 1) / kTJ;
         k_assemble_tiled<<<dim3(capped_blocks(c, (size_t)tiles_i * tiles_j, 1), (unsigned)c->nbatch, 1), kTI * kTJ, 0, c->stream>>>(
-            c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud, geo, o, tiles_j);
+            c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud, geo, o, tiles_j, 0, 0, c->nx, 0);
       } else {
         k_assemble<0><<<g, kBlock, 0, c->stream>>>(c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud, geo, o);
       }
@@ -662,6 +879,7 @@ int sy2d_dump_operator(sy2d_ctx* c, double* diags, double* rhs) {
   if (!c || !diags || !rhs) return SY2D_ERR_INVALID;
   int rc = ready(c, "sy2d_dump_operator");
   if (rc) return rc;
+  if (c->slab) return fail(c, SY2D_ERR_INVALID, "sy2d_dump_operator: not available on a slab context");
   CU(cudaSetDevice(c->device));
   AssembleOut o;
   std::memset(&o, 0, sizeof o);
@@ -681,6 +899,7 @@ int sy2d_dump_vertex_f(sy2d_ctx* c, double* vf) {
   if (!c || !vf) return SY2D_ERR_INVALID;
   int rc = ready(c, "sy2d_dump_vertex_f");
   if (rc) return rc;
+  if (c->slab) return fail(c, SY2D_ERR_INVALID, "sy2d_dump_vertex_f: not available on a slab context");
   CU(cudaSetDevice(c->device));
   const size_t nv = (size_t)(c->nx + 1) * (c->ny + 1) * c->nbatch;
   double* d_vf = nullptr;
@@ -701,6 +920,7 @@ int sy2d_bench_kernel(sy2d_ctx* c, int which, int reps, double* ms_per_launch) {
   if (!c || !ms_per_launch || reps < 1) return SY2D_ERR_INVALID;
   int rc = ready(c, "sy2d_bench_kernel");
   if (rc) return rc;
+  if (c->slab) return fail(c, SY2D_ERR_INVALID, "sy2d_bench_kernel: not available on a slab context");
   CU(cudaSetDevice(c->device));
   const Geometry geo = geometry(c);
   KrylovVecs k = krylov(c);
@@ -714,10 +934,11 @@ int sy2d_bench_kernel(sy2d_ctx* c, int which, int reps, double* ms_per_launch) {
   std::memset(&o, 0, sizeof o);
   o.wW = c->wW; o.wE = c->wE; o.wS = c->wS; o.wN = c->wN; o.rhs = c->rhs; o.cs = c->cs;
   o.scal = c->scal; o.n_active = c->d_nactive; o.tol = -1.0;  // tol < 0: every problem stays active
+  o.local_rows = c->nx;
   auto assemble = [&]() {
     if (tiled)
       k_assemble_tiled<<<dim3(capped_blocks(c, (size_t)tiles_i * tiles_j, 1), (unsigned)c->nbatch, 1), kTI * kTJ, 0, c->stream>>>(
-          c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud, geo, o, tiles_j);
+          c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud, geo, o, tiles_j, 0, 0, c->nx, 0);
     else
       k_assemble<0><<<g, kBlock, 0, c->stream>>>(c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud, geo, o);
   };
@@ -766,6 +987,54 @@ int sy2d_set_profiling(sy2d_ctx* c, int on) {
 int sy2d_get_profile(sy2d_ctx* c, sy2d_profile* out) {
   if (!c || !out) return SY2D_ERR_INVALID;
   *out = c->prof;
+  return SY2D_OK;
+}
+
+int sy2d_nccl_unique_id(void* id_out) {
+  if (!id_out) return SY2D_ERR_INVALID;
+  if (!nccl().ok) { g_create_error = nccl().why; return SY2D_ERR_CUDA; }
+  ncclUniqueId id;
+  if (nccl().GetUniqueId(&id) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return SY2D_ERR_CUDA; }
+  std::memcpy(id_out, &id, sizeof id);
+  return SY2D_OK;
+}
+
+int sy2d_create_slab(sy2d_ctx** out, int device, int nx_global, int ny, int rank, int nranks, const void* nccl_id,
+                     const double* x_edges, const double* y_edges, double dt) {
+  sy2d_ctx* c = nullptr;
+  if (!out || !nccl_id) return fail(c, SY2D_ERR_INVALID, "sy2d_create_slab: NULL argument");
+  if (nranks < 2 || rank < 0 || rank >= nranks) return fail(c, SY2D_ERR_INVALID, "sy2d_create_slab: need nranks >= 2 and 0 <= rank < nranks");
+  if (nx_global / nranks < 2 * kTI) return fail(c, SY2D_ERR_INVALID, "sy2d_create_slab: at least %d rows per rank", 2 * kTI);
+  if (ny % 2 || ny < kTJ) return fail(c, SY2D_ERR_INVALID, "sy2d_create_slab: ny must be even and >= %d", kTJ);
+  if (!nccl().ok) return fail(c, SY2D_ERR_CUDA, "sy2d_create_slab: %s", nccl().why.c_str());
+  int rc = create_impl(out, device, nx_global, ny, 1, x_edges, y_edges, dt, rank, nranks);
+  if (rc) return rc;
+  c = *out;
+  ncclUniqueId id;
+  std::memcpy(&id, nccl_id, sizeof id);
+  ncclComm_t comm = nullptr;
+  ncclResult_t r = nccl().CommInitRank(&comm, nranks, id, rank);
+  if (r != ncclSuccess) {
+    g_create_error = std::string("ncclCommInitRank failed: ") + nccl().GetErrorString(r);
+    sy2d_destroy(c);
+    *out = nullptr;
+    return SY2D_ERR_CUDA;
+  }
+  c->comm = comm;
+  if (cudaMalloc(reinterpret_cast<void**>(&c->d_gather), (size_t)nranks * 5 * sizeof(double)) != cudaSuccess) {
+    g_create_error = "cudaMalloc failed";
+    sy2d_destroy(c);
+    *out = nullptr;
+    return SY2D_ERR_CUDA;
+  }
+  c->opt.use_graph = 0;
+  return SY2D_OK;
+}
+
+int sy2d_slab_rows(const sy2d_ctx* c, int* i_lo, int* i_hi) {
+  if (!c || !i_lo || !i_hi) return SY2D_ERR_INVALID;
+  *i_lo = c->slab ? c->i_lo : 0;
+  *i_hi = c->slab ? c->i_hi : c->nx;
   return SY2D_OK;
 }
 

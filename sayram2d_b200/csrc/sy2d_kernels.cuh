@@ -320,6 +320,7 @@ struct AssembleOut {
   double *diag, *oW, *oE, *oS, *oN, *R;
   // MODE 2 (dump vertex_f): [nbatch][nx+1][ny+1]
   double* vf;
+  int local_rows;  // rows of the (local) arrays: nx, or nx_loc + 2 for a slab with halo rows
 };
 
 // ---------------------------------------------------------------------------
@@ -406,15 +407,20 @@ constexpr int kTI = 8, kTJ = 32;
 __global__ void __launch_bounds__(kTI * kTJ) k_assemble_tiled(const double* __restrict__ f, const double* __restrict__ yprev,
                                                               const double* __restrict__ tx, const double* __restrict__ ty,
                                                               const double* __restrict__ cxy, const double* __restrict__ U,
-                                                              const double* __restrict__ Ud, Geometry g, AssembleOut o, int tiles_j) {
+                                                              const double* __restrict__ Ud, Geometry g, AssembleOut o, int tiles_j,
+                                                              int gi0, int li_begin, int li_end, int defer) {
   __shared__ double fs[kTI + 2][kTJ + 2], cs_[kTI + 2][kTJ + 2], vs[kTI + 1][kTJ + 1];
   __shared__ double WK[kTI + 1][kTJ], WL[kTI + 1][kTJ], SK[kTI][kTJ + 1], SL[kTI][kTJ + 1];
   __shared__ double red[3 * 32];
+  // Rows: memory is indexed with LOCAL rows li (the array may be a slab with halo rows), geometry
+  // and boundary logic with GLOBAL rows i = gi0 + li; the kernel assembles local rows [li_begin, li_end).
+  // Single-GPU: gi0 = 0, li_begin = 0, li_end = nx.
   const int nx = g.nx, ny = g.ny;
-  const size_t N = (size_t)nx * ny;
+  const int nrows_local = o.local_rows;
+  const size_t N = (size_t)nrows_local * ny;
   const size_t base = (size_t)blockIdx.y * N;
   const int tid = threadIdx.x;
-  const int ntiles = tiles_j * ((nx + kTI - 1) / kTI);
+  const int ntiles = tiles_j * ((li_end - li_begin + kTI - 1) / kTI);
   double rr = 0.0, rabs = 0.0;
   const double* fp = f + base;
   const double* yp = yprev + base;
@@ -423,16 +429,16 @@ __global__ void __launch_bounds__(kTI * kTJ) k_assemble_tiled(const double* __re
   const double* cp = cxy + base;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {  // a CTA walks over several tiles: few atomics per problem
   const int tile_i = tile / tiles_j, tile_j = tile - tile_i * tiles_j;
-  const int I0 = tile_i * kTI, J0 = tile_j * kTJ;
+  const int I0 = gi0 + li_begin + tile_i * kTI, J0 = tile_j * kTJ;   // global row of the tile origin
   // 1. f and c with halo (indices clamped at the domain boundary: clamped values only meet zero weights)
   for (int e = tid; e < (kTI + 2) * (kTJ + 2); e += kTI * kTJ) {
     const int a = e / (kTJ + 2), b = e - a * (kTJ + 2);
     int i = I0 + a - 1, j = J0 + b - 1;
     i = i < 0 ? 0 : (i > nx - 1 ? nx - 1 : i);
     j = j < 0 ? 0 : (j > ny - 1 ? ny - 1 : j);
-    const double fv = fp[(size_t)i * ny + j];
+    const double fv = fp[(size_t)(i - gi0) * ny + j];
     fs[a][b] = fv;
-    cs_[a][b] = fv * yp[(size_t)i * ny + j];
+    cs_[a][b] = fv * yp[(size_t)(i - gi0) * ny + j];
   }
   __syncthreads();
   // 2. vertices (I0 + a, J0 + b)
@@ -450,7 +456,7 @@ __global__ void __launch_bounds__(kTI * kTJ) k_assemble_tiled(const double* __re
     const int i = I0 + a, j = J0 + b;
     double AK = 0.0, AL = 0.0;
     if (i >= 1 && i <= nx - 1 && j < ny) {
-      const size_t ck = (size_t)i * ny + j, cl = ck - ny;
+      const size_t ck = (size_t)(i - gi0) * ny + j, cl = ck - ny;
       const double tK = txp[ck], cK = cp[ck], tL = txp[cl], cL = cp[cl];
       const double vSW = vs[a][b], vNW = vs[a][b + 1];
       const double kA = tK - cK, kB = tK + cK;   // W face of K: A = NW, B = SW
@@ -466,7 +472,7 @@ __global__ void __launch_bounds__(kTI * kTJ) k_assemble_tiled(const double* __re
     const int i = I0 + a, j = J0 + b;
     double AK = 0.0, AL = 0.0;
     if (j >= 1 && j <= ny - 1 && i < nx) {
-      const size_t ck = (size_t)i * ny + j, cl = ck - 1;
+      const size_t ck = (size_t)(i - gi0) * ny + j, cl = ck - 1;
       const double tK = typ[ck], cK = cp[ck], tL = typ[cl], cL = cp[cl];
       const double vSW = vs[a][b], vSE = vs[a + 1][b];
       const double kA = tK + cK, kB = tK - cK;   // S face of K: A = SW, B = SE
@@ -480,8 +486,8 @@ __global__ void __launch_bounds__(kTI * kTJ) k_assemble_tiled(const double* __re
   // 4. rows
   const int a = tid / kTJ, b = tid - a * kTJ;
   const int i = I0 + a, j = J0 + b;
-  if (i < nx && j < ny) {
-    const size_t n = (size_t)i * ny + j, c0 = base + n;
+  if (i < nx && i - gi0 < li_end && j < ny) {
+    const size_t n = (size_t)(i - gi0) * ny + j, c0 = base + n;
     const double f00 = fs[a + 1][b + 1];
     double diag = 0.0, R = 0.0, oW = 0.0, oE = 0.0, oS = 0.0, oN = 0.0;
     if (i > 0) { diag += WK[a][b]; oW = -WL[a][b]; }
@@ -518,7 +524,7 @@ __global__ void __launch_bounds__(kTI * kTJ) k_assemble_tiled(const double* __re
   if (threadIdx.x == 0) {
     atomicAdd(&sc->acc_rho, sums[0]);
     atomicMax(&sc->acc_rmax, (unsigned long long)__double_as_longlong(bmax));
-    if (last_block_done(sc, gridDim.x)) {
+    if (last_block_done(sc, gridDim.x) && !defer) {
       const double rmax = __longlong_as_double((long long)sc->acc_rmax);
       sc->rho = sc->acc_rho;
       sc->rmax = rmax;
@@ -552,6 +558,11 @@ struct KrylovVecs {
   double tol;
   int maxit;
   int freeze_state;  // sy2d_bench_kernel: keep every problem active whatever the residual does
+  // row-slab mode (one grid split over ranks): the kernels update cells [n_begin, n_end) of a local
+  // array that carries one halo row on each side, and leave the reduction accumulators untouched
+  // (defer = 1) - they are all-gathered over NCCL and turned into scalars by k_slab_scalars.
+  size_t n_begin, n_end;
+  int defer;
 };
 
 // End-of-iteration bookkeeping done by the last block of a problem: iteration count,
@@ -702,7 +713,7 @@ __global__ void __launch_bounds__(kBlock) k_p_update2(KrylovVecs k, size_t N) {
   const size_t stride = 2 * (size_t)gridDim.x * blockDim.x;
   const bool first = sc->first;
   const double beta = sc->beta, omega = sc->omega;
-  for (size_t n = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); n < N; n += stride) {
+  for (size_t n = k.n_begin + 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); n < k.n_end; n += stride) {
     const size_t g = (size_t)blockIdx.y * N + n;
     if (first) {
       const double2 r = ld2(k.rhs + g);
@@ -732,7 +743,7 @@ __global__ void __launch_bounds__(kBlock) k_spmv_v2(KrylovVecs k, size_t N, int 
   const size_t stride = 2 * (size_t)gridDim.x * blockDim.x;
   const size_t base = (size_t)blockIdx.y * N;
   double dot = 0.0;
-  for (size_t n = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); n < N; n += stride) {
+  for (size_t n = k.n_begin + 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); n < k.n_end; n += stride) {
     const size_t g = base + n;
     const double* p = k.p + base;
     double v0, v1;
@@ -745,7 +756,7 @@ __global__ void __launch_bounds__(kBlock) k_spmv_v2(KrylovVecs k, size_t N, int 
   block_sums<1>(sums, red);
   if (threadIdx.x == 0) {
     atomicAdd(&sc->acc_rv, sums[0]);
-    if (last_block_done(sc, gridDim.x)) {
+    if (last_block_done(sc, gridDim.x) && !k.defer) {
       const double rv = sc->acc_rv;
       sc->acc_rv = 0.0;
       sc->alpha = rv != 0.0 ? sc->rho / rv : 0.0;
@@ -759,7 +770,7 @@ __global__ void __launch_bounds__(kBlock) k_s_update2(KrylovVecs k, size_t N) {
   const size_t stride = 2 * (size_t)gridDim.x * blockDim.x;
   const double alpha = sc->alpha;
   const double* rsrc = sc->first ? k.rhs : k.r;
-  for (size_t n = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); n < N; n += stride) {
+  for (size_t n = k.n_begin + 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); n < k.n_end; n += stride) {
     const size_t g = (size_t)blockIdx.y * N + n;
     const double2 r = ld2(rsrc + g), v = ld2(k.v + g);
     st2(k.s + g, r.x - alpha * v.x, r.y - alpha * v.y);
@@ -773,7 +784,7 @@ __global__ void __launch_bounds__(kBlock) k_spmv_t2(KrylovVecs k, size_t N, int 
   const size_t stride = 2 * (size_t)gridDim.x * blockDim.x;
   const size_t base = (size_t)blockIdx.y * N;
   double ts = 0.0, tt = 0.0;
-  for (size_t n = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); n < N; n += stride) {
+  for (size_t n = k.n_begin + 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); n < k.n_end; n += stride) {
     const size_t g = base + n;
     const double* s = k.s + base;
     const double2 sc0 = ld2(s + n);
@@ -788,7 +799,7 @@ __global__ void __launch_bounds__(kBlock) k_spmv_t2(KrylovVecs k, size_t N, int 
   if (threadIdx.x == 0) {
     atomicAdd(&sc->acc_ts, sums[0]);
     atomicAdd(&sc->acc_tt, sums[1]);
-    if (last_block_done(sc, gridDim.x)) {
+    if (last_block_done(sc, gridDim.x) && !k.defer) {
       const double a = sc->acc_ts, b = sc->acc_tt;
       sc->acc_ts = 0.0;
       sc->acc_tt = 0.0;
@@ -805,7 +816,7 @@ __global__ void __launch_bounds__(kBlock) k_xr_update2(KrylovVecs k, size_t N) {
   double dot = 0.0, rabs = 0.0;
   const double alpha = sc->alpha, omega = sc->omega;
   const bool first = sc->first;
-  for (size_t n = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); n < N; n += stride) {
+  for (size_t n = k.n_begin + 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); n < k.n_end; n += stride) {
     const size_t g = (size_t)blockIdx.y * N + n;
     const double2 s = ld2(k.s + g), p = ld2(k.p + g), t = ld2(k.t + g), rh = ld2(k.rhs + g);
     double2 x = make_double2(0.0, 0.0);
@@ -822,7 +833,40 @@ __global__ void __launch_bounds__(kBlock) k_xr_update2(KrylovVecs k, size_t N) {
   if (threadIdx.x == 0) {
     atomicAdd(&sc->acc_rho, sums[0]);
     atomicMax(&sc->acc_rmax, (unsigned long long)__double_as_longlong(bmax));
-    if (last_block_done(sc, gridDim.x)) xr_finish_iteration(sc, k);
+    if (last_block_done(sc, gridDim.x) && !k.defer) xr_finish_iteration(sc, k);
+  }
+}
+
+// Row-slab mode: every rank contributed its five accumulators {acc_rv, acc_ts, acc_tt, acc_rho,
+// acc_rmax} through ncclAllGather into gathered[nranks][5]; one thread reduces them in rank order
+// (identical on every rank, so all ranks take the same decisions) and does what the last block of
+// the single-GPU kernels does.  phase: 0 after the assembly, 1 after v = A p, 2 after t = A s,
+// 3 after the x, r update.
+__global__ void k_slab_scalars(int phase, Scal* sc, const double* __restrict__ gathered, int nranks, KrylovVecs k) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double rv = 0.0, ts = 0.0, tt = 0.0, rho = 0.0, rmax = 0.0;
+  for (int r = 0; r < nranks; ++r) {
+    const double* q = gathered + 5 * r;
+    rv += q[0]; ts += q[1]; tt += q[2]; rho += q[3];
+    rmax = fmax(rmax, __longlong_as_double(__double_as_longlong(q[4])));  // raw bits of a non-negative double
+  }
+  sc->acc_rv = 0.0; sc->acc_ts = 0.0; sc->acc_tt = 0.0;
+  if (phase == 0) {
+    sc->rho = rho; sc->rmax = rmax;
+    sc->alpha = 1.0; sc->omega = 1.0; sc->beta = 0.0;
+    sc->acc_rho = 0.0; sc->acc_rmax = 0ull;
+    sc->it = 0; sc->first = 1;
+    const int active_now = !(rmax <= k.tol);
+    sc->state = active_now ? 0 : 1;
+    if (active_now) atomicAdd(k.n_active, 1);
+  } else if (phase == 1) {
+    sc->alpha = rv != 0.0 ? sc->rho / rv : 0.0;
+  } else if (phase == 2) {
+    sc->omega = tt > 0.0 ? ts / tt : 0.0;
+  } else {
+    sc->acc_rho = rho;
+    sc->acc_rmax = (unsigned long long)__double_as_longlong(rmax);
+    xr_finish_iteration(sc, k);
   }
 }
 

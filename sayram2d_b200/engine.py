@@ -75,6 +75,9 @@ def load_library():
         "sy2d_dump_vertex_f": (C.c_int, [vp, dp]),
         "sy2d_set_profiling": (C.c_int, [vp, C.c_int]),
         "sy2d_get_profile": (C.c_int, [vp, C.POINTER(Profile)]),
+        "sy2d_nccl_unique_id": (C.c_int, [C.c_char_p]),
+        "sy2d_create_slab": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, dp, dp, C.c_double]),
+        "sy2d_slab_rows": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "sy2d_bench_kernel": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_double)]),
         "sy2d_build_info": (C.c_char_p, []),
         "sy2d_device_count": (C.c_int, []),
@@ -84,6 +87,16 @@ def load_library():
         fn.restype, fn.argtypes = res, args
     _LIB = lib
     return lib
+
+
+def nccl_unique_id():
+    """128-byte NCCL id created by this process (rank 0); distribute it to the other ranks."""
+    lib = load_library()
+    buf = C.create_string_buffer(128)
+    rc = lib.sy2d_nccl_unique_id(buf)
+    if rc != 0:
+        raise Sy2dError(rc, lib.sy2d_last_error(None).decode())
+    return buf.raw
 
 
 def _dp(a):
@@ -106,18 +119,30 @@ class Engine:
     """Device-resident time stepper: Solver::update() of the reference (Solver.cc:270-290)
     for nbatch independent problems sharing one mesh and one set of BCs."""
 
-    def __init__(self, x_edges, y_edges, dt, nbatch=1, device=0):
+    def __init__(self, x_edges, y_edges, dt, nbatch=1, device=0, slab=None):
+        """slab = (rank, nranks, nccl_id_bytes): this engine holds one row slab of the grid
+        (sy2d_create_slab); field arguments are then the owned rows [i_lo:i_hi]."""
         self.lib = load_library()
         xe = _f64(x_edges)
         ye = _f64(y_edges)
         self.nx, self.ny, self.nbatch, self.dt = xe.size - 1, ye.size - 1, int(nbatch), float(dt)
-        self.shape = (self.nbatch, self.nx, self.ny)
         self._ctx = C.c_void_p()
-        rc = self.lib.sy2d_create(C.byref(self._ctx), int(device), self.nx, self.ny, self.nbatch, _dp(xe), _dp(ye), self.dt)
+        if slab is None:
+            rc = self.lib.sy2d_create(C.byref(self._ctx), int(device), self.nx, self.ny, self.nbatch, _dp(xe), _dp(ye), self.dt)
+        else:
+            rank, nranks, nccl_id = slab
+            rc = self.lib.sy2d_create_slab(C.byref(self._ctx), int(device), self.nx, self.ny, int(rank), int(nranks),
+                                           bytes(nccl_id), _dp(xe), _dp(ye), self.dt)
         if rc != 0:
             msg = self.lib.sy2d_last_error(None).decode()
             self._ctx = None
             raise Sy2dError(rc, msg)
+        self.i_lo, self.i_hi = 0, self.nx
+        if slab is not None:
+            lo, hi = C.c_int(), C.c_int()
+            self.lib.sy2d_slab_rows(self._ctx, C.byref(lo), C.byref(hi))
+            self.i_lo, self.i_hi = lo.value, hi.value
+        self.shape = (self.nbatch, self.i_hi - self.i_lo, self.ny)
 
     def _check(self, rc):
         if rc != 0:

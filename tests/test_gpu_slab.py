@@ -1,0 +1,76 @@
+"""Row-slab decomposition (BASELINE config 5) on 2 GPUs: one grid split along i over two ranks
+with NCCL halo exchange and all-gathered dot products must reproduce the single-GPU result."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, idfile, outdir):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.cuda.set_device(rank)
+    torch.zeros(1, device=f"cuda:{rank}")  # make sure torch's CUDA context (and its NCCL copy) comes first
+    sys.path.insert(0, ROOT)
+    import sayram2d_b200 as sy
+    from sayram2d_b200 import fields
+    ids = [sy.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    nx, ny = 256, 64
+    xe, ye = fields.uniform_edges(nx, ny)
+    Dxx, Dxy, Dyy, inv_tau = fields.synthetic_tensor(xe, ye)
+    G = fields.ay_G(xe, ye)
+    f0, bct, lines = fields.ay_init_and_bc(xe, ye)
+    eng = sy.Engine(xe, ye, 0.002, device=rank, slab=(rank, world, ids[0]))
+    lo, hi = eng.i_lo, eng.i_hi
+    eng.set_coeffs(G[lo:hi], Dxx[lo:hi], Dxy[lo:hi], Dyy[lo:hi], inv_tau[lo:hi])
+    eng.set_bc(bct, *lines)
+    eng.set_f(f0[lo:hi])
+    st = eng.step(3)
+    np.save(os.path.join(outdir, f"f_{rank}.npy"), eng.get_f()[0])
+    np.save(os.path.join(outdir, f"meta_{rank}.npy"), np.array([lo, hi, st["iters_total"], st["negatives"], st["resid_last"]]))
+    eng.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_slab_matches_single_gpu(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    import sayram2d_b200 as sy
+    from sayram2d_b200 import fields
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mp.spawn(_worker, args=(2, port, None, str(tmp_path)), nprocs=2, join=True)
+    nx, ny = 256, 64
+    xe, ye = fields.uniform_edges(nx, ny)
+    Dxx, Dxy, Dyy, inv_tau = fields.synthetic_tensor(xe, ye)
+    f0, bct, lines = fields.ay_init_and_bc(xe, ye)
+    ref = sy.Engine(xe, ye, 0.002)
+    ref.set_options(engine=1)
+    ref.set_coeffs(fields.ay_G(xe, ye), Dxx, Dxy, Dyy, inv_tau)
+    ref.set_bc(bct, *lines)
+    ref.set_f(f0)
+    st = ref.step(3)
+    fref = ref.get_f()[0]
+    ref.close()
+    rows = 0
+    for r in range(2):
+        lo, hi, its, neg, res = np.load(tmp_path / f"meta_{r}.npy")
+        f = np.load(tmp_path / f"f_{r}.npy")
+        lo, hi = int(lo), int(hi)
+        assert f.shape == (hi - lo, ny)
+        assert np.max(np.abs(f - fref[lo:hi]) / np.abs(fref[lo:hi])) < 1e-10
+        assert neg == 0 and res < 1e-13 and abs(its - st["iters_total"]) <= 0.2 * st["iters_total"]
+        rows += hi - lo
+    assert rows == nx
