@@ -373,6 +373,9 @@ def ours(args):
             line["grid1024"] = grid_object(1024, local_rank, args, torch)
             line["grid4096"] = big_grid_object(4096, local_rank)
         line["cpu_baseline"] = cpu_baseline_ensemble() if not args.no_cpu else None
+    if world > 1 and args.slab_n > 0:
+        slab = slab_object(args.slab_n, args.slab_iters, rank, world, local_rank, dist, torch)
+        line["slab"] = slab
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -429,6 +432,50 @@ def big_grid_object(n, device):
     return out
 
 
+def slab_object(n, iters, rank, world, local_rank, dist, torch):
+    """BASELINE config 5: one n x n grid (config-3 fields) split into row slabs over the ranks, NCCL
+    one-line halo exchange + all-gathered dots.  A direct solve is infeasible at this size and the
+    Jacobi-BiCGSTAB needs O(1e4) iterations per step, so the run uses a FIXED ITERATION BUDGET:
+    the first `iters` BiCGSTAB iterations of one time step (216 B/cell algorithmic traffic each)."""
+    import sayram2d_b200 as sy
+    from sayram2d_b200 import fields
+    from sayram2d_b200.shard import slab_range
+    ids = [sy.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    xe, ye = fields.uniform_edges(n, n)
+    lo, hi = slab_range(n, rank, world)
+    eng = sy.Engine(xe, ye, DT, device=local_rank, slab=(rank, world, ids[0]))
+    assert (eng.i_lo, eng.i_hi) == (lo, hi)
+    Dxx, Dxy, Dyy, inv_tau = fields.synthetic_tensor(xe, ye, rows=(lo, hi))
+    eng.set_coeffs(fields.ay_G(xe, ye, rows=(lo, hi)), Dxx, Dxy, Dyy, inv_tau)
+    del Dxx, Dxy, Dyy, inv_tau
+    f0, bct, lines = fields.ay_init_and_bc(xe, ye, rows=(lo, hi))
+    eng.set_bc(bct, *lines)
+    eng.set_f(f0)
+    del f0
+    o = eng.options(); o.maxit = 16; o.check_every = 16; o.reserved[1] = 1
+    eng._check(eng.lib.sy2d_set_options(eng._ctx, o))
+    eng.step(1)                                   # warm-up: 16 iterations
+    eng.set_f(fields.ay_init_and_bc(xe, ye, rows=(lo, hi))[0])
+    o.maxit = iters
+    eng._check(eng.lib.sy2d_set_options(eng._ctx, o))
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    st = eng.step(1)
+    t = torch.tensor([st["seconds_device"]], dtype=torch.float64, device=f"cuda:{local_rank}")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sec = float(t.item())
+    its = st["iters_total"]
+    peak, _ = measured_peak()
+    gbs = n * n * (104 + 216.0 * its) / sec / 1e9
+    out = {"workload": f"slab{n}", "n_gpus": world, "rows_per_gpu": hi - lo, "iterations": its, "seconds": sec,
+           "ms_per_iteration": 1e3 * sec / max(its, 1), "cell_iterations_per_sec": n * n * its / sec,
+           "algorithmic_GBps_aggregate": gbs, "frac_of_aggregate_hbm_peak": gbs / (peak * world),
+           "budget": f"fixed iteration budget: assembly + first {its} BiCGSTAB iterations of one time step (not converged by design)",
+           "exchange": "per iteration: 2 one-line halo ncclSend/Recv pairs (128 KB lines at 16384) + 3 all-gathers of 5 doubles"}
+    eng.close()
+    return out
+
+
 def main():
     global NB_TOTAL
     ap = argparse.ArgumentParser()
@@ -438,6 +485,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-grid1024", action="store_true")
     ap.add_argument("--members", type=int, default=NB_TOTAL, help="ensemble size (profiling runs use a smaller one)")
+    ap.add_argument("--slab-n", type=int, default=16384, help="N>1 only: side of the single grid split into row slabs (0 = skip)")
+    ap.add_argument("--slab-iters", type=int, default=48, help="iteration budget of the slab run")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs")
     ap.add_argument("--no-grid-cpu", action="store_true", help="skip the ~40 s CPU baseline of the 1024^2 grid")
     args = ap.parse_args()

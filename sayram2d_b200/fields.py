@@ -38,9 +38,10 @@ def _dlogE_dp(logE):  # utils.h:17-20
     return _e2p(E) / (E * (E + gE0))
 
 
-def ay_G(xe, ye):
-    """Albert_Young.h:42-45 on cell centres -> (nx, ny)."""
-    A, L = np.meshgrid(centres(xe), centres(ye), indexing="ij")
+def ay_G(xe, ye, rows=None):
+    """Albert_Young.h:42-45 on cell centres -> (nx, ny); rows=(lo, hi) restricts to a row slab."""
+    xc = centres(xe) if rows is None else centres(xe)[rows[0]:rows[1]]
+    A, L = np.meshgrid(xc, centres(ye), indexing="ij")
     t = 1.30 - 0.56 * np.sin(A)
     return _e2p(np.exp(L)) ** 2 * t * np.sin(A) * np.cos(A) / _dlogE_dp(L)
 
@@ -52,10 +53,12 @@ def ay_f0(a, logE, loss_cone_deg=5.0):
     return np.exp(-(np.exp(logE) - 0.2) / 0.1) * (np.sin(a) - s0) / (p * p) + gEPS
 
 
-def ay_init_and_bc(xe, ye, lc=False):
+def ay_init_and_bc(xe, ye, lc=False, rows=None):
     """Initial f on cell centres and the boundary description of the AY / LC cases
-    (Albert_Young.cc:42-92, Albert_Young_LC.cc:56-106): returns f0, bc_type[4], lines[4]."""
-    A, L = np.meshgrid(centres(xe), centres(ye), indexing="ij")
+    (Albert_Young.cc:42-92, Albert_Young_LC.cc:56-106): returns f0, bc_type[4], lines[4].
+    rows=(lo, hi) restricts f0 to a row slab (the boundary lines stay global)."""
+    xc = centres(xe) if rows is None else centres(xe)[rows[0]:rows[1]]
+    A, L = np.meshgrid(xc, centres(ye), indexing="ij")
     cone = None if lc else 5.0
     f0 = ay_f0(A, L, cone)
     ymin = ay_f0(xe, ye[0], cone)
@@ -65,10 +68,12 @@ def ay_init_and_bc(xe, ye, lc=False):
     return f0, [DIRICHLET, ZEROFLUX, DIRICHLET, DIRICHLET], [np.zeros(ye.size), None, ymin, ymax]
 
 
-def synthetic_tensor(xe, ye):
+def synthetic_tensor(xe, ye, rows=None):
     """BASELINE config 3 / 5: deterministic analytic full tensor with a sign-changing
-    cross term and an f/tau loss strip.  Returns Dxx, Dxy, Dyy, inv_tau."""
-    A, L = np.meshgrid(centres(xe), centres(ye), indexing="ij")
+    cross term and an f/tau loss strip (SURVEY.md section 8d).  Returns Dxx, Dxy, Dyy, inv_tau;
+    rows=(lo, hi) restricts to a row slab (normalised coordinates stay global)."""
+    xc = centres(xe) if rows is None else centres(xe)[rows[0]:rows[1]]
+    A, L = np.meshgrid(xc, centres(ye), indexing="ij")
     xi = (A - xe[0]) / (xe[-1] - xe[0])
     eta = (L - ye[0]) / (ye[-1] - ye[0])
     Dxx = 10.0 * np.exp(-3.0 * eta) * (0.05 + np.sin(gPI * xi) ** 2)
