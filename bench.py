@@ -370,8 +370,19 @@ def ours(args):
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
     if dom:
         r = rows[dom]
+        traffic, traffic_src = None, None
+        try:  # DRAM bytes per launch from the committed ncu --set full capture, scaled to this launch's cell-steps
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            if dom == "problem_steps" and pst.get("precond", 0) == 1:
+                traffic = tj["k_problem_xline"]["dram_bytes_per_cell_step"] * prof[dom]["cells"]
+                traffic_src = tj["k_problem_xline"]["source"]
+        except Exception:
+            pass
         line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": r["achieved"], "peak": peak, "unit": "GB/s",
-                            "frac": r["frac"], "traffic": None, "peak_source": peak_src, "kernels": rows}
+                            "frac": r["frac"], "traffic": traffic, "traffic_source": traffic_src,
+                            "note": "engine-2 kernel: achieved = streaming-equivalent bytes / time; the state is on-chip, so "
+                                    "DRAM traffic is far below it and frac > 1 measures the residency, not HBM speed",
+                            "peak_source": peak_src, "kernels": rows}
     eng.close()
 
     if rank == 0 and world == 1:
