@@ -135,6 +135,11 @@ int sy2d_get_f_dev(sy2d_ctx* ctx, double* f_out_dev);
 
 /* Solver::update() x nsteps (Solver.cc:270-290) without leaving the device; stats may be NULL. */
 int sy2d_step(sy2d_ctx* ctx, int nsteps, sy2d_stats* stats);
+/* Solver::update() x nsteps with f resident on the HOST, as in the reference (f_ is a host array there):
+ * f_in (may be NULL = keep the device state) is uploaded, nsteps are taken, the result is written to
+ * f_out (may be NULL).  For batches the copies and the kernels of contiguous sub-batches are pipelined
+ * over several streams; pass pinned memory to get the overlap.  Does not reset the step counter. */
+int sy2d_step_host(sy2d_ctx* ctx, const double* f_in, double* f_out, int nsteps, sy2d_stats* stats);
 /* Solver::t() (Solver.h:23). */
 double sy2d_time(const sy2d_ctx* ctx);
 long long sy2d_step_count(const sy2d_ctx* ctx);

@@ -66,6 +66,9 @@ struct sy2d_ctx {
   int* d_cost = nullptr;
   std::vector<int> h_cost, h_order;
   bool have_order = false;
+  std::vector<cudaStream_t> pipe_streams;   // sy2d_step_host: one stream per sub-batch
+  std::vector<cudaEvent_t> pipe_events;
+  cudaEvent_t pipe_start = nullptr;
   double* xl_scratch = nullptr;
   int xl_R = 0, xl_NT = 0, xl_S = 0;
   size_t xl_smem = 0;
@@ -386,6 +389,9 @@ int step_slab(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
 }
 }  // namespace
 
+static int step_per_problem(sy2d_ctx* c, int nsteps, sy2d_stats* stats, const double* h_in, double* h_out);
+static int engine_of(const sy2d_ctx* c);
+
 extern "C" {
 
 const char* sy2d_build_info(void) {
@@ -505,6 +511,9 @@ void sy2d_destroy(sy2d_ctx* c) {
                     c->x, c->r, c->p, c->v, c->s, c->t, c->stage, c->xl_scratch};
   for (double* b : bufs) if (b) cudaFree(b);
   if (c->scal) cudaFree(c->scal);
+  for (cudaStream_t sk : c->pipe_streams) if (sk) { cudaStreamSynchronize(sk); cudaStreamDestroy(sk); }
+  for (cudaEvent_t ek : c->pipe_events) if (ek) cudaEventDestroy(ek);
+  if (c->pipe_start) cudaEventDestroy(c->pipe_start);
   if (c->d_order) cudaFree(c->d_order);
   if (c->d_cost) cudaFree(c->d_cost);
   if (c->d_gather) cudaFree(c->d_gather);
@@ -693,11 +702,21 @@ static cudaError_t dispatch_xline(const XlineArgs& xa, int R, int nbatch, size_t
 }
 
 // Engine 2: the whole call (nsteps time steps of every problem) is ONE kernel launch.
-static int step_per_problem(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
+// Number of sub-batches a host-buffer call is pipelined over (and within which problems are sorted
+// by cost): at least two waves of CTAs per sub-batch, at most 8.
+static int pipe_chunks(const sy2d_ctx* c) { return std::max(1, std::min(8, c->nbatch / (2 * c->sm_count))); }
+
+// Engine 2: nsteps time steps of every problem in ONE kernel launch per sub-batch.  With host
+// buffers (h_in / h_out non-NULL) the batch is cut into pipe_chunks() contiguous sub-batches on
+// separate streams, so that the H2D copy of sub-batch k+1, the kernel of sub-batch k and the D2H
+// copy of sub-batch k-1 overlap (and the tail wave of one kernel is filled by the next one).
+static int step_per_problem(sy2d_ctx* c, int nsteps, sy2d_stats* stats, const double* h_in, double* h_out) {
   sy2d_stats st;
   std::memset(&st, 0, sizeof st);
   st.engine = 2;
   if (nsteps == 0) { if (stats) *stats = st; return SY2D_OK; }
+  const bool piped = (h_in || h_out) && !c->profiling;
+  const int C = pipe_chunks(c);
   StepStats init;
   std::memset(&init, 0, sizeof init);
   init.fmin = 1.0e300;
@@ -716,8 +735,9 @@ static int step_per_problem(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
     CU(cudaMalloc(reinterpret_cast<void**>(&c->d_cost), c->nbatch * sizeof(int)));
     c->h_cost.assign(c->nbatch, 0);
     c->h_order.resize(c->nbatch);
+    for (int b = 0; b < c->nbatch; ++b) c->h_order[b] = b;
+    CU(cudaMemcpyAsync(c->d_order, c->h_order.data(), c->nbatch * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   }
-  a.order = c->have_order ? c->d_order : nullptr;
   a.cost = c->d_cost;
   c->cur_cells = (double)c->total * nsteps;
   int R = 0, NT = 0, S = 0, HS = 0;
@@ -726,20 +746,54 @@ static int step_per_problem(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
   if (c->opt.precond == SY2D_PRECOND_XLINE && !xline)
     return fail(c, SY2D_ERR_INVALID, "sy2d_step: the x-line preconditioner needs nx <= 80, ny <= 128 and engine 2");
   st.precond = xline ? SY2D_PRECOND_XLINE : SY2D_PRECOND_JACOBI;
-  if (xline) {
-    if (!c->xl_scratch || c->xl_S != S) {
-      if (c->xl_scratch) cudaFree(c->xl_scratch);
-      c->xl_scratch = nullptr;
-      CU(cudaMalloc(reinterpret_cast<void**>(&c->xl_scratch), (size_t)c->nbatch * 5 * S * sizeof(double)));
-      c->xl_S = S;
+  if (xline && (!c->xl_scratch || c->xl_S != S)) {
+    if (c->xl_scratch) cudaFree(c->xl_scratch);
+    c->xl_scratch = nullptr;
+    CU(cudaMalloc(reinterpret_cast<void**>(&c->xl_scratch), (size_t)c->nbatch * 5 * S * sizeof(double)));
+    c->xl_S = S;
+  }
+  auto launch = [&](int b0, int b1, cudaStream_t stream) -> cudaError_t {
+    ProblemArgs aa = a;
+    aa.order = c->d_order + b0;   // CTA b of this launch works on problem order[b0 + b]
+    if (xline) {
+      XlineArgs xa;
+      xa.a = aa; xa.scratch = c->xl_scratch; xa.NT = NT; xa.S = S; xa.hs = HS;
+      return dispatch_xline(xa, R, b1 - b0, smem, stream);
     }
-    XlineArgs xa;
-    xa.a = a; xa.scratch = c->xl_scratch; xa.NT = NT; xa.S = S; xa.hs = HS;
-    Prof p(c, SY2D_K_PROBLEM_STEPS);
-    CU(dispatch_xline(xa, R, c->nbatch, smem, c->stream));
+    k_problem_steps<<<b1 - b0, kProblemThreads, 0, stream>>>(aa);
+    return cudaGetLastError();
+  };
+  if (!piped) {
+    if (h_in) CU(cudaMemcpyAsync(c->f, h_in, c->total * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    {
+      Prof p(c, SY2D_K_PROBLEM_STEPS);
+      CU(launch(0, c->nbatch, c->stream));
+    }
+    if (h_out) CU(cudaMemcpyAsync(h_out, c->f, c->total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    st.kernel_launches = 1;
   } else {
-    Prof p(c, SY2D_K_PROBLEM_STEPS);
-    k_problem_steps<<<c->nbatch, kProblemThreads, 0, c->stream>>>(a);
+    if (c->pipe_streams.empty()) {
+      c->pipe_streams.resize(C);
+      c->pipe_events.resize(C);
+      for (int k = 0; k < C; ++k) {
+        CU(cudaStreamCreateWithFlags(&c->pipe_streams[k], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&c->pipe_events[k], cudaEventDisableTiming));
+      }
+      CU(cudaEventCreateWithFlags(&c->pipe_start, cudaEventDisableTiming));
+    }
+    CU(cudaEventRecord(c->pipe_start, c->stream));  // stats initialised, order uploaded
+    for (int k = 0; k < C; ++k) {
+      const int b0 = (int)((long long)c->nbatch * k / C), b1 = (int)((long long)c->nbatch * (k + 1) / C);
+      const size_t off = (size_t)b0 * c->N, bytes = (size_t)(b1 - b0) * c->N * sizeof(double);
+      cudaStream_t sk = c->pipe_streams[k];
+      CU(cudaStreamWaitEvent(sk, c->pipe_start, 0));
+      if (h_in) CU(cudaMemcpyAsync(c->f + off, h_in + off, bytes, cudaMemcpyHostToDevice, sk));
+      CU(launch(b0, b1, sk));
+      if (h_out) CU(cudaMemcpyAsync(h_out + off, c->f + off, bytes, cudaMemcpyDeviceToHost, sk));
+      CU(cudaEventRecord(c->pipe_events[k], sk));
+    }
+    for (int k = 0; k < C; ++k) CU(cudaStreamWaitEvent(c->stream, c->pipe_events[k], 0));
+    st.kernel_launches = C;
   }
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(StepStats), cudaMemcpyDeviceToHost, c->stream));
@@ -748,11 +802,13 @@ static int step_per_problem(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
   CU(cudaStreamSynchronize(c->stream));
   float ms = 0.f;
   CU(cudaEventElapsedTime(&ms, c->ev_call0, c->ev_call1));
-  if (c->nbatch > 1) {  // order for the next call: most expensive problems first
+  if (c->nbatch > 1) {  // issue order for the next call: inside every sub-batch, most expensive problems first
     for (int b = 0; b < c->nbatch; ++b) c->h_order[b] = b;
-    std::stable_sort(c->h_order.begin(), c->h_order.end(), [&](int x, int y) { return c->h_cost[x] > c->h_cost[y]; });
+    for (int k = 0; k < C; ++k) {
+      const int b0 = (int)((long long)c->nbatch * k / C), b1 = (int)((long long)c->nbatch * (k + 1) / C);
+      std::stable_sort(c->h_order.begin() + b0, c->h_order.begin() + b1, [&](int x, int y) { return c->h_cost[x] > c->h_cost[y]; });
+    }
     CU(cudaMemcpyAsync(c->d_order, c->h_order.data(), c->nbatch * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    c->have_order = true;
   }
   int rc = collect_profile(c);
   if (rc) return rc;
@@ -766,7 +822,6 @@ static int step_per_problem(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
   st.fmin = h.fmin;
   st.negatives = (long long)h.negatives;
   st.seconds_device = ms * 1e-3;
-  st.kernel_launches = 1;
   if (stats) *stats = st;
   if (h.n_bad > 0)
     return fail(c, SY2D_ERR_NOT_CONVERGED, "sy2d_step: BiCGSTAB did not converge (%d problems, up to %d iterations in a step)",
@@ -782,7 +837,7 @@ int sy2d_step(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
   if (rc) return rc;
   CU(cudaSetDevice(c->device));
   if (c->slab) return step_slab(c, nsteps, stats);
-  if (engine_of(c) == 2) return step_per_problem(c, nsteps, stats);
+  if (engine_of(c) == 2) return step_per_problem(c, nsteps, stats, nullptr, nullptr);
   const dim3 g = grid_of(c);
   const Geometry geo = geometry(c);
   const bool graph = c->opt.use_graph && !c->profiling;
@@ -873,6 +928,19 @@ int sy2d_step(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
   rc = collect_profile(c);
   if (stats) *stats = st;
   return rc;
+}
+
+int sy2d_step_host(sy2d_ctx* c, const double* f_in, double* f_out, int nsteps, sy2d_stats* stats) {
+  if (!c || nsteps < 0) return SY2D_ERR_INVALID;
+  if (f_in && !c->have_f) { int rc0 = sy2d_set_f(c, f_in); if (rc0) return rc0; }
+  int rc = ready(c, "sy2d_step_host");
+  if (rc) return rc;
+  CU(cudaSetDevice(c->device));
+  if (!c->slab && engine_of(c) == 2) return step_per_problem(c, nsteps, stats, f_in, f_out);
+  if (f_in) { rc = sy2d_put_f(c, f_in); if (rc) return rc; }
+  rc = sy2d_step(c, nsteps, stats);
+  if (rc) return rc;
+  return f_out ? sy2d_get_f(c, f_out) : SY2D_OK;
 }
 
 int sy2d_dump_operator(sy2d_ctx* c, double* diags, double* rhs) {

@@ -69,6 +69,7 @@ def load_library():
         "sy2d_get_f": (C.c_int, [vp, dp]),
         "sy2d_get_f_dev": (C.c_int, [vp, vp]),
         "sy2d_step": (C.c_int, [vp, C.c_int, C.POINTER(Stats)]),
+        "sy2d_step_host": (C.c_int, [vp, dp, dp, C.c_int, C.POINTER(Stats)]),
         "sy2d_time": (C.c_double, [vp]),
         "sy2d_step_count": (C.c_longlong, [vp]),
         "sy2d_dump_operator": (C.c_int, [vp, dp, dp]),
@@ -201,6 +202,18 @@ class Engine:
     def step(self, nsteps=1):
         st = Stats()
         rc = self.lib.sy2d_step(self._ctx, int(nsteps), C.byref(st))
+        self.last_stats = st.as_dict()
+        self._check(rc)
+        return self.last_stats
+
+    def step_host(self, f_in, f_out, nsteps=1):
+        """Host-resident f: upload f_in, take nsteps, download into f_out (pipelined over
+        sub-batches when the arrays are pinned).  Arrays must be C-contiguous float64 of self.shape."""
+        st = Stats()
+        for a in (f_in, f_out):
+            if a is not None and (a.dtype != np.float64 or not a.flags["C_CONTIGUOUS"] or a.size != int(np.prod(self.shape))):
+                raise ValueError("step_host: arrays must be C-contiguous float64 of the engine's shape")
+        rc = self.lib.sy2d_step_host(self._ctx, _dp(f_in), _dp(f_out), int(nsteps), C.byref(st))
         self.last_stats = st.as_dict()
         self._check(rc)
         return self.last_stats

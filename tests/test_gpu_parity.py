@@ -334,3 +334,30 @@ def test_tiled_assembly_equals_per_cell_assembly(tag):
     a.step(6); b.step(6)
     assert max_rel(a.get_f(), b.get_f()) < 1e-12
     a.close(); b.close()
+
+
+def test_step_host_pipelined_matches_resident_stepping():
+    """sy2d_step_host (host-resident f, sub-batches pipelined over streams) == set_f + step + get_f."""
+    lc = load_golden("lc80")
+    nb = 1200   # > 2 * 148 * 4: several pipelined sub-batches
+    a, b = fields.ensemble_scales(np.arange(nb) * 3)
+    sc = lambda arr, s: np.ascontiguousarray(arr[None] * s[:, None, None])
+    one = np.ones(nb)
+    bct, lines = bc_for("LC", lc["x_edges"], lc["y_edges"])
+    engs = []
+    for _ in range(2):
+        e = sy.Engine(lc["x_edges"], lc["y_edges"], lc["meta"]["dt"], nbatch=nb)
+        e.set_coeffs(sc(lc["G"], one), sc(lc["Dxx"], a), sc(lc["Dxy"], a), sc(lc["Dyy"], a), sc(lc["inv_tau"], b))
+        e.set_bc(bct, *lines)
+        e.set_f(sc(lc["f_0"], one))
+        engs.append(e)
+    ref, piped = engs
+    ref.step(3)
+    f_ref = ref.get_f()
+    h_in, h_out = sc(lc["f_0"], one), np.empty((nb, 80, 80))
+    for _ in range(3):
+        st = piped.step_host(h_in, h_out, 1)
+        h_in, h_out = h_out, h_in
+    assert st["kernel_launches"] >= 2 and piped.step_count() == 3
+    assert max_rel(h_in, f_ref) < 1e-11 and max_rel(piped.get_f(), f_ref) < 1e-11
+    ref.close(); piped.close()
