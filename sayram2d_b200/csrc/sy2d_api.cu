@@ -682,16 +682,18 @@ static bool xline_shape(const sy2d_ctx* c, int* R, int* NT, int* S, int* HS, siz
   return true;
 }
 
-template <int R, int MAXT, int NTC>
+template <int R, int MAXT, int NTC, int HSC = 0>
 static cudaError_t launch_xline(const XlineArgs& xa, int nbatch, size_t smem, cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(k_problem_xline<R, MAXT, NTC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(k_problem_xline<R, MAXT, NTC, HSC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_problem_xline<R, MAXT, NTC><<<nbatch, xa.NT, smem, stream>>>(xa);
+  k_problem_xline<R, MAXT, NTC, HSC><<<nbatch, xa.NT, smem, stream>>>(xa);
   return cudaGetLastError();
 }
 
 static cudaError_t dispatch_xline(const XlineArgs& xa, int R, int nbatch, size_t smem, cudaStream_t stream) {
-  if (R == 10 && xa.NT == 640) return launch_xline<10, 640, 640>(xa, nbatch, smem, stream);  // 80 x 80: the production shape
+  if (R == 10 && xa.NT == 640 && xa.hs == 82 && xa.a.g.nx == 80 && xa.a.g.ny == 80)
+    return launch_xline<10, 640, 640, 82>(xa, nbatch, smem, stream);   // 80 x 80: the production shape, everything compile-time
+  if (R == 10 && xa.NT == 640) return launch_xline<10, 640, 640>(xa, nbatch, smem, stream);
   const bool small = xa.NT <= 640;
   switch (R) {
     case 4: return small ? launch_xline<4, 640, 0>(xa, nbatch, smem, stream) : launch_xline<4, 1024, 0>(xa, nbatch, smem, stream);

@@ -54,6 +54,23 @@ struct Geometry {  // 1-D device arrays shared by the batch
   int nx, ny;
 };
 
+// a / b for the assembly (mu, B/(f+eps), row scaling, LU pivots).  On the device: reciprocal seed
+// (MUFU.RCP64H, ~20 bits), two Newton steps, one residual correction of the quotient - 8 fp64
+// instructions without the special-case branches of the IEEE division sequence (denominators here
+// are normal, positive numbers); the result is within 1 ulp of a / b.  On the host (tests/emul): a / b.
+__host__ __device__ __forceinline__ double sy2d_div(double a, double b) {
+#ifdef __CUDA_ARCH__
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+  r = fma(r, fma(-b, r, 1.0), r);
+  r = fma(r, fma(-b, r, 1.0), r);
+  const double q = a * r;
+  return fma(r, fma(-b, q, a), q);
+#else
+  return a / b;
+#endif
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -171,13 +188,13 @@ __host__ __device__ __forceinline__ void face_pair(double asK, double sumK, doub
                                                    double fL, double& AK, double& AL) {
   const double aK = fabs(asK), aL = fabs(asL);
   const double denom = aK + aL + 2.0 * kEps;
-  const double muK = (aL + kEps) / denom;
+  const double muK = sy2d_div(aL + kEps, denom);
   const double muL = 1.0 - muK;
   const double B = muL * asL - muK * asK;
   const double Babs = fabs(B);
   const double Bp = (Babs + B) / 2.0, Bm = (Babs - B) / 2.0;
   // exactly one of Bp, Bm is non-zero and 0/(f+eps) == 0, so one division serves both
-  const double q = (B > 0.0 ? Bp : Bm) / ((B > 0.0 ? fK : fL) + kEps);
+  const double q = sy2d_div(B > 0.0 ? Bp : Bm, (B > 0.0 ? fK : fL) + kEps);
   AK = muK * sumK + (B > 0.0 ? q : 0.0);
   AL = muL * sumL + (B > 0.0 ? 0.0 : q);
 }
@@ -188,7 +205,7 @@ __host__ __device__ __forceinline__ double dirichlet_face(double asK, double sum
   const double Babs = fabs(B);
   const double Bp = (Babs + B) / 2.0, Bm = (Babs - B) / 2.0;
   R += Bm;
-  return sumK + Bp / (fK + kEps);
+  return sumK + sy2d_div(Bp, fK + kEps);
 }
 
 struct Row {  // one row of the reference's M and R (unscaled)
@@ -289,7 +306,7 @@ struct Scaled {  // row of the scaled unit-diagonal system A d = rhs
 __host__ __device__ __forceinline__ void scale_row(const Row& r, double ypC, double ypW, double ypE, double ypS,
                                                    double ypN, Scaled& s) {
   const double cs0 = r.f00 * ypC;
-  const double dscale = 1.0 / (r.diag * cs0);
+  const double dscale = sy2d_div(1.0, r.diag * cs0);
   s.wW = r.oW * (r.fW * ypW) * dscale;
   s.wE = r.oE * (r.fE * ypE) * dscale;
   s.wS = r.oS * (r.fS * ypS) * dscale;
@@ -304,9 +321,9 @@ __host__ __device__ __forceinline__ void scale_row(const Row& r, double ypC, dou
 struct XlineFactor { double l, d, dinv; };
 __host__ __device__ __forceinline__ XlineFactor xline_factor(double wW_i, double wE_prev, double d_prev, bool first_row) {
   XlineFactor f;
-  f.l = first_row ? 0.0 : wW_i / d_prev;
+  f.l = first_row ? 0.0 : sy2d_div(wW_i, d_prev);
   f.d = 1.0 - f.l * wE_prev;
-  f.dinv = 1.0 / f.d;
+  f.dinv = sy2d_div(1.0, f.d);
   return f;
 }
 
@@ -505,7 +522,7 @@ __global__ void __launch_bounds__(kTI * kTJ) k_assemble_tiled(const double* __re
     diag += Ud[c0];
     R += U[c0] * f00;
     const double cs0 = cs_[a + 1][b + 1];
-    const double dscale = 1.0 / (diag * cs0);
+    const double dscale = sy2d_div(1.0, diag * cs0);
     const double wW = oW * cs_[a][b + 1] * dscale, wE = oE * cs_[a + 2][b + 1] * dscale;
     const double wS = oS * cs_[a + 1][b] * dscale, wN = oN * cs_[a + 1][b + 2] * dscale;
     const double rhs = R * dscale - 1.0 - ((wW + wE) + (wS + wN));

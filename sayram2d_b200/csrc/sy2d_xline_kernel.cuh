@@ -75,7 +75,9 @@ __device__ __noinline__ Scaled assemble_scaled_cell(const double* f, const doubl
 
 // NTC > 0 fixes the CTA size at compile time (the 80-column production shape: 640 threads), so
 // that every thread-private slot m*NT + tid is base + immediate and costs no address registers.
-template <int R, int MAXT, int NTC>
+// HSC > 0 fixes the hat row stride too and promises a FULL tile (nx = NCH*R rows, ny = NT/NCH columns:
+// every slot is a cell, no validity predicates): together the 80 x 80 instance.
+template <int R, int MAXT, int NTC, int HSC>
 __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
   constexpr int NCH = kXlineNCH;
   extern __shared__ double sm[];
@@ -86,9 +88,10 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int k = lane % NCH, jj = lane / NCH;
   const int j = w * kXlineCPW + jj;
-  const bool col_ok = j < ny;
+  constexpr bool FULL = HSC > 0;
+  const bool col_ok = FULL || j < ny;
   const int i0 = k * R;
-  const int hs = xa.hs;   // hat row stride, chosen on the host so that the NCH lanes of a column hit distinct banks
+  const int hs = HSC > 0 ? HSC : xa.hs;   // hat row stride, chosen on the host so that the NCH lanes of a column hit distinct banks
   double* hat = sm;
   double* l_s = hat + nx * hs;
   double* di_s = l_s + S;
@@ -118,7 +121,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
     for (int m = 0; m < R; ++m) {
       const int i = i0 + m, q = m * NT + tid;
       double wW = 0.0, wE = 0.0, wS = 0.0, wN = 0.0, rh = 0.0;
-      if (col_ok && i < nx) {
+      if (FULL || (col_ok && i < nx)) {
         const Scaled sc = assemble_scaled_cell(f, yprev, tx, ty, cxy, U, Ud, a.g, i, j);
         wW = sc.wW; wE = sc.wE; wS = sc.wS; wN = sc.wN; rh = sc.rhs;
       }
@@ -213,7 +216,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
 #pragma unroll
       for (int m = 0; m < R; ++m) {
         const int i = i0 + m;
-        if (col_ok && i < nx) hat[i * hs + j] = z[m];
+        if (FULL || (col_ok && i < nx)) hat[i * hs + j] = z[m];
       }
       __syncthreads();
     };
@@ -233,7 +236,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
       for (int m = 0; m < R; ++m) {
         const int i = i0 + m, q = m * NT + tid;
         double val = 0.0;
-        if (col_ok && i < nx) val = p[m] + (wS_g[q] * hat[i * hs + jS] + wN_g[q] * hat[i * hs + jN]);
+        if (FULL || (col_ok && i < nx)) val = p[m] + (wS_g[q] * hat[i * hs + jS] + wN_g[q] * hat[i * hs + jN]);
         vv[m] = val;
         v_g[q] = val;
         a1[0] += rhs_g[q] * val;
@@ -245,7 +248,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
       for (int m = 0; m < R; ++m) {
         const int i = i0 + m, q = m * NT + tid;
         rs[m] -= alpha * vv[m];
-        const double ph = (col_ok && i < nx) ? hat[i * hs + j] : 0.0;
+        const double ph = (FULL || (col_ok && i < nx)) ? hat[i * hs + j] : 0.0;
         x_g[q] = (first ? 0.0 : x_g[q]) + alpha * ph;
       }
       tsolve(rs);
@@ -256,7 +259,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
       for (int m = 0; m < R; ++m) {
         const int i = i0 + m, q = m * NT + tid;
         double val = 0.0;
-        if (col_ok && i < nx) val = rs[m] + (wS_g[q] * hat[i * hs + jS] + wN_g[q] * hat[i * hs + jN]);
+        if (FULL || (col_ok && i < nx)) val = rs[m] + (wS_g[q] * hat[i * hs + jS] + wN_g[q] * hat[i * hs + jN]);
         vv[m] = val;  // t
         a2[0] += val * rs[m];
         a2[1] += val * val;
@@ -268,7 +271,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
 #pragma unroll
       for (int m = 0; m < R; ++m) {
         const int i = i0 + m, q = m * NT + tid;
-        const double sh = (col_ok && i < nx) ? hat[i * hs + j] : 0.0;
+        const double sh = (FULL || (col_ok && i < nx)) ? hat[i * hs + j] : 0.0;
         x_g[q] += omega * sh;
         rs[m] -= omega * vv[m];
         a3[0] += rhs_g[q] * rs[m];
@@ -300,7 +303,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
 #pragma unroll
       for (int m = 0; m < R; ++m) {
         const int i = i0 + m, q = m * NT + tid;
-        if (col_ok && i < nx) {
+        if (FULL || (col_ok && i < nx)) {
           const double d_i = 1.0 / di_s[q];
           const double wE = e_s[q] * d_i;
           // d_prev: 1/d of the row above (i-1) lives in the previous slot of this thread or in lane k-1
@@ -323,7 +326,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
 #pragma unroll
     for (int m = 0; m < R; ++m) {
       const int i = i0 + m;
-      if (col_ok && i < nx) {
+      if (FULL || (col_ok && i < nx)) {
         const int n = i * ny + j;
         const double fold = f[n];
         const double yp = yprev[n];
