@@ -416,27 +416,29 @@ __global__ void __launch_bounds__(kBlock) k_assemble(const double* __restrict__ 
 //      instead of once per adjacent cell
 //   4. the operator row of every cell, gathered from its four faces, scaled, written coalesced.
 // Per cell: ~1.1 vertex, ~2.2 face evaluations and 5 divisions instead of 4, 4 and 9 in the
-// one-thread-per-cell kernel, 16.6 KB of shared memory per CTA.  Same arithmetic per face, so the
+// one-thread-per-cell kernel, 29 KB of shared memory per CTA; every global load happens in stage 1
+// (coalesced rows of the halo tile), the later stages read shared memory only.  Same arithmetic per face, so the
 // rows are bit-identical to k_assemble<0>.
 // ---------------------------------------------------------------------------
 constexpr int kTI = 8, kTJ = 32;
 
-__global__ void __launch_bounds__(kTI * kTJ) k_assemble_tiled(const double* __restrict__ f, const double* __restrict__ yprev,
+__global__ void __launch_bounds__(kTI * kTJ, 4) k_assemble_tiled(const double* __restrict__ f, const double* __restrict__ yprev,
                                                               const double* __restrict__ tx, const double* __restrict__ ty,
                                                               const double* __restrict__ cxy, const double* __restrict__ U,
                                                               const double* __restrict__ Ud, Geometry g, AssembleOut o, int tiles_j,
                                                               int gi0, int li_begin, int li_end, int defer) {
-  __shared__ double fs[kTI + 2][kTJ + 2], cs_[kTI + 2][kTJ + 2], vs[kTI + 1][kTJ + 1];
+  // halo tiles (one cell around the 8 x 32 tile): f, c = f*yprev and the face coefficients
+  __shared__ double fs[kTI + 2][kTJ + 2], cs_[kTI + 2][kTJ + 2], txs[kTI + 2][kTJ + 2], tys[kTI + 2][kTJ + 2], cxs[kTI + 2][kTJ + 2];
+  __shared__ double vs[kTI + 1][kTJ + 1];
   __shared__ double WK[kTI + 1][kTJ], WL[kTI + 1][kTJ], SK[kTI][kTJ + 1], SL[kTI][kTJ + 1];
   __shared__ double red[3 * 32];
   // Rows: memory is indexed with LOCAL rows li (the array may be a slab with halo rows), geometry
   // and boundary logic with GLOBAL rows i = gi0 + li; the kernel assembles local rows [li_begin, li_end).
-  // Single-GPU: gi0 = 0, li_begin = 0, li_end = nx.
+  // Single-GPU: gi0 = 0, li_begin = 0, li_end = nx.  All in-problem indices fit 32 bits.
   const int nx = g.nx, ny = g.ny;
-  const int nrows_local = o.local_rows;
-  const size_t N = (size_t)nrows_local * ny;
-  const size_t base = (size_t)blockIdx.y * N;
+  const size_t base = (size_t)blockIdx.y * ((size_t)o.local_rows * ny);
   const int tid = threadIdx.x;
+  const int ta = tid >> 5, tb = tid & 31;   // thread's cell inside the tile
   const int ntiles = tiles_j * ((li_end - li_begin + kTI - 1) / kTI);
   double rr = 0.0, rabs = 0.0;
   const double* fp = f + base;
@@ -445,94 +447,110 @@ __global__ void __launch_bounds__(kTI * kTJ) k_assemble_tiled(const double* __re
   const double* typ = ty + base;
   const double* cp = cxy + base;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {  // a CTA walks over several tiles: few atomics per problem
-  const int tile_i = tile / tiles_j, tile_j = tile - tile_i * tiles_j;
-  const int I0 = gi0 + li_begin + tile_i * kTI, J0 = tile_j * kTJ;   // global row of the tile origin
-  // 1. f and c with halo (indices clamped at the domain boundary: clamped values only meet zero weights)
-  for (int e = tid; e < (kTI + 2) * (kTJ + 2); e += kTI * kTJ) {
-    const int a = e / (kTJ + 2), b = e - a * (kTJ + 2);
-    int i = I0 + a - 1, j = J0 + b - 1;
-    i = i < 0 ? 0 : (i > nx - 1 ? nx - 1 : i);
-    j = j < 0 ? 0 : (j > ny - 1 ? ny - 1 : j);
-    const double fv = fp[(size_t)(i - gi0) * ny + j];
-    fs[a][b] = fv;
-    cs_[a][b] = fv * yp[(size_t)(i - gi0) * ny + j];
-  }
-  __syncthreads();
-  // 2. vertices (I0 + a, J0 + b)
-  for (int e = tid; e < (kTI + 1) * (kTJ + 1); e += kTI * kTJ) {
-    const int a = e / (kTJ + 1), b = e - a * (kTJ + 1);
-    const int vi = I0 + a, vj = J0 + b;
-    double v = 0.0;
-    if (vi <= nx && vj <= ny) v = vertex_value(g, vi, vj, fs[a][b], fs[a + 1][b], fs[a][b + 1], fs[a + 1][b + 1]);
-    vs[a][b] = v;
-  }
-  __syncthreads();
-  // 3a. west faces of cells (I0 + a, J0 + b), a = 0..TI: K = (i, j), L = (i-1, j)
-  for (int e = tid; e < (kTI + 1) * kTJ; e += kTI * kTJ) {
-    const int a = e / kTJ, b = e - a * kTJ;
+    const int tile_i = tile / tiles_j, tile_j = tile - tile_i * tiles_j;
+    const int I0 = gi0 + li_begin + tile_i * kTI, J0 = tile_j * kTJ;   // global row / column of the tile origin
+    // 1. halo tiles; indices clamped at the domain boundary (clamped values only meet zero weights)
+    auto stage = [&](int a, int b) {
+      int i = I0 + a - 1, j = J0 + b - 1;
+      i = i < 0 ? 0 : (i > nx - 1 ? nx - 1 : i);
+      j = j < 0 ? 0 : (j > ny - 1 ? ny - 1 : j);
+      const int n = (i - gi0) * ny + j;
+      const double fv = fp[n];
+      fs[a][b] = fv;
+      cs_[a][b] = fv * yp[n];
+      txs[a][b] = txp[n];
+      tys[a][b] = typ[n];
+      cxs[a][b] = cp[n];
+    };
+    stage(ta, tb);
+    if (ta < 2) stage(ta + kTI, tb);
+    if (tb < 2) stage(ta, tb + kTJ);
+    if (ta < 2 && tb < 2) stage(ta + kTI, tb + kTJ);
+    __syncthreads();
+    // 2. vertices (I0 + a, J0 + b); tiles that do not touch the boundary skip the Dirichlet / edge logic
+    const bool edge_tile = I0 == 0 || I0 + kTI >= nx || J0 == 0 || J0 + kTJ >= ny;
+    auto vertex = [&](int a, int b) {
+      const int vi = I0 + a, vj = J0 + b;
+      double v = 0.0;
+      if (!edge_tile) {
+        const double wl = g.wxL[vi], wr = g.wxR[vi], wb = g.wyB[vj], wt = g.wyT[vj];
+        v = wl * wb * fs[a][b] + wr * wb * fs[a + 1][b] + wl * wt * fs[a][b + 1] + wr * wt * fs[a + 1][b + 1];
+      } else if (vi <= nx && vj <= ny) {
+        v = vertex_value(g, vi, vj, fs[a][b], fs[a + 1][b], fs[a][b + 1], fs[a + 1][b + 1]);
+      }
+      vs[a][b] = v;
+    };
+    vertex(ta, tb);
+    if (ta == 0) vertex(kTI, tb);
+    if (tid <= kTI) vertex(tid, kTJ);
+    __syncthreads();
+    // 3a. west faces of cells (I0 + a, J0 + b), a = 0..TI: K = (i, j), L = (i-1, j)
+    auto wface = [&](int a, int b) {
+      const int i = I0 + a, j = J0 + b;
+      double AK = 0.0, AL = 0.0;
+      if (i >= 1 && i <= nx - 1 && j < ny) {
+        const double tK = txs[a + 1][b + 1], cK = cxs[a + 1][b + 1], tL = txs[a][b + 1], cL = cxs[a][b + 1];
+        const double vSW = vs[a][b], vNW = vs[a][b + 1];
+        const double kA = tK - cK, kB = tK + cK;   // W face of K: A = NW, B = SW
+        const double lA = tL - cL, lB = tL + cL;   // E face of L: A = SE_L = SW_K, B = NE_L = NW_K
+        face_pair(kA * vNW + kB * vSW, kA + kB, fs[a + 1][b + 1], lA * vSW + lB * vNW, lA + lB, fs[a][b + 1], AK, AL);
+      }
+      WK[a][b] = AK;
+      WL[a][b] = AL;
+    };
+    wface(ta, tb);
+    if (ta == 0) wface(kTI, tb);
+    // 3b. south faces of cells (I0 + a, J0 + b), b = 0..TJ: K = (i, j), L = (i, j-1)
+    auto sface = [&](int a, int b) {
+      const int i = I0 + a, j = J0 + b;
+      double AK = 0.0, AL = 0.0;
+      if (j >= 1 && j <= ny - 1 && i < nx) {
+        const double tK = tys[a + 1][b + 1], cK = cxs[a + 1][b + 1], tL = tys[a + 1][b], cL = cxs[a + 1][b];
+        const double vSW = vs[a][b], vSE = vs[a + 1][b];
+        const double kA = tK + cK, kB = tK - cK;   // S face of K: A = SW, B = SE
+        const double lA = tL + cL, lB = tL - cL;   // N face of L: A = NE_L = SE_K, B = NW_L = SW_K
+        face_pair(kA * vSW + kB * vSE, kA + kB, fs[a + 1][b + 1], lA * vSE + lB * vSW, lA + lB, fs[a + 1][b], AK, AL);
+      }
+      SK[a][b] = AK;
+      SL[a][b] = AL;
+    };
+    sface(ta, tb);
+    if (tid < kTI) sface(tid, kTJ);
+    __syncthreads();
+    // 4. rows
+    const int a = ta, b = tb;
     const int i = I0 + a, j = J0 + b;
-    double AK = 0.0, AL = 0.0;
-    if (i >= 1 && i <= nx - 1 && j < ny) {
-      const size_t ck = (size_t)(i - gi0) * ny + j, cl = ck - ny;
-      const double tK = txp[ck], cK = cp[ck], tL = txp[cl], cL = cp[cl];
-      const double vSW = vs[a][b], vNW = vs[a][b + 1];
-      const double kA = tK - cK, kB = tK + cK;   // W face of K: A = NW, B = SW
-      const double lA = tL - cL, lB = tL + cL;   // E face of L: A = SE_L = SW_K, B = NE_L = NW_K
-      face_pair(kA * vNW + kB * vSW, kA + kB, fs[a + 1][b + 1], lA * vSW + lB * vNW, lA + lB, fs[a][b + 1], AK, AL);
+    if (i < nx && i - gi0 < li_end && j < ny) {
+      const int n = (i - gi0) * ny + j;
+      const size_t c0 = base + n;
+      const double f00 = fs[a + 1][b + 1];
+      double diag = 0.0, R = 0.0, oW = 0.0, oE = 0.0, oS = 0.0, oN = 0.0;
+      if (i > 0) { diag += WK[a][b]; oW = -WL[a][b]; }
+      if (i < nx - 1) { diag += WL[a + 1][b]; oE = -WK[a + 1][b]; }
+      if (j > 0) { diag += SK[a][b]; oS = -SL[a][b]; }
+      if (j < ny - 1) { diag += SL[a][b + 1]; oN = -SK[a][b + 1]; }
+      if (edge_tile && (i == 0 || i == nx - 1 || j == 0 || j == ny - 1)) {  // Dirichlet boundary faces (Solver.cc:143-164, 204-267)
+        const double txP = txs[a + 1][b + 1], tyP = tys[a + 1][b + 1], cP = cxs[a + 1][b + 1];
+        const double vSW = vs[a][b], vSE = vs[a + 1][b], vNW = vs[a][b + 1], vNE = vs[a + 1][b + 1];
+        if (i == 0 && g.bc[0] == 0) diag += dirichlet_face((txP - cP) * vNW + (txP + cP) * vSW, (txP - cP) + (txP + cP), f00, R);
+        if (i == nx - 1 && g.bc[1] == 0) diag += dirichlet_face((txP - cP) * vSE + (txP + cP) * vNE, (txP - cP) + (txP + cP), f00, R);
+        if (j == 0 && g.bc[2] == 0) diag += dirichlet_face((tyP + cP) * vSW + (tyP - cP) * vSE, (tyP + cP) + (tyP - cP), f00, R);
+        if (j == ny - 1 && g.bc[3] == 0) diag += dirichlet_face((tyP + cP) * vNE + (tyP - cP) * vNW, (tyP + cP) + (tyP - cP), f00, R);
+      }
+      diag += Ud[c0];
+      R += U[c0] * f00;
+      const double cs0 = cs_[a + 1][b + 1];
+      const double dscale = sy2d_div(1.0, diag * cs0);
+      const double wW = oW * cs_[a][b + 1] * dscale, wE = oE * cs_[a + 2][b + 1] * dscale;
+      const double wS = oS * cs_[a + 1][b] * dscale, wN = oN * cs_[a + 1][b + 2] * dscale;
+      const double rhs = R * dscale - 1.0 - ((wW + wE) + (wS + wN));
+      o.wW[c0] = wW; o.wE[c0] = wE; o.wS[c0] = wS; o.wN[c0] = wN;
+      o.rhs[c0] = rhs;
+      o.cs[c0] = cs0;
+      rr += rhs * rhs;
+      rabs = fmax(rabs, fabs(rhs));
     }
-    WK[a][b] = AK;
-    WL[a][b] = AL;
-  }
-  // 3b. south faces of cells (I0 + a, J0 + b), b = 0..TJ: K = (i, j), L = (i, j-1)
-  for (int e = tid; e < kTI * (kTJ + 1); e += kTI * kTJ) {
-    const int a = e / (kTJ + 1), b = e - a * (kTJ + 1);
-    const int i = I0 + a, j = J0 + b;
-    double AK = 0.0, AL = 0.0;
-    if (j >= 1 && j <= ny - 1 && i < nx) {
-      const size_t ck = (size_t)(i - gi0) * ny + j, cl = ck - 1;
-      const double tK = typ[ck], cK = cp[ck], tL = typ[cl], cL = cp[cl];
-      const double vSW = vs[a][b], vSE = vs[a + 1][b];
-      const double kA = tK + cK, kB = tK - cK;   // S face of K: A = SW, B = SE
-      const double lA = tL + cL, lB = tL - cL;   // N face of L: A = NE_L = SE_K, B = NW_L = SW_K
-      face_pair(kA * vSW + kB * vSE, kA + kB, fs[a + 1][b + 1], lA * vSE + lB * vSW, lA + lB, fs[a + 1][b], AK, AL);
-    }
-    SK[a][b] = AK;
-    SL[a][b] = AL;
-  }
-  __syncthreads();
-  // 4. rows
-  const int a = tid / kTJ, b = tid - a * kTJ;
-  const int i = I0 + a, j = J0 + b;
-  if (i < nx && i - gi0 < li_end && j < ny) {
-    const size_t n = (size_t)(i - gi0) * ny + j, c0 = base + n;
-    const double f00 = fs[a + 1][b + 1];
-    double diag = 0.0, R = 0.0, oW = 0.0, oE = 0.0, oS = 0.0, oN = 0.0;
-    if (i > 0) { diag += WK[a][b]; oW = -WL[a][b]; }
-    if (i < nx - 1) { diag += WL[a + 1][b]; oE = -WK[a + 1][b]; }
-    if (j > 0) { diag += SK[a][b]; oS = -SL[a][b]; }
-    if (j < ny - 1) { diag += SL[a][b + 1]; oN = -SK[a][b + 1]; }
-    if (i == 0 || i == nx - 1 || j == 0 || j == ny - 1) {  // Dirichlet boundary faces (Solver.cc:143-164, 204-267)
-      const double txP = txp[n], tyP = typ[n], cP = cp[n];
-      const double vSW = vs[a][b], vSE = vs[a + 1][b], vNW = vs[a][b + 1], vNE = vs[a + 1][b + 1];
-      if (i == 0 && g.bc[0] == 0) diag += dirichlet_face((txP - cP) * vNW + (txP + cP) * vSW, (txP - cP) + (txP + cP), f00, R);
-      if (i == nx - 1 && g.bc[1] == 0) diag += dirichlet_face((txP - cP) * vSE + (txP + cP) * vNE, (txP - cP) + (txP + cP), f00, R);
-      if (j == 0 && g.bc[2] == 0) diag += dirichlet_face((tyP + cP) * vSW + (tyP - cP) * vSE, (tyP + cP) + (tyP - cP), f00, R);
-      if (j == ny - 1 && g.bc[3] == 0) diag += dirichlet_face((tyP + cP) * vNE + (tyP - cP) * vNW, (tyP + cP) + (tyP - cP), f00, R);
-    }
-    diag += Ud[c0];
-    R += U[c0] * f00;
-    const double cs0 = cs_[a + 1][b + 1];
-    const double dscale = sy2d_div(1.0, diag * cs0);
-    const double wW = oW * cs_[a][b + 1] * dscale, wE = oE * cs_[a + 2][b + 1] * dscale;
-    const double wS = oS * cs_[a + 1][b] * dscale, wN = oN * cs_[a + 1][b + 2] * dscale;
-    const double rhs = R * dscale - 1.0 - ((wW + wE) + (wS + wN));
-    o.wW[c0] = wW; o.wE[c0] = wE; o.wS[c0] = wS; o.wN[c0] = wN;
-    o.rhs[c0] = rhs;
-    o.cs[c0] = cs0;
-    rr += rhs * rhs;
-    rabs = fmax(rabs, fabs(rhs));
-  }
-  __syncthreads();  // the tile's shared arrays are rewritten by the next tile
+    __syncthreads();  // the tile's shared arrays are rewritten by the next tile
   }
   double sums[1] = {rr};
   block_sums<1>(sums, red);
