@@ -154,6 +154,10 @@ def make_grid(n, device):
     return eng, f0
 
 
+# lockstep engine with the segmented x-line preconditioner: the five kernel classes move these bytes
+BYTES_PER_CELL_XLINE = {"p_update": 64, "spmv_v": 48, "s_update": 80, "spmv_t": 40, "xr_update": 56}
+
+
 def roofline_from_profile(prof, only=None, stats=None, cells_per_problem=None):
     """achieved = algorithmic bytes / CUDA-event time per kernel.  The engine-2 kernel does whole
     time steps; its "algorithmic bytes" are what the same arithmetic moves when every array streams
@@ -176,10 +180,13 @@ def roofline_from_profile(prof, only=None, stats=None, cells_per_problem=None):
                           "hbm_bytes_min": p["cells"] * 72, "precond": "xline" if per_iter == 288 else "jacobi",
                           "mean_iters_per_step": stats["iters_sum_all"] * cells_per_problem / p["cells"]}
             continue
-        gbs = p["cells"] * BYTES_PER_CELL[name] / (p["ms"] * 1e-3) / 1e9
+        bpc = BYTES_PER_CELL[name]
+        if stats and stats.get("precond", 0) == 1 and stats.get("engine", 0) == 1:
+            bpc = BYTES_PER_CELL_XLINE.get(name, bpc)
+        gbs = p["cells"] * bpc / (p["ms"] * 1e-3) / 1e9
         rows[name] = {"achieved": round(gbs, 1), "frac": round(gbs / peak, 4), "ms_total": round(p["ms"], 3),
                       "launches": p["launches"], "us_per_launch": round(1e3 * p["ms"] / p["launches"], 2),
-                      "bytes_per_cell": BYTES_PER_CELL[name]}
+                      "bytes_per_cell": bpc}
     cand = {k: v for k, v in rows.items() if only is None or k in only or k == "problem_steps"}
     dom = max(cand, key=lambda k: cand[k]["ms_total"]) if cand else None
     return rows, dom, peak, peak_src
@@ -417,6 +424,7 @@ def grid_object(n, device, args, torch):
     rows, dom, peak, peak_src = roofline_from_profile(prof, stats=pst, cells_per_problem=n * n)
     out = {"workload": f"grid{n}", "value": n * n * steps / dev_s, "unit": UNIT, "steps": steps, "ms_per_step": 1e3 * dev_s / steps,
            "iters_per_step": iters / steps, "negatives": st["negatives"], "resid_last": st["resid_last"],
+           "precond": "xline16" if st.get("precond", 0) == 1 else "jacobi",
            "l2": "256 MB flush between timed steps; the 19-array working set (~160 MB) cycles through L2 within a step",
            "roofline": {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src, "dominant": dom, "kernels": rows}}
     out["roofline"]["sustained"] = sustained_kernels(eng, n * n, peak)
@@ -484,10 +492,12 @@ def slab_object(n, iters, rank, world, local_rank, dist, torch):
     sec = float(t.item())
     its = st["iters_total"]
     peak, _ = measured_peak()
-    gbs = n * n * (104 + 216.0 * its) / sec / 1e9
+    per_iter = 288.0 if st.get("precond", 0) == 1 else 216.0
+    gbs = n * n * (104 + per_iter * its) / sec / 1e9
     out = {"workload": f"slab{n}", "n_gpus": world, "rows_per_gpu": hi - lo, "iterations": its, "seconds": sec,
            "ms_per_iteration": 1e3 * sec / max(its, 1), "cell_iterations_per_sec": n * n * its / sec,
            "algorithmic_GBps_aggregate": gbs, "frac_of_aggregate_hbm_peak": gbs / (peak * world),
+           "precond": "xline16" if st.get("precond", 0) == 1 else "jacobi", "bytes_per_cell_iteration": per_iter,
            "budget": f"fixed iteration budget: assembly + first {its} BiCGSTAB iterations of one time step (not converged by design)",
            "exchange": "per iteration: 2 one-line halo ncclSend/Recv pairs (128 KB lines at 16384) + 3 all-gathers of 5 doubles"}
     eng.close()

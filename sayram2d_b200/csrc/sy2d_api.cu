@@ -17,6 +17,7 @@
 #include "sy2d_kernels.cuh"
 #include "sy2d_problem_kernel.cuh"
 #include "sy2d_xline_kernel.cuh"
+#include "sy2d_xline_lockstep.cuh"
 
 using namespace sy2d;
 
@@ -48,6 +49,7 @@ struct sy2d_ctx {
   // operator + Krylov vectors
   double *wW = nullptr, *wE = nullptr, *wS = nullptr, *wN = nullptr, *rhs = nullptr;
   double *x = nullptr, *r = nullptr, *p = nullptr, *v = nullptr, *s = nullptr, *t = nullptr;
+  double *xl_l = nullptr, *xl_dinv = nullptr, *xl_e = nullptr, *xl_hat = nullptr;  // engine 1 x-line: LU factors, hat vector
   Scal* scal = nullptr;
   int* d_nactive = nullptr;
   int* h_nactive = nullptr;  // pinned
@@ -75,6 +77,7 @@ struct sy2d_ctx {
   // iteration-chunk graph
   cudaGraphExec_t chunk_exec = nullptr;
   int chunk_iters = 0;
+  int chunk_variant = -1;
   // profiling
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
@@ -136,6 +139,14 @@ unsigned capped_blocks(const sy2d_ctx* c, size_t work_items_per_problem, int thr
   return (unsigned)std::min(need, cap);
 }
 
+// Engine 1 uses the segmented x-line preconditioner unless Jacobi is requested (needs at least one full segment)
+bool lockstep_xline(const sy2d_ctx* c) {
+  const int rows = c->slab ? c->nx - 2 : c->nx;
+  return c->opt.precond != SY2D_PRECOND_JACOBI && rows >= kSeg;
+}
+
+XlVecs xl_vecs(const sy2d_ctx* c);
+
 // RAII-less event bracket used only in profiling mode
 struct Prof {
   sy2d_ctx* c;
@@ -160,7 +171,40 @@ struct Prof {
   }
 };
 
+XlVecs xl_vecs(const sy2d_ctx* c) {
+  XlVecs x;
+  x.k = krylov(c);
+  x.l = c->xl_l; x.dinv = c->xl_dinv; x.e = c->xl_e; x.hat = c->xl_hat;
+  x.ny = c->ny;
+  x.row0 = c->slab ? 1 : 0;
+  x.nrows = c->slab ? c->nx - 2 : c->nx;
+  return x;
+}
+
+int xl_alloc(sy2d_ctx* c) {
+  if (c->xl_hat) return SY2D_OK;
+  double** arrs[4] = {&c->xl_l, &c->xl_dinv, &c->xl_e, &c->xl_hat};
+  for (double** a : arrs) {
+    CU(cudaMalloc(reinterpret_cast<void**>(a), c->total * sizeof(double)));
+    CU(cudaMemsetAsync(*a, 0, c->total * sizeof(double), c->stream));
+  }
+  return SY2D_OK;
+}
+
+void launch_iteration_xline(sy2d_ctx* c) {
+  const XlVecs x = xl_vecs(c);
+  const int nseg = (x.nrows + kSeg - 1) / kSeg;
+  const dim3 gs(capped_blocks(c, (size_t)nseg * c->ny, kBlock), (unsigned)c->nbatch, 1);
+  const dim3 gc(capped_blocks(c, x.k.n_end - x.k.n_begin, kBlock), (unsigned)c->nbatch, 1);
+  { Prof p(c, SY2D_K_P_UPDATE); k_xl_sweep<0><<<gs, kBlock, 0, c->stream>>>(x, c->N); }
+  { Prof p(c, SY2D_K_SPMV_V); k_xl_spmv_v<<<gc, kBlock, 0, c->stream>>>(x, c->N); }
+  { Prof p(c, SY2D_K_S_UPDATE); k_xl_sweep<1><<<gs, kBlock, 0, c->stream>>>(x, c->N); }
+  { Prof p(c, SY2D_K_SPMV_T); k_xl_spmv_t<<<gc, kBlock, 0, c->stream>>>(x, c->N); }
+  { Prof p(c, SY2D_K_XR_UPDATE); k_xl_xr<<<gc, kBlock, 0, c->stream>>>(x, c->N); }
+}
+
 void launch_iteration(sy2d_ctx* c) {
+  if (lockstep_xline(c)) { launch_iteration_xline(c); return; }
   const KrylovVecs k = krylov(c);
   if (c->ny % 2 == 0) {  // two cells per thread, 16-byte accesses
     const dim3 g2(capped_blocks(c, c->N / 2, kBlock), (unsigned)c->nbatch, 1);
@@ -181,7 +225,9 @@ void launch_iteration(sy2d_ctx* c) {
 constexpr int kKernelsPerIteration = 5;
 
 int build_chunk_graph(sy2d_ctx* c) {
-  if (c->chunk_exec && c->chunk_iters == c->opt.check_every) return SY2D_OK;
+  const int variant = lockstep_xline(c) ? 1 : 0;
+  if (c->chunk_exec && c->chunk_iters == c->opt.check_every && c->chunk_variant == variant) return SY2D_OK;
+  c->chunk_variant = variant;
   if (c->chunk_exec) { cudaGraphExecDestroy(c->chunk_exec); c->chunk_exec = nullptr; }
   cudaGraph_t graph = nullptr;
   CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
@@ -314,6 +360,13 @@ int step_slab(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
   sy2d_stats st;
   std::memset(&st, 0, sizeof st);
   st.engine = 1;
+  const bool xl = lockstep_xline(c);
+  st.precond = xl ? SY2D_PRECOND_XLINE : SY2D_PRECOND_JACOBI;
+  if (xl) { int rc0 = xl_alloc(c); if (rc0) return rc0; }
+  const XlVecs xv = xl_vecs(c);
+  const int nseg = (rows + kSeg - 1) / kSeg;
+  const dim3 gs(capped_blocks(c, (size_t)nseg * c->ny, kBlock), 1, 1);
+  const dim3 gc(capped_blocks(c, own, kBlock), 1, 1);
   CU(cudaEventRecord(c->ev_call0, c->stream));
   for (int step = 0; step < nsteps; ++step) {
     int rc = slab_halo_exchange(c, c->f);
@@ -329,12 +382,25 @@ int step_slab(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
     CU(cudaGetLastError());
     rc = slab_reduce(c, 0, k);
     if (rc) return rc;
-    c->launches += 2;
+    if (xl) k_xl_factor<<<gs, kBlock, 0, c->stream>>>(xv, c->N);
+    c->launches += 3;
     CU(cudaMemcpyAsync(c->h_nactive, c->d_nactive, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     int done_its = 0;
     while (*c->h_nactive > 0 && done_its < c->opt.maxit + c->opt.check_every) {
-      for (int it = 0; it < c->opt.check_every; ++it) {
+      for (int it = 0; it < c->opt.check_every && xl; ++it) {
+        k_xl_sweep<0><<<gs, kBlock, 0, c->stream>>>(xv, c->N);
+        if ((rc = slab_halo_exchange(c, c->xl_hat))) return rc;
+        k_xl_spmv_v<<<gc, kBlock, 0, c->stream>>>(xv, c->N);
+        if ((rc = slab_reduce(c, 1, k))) return rc;
+        k_xl_sweep<1><<<gs, kBlock, 0, c->stream>>>(xv, c->N);
+        if ((rc = slab_halo_exchange(c, c->xl_hat))) return rc;
+        k_xl_spmv_t<<<gc, kBlock, 0, c->stream>>>(xv, c->N);
+        if ((rc = slab_reduce(c, 2, k))) return rc;
+        k_xl_xr<<<gc, kBlock, 0, c->stream>>>(xv, c->N);
+        if ((rc = slab_reduce(c, 3, k))) return rc;
+      }
+      for (int it = 0; it < c->opt.check_every && !xl; ++it) {
         k_p_update2<<<g2, kBlock, 0, c->stream>>>(k, c->N);
         if ((rc = slab_halo_exchange(c, c->p))) return rc;
         k_spmv_v2<<<g2, kBlock, 0, c->stream>>>(k, c->N, c->ny);
@@ -508,7 +574,7 @@ void sy2d_destroy(sy2d_ctx* c) {
   if (c->chunk_exec) cudaGraphExecDestroy(c->chunk_exec);
   double* bufs[] = {c->d_wxL, c->d_wxR, c->d_wyB, c->d_wyT, c->d_dx, c->d_dy, c->d_bc[0], c->d_bc[1], c->d_bc[2], c->d_bc[3],
                     c->tx, c->ty, c->cxy, c->U, c->Ud, c->f, c->yprev, c->cs, c->wW, c->wE, c->wS, c->wN, c->rhs,
-                    c->x, c->r, c->p, c->v, c->s, c->t, c->stage, c->xl_scratch};
+                    c->x, c->r, c->p, c->v, c->s, c->t, c->stage, c->xl_scratch, c->xl_l, c->xl_dinv, c->xl_e, c->xl_hat};
   for (double* b : bufs) if (b) cudaFree(b);
   if (c->scal) cudaFree(c->scal);
   for (cudaStream_t sk : c->pipe_streams) if (sk) { cudaStreamSynchronize(sk); cudaStreamDestroy(sk); }
@@ -845,10 +911,14 @@ int sy2d_step(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
   const bool graph = c->opt.use_graph && !c->profiling;
   const int check_every = c->profiling ? 1 : c->opt.check_every;  // profiling: no zero-work launches
   c->launches = 0;
-  if (graph) { rc = build_chunk_graph(c); if (rc) return rc; }
   sy2d_stats st;
   std::memset(&st, 0, sizeof st);
   st.engine = 1;
+  const bool xl = lockstep_xline(c);
+  if (c->opt.precond == SY2D_PRECOND_XLINE && !xl) return fail(c, SY2D_ERR_INVALID, "sy2d_step: the x-line preconditioner needs nx >= %d", kSeg);
+  st.precond = xl ? SY2D_PRECOND_XLINE : SY2D_PRECOND_JACOBI;
+  if (xl) { rc = xl_alloc(c); if (rc) return rc; }
+  if (graph) { rc = build_chunk_graph(c); if (rc) return rc; }
   CU(cudaEventRecord(c->ev_call0, c->stream));
   for (int step = 0; step < nsteps; ++step) {
     CU(cudaMemsetAsync(c->d_nactive, 0, sizeof(int), c->stream));
@@ -866,6 +936,13 @@ int sy2d_step(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
       } else {
         k_assemble<0><<<g, kBlock, 0, c->stream>>>(c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud, geo, o);
       }
+    }
+    if (xl) {  // LU of the x-line segments for this step's operator
+      Prof p(c, SY2D_K_OTHER);
+      const XlVecs x = xl_vecs(c);
+      const int nseg = (x.nrows + kSeg - 1) / kSeg;
+      k_xl_factor<<<dim3(capped_blocks(c, (size_t)nseg * c->ny, kBlock), (unsigned)c->nbatch, 1), kBlock, 0, c->stream>>>(x, c->N);
+      c->launches += 1;
     }
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(c->h_nactive, c->d_nactive, sizeof(int), cudaMemcpyDeviceToHost, c->stream));

@@ -35,7 +35,8 @@ def test_operator_and_vertex_values_match_reference(tag):
     eng.close()
 
 
-ENGINES = [(1, 0), (2, 0), (2, 1)]  # (engine, precond): lockstep; CTA per problem with Jacobi / x-line
+# (engine, precond): lockstep with Jacobi / segmented x-line; CTA per problem with Jacobi / x-line
+ENGINES = [(1, 0), (1, 1), (2, 0), (2, 1)]
 
 
 @pytest.mark.parametrize("engine,precond", ENGINES)
@@ -186,6 +187,8 @@ def test_random_problems_match_oracle(seed, nx, ny, bc, engine, precond):
     import ppfv_oracle as O
     m, eq, lines, f = _random_case(seed, nx, ny, bc)
     eng = sy.Engine(m.x_edges, m.y_edges, m.dt)
+    if precond == 1 and ((engine == 1 and nx < 16) or (engine == 2 and (nx > 80 or ny > 128))):
+        pytest.skip("x-line preconditioner not available for this shape")
     eng.set_options(engine=engine, precond=precond)
     eng.set_coeffs(eq.G, eq.Dxx, eq.Dxy, eq.Dyy, eq.inv_tau)
     eng.set_bc(bc, *[l if b == 0 else None for l, b in zip(lines, bc)])
