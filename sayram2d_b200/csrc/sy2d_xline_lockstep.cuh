@@ -57,9 +57,12 @@ __global__ void __launch_bounds__(kBlock) k_xl_factor(XlVecs x, size_t N) {
   }
 }
 
-// MODE 0: p-update + solve;  MODE 1: s-update, x += alpha*phat, solve
+// MODE 0: p-update + solve;  MODE 1: s-update, x += alpha*phat, solve.
+// Only (rows/kSeg)*ny threads exist (65 k at 1024^2), so each thread must keep many loads in flight:
+// all right-hand sides and factors of its segment are loaded into registers first (4 x 16 independent
+// loads), the two recurrences then run on registers only.
 template <int MODE>
-__global__ void __launch_bounds__(kBlock) k_xl_sweep(XlVecs x, size_t N) {
+__global__ void __launch_bounds__(128) k_xl_sweep(XlVecs x, size_t N) {
   const Scal* sc = x.k.scal + blockIdx.y;
   if (sc->state != 0) return;
   const int ny = x.ny;
@@ -72,34 +75,50 @@ __global__ void __launch_bounds__(kBlock) k_xl_sweep(XlVecs x, size_t N) {
     const int r0 = s * kSeg;
     const int cnt = min(kSeg, x.nrows - r0);
     const size_t n0 = base + (size_t)(x.row0 + r0) * ny + j;
-    double z[kSeg];
-    double carry = 0.0;
+    double z[kSeg], c1[kSeg], c2[kSeg];
+    // right-hand sides (and the vector updates they come from) + forward multipliers
+#pragma unroll
+    for (int m = 0; m < kSeg; ++m) {
+      z[m] = 0.0; c1[m] = 0.0;
+      if (m < cnt) {
+        const size_t n = n0 + (size_t)m * ny;
+        const double rr = first ? x.k.rhs[n] : x.k.r[n];
+        const double vv = first && MODE == 0 ? 0.0 : x.k.v[n];
+        if (MODE == 0) {
+          z[m] = first ? rr : rr + beta * (x.k.p[n] - omega * vv);
+        } else {
+          z[m] = rr - alpha * vv;
+          c2[m] = (first ? 0.0 : x.k.x[n]) + alpha * x.hat[n];
+        }
+        c1[m] = x.l[n];
+      }
+    }
 #pragma unroll
     for (int m = 0; m < kSeg; ++m) {
       if (m < cnt) {
         const size_t n = n0 + (size_t)m * ny;
-        double b;
-        if (MODE == 0) {
-          b = first ? x.k.rhs[n] : x.k.r[n] + beta * (x.k.p[n] - omega * x.k.v[n]);
-          x.k.p[n] = b;
-        } else {
-          b = (first ? x.k.rhs[n] : x.k.r[n]) - alpha * x.k.v[n];
-          x.k.s[n] = b;
-          x.k.x[n] = (first ? 0.0 : x.k.x[n]) + alpha * x.hat[n];
-        }
-        carry = b - x.l[n] * carry;
-        z[m] = carry;
+        if (MODE == 0) x.k.p[n] = z[m]; else { x.k.s[n] = z[m]; x.k.x[n] = c2[m]; }
+      }
+    }
+    double carry = 0.0;
+#pragma unroll
+    for (int m = 0; m < kSeg; ++m) { carry = z[m] - c1[m] * carry; z[m] = carry; }
+    // backward factors
+#pragma unroll
+    for (int m = 0; m < kSeg; ++m) {
+      c1[m] = 1.0; c2[m] = 0.0;
+      if (m < cnt) {
+        const size_t n = n0 + (size_t)m * ny;
+        c1[m] = x.dinv[n];
+        c2[m] = x.e[n];
       }
     }
     carry = 0.0;
 #pragma unroll
-    for (int m = kSeg - 1; m >= 0; --m) {
-      if (m < cnt) {
-        const size_t n = n0 + (size_t)m * ny;
-        carry = z[m] * x.dinv[n] - x.e[n] * carry;
-        x.hat[n] = carry;
-      }
-    }
+    for (int m = kSeg - 1; m >= 0; --m) { carry = m < cnt ? z[m] * c1[m] - c2[m] * carry : 0.0; z[m] = carry; }
+#pragma unroll
+    for (int m = 0; m < kSeg; ++m)
+      if (m < cnt) x.hat[n0 + (size_t)m * ny] = z[m];
   }
 }
 
