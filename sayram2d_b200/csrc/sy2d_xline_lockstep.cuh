@@ -25,6 +25,7 @@
 namespace sy2d {
 
 constexpr int kSeg = 16;  // rows per segment (power of two)
+constexpr int kSweepThreads = 128;
 
 struct XlVecs {
   KrylovVecs k;
@@ -58,11 +59,52 @@ __global__ void __launch_bounds__(kBlock) k_xl_factor(XlVecs x, size_t N) {
 }
 
 // MODE 0: p-update + solve;  MODE 1: s-update, x += alpha*phat, solve.
-// Only (rows/kSeg)*ny threads exist (65 k at 1024^2), so each thread must keep many loads in flight:
-// all right-hand sides and factors of its segment are loaded into registers first (4 x 16 independent
-// loads), the two recurrences then run on registers only.
+// Only (rows/kSeg)*ny threads exist (65 k at 1024^2), so a thread must keep many loads in flight.  The
+// body is straight-line code for a full segment (CNT == kSeg, no per-row predicates, `first` resolved
+// outside), which lets the compiler issue the loads of all rows ahead of the recurrences; ragged last
+// segments take the generic path.
+template <int MODE, bool FIRST, bool FULL>
+__device__ __forceinline__ void xl_sweep_segment(const XlVecs& x, size_t n0, int ny, int cnt, double alpha, double beta, double omega) {
+  double z[kSeg], lm[kSeg];
+  const double* rsrc = FIRST ? x.k.rhs : x.k.r;
+#pragma unroll
+  for (int m = 0; m < kSeg; ++m) {
+    z[m] = 0.0; lm[m] = 0.0;
+    if (FULL || m < cnt) {
+      const size_t n = n0 + (size_t)m * ny;
+      const double rr = rsrc[n];
+      if (MODE == 0) {
+        z[m] = FIRST ? rr : rr + beta * (x.k.p[n] - omega * x.k.v[n]);
+      } else {
+        z[m] = rr - alpha * x.k.v[n];
+        const double xn = (FIRST ? 0.0 : x.k.x[n]) + alpha * x.hat[n];
+        x.k.x[n] = xn;
+      }
+      lm[m] = x.l[n];
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < kSeg; ++m)
+    if (FULL || m < cnt) { if (MODE == 0) x.k.p[n0 + (size_t)m * ny] = z[m]; else x.k.s[n0 + (size_t)m * ny] = z[m]; }
+  double carry = 0.0;
+#pragma unroll
+  for (int m = 0; m < kSeg; ++m) { carry = z[m] - lm[m] * carry; z[m] = carry; }
+  double em[kSeg];
+#pragma unroll
+  for (int m = 0; m < kSeg; ++m) {
+    lm[m] = 1.0; em[m] = 0.0;
+    if (FULL || m < cnt) { lm[m] = x.dinv[n0 + (size_t)m * ny]; em[m] = x.e[n0 + (size_t)m * ny]; }
+  }
+  carry = 0.0;
+#pragma unroll
+  for (int m = kSeg - 1; m >= 0; --m) { carry = (FULL || m < cnt) ? z[m] * lm[m] - em[m] * carry : 0.0; z[m] = carry; }
+#pragma unroll
+  for (int m = 0; m < kSeg; ++m)
+    if (FULL || m < cnt) x.hat[n0 + (size_t)m * ny] = z[m];
+}
+
 template <int MODE>
-__global__ void __launch_bounds__(128) k_xl_sweep(XlVecs x, size_t N) {
+__global__ void __launch_bounds__(kSweepThreads) k_xl_sweep(XlVecs x, size_t N) {
   const Scal* sc = x.k.scal + blockIdx.y;
   if (sc->state != 0) return;
   const int ny = x.ny;
@@ -75,50 +117,13 @@ __global__ void __launch_bounds__(128) k_xl_sweep(XlVecs x, size_t N) {
     const int r0 = s * kSeg;
     const int cnt = min(kSeg, x.nrows - r0);
     const size_t n0 = base + (size_t)(x.row0 + r0) * ny + j;
-    double z[kSeg], c1[kSeg], c2[kSeg];
-    // right-hand sides (and the vector updates they come from) + forward multipliers
-#pragma unroll
-    for (int m = 0; m < kSeg; ++m) {
-      z[m] = 0.0; c1[m] = 0.0;
-      if (m < cnt) {
-        const size_t n = n0 + (size_t)m * ny;
-        const double rr = first ? x.k.rhs[n] : x.k.r[n];
-        const double vv = first && MODE == 0 ? 0.0 : x.k.v[n];
-        if (MODE == 0) {
-          z[m] = first ? rr : rr + beta * (x.k.p[n] - omega * vv);
-        } else {
-          z[m] = rr - alpha * vv;
-          c2[m] = (first ? 0.0 : x.k.x[n]) + alpha * x.hat[n];
-        }
-        c1[m] = x.l[n];
-      }
+    if (cnt == kSeg) {
+      if (first) xl_sweep_segment<MODE, true, true>(x, n0, ny, cnt, alpha, beta, omega);
+      else xl_sweep_segment<MODE, false, true>(x, n0, ny, cnt, alpha, beta, omega);
+    } else {
+      if (first) xl_sweep_segment<MODE, true, false>(x, n0, ny, cnt, alpha, beta, omega);
+      else xl_sweep_segment<MODE, false, false>(x, n0, ny, cnt, alpha, beta, omega);
     }
-#pragma unroll
-    for (int m = 0; m < kSeg; ++m) {
-      if (m < cnt) {
-        const size_t n = n0 + (size_t)m * ny;
-        if (MODE == 0) x.k.p[n] = z[m]; else { x.k.s[n] = z[m]; x.k.x[n] = c2[m]; }
-      }
-    }
-    double carry = 0.0;
-#pragma unroll
-    for (int m = 0; m < kSeg; ++m) { carry = z[m] - c1[m] * carry; z[m] = carry; }
-    // backward factors
-#pragma unroll
-    for (int m = 0; m < kSeg; ++m) {
-      c1[m] = 1.0; c2[m] = 0.0;
-      if (m < cnt) {
-        const size_t n = n0 + (size_t)m * ny;
-        c1[m] = x.dinv[n];
-        c2[m] = x.e[n];
-      }
-    }
-    carry = 0.0;
-#pragma unroll
-    for (int m = kSeg - 1; m >= 0; --m) { carry = m < cnt ? z[m] * c1[m] - c2[m] * carry : 0.0; z[m] = carry; }
-#pragma unroll
-    for (int m = 0; m < kSeg; ++m)
-      if (m < cnt) x.hat[n0 + (size_t)m * ny] = z[m];
   }
 }
 
