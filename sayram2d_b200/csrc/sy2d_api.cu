@@ -195,12 +195,13 @@ void launch_iteration_xline(sy2d_ctx* c) {
   const XlVecs x = xl_vecs(c);
   const int nseg = (x.nrows + kSeg - 1) / kSeg;
   const dim3 gs(capped_blocks(c, (size_t)nseg * c->ny, kSweepThreads), (unsigned)c->nbatch, 1);
-  const dim3 gc(capped_blocks(c, x.k.n_end - x.k.n_begin, kBlock), (unsigned)c->nbatch, 1);
+  const bool v2 = c->ny % 2 == 0;
+  const dim3 gc(capped_blocks(c, (x.k.n_end - x.k.n_begin) / (v2 ? 2 : 1), kBlock), (unsigned)c->nbatch, 1);
   { Prof p(c, SY2D_K_P_UPDATE); k_xl_sweep<0><<<gs, kSweepThreads, 0, c->stream>>>(x, c->N); }
-  { Prof p(c, SY2D_K_SPMV_V); k_xl_spmv_v<<<gc, kBlock, 0, c->stream>>>(x, c->N); }
+  { Prof p(c, SY2D_K_SPMV_V); if (v2) k_xl_spmv_v<2><<<gc, kBlock, 0, c->stream>>>(x, c->N); else k_xl_spmv_v<1><<<gc, kBlock, 0, c->stream>>>(x, c->N); }
   { Prof p(c, SY2D_K_S_UPDATE); k_xl_sweep<1><<<gs, kSweepThreads, 0, c->stream>>>(x, c->N); }
-  { Prof p(c, SY2D_K_SPMV_T); k_xl_spmv_t<<<gc, kBlock, 0, c->stream>>>(x, c->N); }
-  { Prof p(c, SY2D_K_XR_UPDATE); k_xl_xr<<<gc, kBlock, 0, c->stream>>>(x, c->N); }
+  { Prof p(c, SY2D_K_SPMV_T); if (v2) k_xl_spmv_t<2><<<gc, kBlock, 0, c->stream>>>(x, c->N); else k_xl_spmv_t<1><<<gc, kBlock, 0, c->stream>>>(x, c->N); }
+  { Prof p(c, SY2D_K_XR_UPDATE); if (v2) k_xl_xr<2><<<gc, kBlock, 0, c->stream>>>(x, c->N); else k_xl_xr<1><<<gc, kBlock, 0, c->stream>>>(x, c->N); }
 }
 
 void launch_iteration(sy2d_ctx* c) {
@@ -366,7 +367,7 @@ int step_slab(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
   const XlVecs xv = xl_vecs(c);
   const int nseg = (rows + kSeg - 1) / kSeg;
   const dim3 gs(capped_blocks(c, (size_t)nseg * c->ny, kSweepThreads), 1, 1);
-  const dim3 gc(capped_blocks(c, own, kBlock), 1, 1);
+  const dim3 gc(capped_blocks(c, own / 2, kBlock), 1, 1);
   CU(cudaEventRecord(c->ev_call0, c->stream));
   for (int step = 0; step < nsteps; ++step) {
     int rc = slab_halo_exchange(c, c->f);
@@ -391,13 +392,13 @@ int step_slab(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
       for (int it = 0; it < c->opt.check_every && xl; ++it) {
         k_xl_sweep<0><<<gs, kSweepThreads, 0, c->stream>>>(xv, c->N);
         if ((rc = slab_halo_exchange(c, c->xl_hat))) return rc;
-        k_xl_spmv_v<<<gc, kBlock, 0, c->stream>>>(xv, c->N);
+        k_xl_spmv_v<2><<<gc, kBlock, 0, c->stream>>>(xv, c->N);
         if ((rc = slab_reduce(c, 1, k))) return rc;
         k_xl_sweep<1><<<gs, kSweepThreads, 0, c->stream>>>(xv, c->N);
         if ((rc = slab_halo_exchange(c, c->xl_hat))) return rc;
-        k_xl_spmv_t<<<gc, kBlock, 0, c->stream>>>(xv, c->N);
+        k_xl_spmv_t<2><<<gc, kBlock, 0, c->stream>>>(xv, c->N);
         if ((rc = slab_reduce(c, 2, k))) return rc;
-        k_xl_xr<<<gc, kBlock, 0, c->stream>>>(xv, c->N);
+        k_xl_xr<2><<<gc, kBlock, 0, c->stream>>>(xv, c->N);
         if ((rc = slab_reduce(c, 3, k))) return rc;
       }
       for (int it = 0; it < c->opt.check_every && !xl; ++it) {

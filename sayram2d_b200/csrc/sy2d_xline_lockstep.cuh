@@ -138,18 +138,46 @@ __device__ __forceinline__ double xl_apply(const XlVecs& x, const double* __rest
   return y;
 }
 
+// two cells (n, n+1; ny even => same row) of y = c + wS hat_S + wN hat_N + cut W/E couplings
+__device__ __forceinline__ void xl_apply2(const XlVecs& x, const double* __restrict__ c, size_t g, size_t n, size_t N, int ny,
+                                          double& y0, double& y1) {
+  const double* hat = x.hat + (g - n);
+  const int li = (int)(n / ny) - x.row0;
+  const double2 cc = ld2(c + g), h = ld2(hat + n), wS = ld2(x.k.wS + g), wN = ld2(x.k.wN + g);
+  const double hS = hat[n > 0 ? n - 1 : n], hN = hat[n + 2 < N ? n + 2 : n + 1];
+  y0 = cc.x + (wS.x * hS + wN.x * h.y);
+  y1 = cc.y + (wS.y * h.x + wN.y * hN);
+  if ((li & (kSeg - 1)) == 0) {
+    const double2 wW = ld2(x.k.wW + g), hW = ld2(hat + (n >= (size_t)ny ? n - ny : n));
+    y0 += wW.x * hW.x; y1 += wW.y * hW.y;
+  }
+  if ((li & (kSeg - 1)) == kSeg - 1 || li == x.nrows - 1) {
+    const double2 wE = ld2(x.k.wE + g), hE = ld2(hat + (n + ny < N ? n + ny : n));
+    y0 += wE.x * hE.x; y1 += wE.y * hE.y;
+  }
+}
+
+template <int V>
 __global__ void __launch_bounds__(kBlock) k_xl_spmv_v(XlVecs x, size_t N) {
   __shared__ double red[32];
   Scal* sc = x.k.scal + blockIdx.y;
   if (sc->state != 0) return;
   const size_t base = (size_t)blockIdx.y * N;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t stride = (size_t)V * gridDim.x * blockDim.x;
   double dot = 0.0;
-  for (size_t n = x.k.n_begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < x.k.n_end; n += stride) {
+  for (size_t n = x.k.n_begin + (size_t)V * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); n < x.k.n_end; n += stride) {
     const size_t g = base + n;
-    const double v = xl_apply(x, x.k.p, g, n, N, x.ny);
-    x.k.v[g] = v;
-    dot += x.k.rhs[g] * v;
+    if (V == 2) {
+      double v0, v1;
+      xl_apply2(x, x.k.p, g, n, N, x.ny, v0, v1);
+      st2(x.k.v + g, v0, v1);
+      const double2 rh = ld2(x.k.rhs + g);
+      dot += rh.x * v0 + rh.y * v1;
+    } else {
+      const double v = xl_apply(x, x.k.p, g, n, N, x.ny);
+      x.k.v[g] = v;
+      dot += x.k.rhs[g] * v;
+    }
   }
   double sums[1] = {dot};
   block_sums<1>(sums, red);
@@ -163,19 +191,29 @@ __global__ void __launch_bounds__(kBlock) k_xl_spmv_v(XlVecs x, size_t N) {
   }
 }
 
+template <int V>
 __global__ void __launch_bounds__(kBlock) k_xl_spmv_t(XlVecs x, size_t N) {
   __shared__ double red[2 * 32];
   Scal* sc = x.k.scal + blockIdx.y;
   if (sc->state != 0) return;
   const size_t base = (size_t)blockIdx.y * N;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t stride = (size_t)V * gridDim.x * blockDim.x;
   double ts = 0.0, tt = 0.0;
-  for (size_t n = x.k.n_begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < x.k.n_end; n += stride) {
+  for (size_t n = x.k.n_begin + (size_t)V * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); n < x.k.n_end; n += stride) {
     const size_t g = base + n;
-    const double t = xl_apply(x, x.k.s, g, n, N, x.ny);
-    x.k.t[g] = t;
-    ts += t * x.k.s[g];
-    tt += t * t;
+    if (V == 2) {
+      double t0, t1;
+      xl_apply2(x, x.k.s, g, n, N, x.ny, t0, t1);
+      st2(x.k.t + g, t0, t1);
+      const double2 sv = ld2(x.k.s + g);
+      ts += t0 * sv.x + t1 * sv.y;
+      tt += t0 * t0 + t1 * t1;
+    } else {
+      const double t = xl_apply(x, x.k.s, g, n, N, x.ny);
+      x.k.t[g] = t;
+      ts += t * x.k.s[g];
+      tt += t * t;
+    }
   }
   double sums[2] = {ts, tt};
   block_sums<2>(sums, red);
@@ -191,22 +229,32 @@ __global__ void __launch_bounds__(kBlock) k_xl_spmv_t(XlVecs x, size_t N) {
   }
 }
 
+template <int V>
 __global__ void __launch_bounds__(kBlock) k_xl_xr(XlVecs x, size_t N) {
   __shared__ double red[32];
   Scal* sc = x.k.scal + blockIdx.y;
   if (sc->state != 0) return;
   const size_t base = (size_t)blockIdx.y * N;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t stride = (size_t)V * gridDim.x * blockDim.x;
   const double omega = sc->omega;
   double dot = 0.0, rabs = 0.0;
-  for (size_t n = x.k.n_begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < x.k.n_end; n += stride) {
+  for (size_t n = x.k.n_begin + (size_t)V * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); n < x.k.n_end; n += stride) {
     const size_t g = base + n;
-    const double s = x.k.s[g];
-    x.k.x[g] += omega * x.hat[g];
-    const double r = s - omega * x.k.t[g];
-    x.k.r[g] = r;
-    dot += x.k.rhs[g] * r;
-    rabs = fmax(rabs, fabs(r));
+    if (V == 2) {
+      const double2 s = ld2(x.k.s + g), h = ld2(x.hat + g), xx = ld2(x.k.x + g), t = ld2(x.k.t + g), rh = ld2(x.k.rhs + g);
+      st2(x.k.x + g, xx.x + omega * h.x, xx.y + omega * h.y);
+      const double r0 = s.x - omega * t.x, r1 = s.y - omega * t.y;
+      st2(x.k.r + g, r0, r1);
+      dot += rh.x * r0 + rh.y * r1;
+      rabs = fmax(rabs, fmax(fabs(r0), fabs(r1)));
+    } else {
+      const double s = x.k.s[g];
+      x.k.x[g] += omega * x.hat[g];
+      const double r = s - omega * x.k.t[g];
+      x.k.r[g] = r;
+      dot += x.k.rhs[g] * r;
+      rabs = fmax(rabs, fabs(r));
+    }
   }
   double sums[1] = {dot};
   block_sums<1>(sums, red);
