@@ -772,8 +772,9 @@ static cudaError_t dispatch_xline(const XlineArgs& xa, int R, int nbatch, size_t
 
 // Engine 2: the whole call (nsteps time steps of every problem) is ONE kernel launch.
 // Number of sub-batches a host-buffer call is pipelined over (and within which problems are sorted
-// by cost): at least two waves of CTAs per sub-batch, at most 8.
-static int pipe_chunks(const sy2d_ctx* c) { return std::max(1, std::min(8, c->nbatch / (2 * c->sm_count))); }
+// by cost): at least one wave of CTAs per sub-batch (the tail of a sub-batch is filled by the next
+// one's CTAs, the streams run concurrently), at most 8.
+static int pipe_chunks(const sy2d_ctx* c) { return std::max(1, std::min(8, c->nbatch / c->sm_count)); }
 
 // Engine 2: nsteps time steps of every problem in ONE kernel launch per sub-batch.  With host
 // buffers (h_in / h_out non-NULL) the batch is cut into pipe_chunks() contiguous sub-batches on
