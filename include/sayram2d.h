@@ -44,9 +44,13 @@ enum { SY2D_DIRICHLET = 0, SY2D_ZEROFLUX = 1 };
 
 /* preconditioner inside the BiCGSTAB loop */
 enum {
-  SY2D_PRECOND_AUTO = -1,  /* XLINE where the engine supports it (engine 2, nx <= 80, ny <= 128), else JACOBI */
+  SY2D_PRECOND_AUTO = -1,  /* engine 2: XLINE where the grid fits (nx <= 80, ny <= 128), else JACOBI;
+                              engine 1: MG where the grid fits (nx <= 2048, ny a multiple of 4), else XLINE */
   SY2D_PRECOND_JACOBI = 0, /* the unit-diagonal scaling itself */
-  SY2D_PRECOND_XLINE = 1   /* right preconditioning by the tridiagonal along i (alpha0): ~4x fewer iterations */
+  SY2D_PRECOND_XLINE = 1,  /* right preconditioning by the tridiagonal along i (alpha0): ~4x fewer iterations
+                              (engine 1: block-Jacobi with 16-row line segments) */
+  SY2D_PRECOND_MG = 2      /* engine 1: one V(1,1) multigrid cycle, semi-coarsening along j (log E), damped
+                              whole-x-line Jacobi smoother on every level: O(15) iterations independent of the grid */
 };
 
 typedef struct {
@@ -58,7 +62,9 @@ typedef struct {
   int use_graph;     /* 1: replay the iteration chunk as a CUDA graph; default 1 */
   int engine;        /* 0 auto (2 when nx*ny <= 16384, else 1), 1 lockstep multi-kernel,
                         2 one persistent CTA per problem (whole time loop in one launch) */
-  int reserved[5];
+  int mg_levels;     /* SY2D_PRECOND_MG: maximum number of grid levels (0 = default 5) */
+  int reserved[4];   /* reserved[0]: force the one-thread-per-cell assembly (tests); reserved[1]: slab mode, fixed
+                        iteration budget without a convergence error (bench) */
 } sy2d_options;
 
 typedef struct {
@@ -74,7 +80,7 @@ typedef struct {
   long long iters_sum_all;    /* iterations summed over steps AND batch members (mean = / (steps*nbatch));
                                  lockstep engine: iters_total * nbatch (all members iterate together) */
   int engine;                 /* engine that ran: 1 lockstep multi-kernel, 2 one CTA per problem */
-  int precond;                /* preconditioner that ran (SY2D_PRECOND_JACOBI or _XLINE) */
+  int precond;                /* preconditioner that ran (SY2D_PRECOND_JACOBI, _XLINE or _MG) */
 } sy2d_stats;
 
 /* per-kernel device time of profiled sy2d_step calls (see sy2d_set_profiling) */
@@ -88,6 +94,9 @@ enum {
   SY2D_K_FINISH,       /* f = c (1 + d), statistics                    */
   SY2D_K_OTHER,        /* true-residual check                          */
   SY2D_K_PROBLEM_STEPS,/* engine 2: whole time steps, one CTA per problem */
+  SY2D_K_MG_LINE,      /* multigrid: whole-column Thomas solves (smoother), all levels */
+  SY2D_K_MG_RESID,     /* multigrid: residual + restriction / prolongation + residual, all levels */
+  SY2D_K_MG_SETUP,     /* multigrid: coarse operators and line factorisations, once per time step */
   SY2D_K_COUNT
 };
 typedef struct {
@@ -150,6 +159,12 @@ long long sy2d_step_count(const sy2d_ctx* ctx);
 int sy2d_dump_operator(sy2d_ctx* ctx, double* diags, double* rhs);
 /* vertex_f_ (Solver.cc:292-422) for the current f: [nbatch][nx+1][ny+1]. For parity tests. */
 int sy2d_dump_vertex_f(sy2d_ctx* ctx, double* vf);
+
+/* Test hook for the multigrid preconditioner (SY2D_PRECOND_MG): assembles the scaled operator of the
+ * current f, builds the hierarchy and applies ONE V-cycle to r -> z ([nbatch][nx][ny], host).  w4 (may be
+ * NULL) receives the scaled unit-diagonal operator [4][nbatch][nx][ny] = wW, wE, wS, wN; om (may be NULL)
+ * the row weights M_KK c_K.  Does not advance time. */
+int sy2d_debug_vcycle(sy2d_ctx* ctx, const double* r, double* z, double* w4, double* om);
 
 /* Per-kernel CUDA-event timing of subsequent sy2d_step calls (adds event overhead; off by default). */
 int sy2d_set_profiling(sy2d_ctx* ctx, int on);

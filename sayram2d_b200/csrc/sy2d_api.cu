@@ -18,6 +18,7 @@
 #include "sy2d_problem_kernel.cuh"
 #include "sy2d_xline_kernel.cuh"
 #include "sy2d_xline_lockstep.cuh"
+#include "sy2d_mg.cuh"
 
 using namespace sy2d;
 
@@ -50,6 +51,13 @@ struct sy2d_ctx {
   double *wW = nullptr, *wE = nullptr, *wS = nullptr, *wN = nullptr, *rhs = nullptr;
   double *x = nullptr, *r = nullptr, *p = nullptr, *v = nullptr, *s = nullptr, *t = nullptr;
   double *xl_l = nullptr, *xl_dinv = nullptr, *xl_e = nullptr, *xl_hat = nullptr;  // engine 1 x-line: LU factors, hat vector
+  // engine 1 multigrid preconditioner (sy2d_mg.cuh): level 0 reuses wW..wN, xl_l/xl_dinv/xl_e (line LU) and
+  // xl_hat (phat); everything else lives in mg_bufs
+  int mg_nlev = 0, mg_seg = 16;
+  MgLevels mg;
+  double* mg_rc[kMgMaxLevels] = {};   // writable right-hand sides of the coarse levels
+  double *mg_om0 = nullptr, *mg_shat = nullptr;
+  std::vector<double*> mg_bufs;
   Scal* scal = nullptr;
   int* d_nactive = nullptr;
   int* h_nactive = nullptr;  // pinned
@@ -139,10 +147,24 @@ unsigned capped_blocks(const sy2d_ctx* c, size_t work_items_per_problem, int thr
   return (unsigned)std::min(need, cap);
 }
 
-// Engine 1 uses the segmented x-line preconditioner unless Jacobi is requested (needs at least one full segment)
+// Multigrid (sy2d_mg.cuh) needs whole columns inside one CTA of the line kernel (nx <= 64 segments of 16 or
+// 32 rows), pairs of columns on every level (ny a multiple of 4 gives at least two levels) and a single GPU.
+int mg_level_count(const sy2d_ctx* c) {
+  if (c->slab || c->nx > 2048 || c->nx < 8 || c->ny % 4 != 0 || c->ny < 16) return 0;
+  const int want = c->opt.mg_levels > 0 ? std::min(c->opt.mg_levels, kMgMaxLevels) : 5;
+  int nlev = 1, ny = c->ny;
+  while (nlev < want && ny % 4 == 0 && ny >= 16) { ny /= 2; ++nlev; }   // the coarsest level keeps an even ny >= 8
+  return nlev >= 2 ? nlev : 0;
+}
+bool lockstep_mg(const sy2d_ctx* c) {
+  if (c->opt.precond != SY2D_PRECOND_AUTO && c->opt.precond != SY2D_PRECOND_MG) return false;
+  return mg_level_count(c) > 0;
+}
+// Engine 1 falls back to the segmented x-line preconditioner (needs at least one full segment)
 bool lockstep_xline(const sy2d_ctx* c) {
   const int rows = c->slab ? c->nx - 2 : c->nx;
-  return c->opt.precond != SY2D_PRECOND_JACOBI && rows >= kSeg;
+  if (lockstep_mg(c)) return false;
+  return c->opt.precond != SY2D_PRECOND_JACOBI && c->opt.precond != SY2D_PRECOND_MG && rows >= kSeg;
 }
 
 XlVecs xl_vecs(const sy2d_ctx* c);
@@ -204,7 +226,129 @@ void launch_iteration_xline(sy2d_ctx* c) {
   { Prof p(c, SY2D_K_XR_UPDATE); if (v2) k_xl_xr<2><<<gc, kBlock, 0, c->stream>>>(x, c->N); else k_xl_xr<1><<<gc, kBlock, 0, c->stream>>>(x, c->N); }
 }
 
+
+// ---- multigrid preconditioner: allocation, per-step setup, V-cycle, iteration ----
+int mg_alloc(sy2d_ctx* c) {
+  const int nlev = mg_level_count(c);
+  if (c->mg_nlev == nlev && !c->mg_bufs.empty()) return SY2D_OK;
+  for (double* b : c->mg_bufs) cudaFree(b);
+  c->mg_bufs.clear();
+  int rc = xl_alloc(c);
+  if (rc) return rc;
+  auto grab = [&](size_t n, double** out) -> int {
+    CU(cudaMalloc(reinterpret_cast<void**>(out), n * sizeof(double)));
+    CU(cudaMemsetAsync(*out, 0, n * sizeof(double), c->stream));
+    c->mg_bufs.push_back(*out);
+    return SY2D_OK;
+  };
+  c->mg_seg = c->nx <= 1024 ? 16 : 32;
+  std::memset(&c->mg, 0, sizeof c->mg);
+  c->mg.nlev = nlev;
+  double* t0 = nullptr;
+  if ((rc = grab(c->total, &c->mg_om0)) || (rc = grab(c->total, &c->mg_shat)) || (rc = grab(c->total, &t0))) return rc;
+  MgLevel& l0 = c->mg.lv[0];
+  l0.wW = c->wW; l0.wE = c->wE; l0.wS = c->wS; l0.wN = c->wN; l0.om = c->mg_om0;
+  l0.l = c->xl_l; l0.dinv = c->xl_dinv; l0.e = c->xl_e;
+  l0.r = nullptr; l0.z = nullptr; l0.t = t0;
+  l0.ny = c->ny; l0.N = c->N;
+  int ny = c->ny;
+  for (int k = 1; k < nlev; ++k) {
+    ny /= 2;
+    const size_t n = (size_t)c->nx * ny * c->nbatch;
+    double* a[11];
+    for (double*& q : a) if ((rc = grab(n, &q))) return rc;
+    MgLevel& lv = c->mg.lv[k];
+    lv.wW = a[0]; lv.wE = a[1]; lv.wS = a[2]; lv.wN = a[3]; lv.om = a[4];
+    lv.l = a[5]; lv.dinv = a[6]; lv.e = a[7];
+    lv.r = a[8]; c->mg_rc[k] = a[8];
+    lv.z = a[9]; lv.t = a[10];
+    lv.ny = ny; lv.N = (size_t)c->nx * ny;
+  }
+  c->mg_nlev = nlev;
+  return SY2D_OK;
+}
+
+// coarse operators (level by level) and the line LU of every level (one launch) for this step's operator
+void mg_setup(sy2d_ctx* c) {
+  Prof p(c, SY2D_K_MG_SETUP);
+  for (int k = 0; k + 1 < c->mg_nlev; ++k) {
+    const MgLevel& f = c->mg.lv[k];
+    const MgLevel& g = c->mg.lv[k + 1];
+    k_mg_coarsen<<<dim3(capped_blocks(c, g.N, kBlock), (unsigned)c->nbatch, 1), kBlock, 0, c->stream>>>(
+        f, const_cast<double*>(g.wW), const_cast<double*>(g.wE), const_cast<double*>(g.wS), const_cast<double*>(g.wN),
+        const_cast<double*>(g.om), c->nx);
+  }
+  k_mg_factor<<<dim3((unsigned)((c->ny + 127) / 128), (unsigned)c->nbatch, (unsigned)c->mg_nlev), 128, 0, c->stream>>>(c->mg, c->nx);
+  c->launches += c->mg_nlev;
+}
+
+template <int MODE>
+void mg_line(sy2d_ctx* c, const MgLevel& lv, const double* zc) {
+  Prof p(c, SY2D_K_MG_LINE);
+  const MgArgs a{c->scal, c->nx};
+  const int nseg = (c->nx + c->mg_seg - 1) / c->mg_seg;
+  const int threads = (nseg * kMgCols + 31) / 32 * 32;
+  const size_t smem = (size_t)3 * nseg * kMgCols * sizeof(double);
+  const dim3 g((unsigned)((lv.ny + kMgCols - 1) / kMgCols), (unsigned)c->nbatch, 1);
+  if (c->mg_seg == 16) k_mg_line<16, MODE><<<g, threads, smem, c->stream>>>(lv, zc, a);
+  else k_mg_line<32, MODE><<<g, threads, smem, c->stream>>>(lv, zc, a);
+}
+
+template <int KIND>
+void mg_resid(sy2d_ctx* c, const MgLevel& lv, const double* zc, const double* omc, double* rc) {
+  Prof p(c, SY2D_K_MG_RESID);
+  const MgArgs a{c->scal, c->nx};
+  k_mg_resid<KIND><<<dim3(capped_blocks(c, lv.N / 2, kBlock), (unsigned)c->nbatch, 1), kBlock, 0, c->stream>>>(lv, zc, omc, rc, a);
+}
+
+// z = V(r): one V(1,1) cycle on the fine grid; r and z are [nbatch][nx][ny] device vectors
+void mg_vcycle(sy2d_ctx* c, const double* r, double* z) {
+  const int L = c->mg_nlev;
+  MgLevel lv0 = c->mg.lv[0];
+  lv0.r = r; lv0.z = z;
+  auto level = [&](int k) -> const MgLevel& { return k == 0 ? lv0 : c->mg.lv[k]; };
+  const double scale0 = c->cur_cells;
+  for (int k = 0; k + 1 < L; ++k) {
+    c->cur_cells = scale0 / (double)(1 << k);
+    mg_line<0>(c, level(k), nullptr);
+    mg_resid<1>(c, level(k), nullptr, c->mg.lv[k + 1].om, c->mg_rc[k + 1]);
+  }
+  c->cur_cells = scale0 / (double)(1 << (L - 1));
+  mg_line<0>(c, level(L - 1), nullptr);
+  for (int sweep = 1; sweep < kMgCoarseSweeps; ++sweep) {
+    mg_resid<0>(c, level(L - 1), nullptr, nullptr, nullptr);
+    mg_line<2>(c, level(L - 1), nullptr);
+  }
+  for (int k = L - 2; k >= 0; --k) {
+    c->cur_cells = scale0 / (double)(1 << k);
+    mg_resid<2>(c, level(k), c->mg.lv[k + 1].z, nullptr, nullptr);
+    mg_line<1>(c, level(k), c->mg.lv[k + 1].z);
+  }
+  c->cur_cells = scale0;
+}
+int mg_kernels_per_vcycle(const sy2d_ctx* c) { return 4 * (c->mg_nlev - 1) + 1 + 2 * (kMgCoarseSweeps - 1); }
+
+void launch_iteration_mg(sy2d_ctx* c) {
+  KrylovVecs k = krylov(c);
+  const dim3 g2(capped_blocks(c, c->N / 2, kBlock), (unsigned)c->nbatch, 1);
+  double* phat = c->xl_hat;
+  double* shat = c->mg_shat;
+  { Prof p(c, SY2D_K_P_UPDATE); k_p_update2<<<g2, kBlock, 0, c->stream>>>(k, c->N); }
+  mg_vcycle(c, c->p, phat);
+  {
+    Prof p(c, SY2D_K_SPMV_V);
+    KrylovVecs kv = k;
+    kv.p = phat;   // v = A phat, (rhat, v)
+    k_spmv_v2<<<g2, kBlock, 0, c->stream>>>(kv, c->N, c->ny);
+  }
+  { Prof p(c, SY2D_K_S_UPDATE); k_s_update2<<<g2, kBlock, 0, c->stream>>>(k, c->N); }
+  mg_vcycle(c, c->s, shat);
+  { Prof p(c, SY2D_K_SPMV_T); k_mg_spmv_t<<<g2, kBlock, 0, c->stream>>>(k, shat, c->N, c->ny); }
+  { Prof p(c, SY2D_K_XR_UPDATE); k_mg_xr<<<g2, kBlock, 0, c->stream>>>(k, phat, shat, c->N); }
+}
+
 void launch_iteration(sy2d_ctx* c) {
+  if (lockstep_mg(c)) { launch_iteration_mg(c); return; }
   if (lockstep_xline(c)) { launch_iteration_xline(c); return; }
   const KrylovVecs k = krylov(c);
   if (c->ny % 2 == 0) {  // two cells per thread, 16-byte accesses
@@ -223,21 +367,24 @@ void launch_iteration(sy2d_ctx* c) {
   { Prof p(c, SY2D_K_SPMV_T); k_spmv_t<<<g, kBlock, 0, c->stream>>>(k, c->N, c->ny); }
   { Prof p(c, SY2D_K_XR_UPDATE); k_xr_update<<<g, kBlock, 0, c->stream>>>(k, c->N); }
 }
-constexpr int kKernelsPerIteration = 5;
+int kernels_per_iteration(const sy2d_ctx* c) { return lockstep_mg(c) ? 5 + 2 * mg_kernels_per_vcycle(c) : 5; }
+// with multigrid an iteration is ~50 launches and a solve ~15 iterations: poll more often
+int effective_check_every(const sy2d_ctx* c) { return lockstep_mg(c) ? std::min(c->opt.check_every, 4) : c->opt.check_every; }
 
 int build_chunk_graph(sy2d_ctx* c) {
-  const int variant = lockstep_xline(c) ? 1 : 0;
-  if (c->chunk_exec && c->chunk_iters == c->opt.check_every && c->chunk_variant == variant) return SY2D_OK;
+  const int variant = lockstep_mg(c) ? 2 + c->mg_nlev : (lockstep_xline(c) ? 1 : 0);
+  const int check_every = effective_check_every(c);
+  if (c->chunk_exec && c->chunk_iters == check_every && c->chunk_variant == variant) return SY2D_OK;
   c->chunk_variant = variant;
   if (c->chunk_exec) { cudaGraphExecDestroy(c->chunk_exec); c->chunk_exec = nullptr; }
   cudaGraph_t graph = nullptr;
   CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-  for (int it = 0; it < c->opt.check_every; ++it) launch_iteration(c);
+  for (int it = 0; it < check_every; ++it) launch_iteration(c);
   CU(cudaMemcpyAsync(c->h_nactive, c->d_nactive, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamEndCapture(c->stream, &graph));
   CU(cudaGraphInstantiate(&c->chunk_exec, graph, 0));
   cudaGraphDestroy(graph);
-  c->chunk_iters = c->opt.check_every;
+  c->chunk_iters = check_every;
   return SY2D_OK;
 }
 
@@ -578,6 +725,7 @@ void sy2d_destroy(sy2d_ctx* c) {
                     c->x, c->r, c->p, c->v, c->s, c->t, c->stage, c->xl_scratch, c->xl_l, c->xl_dinv, c->xl_e, c->xl_hat};
   for (double* b : bufs) if (b) cudaFree(b);
   if (c->scal) cudaFree(c->scal);
+  for (double* b : c->mg_bufs) cudaFree(b);
   for (cudaStream_t sk : c->pipe_streams) if (sk) { cudaStreamSynchronize(sk); cudaStreamDestroy(sk); }
   for (cudaEvent_t ek : c->pipe_events) if (ek) cudaEventDestroy(ek);
   if (c->pipe_start) cudaEventDestroy(c->pipe_start);
@@ -600,7 +748,7 @@ int sy2d_set_options(sy2d_ctx* c, const sy2d_options* o) {
   if (!c || !o) return SY2D_ERR_INVALID;
   if (!(o->tol > 0.0) || o->maxit < 1 || o->check_every < 1)
     return fail(c, SY2D_ERR_INVALID, "sy2d_set_options: tol, maxit and check_every must be positive");
-  if (o->precond < SY2D_PRECOND_AUTO || o->precond > SY2D_PRECOND_XLINE)
+  if (o->precond < SY2D_PRECOND_AUTO || o->precond > SY2D_PRECOND_MG)
     return fail(c, SY2D_ERR_INVALID, "sy2d_set_options: unknown preconditioner %d", o->precond);
   c->opt = *o;
   return SY2D_OK;
@@ -911,15 +1059,19 @@ int sy2d_step(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
   const dim3 g = grid_of(c);
   const Geometry geo = geometry(c);
   const bool graph = c->opt.use_graph && !c->profiling;
-  const int check_every = c->profiling ? 1 : c->opt.check_every;  // profiling: no zero-work launches
+  const int check_every = c->profiling ? 1 : effective_check_every(c);  // profiling: no zero-work launches
   c->launches = 0;
   sy2d_stats st;
   std::memset(&st, 0, sizeof st);
   st.engine = 1;
+  const bool mg = lockstep_mg(c);
   const bool xl = lockstep_xline(c);
   if (c->opt.precond == SY2D_PRECOND_XLINE && !xl) return fail(c, SY2D_ERR_INVALID, "sy2d_step: the x-line preconditioner needs nx >= %d", kSeg);
-  st.precond = xl ? SY2D_PRECOND_XLINE : SY2D_PRECOND_JACOBI;
+  if (c->opt.precond == SY2D_PRECOND_MG && !mg)
+    return fail(c, SY2D_ERR_INVALID, "sy2d_step: the multigrid preconditioner needs engine 1 on one GPU, 8 <= nx <= 2048 and ny a multiple of 4, >= 16");
+  st.precond = mg ? SY2D_PRECOND_MG : (xl ? SY2D_PRECOND_XLINE : SY2D_PRECOND_JACOBI);
   if (xl) { rc = xl_alloc(c); if (rc) return rc; }
+  if (mg) { rc = mg_alloc(c); if (rc) return rc; }
   if (graph) { rc = build_chunk_graph(c); if (rc) return rc; }
   CU(cudaEventRecord(c->ev_call0, c->stream));
   for (int step = 0; step < nsteps; ++step) {
@@ -931,6 +1083,7 @@ int sy2d_step(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
       std::memset(&o, 0, sizeof o);
       o.wW = c->wW; o.wE = c->wE; o.wS = c->wS; o.wN = c->wN; o.rhs = c->rhs; o.cs = c->cs;
       o.scal = c->scal; o.n_active = c->d_nactive; o.tol = c->opt.tol; o.local_rows = c->nx;
+      if (mg) o.om = c->mg_om0;
       if (c->nx >= 2 * kTI && c->ny >= kTJ && c->opt.reserved[0] == 0) {  // reserved[0] = 1 forces the per-cell kernel (tests)
         const int tiles_i = (c->nx + kTI - 1) / kTI, tiles_j = (c->ny + kTJ - 1) / kTJ;
         k_assemble_tiled<<<dim3(capped_blocks(c, (size_t)tiles_i * tiles_j, 1), (unsigned)c->nbatch, 1), kTI * kTJ, 0, c->stream>>>(
@@ -946,6 +1099,7 @@ int sy2d_step(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
       k_xl_factor<<<dim3(capped_blocks(c, (size_t)nseg * c->ny, kBlock), (unsigned)c->nbatch, 1), kBlock, 0, c->stream>>>(x, c->N);
       c->launches += 1;
     }
+    if (mg) mg_setup(c);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(c->h_nactive, c->d_nactive, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -962,7 +1116,7 @@ int sy2d_step(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
       }
       CU(cudaStreamSynchronize(c->stream));
       launched += check_every;
-      c->launches += (long long)check_every * kKernelsPerIteration;
+      c->launches += (long long)check_every * kernels_per_iteration(c);
     }
     c->cur_cells = (double)c->total;
     // verification + finish
@@ -1062,6 +1216,48 @@ int sy2d_dump_vertex_f(sy2d_ctx* c, double* vf) {
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   cudaFree(d_vf);
   if (e != cudaSuccess) return fail(c, SY2D_ERR_CUDA, "sy2d_dump_vertex_f: %s", cudaGetErrorString(e));
+  return SY2D_OK;
+}
+
+// Test hook: assembles the scaled operator of the CURRENT f (as the next sy2d_step would), sets the
+// multigrid hierarchy up and applies ONE V-cycle to r (host, [nbatch][nx][ny]) -> z.  Optionally returns
+// the scaled operator (w4 = [4][nbatch][nx][ny]: wW, wE, wS, wN) and the row weights om.
+int sy2d_debug_vcycle(sy2d_ctx* c, const double* r, double* z, double* w4, double* om) {
+  if (!c || !r || !z) return SY2D_ERR_INVALID;
+  int rc = ready(c, "sy2d_debug_vcycle");
+  if (rc) return rc;
+  CU(cudaSetDevice(c->device));
+  const int keep = c->opt.precond;
+  c->opt.precond = SY2D_PRECOND_MG;
+  const bool ok = !c->slab && lockstep_mg(c);
+  if (ok) rc = mg_alloc(c);
+  c->opt.precond = keep;
+  if (!ok) return fail(c, SY2D_ERR_INVALID, "sy2d_debug_vcycle: multigrid does not support this grid");
+  if (rc) return rc;
+  CU(cudaMemsetAsync(c->d_nactive, 0, sizeof(int), c->stream));
+  CU(cudaMemsetAsync(c->scal, 0, c->nbatch * sizeof(Scal), c->stream));
+  AssembleOut o;
+  std::memset(&o, 0, sizeof o);
+  o.wW = c->wW; o.wE = c->wE; o.wS = c->wS; o.wN = c->wN; o.rhs = c->rhs; o.cs = c->cs; o.om = c->mg_om0;
+  o.scal = c->scal; o.n_active = c->d_nactive; o.tol = -1.0;   // every problem stays active
+  o.local_rows = c->nx;
+  k_assemble<0><<<grid_of(c), kBlock, 0, c->stream>>>(c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud, geometry(c), o);
+  CU(cudaGetLastError());
+  mg_setup(c);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(c->p, r, c->total * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  mg_vcycle(c, c->p, c->xl_hat);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(z, c->xl_hat, c->total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (w4) {
+    double* src[4] = {c->wW, c->wE, c->wS, c->wN};
+    for (int k = 0; k < 4; ++k)
+      CU(cudaMemcpyAsync(w4 + (size_t)k * c->total, src[k], c->total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (om) CU(cudaMemcpyAsync(om, c->mg_om0, c->total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaMemsetAsync(c->scal, 0, c->nbatch * sizeof(Scal), c->stream));
+  CU(cudaStreamSynchronize(c->stream));
   return SY2D_OK;
 }
 

@@ -300,13 +300,15 @@ __host__ __device__ __forceinline__ void assemble_row(const double* __restrict__
 
 struct Scaled {  // row of the scaled unit-diagonal system A d = rhs
   double wW, wE, wS, wN, rhs, cs;
+  double om;     // M_KK c_K: the row was divided by this
 };
 
 // Column scale c = f*yprev (neighbours too), row scale 1/(M_KK c_K); rhs = D_r R - A 1.
 __host__ __device__ __forceinline__ void scale_row(const Row& r, double ypC, double ypW, double ypE, double ypS,
                                                    double ypN, Scaled& s) {
   const double cs0 = r.f00 * ypC;
-  const double dscale = sy2d_div(1.0, r.diag * cs0);
+  s.om = r.diag * cs0;
+  const double dscale = sy2d_div(1.0, s.om);
   s.wW = r.oW * (r.fW * ypW) * dscale;
   s.wE = r.oE * (r.fE * ypE) * dscale;
   s.wS = r.oS * (r.fS * ypS) * dscale;
@@ -330,6 +332,7 @@ __host__ __device__ __forceinline__ XlineFactor xline_factor(double wW_i, double
 struct AssembleOut {
   // MODE 0 (solve): scaled unit-diagonal operator + Krylov start
   double *wW, *wE, *wS, *wN, *rhs, *cs;
+  double* om;   // optional: row weight M_KK c_K = 1 / (row scale), the multigrid restriction weight (may be NULL)
   Scal* scal;
   int* n_active;
   double tol;
@@ -378,6 +381,7 @@ __global__ void __launch_bounds__(kBlock) k_assemble(const double* __restrict__ 
       o.wW[c0] = sc.wW; o.wE[c0] = sc.wE; o.wS[c0] = sc.wS; o.wN[c0] = sc.wN;
       o.rhs[c0] = sc.rhs;
       o.cs[c0] = sc.cs;
+      if (o.om) o.om[c0] = sc.om;
       rr = sc.rhs * sc.rhs;
       rabs = fabs(sc.rhs);
     }
@@ -540,13 +544,15 @@ __global__ void __launch_bounds__(kTI * kTJ, 4) k_assemble_tiled(const double* _
       diag += Ud[c0];
       R += U[c0] * f00;
       const double cs0 = cs_[a + 1][b + 1];
-      const double dscale = sy2d_div(1.0, diag * cs0);
+      const double om = diag * cs0;
+      const double dscale = sy2d_div(1.0, om);
       const double wW = oW * cs_[a][b + 1] * dscale, wE = oE * cs_[a + 2][b + 1] * dscale;
       const double wS = oS * cs_[a + 1][b] * dscale, wN = oN * cs_[a + 1][b + 2] * dscale;
       const double rhs = R * dscale - 1.0 - ((wW + wE) + (wS + wN));
       o.wW[c0] = wW; o.wE[c0] = wE; o.wS[c0] = wS; o.wN[c0] = wN;
       o.rhs[c0] = rhs;
       o.cs[c0] = cs0;
+      if (o.om) o.om[c0] = om;
       rr += rhs * rhs;
       rabs = fmax(rabs, fabs(rhs));
     }

@@ -1,0 +1,362 @@
+// Engine 1 with a multigrid preconditioner: y-semi-coarsening + damped x-line Jacobi smoothing.
+//
+// Why: the scaled operator A = I + W/E/S/N couplings is strongly anisotropic along i (alpha0):
+// relative to the mass term the x coupling is O(1e4) and the y coupling O(4e2) at 1024^2.  Exact
+// x-line solves remove the x stiffness, which leaves a 1-D-like problem along
+// j (log E) whose condition number grows like ny^2.  Coarsening j only, with whole x-lines as the
+// smoother on every level, is the textbook cure for this kind of anisotropy: at 1024^2 BiCGSTAB needs
+// 14-16 iterations per time step instead of 290 (full lines) / 390 (16-row segments); prototype and
+// measurements in profiles/proto_mg.py.
+//
+// Levels l = 0..L-1, level l has nx x (ny >> l) cells, all stored like the fine grid ([i][j], j
+// fastest).  Every level holds a UNIT-DIAGONAL 5-point operator A_l = (wW, wE, wS, wN) plus the row
+// weight om_l with B_l = diag(om_l) A_l the "conservative" form (level 0: om = 1, B_0 = A).
+// Coarsening by aggregating the pair (i,2J), (i,2J+1):
+//   B_{l+1} = P^T B_l P   (piecewise-constant P, plain Galerkin)  for the W/E couplings and the diagonal,
+//   the S/N couplings between aggregates are multiplied by theta = 1/2 and the same amount is taken
+//   off the diagonal of the column they sit in (column sums kept): for a 1-D Laplacian this is exactly
+//   the rediscretisation on cells twice as high; plain Galerkin with constant P would be 2x too stiff.
+// V(1,1) cycle, damping kOmega:
+//   z  = omega T^-1 r                                   k_mg_line<MODE 0>
+//   rc = P^T om (r - A z) / om_c                        k_mg_resid<restrict>
+//   zc = V(rc)
+//   t  = r - A (z + P zc)                               k_mg_resid<prolong>
+//   z  = z + P zc + omega T^-1 t                        k_mg_line<MODE 1>
+// coarsest level: kCoarseSweeps damped line-Jacobi sweeps.
+// T = tridiag(wW, 1, wE) along i over the WHOLE column, solved exactly by a partitioned Thomas
+// algorithm: a thread owns kMgSeg consecutive rows of one column, runs both recurrences in registers
+// with carry-in 0, the per-segment affine maps (carry -> last value) are composed by a warp-shuffle
+// scan over the segments of the column, and a correction pass adds carry * (prefix product).  A CTA
+// covers all segments of kMgCols adjacent columns, so neighbouring threads touch adjacent addresses.
+#pragma once
+#include "sy2d_kernels.cuh"
+
+namespace sy2d {
+
+constexpr int kMgMaxLevels = 8;
+constexpr int kMgCols = 8;         // columns per CTA of the line kernel (64-byte row chunks)
+constexpr double kMgOmega = 0.7;   // line-Jacobi damping
+constexpr double kMgTheta = 0.5;   // rescaling of the inter-aggregate couplings
+constexpr int kMgCoarseSweeps = 4;
+
+struct MgLevel {
+  const double *wW, *wE, *wS, *wN;  // unit-diagonal operator
+  const double* om;                 // row weights (nullptr on level 0: all ones)
+  double *l, *dinv, *e;             // LU of the x-lines: l_i = wW_i/d_{i-1}, 1/d_i, wE_i/d_i
+  const double* r;                  // right-hand side of the level (level 0: the vector to precondition)
+  double *z, *t;                    // solution of the level, work vector
+  int ny;                           // columns of this level
+  size_t N;                         // nx * ny
+};
+
+struct MgArgs {
+  const Scal* scal;   // converged problems skip all work
+  int nx;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Setup, once per time step
+// ---------------------------------------------------------------------------------------------
+
+// Coarse operator of level l+1 from level l.  One thread per coarse cell (i, J).
+__global__ void __launch_bounds__(kBlock) k_mg_coarsen(MgLevel f, double* __restrict__ cW, double* __restrict__ cE,
+                                                       double* __restrict__ cS, double* __restrict__ cN,
+                                                       double* __restrict__ cOm, int nx) {
+  const int nyf = f.ny, nyc = nyf >> 1;
+  const size_t Nc = (size_t)nx * nyc;
+  const size_t bf = (size_t)blockIdx.y * f.N, bc = (size_t)blockIdx.y * Nc;
+  for (size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < Nc; n += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(n / nyc), J = (int)(n - (size_t)i * nyc);
+    const size_t a = bf + (size_t)i * nyf + 2 * J;   // fine cells a = (i, 2J), b = a + 1
+    const double2 wW = ld2(f.wW + a), wE = ld2(f.wE + a), wS = ld2(f.wS + a), wN = ld2(f.wN + a);
+    double2 om = make_double2(1.0, 1.0);
+    if (f.om) om = ld2(f.om + a);
+    // entries of the neighbouring aggregates that sit in this aggregate's column
+    double sUp = 0.0, nDn = 0.0;   // row (J+1) col J: om wS of cell (i, 2J+2);  row (J-1) col J: om wN of cell (i, 2J-1)
+    if (J + 1 < nyc) sUp = (f.om ? f.om[a + 2] : 1.0) * f.wS[a + 2];
+    if (J > 0) nDn = (f.om ? f.om[a - 1] : 1.0) * f.wN[a - 1];
+    const double d = om.x * (1.0 + wN.x) + om.y * (1.0 + wS.y) + (1.0 - kMgTheta) * (sUp + nDn);
+    const double inv = sy2d_div(1.0, d);
+    cW[bc + n] = (om.x * wW.x + om.y * wW.y) * inv;
+    cE[bc + n] = (om.x * wE.x + om.y * wE.y) * inv;
+    cS[bc + n] = kMgTheta * om.x * wS.x * inv;
+    cN[bc + n] = kMgTheta * om.y * wN.y * inv;
+    cOm[bc + n] = d;
+  }
+}
+
+struct MgLevels {
+  MgLevel lv[kMgMaxLevels];
+  int nlev;
+};
+
+// LU of every x-line of every level: one thread per (level, column), sequential along i.  The
+// recurrence d_i = 1 - wW_i wE_{i-1} / d_{i-1} has one reciprocal on its critical path.
+__global__ void __launch_bounds__(128) k_mg_factor(MgLevels L, int nx) {
+  const MgLevel& lv = L.lv[blockIdx.z];
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= lv.ny) return;
+  const size_t base = (size_t)blockIdx.y * lv.N + j;
+  double dinv_prev = 0.0, wE_prev = 0.0;
+  for (int i = 0; i < nx; ++i) {
+    const size_t n = base + (size_t)i * lv.ny;
+    const double l = lv.wW[n] * dinv_prev;          // 0 on the first row (wW = 0 there as well)
+    const double d = 1.0 - l * wE_prev;
+    const double dinv = sy2d_div(1.0, d);
+    const double wE = lv.wE[n];
+    lv.l[n] = l;
+    lv.dinv[n] = dinv;
+    lv.e[n] = wE * dinv;
+    dinv_prev = dinv;
+    wE_prev = wE;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Whole-column Thomas solves, partitioned over the threads of a CTA
+// ---------------------------------------------------------------------------------------------
+
+// Carry-in of every segment of the columns of this CTA from the per-segment affine maps
+// carry_out = A[s] + P[s] * carry_in.  Warp w scans column w, w + nwarps, ...; a lane owns q =
+// ceil(nseg/32) consecutive segments.  `reverse`: segments are chained from the last to the first.
+// sA/sP/sC are [nseg][kMgCols].  All threads of the CTA call this (it contains no barrier).
+__device__ __forceinline__ void mg_carry_scan(const double* sA, const double* sP, double* sC, int nseg, bool reverse) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int q = (nseg + 31) >> 5;
+  for (int col = w; col < kMgCols; col += nw) {
+    // lane-local composition of its q segments
+    double A = 0.0, P = 1.0;
+    for (int k = 0; k < q; ++k) {
+      const int s = lane * q + k;
+      if (s < nseg) {
+        const int ss = reverse ? nseg - 1 - s : s;
+        const double a = sA[ss * kMgCols + col], p = sP[ss * kMgCols + col];
+        A = a + p * A;
+        P = p * P;
+      }
+    }
+    // inclusive scan of the affine maps over the lanes
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double Ao = __shfl_up_sync(0xffffffffu, A, o), Po = __shfl_up_sync(0xffffffffu, P, o);
+      if (lane >= o) { A = A + P * Ao; P = P * Po; }
+    }
+    double c = __shfl_up_sync(0xffffffffu, A, 1);   // value carried into this lane's first segment
+    if (lane == 0) c = 0.0;
+    for (int k = 0; k < q; ++k) {
+      const int s = lane * q + k;
+      if (s < nseg) {
+        const int ss = reverse ? nseg - 1 - s : s;
+        sC[ss * kMgCols + col] = c;
+        c = sA[ss * kMgCols + col] + sP[ss * kMgCols + col] * c;
+      }
+    }
+  }
+}
+
+// MODE 0: z = omega T^-1 r
+// MODE 1: z = z + P zc + omega T^-1 t      (zc: solution of the next coarser level)
+// MODE 2: z = z + omega T^-1 t
+// grid: (ceil(ny / kMgCols), nbatch), block: nseg * kMgCols threads with nseg = ceil(nx / SEG).
+template <int SEG, int MODE>
+__global__ void __launch_bounds__(512) k_mg_line(MgLevel lv, const double* __restrict__ zc, MgArgs a) {
+  extern __shared__ double mg_smem[];
+  if (a.scal[blockIdx.y].state != 0) return;
+  const int nx = a.nx, ny = lv.ny;
+  const int nseg = (nx + SEG - 1) / SEG;
+  double* sA = mg_smem;
+  double* sP = sA + nseg * kMgCols;
+  double* sC = sP + nseg * kMgCols;
+  const int col = threadIdx.x % kMgCols, seg = threadIdx.x / kMgCols;   // blockDim is rounded up to whole warps
+  const int j = blockIdx.x * kMgCols + col;
+  const bool in_cta = seg < nseg;
+  const bool live = in_cta && j < ny;
+  const int r0 = seg * SEG;
+  const int cnt = live ? min(SEG, nx - r0) : 0;
+  const size_t n0 = (size_t)blockIdx.y * lv.N + (size_t)r0 * ny + j;   // only dereferenced when live
+  const double* __restrict__ src = MODE == 0 ? lv.r : lv.t;
+  double y[SEG], c[SEG];
+  // forward sweep y_m = b_m - l_m y_{m-1} with carry-in 0; P = product of (-l) over the segment
+#pragma unroll
+  for (int m = 0; m < SEG; ++m) {
+    y[m] = 0.0; c[m] = 0.0;
+    if (m < cnt) { y[m] = src[n0 + (size_t)m * ny]; c[m] = lv.l[n0 + (size_t)m * ny]; }
+  }
+  double carry = 0.0, P = 1.0, last = 0.0;
+#pragma unroll
+  for (int m = 0; m < SEG; ++m) {
+    if (m < cnt) {
+      carry = y[m] - c[m] * carry;
+      y[m] = carry;
+      P = -c[m] * P;
+      last = carry;
+    }
+  }
+  if (in_cta) {
+    sA[seg * kMgCols + col] = last;
+    sP[seg * kMgCols + col] = cnt > 0 ? P : 0.0;
+  }
+  __syncthreads();
+  mg_carry_scan(sA, sP, sC, nseg, false);
+  __syncthreads();
+  {
+    double q = in_cta ? sC[seg * kMgCols + col] : 0.0;
+#pragma unroll
+    for (int m = 0; m < SEG; ++m) { q = -c[m] * q; y[m] += q; }   // rows past cnt have c = 0
+  }
+  // backward sweep z_m = y_m / d_m - e_m z_{m+1} with carry-in 0; P = product of (-e)
+#pragma unroll
+  for (int m = 0; m < SEG; ++m) {
+    c[m] = 0.0;
+    if (m < cnt) { y[m] *= lv.dinv[n0 + (size_t)m * ny]; c[m] = lv.e[n0 + (size_t)m * ny]; }
+  }
+  carry = 0.0; P = 1.0;
+#pragma unroll
+  for (int m = SEG - 1; m >= 0; --m) {
+    if (m < cnt) {
+      carry = y[m] - c[m] * carry;
+      y[m] = carry;
+      P = -c[m] * P;
+    }
+  }
+  __syncthreads();   // sA/sP/sC are reused
+  if (in_cta) {
+    sA[seg * kMgCols + col] = y[0];
+    sP[seg * kMgCols + col] = cnt > 0 ? P : 0.0;
+  }
+  __syncthreads();
+  mg_carry_scan(sA, sP, sC, nseg, true);
+  __syncthreads();
+  {
+    double q = in_cta ? sC[seg * kMgCols + col] : 0.0;
+#pragma unroll
+    for (int m = SEG - 1; m >= 0; --m) { q = -c[m] * q; y[m] += q; }
+  }
+#pragma unroll
+  for (int m = 0; m < SEG; ++m) {
+    if (m < cnt) {
+      const size_t n = n0 + (size_t)m * ny;
+      double out = kMgOmega * y[m];
+      if (MODE != 0) out += lv.z[n];
+      if (MODE == 1) out += zc[(size_t)blockIdx.y * (lv.N >> 1) + (size_t)(r0 + m) * (ny >> 1) + (j >> 1)];
+      lv.z[n] = out;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Residuals.  One thread per pair of cells (i, 2J), (i, 2J+1): 16-byte accesses, ny even.
+//   KIND 0: t = r - A z                                          (coarsest-level sweeps)
+//   KIND 1: rc(i,J) = (om_a res_a + om_b res_b) / om_c(i,J)       (restriction to the next level)
+//   KIND 2: t = r - A (z + P zc)                                  (after the coarse-grid correction)
+// Out-of-range neighbours are clamped: their weights are exactly zero.
+// ---------------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(kBlock) k_mg_resid(MgLevel lv, const double* __restrict__ zc, const double* __restrict__ omc,
+                                                     double* __restrict__ rc, MgArgs a) {
+  if (a.scal[blockIdx.y].state != 0) return;
+  const int nx = a.nx, ny = lv.ny, nyc = ny >> 1;
+  const size_t Nc = (size_t)nx * nyc;
+  const size_t bf = (size_t)blockIdx.y * lv.N, bc = (size_t)blockIdx.y * Nc;
+  const double* __restrict__ z = lv.z + bf;
+  const double* __restrict__ zcp = KIND == 2 ? zc + bc : nullptr;
+  for (size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < Nc; n += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(n / nyc), J = (int)(n - (size_t)i * nyc);
+    const size_t p = (size_t)i * ny + 2 * J;          // in-problem index of cell a
+    const size_t pW = i > 0 ? p - ny : p, pE = i < nx - 1 ? p + ny : p;
+    const size_t pS = J > 0 ? p - 1 : p, pN = J < nyc - 1 ? p + 2 : p + 1;
+    double2 zz = ld2(z + p), zW = ld2(z + pW), zE = ld2(z + pE);
+    double zS = z[pS], zN = z[pN];
+    if (KIND == 2) {
+      const double c0 = zcp[n];
+      zz.x += c0; zz.y += c0;
+      const double cW = zcp[i > 0 ? n - nyc : n], cE = zcp[i < nx - 1 ? n + nyc : n];
+      zW.x += cW; zW.y += cW; zE.x += cE; zE.y += cE;
+      zS += zcp[J > 0 ? n - 1 : n];
+      zN += zcp[J < nyc - 1 ? n + 1 : n];
+    }
+    const double2 wW = ld2(lv.wW + bf + p), wE = ld2(lv.wE + bf + p), wS = ld2(lv.wS + bf + p), wN = ld2(lv.wN + bf + p);
+    const double2 r = ld2(lv.r + bf + p);
+    const double ra = r.x - (zz.x + ((wW.x * zW.x + wE.x * zE.x) + (wS.x * zS + wN.x * zz.y)));
+    const double rb = r.y - (zz.y + ((wW.y * zW.y + wE.y * zE.y) + (wS.y * zz.x + wN.y * zN)));
+    if (KIND == 1) {
+      double2 om = make_double2(1.0, 1.0);
+      if (lv.om) om = ld2(lv.om + bf + p);
+      rc[bc + n] = sy2d_div(om.x * ra + om.y * rb, omc[bc + n]);
+    } else {
+      st2(lv.t + bf + p, ra, rb);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fine-level BiCGSTAB kernels of the right-preconditioned iteration
+//   phat = M^-1 p, v = A phat, s = r - alpha v, shat = M^-1 s, t = A shat,
+//   x += alpha phat + omega shat, r = s - omega t.
+// p-update, v = A phat and s-update are the Jacobi kernels (k_p_update2, k_spmv_v2 on phat, k_s_update2).
+// ---------------------------------------------------------------------------------------------
+
+// t = A shat; (t, s), (t, t); last block: omega                        56 B/cell
+__global__ void __launch_bounds__(kBlock) k_mg_spmv_t(KrylovVecs k, const double* __restrict__ shat, size_t N, int ny) {
+  __shared__ double red[2 * 32];
+  Scal* sc = k.scal + blockIdx.y;
+  if (sc->state != 0) return;
+  const size_t stride = 2 * (size_t)gridDim.x * blockDim.x;
+  const size_t base = (size_t)blockIdx.y * N;
+  double ts = 0.0, tt = 0.0;
+  for (size_t n = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); n < N; n += stride) {
+    const size_t g = base + n;
+    const double* h = shat + base;
+    double t0, t1;
+    stencil_apply2(h, n, N, ny, ld2(h + n), ld2(k.wW + g), ld2(k.wE + g), ld2(k.wS + g), ld2(k.wN + g), t0, t1);
+    st2(k.t + g, t0, t1);
+    const double2 s = ld2(k.s + g);
+    ts += t0 * s.x + t1 * s.y;
+    tt += t0 * t0 + t1 * t1;
+  }
+  double sums[2] = {ts, tt};
+  block_sums<2>(sums, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(&sc->acc_ts, sums[0]);
+    atomicAdd(&sc->acc_tt, sums[1]);
+    if (last_block_done(sc, gridDim.x)) {
+      const double a = sc->acc_ts, b = sc->acc_tt;
+      sc->acc_ts = 0.0;
+      sc->acc_tt = 0.0;
+      sc->omega = b > 0.0 ? a / b : 0.0;
+    }
+  }
+}
+
+// x += alpha phat + omega shat; r = s - omega t; (rhat, r), max|r|; bookkeeping        72 B/cell
+__global__ void __launch_bounds__(kBlock) k_mg_xr(KrylovVecs k, const double* __restrict__ phat, const double* __restrict__ shat,
+                                                  size_t N) {
+  __shared__ double red[32];
+  Scal* sc = k.scal + blockIdx.y;
+  if (sc->state != 0) return;
+  const size_t stride = 2 * (size_t)gridDim.x * blockDim.x;
+  double dot = 0.0, rabs = 0.0;
+  const double alpha = sc->alpha, omega = sc->omega;
+  const bool first = sc->first;
+  for (size_t n = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); n < N; n += stride) {
+    const size_t g = (size_t)blockIdx.y * N + n;
+    const double2 s = ld2(k.s + g), ph = ld2(phat + g), sh = ld2(shat + g), t = ld2(k.t + g), rh = ld2(k.rhs + g);
+    double2 x = make_double2(0.0, 0.0);
+    if (!first) x = ld2(k.x + g);
+    st2(k.x + g, x.x + (alpha * ph.x + omega * sh.x), x.y + (alpha * ph.y + omega * sh.y));
+    const double r0 = s.x - omega * t.x, r1 = s.y - omega * t.y;
+    st2(k.r + g, r0, r1);
+    dot += rh.x * r0 + rh.y * r1;
+    rabs = fmax(rabs, fmax(fabs(r0), fabs(r1)));
+  }
+  double sums[1] = {dot};
+  block_sums<1>(sums, red);
+  const double bmax = block_max(rabs, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(&sc->acc_rho, sums[0]);
+    atomicMax(&sc->acc_rmax, (unsigned long long)__double_as_longlong(bmax));
+    if (last_block_done(sc, gridDim.x)) xr_finish_iteration(sc, k);
+  }
+}
+
+}  // namespace sy2d

@@ -9,7 +9,8 @@ import numpy as np
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-K_NAMES = ("assembly", "p_update", "spmv_v", "s_update", "spmv_t", "xr_update", "finish", "other", "problem_steps")
+K_NAMES = ("assembly", "p_update", "spmv_v", "s_update", "spmv_t", "xr_update", "finish", "other", "problem_steps",
+           "mg_line", "mg_resid", "mg_setup")
 DIRICHLET, ZEROFLUX = 0, 1
 
 
@@ -21,7 +22,8 @@ class Sy2dError(RuntimeError):
 
 class Options(C.Structure):
     _fields_ = [("tol", C.c_double), ("maxit", C.c_int), ("precond", C.c_int), ("predictor", C.c_int),
-                ("check_every", C.c_int), ("use_graph", C.c_int), ("engine", C.c_int), ("reserved", C.c_int * 5)]
+                ("check_every", C.c_int), ("use_graph", C.c_int), ("engine", C.c_int), ("mg_levels", C.c_int),
+                ("reserved", C.c_int * 4)]
 
 
 class Stats(C.Structure):
@@ -74,6 +76,7 @@ def load_library():
         "sy2d_step_count": (C.c_longlong, [vp]),
         "sy2d_dump_operator": (C.c_int, [vp, dp, dp]),
         "sy2d_dump_vertex_f": (C.c_int, [vp, dp]),
+        "sy2d_debug_vcycle": (C.c_int, [vp, dp, dp, dp, dp]),
         "sy2d_set_profiling": (C.c_int, [vp, C.c_int]),
         "sy2d_get_profile": (C.c_int, [vp, C.POINTER(Profile)]),
         "sy2d_nccl_unique_id": (C.c_int, [C.c_char_p]),
@@ -244,6 +247,15 @@ class Engine:
         vf = np.empty((self.nbatch, self.nx + 1, self.ny + 1))
         self._check(self.lib.sy2d_dump_vertex_f(self._ctx, _dp(vf)))
         return vf
+
+    def debug_vcycle(self, r):
+        """One multigrid V-cycle applied to r on the operator of the current f -> (z, w4, om)."""
+        r = _f64(r, self.shape, "r")
+        z = np.empty(self.shape)
+        w4 = np.empty((4,) + self.shape)
+        om = np.empty(self.shape)
+        self._check(self.lib.sy2d_debug_vcycle(self._ctx, _dp(r), _dp(z), _dp(w4), _dp(om)))
+        return z, w4, om
 
     # -- profiling --------------------------------------------------------
     def set_profiling(self, on=True):

@@ -35,8 +35,8 @@ def test_operator_and_vertex_values_match_reference(tag):
     eng.close()
 
 
-# (engine, precond): lockstep with Jacobi / segmented x-line; CTA per problem with Jacobi / x-line
-ENGINES = [(1, 0), (1, 1), (2, 0), (2, 1)]
+# (engine, precond): lockstep with Jacobi / segmented x-line / multigrid; CTA per problem with Jacobi / x-line
+ENGINES = [(1, 0), (1, 1), (1, 2), (2, 0), (2, 1)]
 
 
 @pytest.mark.parametrize("engine,precond", ENGINES)
@@ -152,6 +152,8 @@ def test_grid_1024_matches_reference_subsample():
     f = eng.get_f()[0]
     assert max_rel(f[3::8, 5::8], g["f_3"]) < PARITY
     assert st["negatives"] == 0 and (f < 0).sum() == 0 and st["resid_last"] < 1e-12
+    # the default preconditioner of the lockstep engine is the multigrid cycle: O(15) iterations per step
+    assert st["precond"] == 2 and st["iters_last"] <= 30, st
     eng.close()
 
 
