@@ -84,6 +84,8 @@ struct sy2d_ctx {
   size_t xl_smem = 0;
   // iteration-chunk graph
   cudaGraphExec_t chunk_exec = nullptr;
+  cudaGraphExec_t one_exec = nullptr;   // multigrid: a single iteration + the convergence poll
+  int mg_last_iters = 0;                // iterations of the previous time step (issue plan of the next one)
   int chunk_iters = 0;
   int chunk_variant = -1;
   // profiling
@@ -156,6 +158,7 @@ int mg_level_count(const sy2d_ctx* c) {
   while (nlev < want && ny % 4 == 0 && ny >= 16) { ny /= 2; ++nlev; }   // the coarsest level keeps an even ny >= 8
   return nlev >= 2 ? nlev : 0;
 }
+int mg_coarse_sweeps(const sy2d_ctx* c) { return c->opt.mg_coarse_sweeps > 0 ? c->opt.mg_coarse_sweeps : kMgCoarseSweeps; }
 bool lockstep_mg(const sy2d_ctx* c) {
   if (c->opt.precond != SY2D_PRECOND_AUTO && c->opt.precond != SY2D_PRECOND_MG) return false;
   return mg_level_count(c) > 0;
@@ -241,7 +244,7 @@ int mg_alloc(sy2d_ctx* c) {
     c->mg_bufs.push_back(*out);
     return SY2D_OK;
   };
-  c->mg_seg = c->nx <= 1024 ? 16 : 32;
+  c->mg_seg = c->nx <= 1024 ? 8 : 16;
   std::memset(&c->mg, 0, sizeof c->mg);
   c->mg.nlev = nlev;
   double* t0 = nullptr;
@@ -278,20 +281,29 @@ void mg_setup(sy2d_ctx* c) {
         f, const_cast<double*>(g.wW), const_cast<double*>(g.wE), const_cast<double*>(g.wS), const_cast<double*>(g.wN),
         const_cast<double*>(g.om), c->nx);
   }
-  k_mg_factor<<<dim3((unsigned)((c->ny + 127) / 128), (unsigned)c->nbatch, (unsigned)c->mg_nlev), 128, 0, c->stream>>>(c->mg, c->nx);
+  k_mg_factor<<<dim3((unsigned)((c->ny + 63) / 64), (unsigned)c->nbatch, (unsigned)c->mg_nlev), 64, 0, c->stream>>>(c->mg, c->nx);
   c->launches += c->mg_nlev;
+}
+
+// Shape of the line kernel: rows per thread (SEG) x columns per CTA (COLS); a CTA holds all nx / SEG
+// segments of its columns: nx <= 1024: 8 x 8 (up to 1024 threads of ~60 registers), else 16 x 4.
+template <int SEG, int COLS, int MODE>
+void mg_line_shape(sy2d_ctx* c, const MgLevel& lv, const double* zc) {
+  const MgArgs a{c->scal, c->nx};
+  const int nseg = (c->nx + SEG - 1) / SEG;
+  const int threads = (nseg * COLS + 31) / 32 * 32;
+  const size_t smem = (size_t)3 * COLS * (nseg + 1) * sizeof(double);
+  const dim3 g((unsigned)((lv.ny + COLS - 1) / COLS), (unsigned)c->nbatch, 1);
+  const bool full = c->nx % SEG == 0 && lv.ny % COLS == 0 && nseg * COLS == threads;
+  if (full) k_mg_line<SEG, COLS, MODE, true><<<g, threads, smem, c->stream>>>(lv, zc, a);
+  else k_mg_line<SEG, COLS, MODE, false><<<g, threads, smem, c->stream>>>(lv, zc, a);
 }
 
 template <int MODE>
 void mg_line(sy2d_ctx* c, const MgLevel& lv, const double* zc) {
   Prof p(c, SY2D_K_MG_LINE);
-  const MgArgs a{c->scal, c->nx};
-  const int nseg = (c->nx + c->mg_seg - 1) / c->mg_seg;
-  const int threads = (nseg * kMgCols + 31) / 32 * 32;
-  const size_t smem = (size_t)3 * nseg * kMgCols * sizeof(double);
-  const dim3 g((unsigned)((lv.ny + kMgCols - 1) / kMgCols), (unsigned)c->nbatch, 1);
-  if (c->mg_seg == 16) k_mg_line<16, MODE><<<g, threads, smem, c->stream>>>(lv, zc, a);
-  else k_mg_line<32, MODE><<<g, threads, smem, c->stream>>>(lv, zc, a);
+  if (c->mg_seg == 8) mg_line_shape<8, 8, MODE>(c, lv, zc);
+  else mg_line_shape<16, 4, MODE>(c, lv, zc);
 }
 
 template <int KIND>
@@ -315,7 +327,7 @@ void mg_vcycle(sy2d_ctx* c, const double* r, double* z) {
   }
   c->cur_cells = scale0 / (double)(1 << (L - 1));
   mg_line<0>(c, level(L - 1), nullptr);
-  for (int sweep = 1; sweep < kMgCoarseSweeps; ++sweep) {
+  for (int sweep = 1; sweep < mg_coarse_sweeps(c); ++sweep) {
     mg_resid<0>(c, level(L - 1), nullptr, nullptr, nullptr);
     mg_line<2>(c, level(L - 1), nullptr);
   }
@@ -326,7 +338,7 @@ void mg_vcycle(sy2d_ctx* c, const double* r, double* z) {
   }
   c->cur_cells = scale0;
 }
-int mg_kernels_per_vcycle(const sy2d_ctx* c) { return 4 * (c->mg_nlev - 1) + 1 + 2 * (kMgCoarseSweeps - 1); }
+int mg_kernels_per_vcycle(const sy2d_ctx* c) { return 4 * (c->mg_nlev - 1) + 1 + 2 * (mg_coarse_sweeps(c) - 1); }
 
 void launch_iteration_mg(sy2d_ctx* c) {
   KrylovVecs k = krylov(c);
@@ -372,12 +384,22 @@ int kernels_per_iteration(const sy2d_ctx* c) { return lockstep_mg(c) ? 5 + 2 * m
 int effective_check_every(const sy2d_ctx* c) { return lockstep_mg(c) ? std::min(c->opt.check_every, 4) : c->opt.check_every; }
 
 int build_chunk_graph(sy2d_ctx* c) {
-  const int variant = lockstep_mg(c) ? 2 + c->mg_nlev : (lockstep_xline(c) ? 1 : 0);
+  const int variant = lockstep_mg(c) ? 2 + c->mg_nlev + 16 * mg_coarse_sweeps(c) : (lockstep_xline(c) ? 1 : 0);
   const int check_every = effective_check_every(c);
   if (c->chunk_exec && c->chunk_iters == check_every && c->chunk_variant == variant) return SY2D_OK;
   c->chunk_variant = variant;
   if (c->chunk_exec) { cudaGraphExecDestroy(c->chunk_exec); c->chunk_exec = nullptr; }
+  if (c->one_exec) { cudaGraphExecDestroy(c->one_exec); c->one_exec = nullptr; }
   cudaGraph_t graph = nullptr;
+  if (lockstep_mg(c)) {
+    CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    launch_iteration(c);
+    CU(cudaMemcpyAsync(c->h_nactive, c->d_nactive, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamEndCapture(c->stream, &graph));
+    CU(cudaGraphInstantiate(&c->one_exec, graph, 0));
+    cudaGraphDestroy(graph);
+    graph = nullptr;
+  }
   CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
   for (int it = 0; it < check_every; ++it) launch_iteration(c);
   CU(cudaMemcpyAsync(c->h_nactive, c->d_nactive, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -720,6 +742,7 @@ void sy2d_destroy(sy2d_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->chunk_exec) cudaGraphExecDestroy(c->chunk_exec);
+  if (c->one_exec) cudaGraphExecDestroy(c->one_exec);
   double* bufs[] = {c->d_wxL, c->d_wxR, c->d_wyB, c->d_wyT, c->d_dx, c->d_dy, c->d_bc[0], c->d_bc[1], c->d_bc[2], c->d_bc[3],
                     c->tx, c->ty, c->cxy, c->U, c->Ud, c->f, c->yprev, c->cs, c->wW, c->wE, c->wS, c->wN, c->rhs,
                     c->x, c->r, c->p, c->v, c->s, c->t, c->stage, c->xl_scratch, c->xl_l, c->xl_dinv, c->xl_e, c->xl_hat};
@@ -1105,6 +1128,23 @@ int sy2d_step(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
     CU(cudaStreamSynchronize(c->stream));
     c->launches += 1;
     int launched = 0;
+    if (mg && graph && *c->h_nactive > 0) {
+      // Multigrid iteration counts barely change from one time step to the next: issue last step's
+      // count minus one without polling, then single iterations with a poll after each.
+      int planned = std::min(c->mg_last_iters - 1, c->opt.maxit);
+      c->cur_cells = (double)c->total;
+      if (planned > 0) {
+        for (; planned >= check_every; planned -= check_every, launched += check_every) CU(cudaGraphLaunch(c->chunk_exec, c->stream));
+        for (; planned > 0; --planned, ++launched) CU(cudaGraphLaunch(c->one_exec, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+      }
+      while (*c->h_nactive > 0 && launched < c->opt.maxit + 1) {
+        CU(cudaGraphLaunch(c->one_exec, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        launched += 1;
+      }
+      c->launches += (long long)launched * kernels_per_iteration(c);
+    }
     while (*c->h_nactive > 0 && launched < c->opt.maxit + check_every) {
       c->cur_cells = (double)*c->h_nactive * (double)c->N;
       if (graph) {
@@ -1144,6 +1184,7 @@ int sy2d_step(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
     st.iters_total += c->h_stats->it_max;
     st.iters_sum_all += (long long)c->h_stats->it_max * c->nbatch;
     st.iters_last = c->h_stats->it_max;
+    c->mg_last_iters = c->h_stats->it_max;
     st.resid_last = c->h_stats->resid_max;
     st.fmin = c->h_stats->fmin;
     st.negatives = (long long)c->h_stats->negatives;

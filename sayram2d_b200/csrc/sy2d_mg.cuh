@@ -34,10 +34,9 @@
 namespace sy2d {
 
 constexpr int kMgMaxLevels = 8;
-constexpr int kMgCols = 8;         // columns per CTA of the line kernel (64-byte row chunks)
 constexpr double kMgOmega = 0.7;   // line-Jacobi damping
 constexpr double kMgTheta = 0.5;   // rescaling of the inter-aggregate couplings
-constexpr int kMgCoarseSweeps = 4;
+constexpr int kMgCoarseSweeps = 4;  // default number of smoothing sweeps on the coarsest level
 
 struct MgLevel {
   const double *wW, *wE, *wS, *wN;  // unit-diagonal operator
@@ -91,24 +90,38 @@ struct MgLevels {
 };
 
 // LU of every x-line of every level: one thread per (level, column), sequential along i.  The
-// recurrence d_i = 1 - wW_i wE_{i-1} / d_{i-1} has one reciprocal on its critical path.
-__global__ void __launch_bounds__(128) k_mg_factor(MgLevels L, int nx) {
+// recurrence d_i = 1 - wW_i wE_{i-1} / d_{i-1} has one reciprocal on its critical path; the
+// coefficients of kFactorChunk rows are loaded ahead of the recurrence (the loads do not depend on it).
+constexpr int kFactorChunk = 16;
+__global__ void __launch_bounds__(64) k_mg_factor(MgLevels L, int nx) {
   const MgLevel& lv = L.lv[blockIdx.z];
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= lv.ny) return;
   const size_t base = (size_t)blockIdx.y * lv.N + j;
+  const int ny = lv.ny;
   double dinv_prev = 0.0, wE_prev = 0.0;
-  for (int i = 0; i < nx; ++i) {
-    const size_t n = base + (size_t)i * lv.ny;
-    const double l = lv.wW[n] * dinv_prev;          // 0 on the first row (wW = 0 there as well)
-    const double d = 1.0 - l * wE_prev;
-    const double dinv = sy2d_div(1.0, d);
-    const double wE = lv.wE[n];
-    lv.l[n] = l;
-    lv.dinv[n] = dinv;
-    lv.e[n] = wE * dinv;
-    dinv_prev = dinv;
-    wE_prev = wE;
+  for (int i0 = 0; i0 < nx; i0 += kFactorChunk) {
+    double w[kFactorChunk], e[kFactorChunk];
+#pragma unroll
+    for (int m = 0; m < kFactorChunk; ++m) {
+      const int i = min(i0 + m, nx - 1);
+      w[m] = lv.wW[base + (size_t)i * ny];
+      e[m] = lv.wE[base + (size_t)i * ny];
+    }
+#pragma unroll
+    for (int m = 0; m < kFactorChunk; ++m) {
+      if (i0 + m < nx) {
+        const size_t n = base + (size_t)(i0 + m) * ny;
+        const double l = w[m] * dinv_prev;          // 0 on the first row (wW = 0 there as well)
+        const double d = 1.0 - l * wE_prev;
+        const double dinv = sy2d_div(1.0, d);
+        lv.l[n] = l;
+        lv.dinv[n] = dinv;
+        lv.e[n] = e[m] * dinv;
+        dinv_prev = dinv;
+        wE_prev = e[m];
+      }
+    }
   }
 }
 
@@ -117,39 +130,30 @@ __global__ void __launch_bounds__(128) k_mg_factor(MgLevels L, int nx) {
 // ---------------------------------------------------------------------------------------------
 
 // Carry-in of every segment of the columns of this CTA from the per-segment affine maps
-// carry_out = A[s] + P[s] * carry_in.  Warp w scans column w, w + nwarps, ...; a lane owns q =
-// ceil(nseg/32) consecutive segments.  `reverse`: segments are chained from the last to the first.
-// sA/sP/sC are [nseg][kMgCols].  All threads of the CTA call this (it contains no barrier).
-__device__ __forceinline__ void mg_carry_scan(const double* sA, const double* sP, double* sC, int nseg, bool reverse) {
+// carry_out = A[s] + P[s] * carry_in, s = 0..nseg-1 chained in index order (the backward sweep stores its
+// segments in reversed order).  Shared layout [col][stride] with stride = nseg + 1, so a warp reads 32
+// consecutive segments of one column without bank conflicts.  Warp w scans column w, w + nwarps, ...:
+// blocks of 32 segments, a shuffle scan of the affine maps inside a block, the total carried on to the
+// next block.  Contains no barrier; every thread of the CTA calls it.
+template <int COLS>
+__device__ __forceinline__ void mg_carry_scan(const double* sA, const double* sP, double* sC, int nseg, int stride) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const int q = (nseg + 31) >> 5;
-  for (int col = w; col < kMgCols; col += nw) {
-    // lane-local composition of its q segments
-    double A = 0.0, P = 1.0;
-    for (int k = 0; k < q; ++k) {
-      const int s = lane * q + k;
-      if (s < nseg) {
-        const int ss = reverse ? nseg - 1 - s : s;
-        const double a = sA[ss * kMgCols + col], p = sP[ss * kMgCols + col];
-        A = a + p * A;
-        P = p * P;
-      }
-    }
-    // inclusive scan of the affine maps over the lanes
+  for (int col = w; col < COLS; col += nw) {
+    double cb = 0.0;   // carry into the current block of 32 segments
+    for (int s0 = 0; s0 < nseg; s0 += 32) {
+      const int s = s0 + lane;
+      double A = 0.0, P = 1.0;   // identity for lanes past the end
+      if (s < nseg) { A = sA[col * stride + s]; P = sP[col * stride + s]; }
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const double Ao = __shfl_up_sync(0xffffffffu, A, o), Po = __shfl_up_sync(0xffffffffu, P, o);
-      if (lane >= o) { A = A + P * Ao; P = P * Po; }
-    }
-    double c = __shfl_up_sync(0xffffffffu, A, 1);   // value carried into this lane's first segment
-    if (lane == 0) c = 0.0;
-    for (int k = 0; k < q; ++k) {
-      const int s = lane * q + k;
-      if (s < nseg) {
-        const int ss = reverse ? nseg - 1 - s : s;
-        sC[ss * kMgCols + col] = c;
-        c = sA[ss * kMgCols + col] + sP[ss * kMgCols + col] * c;
+      for (int o = 1; o < 32; o <<= 1) {   // inclusive scan: map of segments s0 .. s applied in order
+        const double Ao = __shfl_up_sync(0xffffffffu, A, o), Po = __shfl_up_sync(0xffffffffu, P, o);
+        if (lane >= o) { A = A + P * Ao; P = P * Po; }
       }
+      double Ae = __shfl_up_sync(0xffffffffu, A, 1), Pe = __shfl_up_sync(0xffffffffu, P, 1);
+      if (lane == 0) { Ae = 0.0; Pe = 1.0; }
+      if (s < nseg) sC[col * stride + s] = Ae + Pe * cb;
+      const double At = __shfl_sync(0xffffffffu, A, 31), Pt = __shfl_sync(0xffffffffu, P, 31);
+      cb = At + Pt * cb;
     }
   }
 }
@@ -157,35 +161,45 @@ __device__ __forceinline__ void mg_carry_scan(const double* sA, const double* sP
 // MODE 0: z = omega T^-1 r
 // MODE 1: z = z + P zc + omega T^-1 t      (zc: solution of the next coarser level)
 // MODE 2: z = z + omega T^-1 t
-// grid: (ceil(ny / kMgCols), nbatch), block: nseg * kMgCols threads with nseg = ceil(nx / SEG).
-template <int SEG, int MODE>
-__global__ void __launch_bounds__(512) k_mg_line(MgLevel lv, const double* __restrict__ zc, MgArgs a) {
+// grid: (ceil(ny / COLS), nbatch), block: nseg * COLS threads rounded up to whole warps, nseg = ceil(nx / SEG).
+// FULL: nx % SEG == 0, ny % COLS == 0 and nseg * COLS % 32 == 0 - no thread and no row needs a predicate.
+// The kernel is latency bound (a CTA is one dependent chain of load - sweep - scan - sweep - scan - store
+// and a level has at most ny / COLS CTAs), so the instruction count per thread is what matters: short
+// segments, running pointers instead of index products, all loads of a phase issued before their use.
+template <int SEG, int COLS, int MODE, bool FULL>
+__global__ void __launch_bounds__(SEG <= 8 ? 1024 : 512, 1) k_mg_line(MgLevel lv, const double* __restrict__ zc, MgArgs a) {
   extern __shared__ double mg_smem[];
-  if (a.scal[blockIdx.y].state != 0) return;
+  const int state = a.scal[blockIdx.y].state;   // used after the first loads are in flight
   const int nx = a.nx, ny = lv.ny;
   const int nseg = (nx + SEG - 1) / SEG;
+  const int stride = nseg + 1;
   double* sA = mg_smem;
-  double* sP = sA + nseg * kMgCols;
-  double* sC = sP + nseg * kMgCols;
-  const int col = threadIdx.x % kMgCols, seg = threadIdx.x / kMgCols;   // blockDim is rounded up to whole warps
-  const int j = blockIdx.x * kMgCols + col;
-  const bool in_cta = seg < nseg;
-  const bool live = in_cta && j < ny;
+  double* sP = sA + COLS * stride;
+  double* sC = sP + COLS * stride;
+  const int col = threadIdx.x % COLS, seg = threadIdx.x / COLS;
+  const int j = blockIdx.x * COLS + col;
+  const bool in_cta = FULL || seg < nseg;
+  const bool live = FULL || (in_cta && j < ny);
   const int r0 = seg * SEG;
-  const int cnt = live ? min(SEG, nx - r0) : 0;
-  const size_t n0 = (size_t)blockIdx.y * lv.N + (size_t)r0 * ny + j;   // only dereferenced when live
-  const double* __restrict__ src = MODE == 0 ? lv.r : lv.t;
+  const int cnt = FULL ? SEG : (live ? min(SEG, nx - r0) : 0);
+  const size_t n0 = live ? (size_t)blockIdx.y * lv.N + (size_t)r0 * ny + j : 0;
   double y[SEG], c[SEG];
   // forward sweep y_m = b_m - l_m y_{m-1} with carry-in 0; P = product of (-l) over the segment
+  {
+    const double* ps = (MODE == 0 ? lv.r : lv.t) + n0;
+    const double* pl = lv.l + n0;
 #pragma unroll
-  for (int m = 0; m < SEG; ++m) {
-    y[m] = 0.0; c[m] = 0.0;
-    if (m < cnt) { y[m] = src[n0 + (size_t)m * ny]; c[m] = lv.l[n0 + (size_t)m * ny]; }
+    for (int m = 0; m < SEG; ++m) {
+      y[m] = 0.0; c[m] = 0.0;
+      if (FULL || m < cnt) { y[m] = *ps; c[m] = *pl; }
+      ps += ny; pl += ny;
+    }
   }
+  if (state != 0) return;   // uniform over the CTA
   double carry = 0.0, P = 1.0, last = 0.0;
 #pragma unroll
   for (int m = 0; m < SEG; ++m) {
-    if (m < cnt) {
+    if (FULL || m < cnt) {
       carry = y[m] - c[m] * carry;
       y[m] = carry;
       P = -c[m] * P;
@@ -193,54 +207,73 @@ __global__ void __launch_bounds__(512) k_mg_line(MgLevel lv, const double* __res
     }
   }
   if (in_cta) {
-    sA[seg * kMgCols + col] = last;
-    sP[seg * kMgCols + col] = cnt > 0 ? P : 0.0;
+    sA[col * stride + seg] = last;
+    sP[col * stride + seg] = (FULL || cnt > 0) ? P : 0.0;
   }
   __syncthreads();
-  mg_carry_scan(sA, sP, sC, nseg, false);
+  mg_carry_scan<COLS>(sA, sP, sC, nseg, stride);
   __syncthreads();
   {
-    double q = in_cta ? sC[seg * kMgCols + col] : 0.0;
+    double q = in_cta ? sC[col * stride + seg] : 0.0;
 #pragma unroll
     for (int m = 0; m < SEG; ++m) { q = -c[m] * q; y[m] += q; }   // rows past cnt have c = 0
   }
   // backward sweep z_m = y_m / d_m - e_m z_{m+1} with carry-in 0; P = product of (-e)
+  {
+    const double* pd = lv.dinv + n0;
+    const double* pe = lv.e + n0;
+    double dv[SEG];
 #pragma unroll
-  for (int m = 0; m < SEG; ++m) {
-    c[m] = 0.0;
-    if (m < cnt) { y[m] *= lv.dinv[n0 + (size_t)m * ny]; c[m] = lv.e[n0 + (size_t)m * ny]; }
+    for (int m = 0; m < SEG; ++m) {
+      dv[m] = 0.0; c[m] = 0.0;
+      if (FULL || m < cnt) { dv[m] = *pd; c[m] = *pe; }
+      pd += ny; pe += ny;
+    }
+#pragma unroll
+    for (int m = 0; m < SEG; ++m) y[m] *= dv[m];
   }
   carry = 0.0; P = 1.0;
 #pragma unroll
   for (int m = SEG - 1; m >= 0; --m) {
-    if (m < cnt) {
+    if (FULL || m < cnt) {
       carry = y[m] - c[m] * carry;
       y[m] = carry;
       P = -c[m] * P;
     }
   }
-  __syncthreads();   // sA/sP/sC are reused
+  __syncthreads();   // sA/sP/sC are reused; segments are stored in reversed order: the scan runs last to first
   if (in_cta) {
-    sA[seg * kMgCols + col] = y[0];
-    sP[seg * kMgCols + col] = cnt > 0 ? P : 0.0;
+    sA[col * stride + (nseg - 1 - seg)] = y[0];
+    sP[col * stride + (nseg - 1 - seg)] = (FULL || cnt > 0) ? P : 0.0;
   }
   __syncthreads();
-  mg_carry_scan(sA, sP, sC, nseg, true);
+  mg_carry_scan<COLS>(sA, sP, sC, nseg, stride);
   __syncthreads();
   {
-    double q = in_cta ? sC[seg * kMgCols + col] : 0.0;
+    double q = in_cta ? sC[col * stride + (nseg - 1 - seg)] : 0.0;
 #pragma unroll
     for (int m = SEG - 1; m >= 0; --m) { q = -c[m] * q; y[m] += q; }
   }
+  // all loads of the update before the first store (z is read and written through the same pointer)
+  double* pz = lv.z + n0;
+  if (MODE != 0) {
+    const double* pq = pz;
+    const double* pc = MODE == 1 ? zc + ((size_t)blockIdx.y * (lv.N >> 1) + (size_t)r0 * (ny >> 1) + (j >> 1)) : nullptr;
+#pragma unroll
+    for (int m = 0; m < SEG; ++m) {
+      c[m] = 0.0;
+      if (FULL || m < cnt) {
+        c[m] = *pq;
+        if (MODE == 1) c[m] += *pc;
+      }
+      pq += ny;
+      if (MODE == 1) pc += ny >> 1;
+    }
+  }
 #pragma unroll
   for (int m = 0; m < SEG; ++m) {
-    if (m < cnt) {
-      const size_t n = n0 + (size_t)m * ny;
-      double out = kMgOmega * y[m];
-      if (MODE != 0) out += lv.z[n];
-      if (MODE == 1) out += zc[(size_t)blockIdx.y * (lv.N >> 1) + (size_t)(r0 + m) * (ny >> 1) + (j >> 1)];
-      lv.z[n] = out;
-    }
+    if (FULL || m < cnt) *pz = MODE == 0 ? kMgOmega * y[m] : c[m] + kMgOmega * y[m];
+    pz += ny;
   }
 }
 

@@ -23,7 +23,7 @@ class Sy2dError(RuntimeError):
 class Options(C.Structure):
     _fields_ = [("tol", C.c_double), ("maxit", C.c_int), ("precond", C.c_int), ("predictor", C.c_int),
                 ("check_every", C.c_int), ("use_graph", C.c_int), ("engine", C.c_int), ("mg_levels", C.c_int),
-                ("reserved", C.c_int * 4)]
+                ("mg_coarse_sweeps", C.c_int), ("reserved", C.c_int * 3)]
 
 
 class Stats(C.Structure):

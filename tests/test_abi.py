@@ -29,8 +29,8 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     text = open(os.path.join(ROOT, "include", "sayram2d.h")).read()
-    assert ctypes.sizeof(sy.Options) == 8 + 4 * 7 + 4 * 4 + 4  # double + 7 ints + reserved[4] + padding
-    assert "reserved[4]" in text
+    assert ctypes.sizeof(sy.Options) == 8 + 4 * 8 + 4 * 3 + 4  # double + 8 ints + reserved[3] + padding
+    assert "reserved[3]" in text
     n_k = len(re.findall(r"^\s*SY2D_K_[A-Z_]+\b", text, flags=re.M)) - 1  # minus SY2D_K_COUNT
     assert n_k == len(sy.K_NAMES)
 
