@@ -45,6 +45,13 @@ LC_INI = os.path.join(ROOT, "data", "p_AlbertYoungLC.ini")
 # algorithmic HBM bytes per cell and launch (DESIGN.md "kernels"; fp64 = 8 B)
 BYTES_PER_CELL = {"assembly": 104, "p_update": 32, "spmv_v": 56, "s_update": 24, "spmv_t": 48, "xr_update": 56,
                   "finish": 40, "other": 56, "problem_steps": None}
+# lockstep engine with the multigrid preconditioner (sy2d_mg.cuh).  mg_* classes are per LEVEL cell (the
+# library counts nx * ny_level cells for a launch on a level): line solves read rhs + 3 LU factors and
+# write z (40 B; +z, +zc/2 on the way up: 52 B) - 46 B on average; residual kernels read r, z, 4 weights,
+# om or zc and write the restricted residual / t: 66 B; setup per FINE cell: coarsening 60 B per level cell
+# and line LU 40 B per level cell, summed over the levels (factor ~1.94): ~190 B.
+BYTES_PER_CELL_MG = {"assembly": 112, "spmv_t": 56, "xr_update": 72, "mg_line": 46, "mg_resid": 66, "mg_setup": 190}
+PRECOND_NAMES = {0: "jacobi", 1: "xline16", 2: "multigrid"}
 
 
 def measured_peak():
@@ -180,9 +187,13 @@ def roofline_from_profile(prof, only=None, stats=None, cells_per_problem=None):
                           "hbm_bytes_min": p["cells"] * 72, "precond": "xline" if per_iter == 288 else "jacobi",
                           "mean_iters_per_step": stats["iters_sum_all"] * cells_per_problem / p["cells"]}
             continue
-        bpc = BYTES_PER_CELL[name]
+        bpc = BYTES_PER_CELL.get(name)
         if stats and stats.get("precond", 0) == 1 and stats.get("engine", 0) == 1:
             bpc = BYTES_PER_CELL_XLINE.get(name, bpc)
+        if stats and stats.get("precond", 0) == 2 and stats.get("engine", 0) == 1:
+            bpc = BYTES_PER_CELL_MG.get(name, bpc)
+        if bpc is None:
+            continue
         gbs = p["cells"] * bpc / (p["ms"] * 1e-3) / 1e9
         rows[name] = {"achieved": round(gbs, 1), "frac": round(gbs / peak, 4), "ms_total": round(p["ms"], 3),
                       "launches": p["launches"], "us_per_launch": round(1e3 * p["ms"] / p["launches"], 2),
@@ -424,8 +435,9 @@ def grid_object(n, device, args, torch):
     rows, dom, peak, peak_src = roofline_from_profile(prof, stats=pst, cells_per_problem=n * n)
     out = {"workload": f"grid{n}", "value": n * n * steps / dev_s, "unit": UNIT, "steps": steps, "ms_per_step": 1e3 * dev_s / steps,
            "iters_per_step": iters / steps, "negatives": st["negatives"], "resid_last": st["resid_last"],
-           "precond": "xline16" if st.get("precond", 0) == 1 else "jacobi",
-           "l2": "256 MB flush between timed steps; the 19-array working set (~160 MB) cycles through L2 within a step",
+           "precond": PRECOND_NAMES.get(st.get("precond", 0), "?"),
+           "kernel_launches_per_step": st["kernel_launches"],
+           "l2": "256 MB flush between timed steps; the working set (~25 fine-grid arrays, 210 MB, plus the coarse levels) cycles through L2 within a step",
            "roofline": {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src, "dominant": dom, "kernels": rows}}
     out["roofline"]["sustained"] = sustained_kernels(eng, n * n, peak)
     eng.close()

@@ -19,6 +19,7 @@
 #include "sy2d_xline_kernel.cuh"
 #include "sy2d_xline_lockstep.cuh"
 #include "sy2d_mg.cuh"
+#include "sy2d_assemble_tma.cuh"
 
 using namespace sy2d;
 
@@ -58,6 +59,10 @@ struct sy2d_ctx {
   double* mg_rc[kMgMaxLevels] = {};   // writable right-hand sides of the coarse levels
   double *mg_om0 = nullptr, *mg_shat = nullptr;
   std::vector<double*> mg_bufs;
+  // TMA-staged assembly (sy2d_assemble_tma.cuh): tensor maps of f, yprev, tx, ty, cxy, U, Ud
+  bool have_tma = false;
+  AsmMaps tma_maps;
+  AsmMaps* d_tma_maps = nullptr;   // device copy read by the TMA unit
   Scal* scal = nullptr;
   int* d_nactive = nullptr;
   int* h_nactive = nullptr;  // pinned
@@ -229,6 +234,61 @@ void launch_iteration_xline(sy2d_ctx* c) {
   { Prof p(c, SY2D_K_XR_UPDATE); if (v2) k_xl_xr<2><<<gc, kBlock, 0, c->stream>>>(x, c->N); else k_xl_xr<1><<<gc, kBlock, 0, c->stream>>>(x, c->N); }
 }
 
+
+// Tensor maps for the TMA-staged assembly: [nbatch][nx][ny] fp64 arrays seen as 3-D tensors (ny fastest),
+// halo boxes of 36 x 10 cells and interior boxes of 32 x 8 cells, out-of-bounds elements zero-filled.
+// cuTensorMapEncodeTiled is a driver entry point; it is resolved through the runtime, so the library
+// keeps linking against libcudart only.
+bool tma_build_maps(sy2d_ctx* c) {
+  if (c->slab || c->ny % 2 != 0 || c->nx < 2 * kTI || c->ny < kTJ) return false;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+      qres != cudaDriverEntryPointSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  EncodeFn encode = reinterpret_cast<EncodeFn>(fn);
+  double* arrs[7] = {c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud};
+  const cuuint64_t dims[3] = {(cuuint64_t)c->ny, (cuuint64_t)c->nx, (cuuint64_t)c->nbatch};
+  const cuuint64_t strides[2] = {(cuuint64_t)c->ny * sizeof(double), (cuuint64_t)c->N * sizeof(double)};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  for (int k = 0; k < 7; ++k) {
+    const cuuint32_t box[3] = {(cuuint32_t)(k < 5 ? kTmaHaloJ : kTJ), (cuuint32_t)(k < 5 ? kTmaHaloI : kTI), 1};
+    const CUresult r = encode(&c->tma_maps.m[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, arrs[k], dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,  // (L2 promotion raises an illegal-instruction fault with these boxes on B200 / driver 580: profiles/tma_probe.cu)
+                             
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+  }
+  if (cudaFuncSetAttribute(k_assemble_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&c->d_tma_maps), sizeof(AsmMaps)) != cudaSuccess ||
+      cudaMemcpy(c->d_tma_maps, &c->tma_maps, sizeof(AsmMaps), cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return true;
+}
+
+// Engine-1 assembly of the whole batch: TMA-staged tiles where available, else the tiled / per-cell kernels.
+// variant: 0 auto, 1 per-cell kernel, 2 tiled kernel without TMA (tests compare the three).
+void launch_assembly(sy2d_ctx* c, const Geometry& geo, const AssembleOut& o, int variant) {
+  const int tiles_i = (c->nx + kTI - 1) / kTI, tiles_j = (c->ny + kTJ - 1) / kTJ;
+  const bool tiled = c->nx >= 2 * kTI && c->ny >= kTJ && variant != 1;
+  if (tiled && c->have_tma && variant == 0) {
+    const int ntiles = tiles_i * tiles_j;
+    const unsigned ctas = (unsigned)std::min<size_t>((size_t)ntiles, std::max<size_t>(1, (size_t)c->sm_count * 4 / (size_t)c->nbatch));
+    k_assemble_tma<<<dim3(ctas, (unsigned)c->nbatch, 1), kTI * kTJ, kTmaSmemBytes, c->stream>>>(c->d_tma_maps, geo, o, tiles_j, ntiles);
+  } else if (tiled) {
+    k_assemble_tiled<<<dim3(capped_blocks(c, (size_t)tiles_i * tiles_j, 1), (unsigned)c->nbatch, 1), kTI * kTJ, 0, c->stream>>>(
+        c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud, geo, o, tiles_j, 0, 0, c->nx, 0);
+  } else {
+    k_assemble<0><<<grid_of(c), kBlock, 0, c->stream>>>(c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud, geo, o);
+  }
+}
 
 // ---- multigrid preconditioner: allocation, per-step setup, V-cycle, iteration ----
 int mg_alloc(sy2d_ctx* c) {
@@ -634,7 +694,7 @@ const char* sy2d_build_info(void) {
   return "sayram2d_b200;arch=sm_100a;cuda="
 #define SY2D_STR2(x) #x
 #define SY2D_STR(x) SY2D_STR2(x)
-      SY2D_STR(CUDART_VERSION) ";fp64;engines=lockstep-bicgstab,cta-per-problem";
+      SY2D_STR(CUDART_VERSION) ";fp64;engines=lockstep-bicgstab,cta-per-problem;precond=jacobi,xline,multigrid;assembly=tma";
 }
 
 int sy2d_device_count(void) {
@@ -726,6 +786,7 @@ static int create_impl(sy2d_ctx** out, int device, int nx, int ny, int nbatch, c
   CUB(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_stats), sizeof(StepStats)));
   CUB(cudaEventCreate(&ctx->ev_call0));
   CUB(cudaEventCreate(&ctx->ev_call1));
+  ctx->have_tma = tma_build_maps(ctx);
 #undef CUB
   *out = ctx;
   return SY2D_OK;
@@ -749,6 +810,7 @@ void sy2d_destroy(sy2d_ctx* c) {
   for (double* b : bufs) if (b) cudaFree(b);
   if (c->scal) cudaFree(c->scal);
   for (double* b : c->mg_bufs) cudaFree(b);
+  if (c->d_tma_maps) cudaFree(c->d_tma_maps);
   for (cudaStream_t sk : c->pipe_streams) if (sk) { cudaStreamSynchronize(sk); cudaStreamDestroy(sk); }
   for (cudaEvent_t ek : c->pipe_events) if (ek) cudaEventDestroy(ek);
   if (c->pipe_start) cudaEventDestroy(c->pipe_start);
@@ -1107,13 +1169,7 @@ int sy2d_step(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
       o.wW = c->wW; o.wE = c->wE; o.wS = c->wS; o.wN = c->wN; o.rhs = c->rhs; o.cs = c->cs;
       o.scal = c->scal; o.n_active = c->d_nactive; o.tol = c->opt.tol; o.local_rows = c->nx;
       if (mg) o.om = c->mg_om0;
-      if (c->nx >= 2 * kTI && c->ny >= kTJ && c->opt.reserved[0] == 0) {  // reserved[0] = 1 forces the per-cell kernel (tests)
-        const int tiles_i = (c->nx + kTI - 1) / kTI, tiles_j = (c->ny + kTJ - 1) / kTJ;
-        k_assemble_tiled<<<dim3(capped_blocks(c, (size_t)tiles_i * tiles_j, 1), (unsigned)c->nbatch, 1), kTI * kTJ, 0, c->stream>>>(
-            c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud, geo, o, tiles_j, 0, 0, c->nx, 0);
-      } else {
-        k_assemble<0><<<g, kBlock, 0, c->stream>>>(c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud, geo, o);
-      }
+      launch_assembly(c, geo, o, c->opt.reserved[0]);  // reserved[0]: 1 forces the per-cell kernel, 2 the tiled kernel without TMA (tests)
     }
     if (xl) {  // LU of the x-line segments for this step's operator
       Prof p(c, SY2D_K_OTHER);
@@ -1314,20 +1370,12 @@ int sy2d_bench_kernel(sy2d_ctx* c, int which, int reps, double* ms_per_launch) {
   const dim3 g = grid_of(c);
   const bool vec2 = c->ny % 2 == 0;
   const dim3 g2(capped_blocks(c, c->N / 2, kBlock), (unsigned)c->nbatch, 1);
-  const bool tiled = c->nx >= 2 * kTI && c->ny >= kTJ;
-  const int tiles_i = (c->nx + kTI - 1) / kTI, tiles_j = (c->ny + kTJ - 1) / kTJ;
   AssembleOut o;
   std::memset(&o, 0, sizeof o);
   o.wW = c->wW; o.wE = c->wE; o.wS = c->wS; o.wN = c->wN; o.rhs = c->rhs; o.cs = c->cs;
   o.scal = c->scal; o.n_active = c->d_nactive; o.tol = -1.0;  // tol < 0: every problem stays active
   o.local_rows = c->nx;
-  auto assemble = [&]() {
-    if (tiled)
-      k_assemble_tiled<<<dim3(capped_blocks(c, (size_t)tiles_i * tiles_j, 1), (unsigned)c->nbatch, 1), kTI * kTJ, 0, c->stream>>>(
-          c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud, geo, o, tiles_j, 0, 0, c->nx, 0);
-    else
-      k_assemble<0><<<g, kBlock, 0, c->stream>>>(c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud, geo, o);
-  };
+  auto assemble = [&]() { launch_assembly(c, geo, o, c->opt.reserved[0]); };
   auto launch = [&](int w) {
     switch (w) {
       case SY2D_K_ASSEMBLY: assemble(); break;

@@ -182,7 +182,8 @@ def _random_case(seed, nx, ny, bc):
 
 
 @pytest.mark.parametrize("seed,nx,ny,bc", [(1, 33, 21, (0, 0, 0, 0)), (2, 7, 50, (1, 1, 1, 1)), (3, 64, 64, (0, 1, 1, 0)),
-                                           (4, 1, 9, (0, 0, 1, 1)), (5, 9, 1, (1, 0, 0, 0)), (6, 2, 2, (0, 1, 0, 1))])
+                                           (4, 1, 9, (0, 0, 1, 1)), (5, 9, 1, (1, 0, 0, 0)), (6, 2, 2, (0, 1, 0, 1)),
+                                           (7, 45, 36, (0, 0, 0, 0)), (8, 24, 20, (1, 1, 1, 1))])
 @pytest.mark.parametrize("engine,precond", ENGINES)
 def test_random_problems_match_oracle(seed, nx, ny, bc, engine, precond):
     """Ragged, tiny and degenerate (single row/column) grids, every BC combination class."""
@@ -191,6 +192,8 @@ def test_random_problems_match_oracle(seed, nx, ny, bc, engine, precond):
     eng = sy.Engine(m.x_edges, m.y_edges, m.dt)
     if precond == 1 and ((engine == 1 and nx < 16) or (engine == 2 and (nx > 80 or ny > 128))):
         pytest.skip("x-line preconditioner not available for this shape")
+    if precond == 2 and (nx < 8 or ny % 4 or ny < 16):
+        pytest.skip("multigrid preconditioner not available for this shape")
     eng.set_options(engine=engine, precond=precond)
     eng.set_coeffs(eq.G, eq.Dxx, eq.Dxy, eq.Dyy, eq.inv_tau)
     eng.set_bc(bc, *[l if b == 0 else None for l, b in zip(lines, bc)])
@@ -327,18 +330,53 @@ def test_reference_main_with_gpu_solver_dropped_in(tmp_path, case, ini, tag, run
         assert max_rel(np.load(d / f"f_{k}.npy"), g[f"f_{k}"]) < PARITY
 
 
+def _force_assembly(eng, variant):
+    o = eng.options(); o.engine = 1; o.reserved[0] = variant
+    eng._check(eng.lib.sy2d_set_options(eng._ctx, o)); eng._opt = o
+
+
 @pytest.mark.parametrize("tag", ["nu48x40", "syn64x48", "lc80"])
 def test_tiled_assembly_equals_per_cell_assembly(tag):
-    """Engine 1 assembles with the shared-memory tile kernel (faces evaluated once per tile);
-    forcing the one-thread-per-cell kernel must give the same f (ragged tiles: 40 = 32 + 8 columns)."""
+    """Engine 1 assembles with the TMA-staged tile kernel (faces evaluated once per tile); forcing the
+    tile kernel without TMA (2) or the one-thread-per-cell kernel (1) must give the same f (ragged
+    tiles: 40 = 32 + 8 columns)."""
     g = load_golden(tag)
-    a = engine_from_golden(g, CASE_OF[tag], engine=1)
-    b = engine_from_golden(g, CASE_OF[tag], engine=1)
-    o = b.options(); o.engine = 1; o.reserved[0] = 1
-    b._check(b.lib.sy2d_set_options(b._ctx, o)); b._opt = o
-    a.step(6); b.step(6)
-    assert max_rel(a.get_f(), b.get_f()) < 1e-12
-    a.close(); b.close()
+    engs = [engine_from_golden(g, CASE_OF[tag], engine=1) for _ in range(3)]
+    _force_assembly(engs[1], 1)
+    _force_assembly(engs[2], 2)
+    for e in engs:
+        e.step(6)
+    assert max_rel(engs[0].get_f(), engs[1].get_f()) < 1e-12
+    # same per-face arithmetic; only the order of the atomics behind the Krylov scalars differs
+    assert max_rel(engs[0].get_f(), engs[2].get_f()) < 1e-12
+    for e in engs:
+        e.close()
+
+
+@pytest.mark.parametrize("nx,ny,nbatch", [(1024, 1024, 1), (100, 70, 3), (23, 34, 2), (264, 96, 1)])
+def test_tma_assembly_equals_the_tiled_kernel(nx, ny, nbatch):
+    """TMA-staged halo tiles (zero-filled outside the domain, two-stage ring, several tiles per CTA)
+    against the tile kernel with plain loads: the same operator rows, hence the same f up to the order of
+    the reduction atomics, on full-size, ragged and batched grids."""
+    xe, ye = fields.uniform_edges(nx, ny)
+    Dxx, Dxy, Dyy, inv_tau = fields.synthetic_tensor(xe, ye)
+    G = fields.ay_G(xe, ye)
+    f0, bct, lines = fields.ay_init_and_bc(xe, ye)
+    rep = lambda a: np.broadcast_to(a, (nbatch,) + a.shape).copy()
+    scale = (1.0 + 0.25 * np.arange(nbatch))[:, None, None]
+    out = []
+    for variant in (0, 2):
+        eng = sy.Engine(xe, ye, 0.002, nbatch=nbatch)
+        eng.set_options(engine=1)
+        _force_assembly(eng, variant)
+        eng.set_coeffs(rep(G), rep(Dxx) * scale, rep(Dxy) * scale, rep(Dyy) * scale, rep(inv_tau))
+        eng.set_bc(bct, *lines)
+        eng.set_f(rep(f0))
+        st = eng.step(2)
+        assert st["negatives"] == 0
+        out.append(eng.get_f())
+        eng.close()
+    assert max_rel(out[0], out[1]) < 1e-11
 
 
 def test_step_host_pipelined_matches_resident_stepping():
