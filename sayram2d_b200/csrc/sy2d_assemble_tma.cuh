@@ -112,24 +112,28 @@ __global__ void __launch_bounds__(kTI * kTJ, 4) k_assemble_tma(const AsmMaps* __
     const double* cxs = tys + kTmaHaloPad;
     const double* Us = cxs + kTmaHaloPad;            // [8][32] interior tiles
     const double* Uds = Us + kTmaInnerElems;
-    mbar_wait(&sm.full[s], parity);
 #define H(arr, aa, bb) arr[(aa) * kTmaHaloJ + (bb) + 1]
     const bool edge_tile = I0 == 0 || I0 + kTI >= nx || J0 == 0 || J0 + kTJ >= ny;
-    // 2. vertices (I0 + a', J0 + b')
-    auto vertex = [&](int va, int vb) {
+    // vertex weights of the thread's own vertex: fetched before the wait so that their latency overlaps it
+    double wl = 0.0, wr = 0.0, wb = 0.0, wt = 0.0;
+    if (!edge_tile) { wl = g.wxL[I0 + a]; wr = g.wxR[I0 + a]; wb = g.wyB[J0 + b]; wt = g.wyT[J0 + b]; }
+    mbar_wait(&sm.full[s], parity);
+    // 2. vertices (I0 + a', J0 + b').  The extra row / column of every stage goes to a different warp
+    // (1 .. 4), so that no warp does more than one extra pass between two barriers.
+    auto vertex = [&](int va, int vb, bool own) {
       const int vi = I0 + va, vj = J0 + vb;
       double v = 0.0;
       if (!edge_tile) {
-        const double wl = g.wxL[vi], wr = g.wxR[vi], wb = g.wyB[vj], wt = g.wyT[vj];
+        if (!own) { wl = g.wxL[vi]; wr = g.wxR[vi]; wb = g.wyB[vj]; wt = g.wyT[vj]; }
         v = wl * wb * H(fs, va, vb) + wr * wb * H(fs, va + 1, vb) + wl * wt * H(fs, va, vb + 1) + wr * wt * H(fs, va + 1, vb + 1);
       } else if (vi <= nx && vj <= ny) {
         v = vertex_value(g, vi, vj, H(fs, va, vb), H(fs, va + 1, vb), H(fs, va, vb + 1), H(fs, va + 1, vb + 1));
       }
       sm.vs[va][vb] = v;
     };
-    vertex(a, b);
-    if (a == 0) vertex(kTI, b);
-    if (tid <= kTI) vertex(tid, kTJ);
+    vertex(a, b, true);
+    if (a == 1) vertex(kTI, b, false);
+    if (a == 2 && b <= kTI) vertex(b, kTJ, false);
     __syncthreads();
     // 3a. west faces of cells (I0 + a', J0 + b'), a' = 0..TI: K = (i, j), L = (i-1, j)
     auto wface = [&](int fa, int fb) {
@@ -146,7 +150,7 @@ __global__ void __launch_bounds__(kTI * kTJ, 4) k_assemble_tma(const AsmMaps* __
       sm.WL[fa][fb] = AL;
     };
     wface(a, b);
-    if (a == 0) wface(kTI, b);
+    if (a == 3) wface(kTI, b);
     // 3b. south faces of cells (I0 + a', J0 + b'), b' = 0..TJ: K = (i, j), L = (i, j-1)
     auto sface = [&](int fa, int fb) {
       const int i = I0 + fa, j = J0 + fb;
@@ -162,7 +166,7 @@ __global__ void __launch_bounds__(kTI * kTJ, 4) k_assemble_tma(const AsmMaps* __
       sm.SL[fa][fb] = AL;
     };
     sface(a, b);
-    if (tid < kTI) sface(tid, kTJ);
+    if (a == 4 && b < kTI) sface(b, kTJ);
     __syncthreads();
     // 4. rows
     const int i = I0 + a, j = J0 + b;

@@ -300,15 +300,13 @@ __host__ __device__ __forceinline__ void assemble_row(const double* __restrict__
 
 struct Scaled {  // row of the scaled unit-diagonal system A d = rhs
   double wW, wE, wS, wN, rhs, cs;
-  double om;     // M_KK c_K: the row was divided by this
 };
 
 // Column scale c = f*yprev (neighbours too), row scale 1/(M_KK c_K); rhs = D_r R - A 1.
 __host__ __device__ __forceinline__ void scale_row(const Row& r, double ypC, double ypW, double ypE, double ypS,
                                                    double ypN, Scaled& s) {
   const double cs0 = r.f00 * ypC;
-  s.om = r.diag * cs0;
-  const double dscale = sy2d_div(1.0, s.om);
+  const double dscale = sy2d_div(1.0, r.diag * cs0);
   s.wW = r.oW * (r.fW * ypW) * dscale;
   s.wE = r.oE * (r.fE * ypE) * dscale;
   s.wS = r.oS * (r.fS * ypS) * dscale;
@@ -381,7 +379,7 @@ __global__ void __launch_bounds__(kBlock) k_assemble(const double* __restrict__ 
       o.wW[c0] = sc.wW; o.wE[c0] = sc.wE; o.wS[c0] = sc.wS; o.wN[c0] = sc.wN;
       o.rhs[c0] = sc.rhs;
       o.cs[c0] = sc.cs;
-      if (o.om) o.om[c0] = sc.om;
+      if (o.om) o.om[c0] = row.diag * sc.cs;   // M_KK c_K: what scale_row divided the row by
       rr = sc.rhs * sc.rhs;
       rabs = fabs(sc.rhs);
     }
