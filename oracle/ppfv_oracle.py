@@ -232,6 +232,29 @@ class AlbertYoung(Equation):
                 self._f0(m.x_edges, self.p.logEmin), np.zeros(m.nx + 1)]
 
 
+class TimeDependent(AlbertYoung):
+    """The time-dependent user case of oracle/ref_driver.cc (Time_Dependent): AY with
+    D(t) = D0 (1 + 0.5 sin(2 pi t / 0.1)), 1/tau(t) = 3 sin^2(pi t / 0.05) on the first quarter of the
+    alpha0 rows, low-energy Dirichlet line x exp(-2 t).  Exercises Solver.cc:286-289."""
+
+    def __init__(self, paras, mesh, table):
+        super().__init__(paras, mesh, table)
+        self.D0 = (self.Dxx.copy(), self.Dxy.copy(), self.Dyy.copy())
+        self.update(0.0)
+
+    def update(self, t):
+        a = 1.0 + 0.5 * math.sin(2.0 * gPI * t / 0.1)
+        s = math.sin(gPI * t / 0.05)
+        self.Dxx, self.Dxy, self.Dyy = a * self.D0[0], a * self.D0[1], a * self.D0[2]
+        self.inv_tau = np.zeros_like(self.Dxx)
+        self.inv_tau[: self.m.nx // 4, :] = 3.0 * s * s
+
+    def dirichlet_lines(self, t):
+        lines = super().dirichlet_lines(t)
+        lines[2] = lines[2] * math.exp(-2.0 * t)
+        return lines
+
+
 class AlbertYoungLC(Equation):
     """source/Cases/Albert_Young_LC.{h,cc}."""
 
@@ -527,6 +550,8 @@ def build_case(case, ini_path=None, table=None, stretch=0.0, member=None, **over
         eq = AlbertYoungLC(p, m, table)
     elif case == "SYN":
         eq = SyntheticTensor(p, m)
+    elif case == "TD":
+        eq = TimeDependent(p, m, table)
     elif case == "ENS":
         eq = AlbertYoungLC(p, m, table)
         a, b = member

@@ -7,11 +7,12 @@
 // "reference" CPU baseline that bench.py times.  It follows main.cc:41-85 (same
 // construction order, same time loop) but writes .npy files and per-step timing.
 //
-//   ref_driver --case AY|LC|SYN|ENS --ini <file> --out <dir> [--steps N]
+//   ref_driver --case AY|LC|SYN|ENS|TD --ini <file> --out <dir> [--steps N]
 //              [--every K] [--skip W] [--dump-op s1,s2,...] [--member a b] [--stretch s] [--cwd <dir>]
 //
 // SYN  = BASELINE config 3 (synthetic full tensor + loss strip on the AY domain);
 // ENS  = BASELINE config 4 member: LC case with D scaled by a, inv_tau by b.
+// TD   = time-dependent D, 1/tau and Dirichlet data (Equation::update(t) path).
 #include <unistd.h>
 
 #include <chrono>
@@ -63,6 +64,35 @@ class Ensemble_Member : public Albert_Young_LC {
         inv_tau_(i, j) *= b;
       }
   }
+};
+
+// A time-dependent user case (README.md:177: "update(t) is where G, D and the BCs are updated"): the
+// AY case with D(t) = D0 (1 + 0.5 sin(2 pi t / 0.1)), a loss term 1/tau(t) = 3 sin^2(pi t / 0.05) day^-1 on
+// the first quarter of the alpha0 rows, and the low-energy Dirichlet line decaying like exp(-2 t).
+// Exercises Solver.cc:286-289 (eq.update(t), update_Lambda, update_vertex_f after every step).
+class Time_Dependent : public Albert_Young {
+ public:
+  Time_Dependent(const Parameters& p, const Mesh& m) : Albert_Young(p, m), m_(m), Dxx0_(Dxx_), Dxy0_(Dxy_), Dyy0_(Dyy_) { update(0.0); }
+  void update(double t) override {
+    const double a = 1.0 + 0.5 * std::sin(2.0 * gPI * t / 0.1);
+    const double s = std::sin(gPI * t / 0.05);
+    for (std::size_t i = 0; i < m_.nx(); ++i)
+      for (std::size_t j = 0; j < m_.ny(); ++j) {
+        Dxx_(i, j) = a * Dxx0_(i, j);
+        Dxy_(i, j) = a * Dxy0_(i, j);
+        Dyy_(i, j) = a * Dyy0_(i, j);
+        inv_tau_(i, j) = i < m_.nx() / 4 ? 3.0 * s * s : 0.0;
+      }
+  }
+  bool dirichlet_vertex_value(BoundaryID side, std::size_t i, std::size_t j, double t, double* out) const override {
+    const bool ok = Albert_Young::dirichlet_vertex_value(side, i, j, t, out);
+    if (ok && side == BoundaryID::YMIN) *out *= std::exp(-2.0 * t);
+    return ok;
+  }
+
+ private:
+  const Mesh& m_;
+  Xtensor2d Dxx0_, Dxy0_, Dyy0_;
 };
 
 // main.cc:20-37; stretch != 0 warps the edges (xi -> xi + stretch*sin(2 pi xi)/(2 pi))
@@ -155,6 +185,7 @@ int main(int argc, char** argv) {
   else if (kase == "LC") eq = new Albert_Young_LC(paras, m);
   else if (kase == "SYN") eq = new Synthetic_Tensor(paras, m);
   else if (kase == "ENS") eq = new Ensemble_Member(paras, m, ma, mb);
+  else if (kase == "TD") eq = new Time_Dependent(paras, m);
   else { std::fprintf(stderr, "unknown case %s\n", kase.c_str()); return 2; }
 
   std::filesystem::create_directories(out);

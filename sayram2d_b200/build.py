@@ -67,9 +67,28 @@ def build_host(force=False):
     return BIN
 
 
+TD_BIN = os.path.join(PKG, "bin", "sayram2d_td")
+
+
+def build_examples(force=False):
+    """examples/time_dependent_case.cc: a user-defined time-dependent Equation run with the GPU Solver."""
+    hdir = os.path.join(PKG, "host")
+    src = os.path.join(PKG, "examples", "time_dependent_case.cc")
+    if not os.path.exists(src):
+        return None
+    srcs = [s for s in host_sources() if not s.endswith(os.sep + "main.cc")] + [src]
+    deps = srcs + [os.path.join(hdir, f) for f in os.listdir(hdir) if f.endswith(".h")] + [LIB, os.path.join(DROPIN, "Solver.h")]
+    if force or _stale(TD_BIN, deps):
+        os.makedirs(os.path.dirname(TD_BIN), exist_ok=True)
+        _run(["/usr/bin/g++", "-O2", "-std=c++17", "-I" + hdir, "-I" + DROPIN, "-I" + os.path.join(ROOT, "include"), *srcs,
+              "-L" + os.path.dirname(LIB), "-lsayram2d_b200", "-Wl,-rpath,$ORIGIN/../lib", "-o", TD_BIN])
+    return TD_BIN
+
+
 def build_all(force=False):
     build_library(force)
     build_host(force)
+    build_examples(force)
 
 
 if __name__ == "__main__":

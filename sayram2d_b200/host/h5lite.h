@@ -3,10 +3,12 @@
 //  read : the subset D/AlbertYoung_chorus.h5 uses - superblock v0, v1 group B-tree +
 //         local heap + symbol-table nodes (walked, not hard-coded offsets), v1 object
 //         headers, contiguous (layout v3) little-endian f64 datasets without filters.
-//  write: NumPy .npy (the /f/<k> snapshots of main.cc:74,83 become f_<k>.npy).
+//  write: the same HDF5 subset (h5lite::Writer: /alpha0, /logEN, /f/<k>, /t of main.cc:58-89, readable
+//         by libhdf5 / h5py / plot/cmp_ay.py) and NumPy .npy copies of the snapshots.
 #ifndef SY2D_HOST_H5LITE_H_
 #define SY2D_HOST_H5LITE_H_
 
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <fstream>
@@ -158,6 +160,194 @@ inline void write_npy(const std::string& path, const double* data, const std::ve
   out.write(hdr.data(), static_cast<std::streamsize>(hdr.size()));
   out.write(reinterpret_cast<const char*>(data), static_cast<std::streamsize>(n * 8));
 }
+
+// ---------------------------------------------------------------------------------------------
+// HDF5 WRITER for the output file of main.cc:58-67,74,83,87-89 (/alpha0, /logEN, /f/<k>, /t):
+// the same on-disk flavour as the files the reference reads and writes through HighFive with the
+// library defaults - superblock version 0, "old style" groups (version-1 object header with a
+// symbol-table message, version-1 B-tree node + local heap + one symbol-table node per group),
+// version-1 dataset headers with dataspace (v1), IEEE f64 little-endian datatype, fill-value (v2)
+// and contiguous layout (v3) messages, byte for byte the messages of data/D/AlbertYoung_chorus.h5.
+// Every group gets ONE symbol-table node, so the superblock's "group leaf node K" is raised to
+// half the largest group when a group has more than 8 members (the K values are per-file
+// parameters in the superblock; readers take them from there).
+// ---------------------------------------------------------------------------------------------
+class Writer {
+ public:
+  // path: "/name" or "/group/.../name"; data is copied
+  void add(const std::string& path, const double* data, const std::vector<std::size_t>& shape) {
+    if (path.empty() || path[0] != '/') throw std::runtime_error("h5lite::Writer: absolute path expected: " + path);
+    Item it;
+    it.shape = shape;
+    std::size_t n = 1;
+    for (auto d : shape) n *= d;
+    it.data.assign(data, data + n);
+    Group* g = &root_;
+    std::size_t pos = 1;
+    for (;;) {
+      const std::size_t slash = path.find('/', pos);
+      if (slash == std::string::npos) break;
+      const std::string name = path.substr(pos, slash - pos);
+      if (!g->groups.count(name)) g->order.push_back(name);
+      g = &g->groups[name];
+      pos = slash + 1;
+    }
+    const std::string leaf = path.substr(pos);
+    if (leaf.empty() || g->groups.count(leaf)) throw std::runtime_error("h5lite::Writer: bad dataset name in " + path);
+    items_.push_back(std::move(it));
+    if (!g->datasets.count(leaf)) g->order.push_back(leaf);
+    g->datasets[leaf] = items_.size() - 1;
+  }
+
+  void save(const std::string& filename) {
+    leafK_ = 4;
+    size_leafk(root_);
+    buf_.assign(96, 0);          // superblock (56 bytes) + root symbol-table entry (40 bytes)
+    const Placed r = place_group(root_);
+    const std::uint64_t undef = ~0ull;
+    static const unsigned char magic[8] = {0x89, 'H', 'D', 'F', '\r', '\n', 0x1a, '\n'};
+    std::memcpy(buf_.data(), magic, 8);
+    buf_[13] = 8; buf_[14] = 8;                                   // sizes of offsets / lengths
+    put<std::uint16_t>(16, static_cast<std::uint16_t>(leafK_));   // group leaf node K
+    put<std::uint16_t>(18, 16);                                   // group internal node K
+    put<std::uint64_t>(24, 0);                                    // base address
+    put<std::uint64_t>(32, undef);                                // free-space info
+    put<std::uint64_t>(40, buf_.size());                          // end-of-file address
+    put<std::uint64_t>(48, undef);                                // driver info
+    put<std::uint64_t>(56, 0);                                    // root entry: link name offset
+    put<std::uint64_t>(64, r.header);
+    put<std::uint32_t>(72, 1);                                    // cache type 1: scratch = B-tree, heap
+    put<std::uint64_t>(80, r.btree);
+    put<std::uint64_t>(88, r.heap);
+    std::ofstream out(filename, std::ios::binary);
+    if (!out) throw std::runtime_error("h5lite: cannot write " + filename);
+    out.write(reinterpret_cast<const char*>(buf_.data()), static_cast<std::streamsize>(buf_.size()));
+  }
+
+ private:
+  struct Item { std::vector<std::size_t> shape; std::vector<double> data; };
+  struct Group { std::map<std::string, Group> groups; std::map<std::string, std::size_t> datasets; std::vector<std::string> order; };
+  struct Placed { std::uint64_t header = 0, btree = 0, heap = 0; };
+
+  void size_leafk(const Group& g) {
+    const std::size_t n = g.groups.size() + g.datasets.size();
+    if (n > 2 * leafK_) leafK_ = (n + 1) / 2;
+    for (const auto& kv : g.groups) size_leafk(kv.second);
+  }
+  std::uint64_t alloc(std::size_t bytes) {
+    const std::uint64_t at = (buf_.size() + 7) & ~std::uint64_t(7);
+    buf_.resize(at + bytes, 0);
+    return at;
+  }
+  template <class T>
+  void put(std::uint64_t off, T v) { std::memcpy(buf_.data() + off, &v, sizeof v); }
+
+  // version-1 object header with one symbol-table message; B-tree node; local heap; symbol-table node
+  Placed place_group(const Group& g) {
+    Placed p;
+    p.header = alloc(16 + 24);
+    p.btree = alloc(24 + (2 * 16 + 1) * 8 + 2 * 16 * 8);
+    p.heap = alloc(32);
+    // heap data: "" at offset 0, then the member names in creation order (as libhdf5 lays them out),
+    // then one free block; the symbol-table node lists the members in strcmp order (std::map order)
+    std::map<std::string, bool> members;
+    for (const auto& kv : g.groups) members[kv.first] = true;
+    for (const auto& kv : g.datasets) members[kv.first] = false;
+    std::map<std::string, std::uint64_t> offset;
+    std::size_t hsize = 8;
+    for (const auto& name : g.order) { offset[name] = hsize; hsize += (name.size() + 1 + 7) & ~std::size_t(7); }
+    std::vector<std::pair<std::string, std::uint64_t>> names;   // sorted name -> heap offset
+    for (const auto& kv : members) names.emplace_back(kv.first, offset[kv.first]);
+    const std::size_t free_off = hsize;
+    hsize += 16;
+    const std::uint64_t hdata = alloc(hsize);
+    for (const auto& nm : names) std::memcpy(buf_.data() + hdata + nm.second, nm.first.data(), nm.first.size());
+    put<std::uint64_t>(hdata + free_off, 1);       // free block: next = 1 (end of list), size = 16
+    put<std::uint64_t>(hdata + free_off + 8, 16);
+    std::memcpy(buf_.data() + p.heap, "HEAP", 4);
+    put<std::uint64_t>(p.heap + 8, hsize);
+    put<std::uint64_t>(p.heap + 16, free_off);
+    put<std::uint64_t>(p.heap + 24, hdata);
+    const std::uint64_t snod = alloc(8 + 2 * leafK_ * 40);
+    // object header
+    buf_[p.header] = 1;
+    put<std::uint16_t>(p.header + 2, 1);            // one message
+    put<std::uint32_t>(p.header + 4, 1);            // reference count
+    put<std::uint32_t>(p.header + 8, 24);           // header data size
+    put<std::uint16_t>(p.header + 16, 0x0011);      // symbol-table message
+    put<std::uint16_t>(p.header + 18, 16);
+    put<std::uint64_t>(p.header + 24, p.btree);
+    put<std::uint64_t>(p.header + 32, p.heap);
+    // B-tree: one leaf entry pointing at the symbol-table node
+    std::memcpy(buf_.data() + p.btree, "TREE", 4);
+    buf_[p.btree + 4] = 0;                          // node type 0: group
+    buf_[p.btree + 5] = 0;                          // level 0
+    put<std::uint16_t>(p.btree + 6, names.empty() ? 0 : 1);
+    put<std::uint64_t>(p.btree + 8, ~0ull);
+    put<std::uint64_t>(p.btree + 16, ~0ull);
+    put<std::uint64_t>(p.btree + 24, 0);            // key 0: the empty string
+    put<std::uint64_t>(p.btree + 32, snod);
+    put<std::uint64_t>(p.btree + 40, names.empty() ? 0 : names.back().second);   // key 1: the largest name
+    // symbol-table node
+    std::memcpy(buf_.data() + snod, "SNOD", 4);
+    buf_[snod + 4] = 1;
+    put<std::uint16_t>(snod + 6, static_cast<std::uint16_t>(names.size()));
+    std::size_t k = 0;
+    for (const auto& nm : names) {
+      const std::uint64_t e = snod + 8 + 40 * k++;
+      put<std::uint64_t>(e, nm.second);
+      if (members[nm.first]) {
+        const Placed sub = place_group(g.groups.at(nm.first));
+        put<std::uint64_t>(e + 8, sub.header);
+        put<std::uint32_t>(e + 16, 1);
+        put<std::uint64_t>(e + 24, sub.btree);
+        put<std::uint64_t>(e + 32, sub.heap);
+      } else {
+        put<std::uint64_t>(e + 8, place_dataset(items_[g.datasets.at(nm.first)]));
+      }
+    }
+    return p;
+  }
+
+  std::uint64_t place_dataset(const Item& it) {
+    const std::size_t rank = it.shape.size();
+    const std::size_t space = 8 + 16 * rank;                                  // dataspace message body
+    const std::size_t used = (8 + space) + (8 + 24) + (8 + 8) + (8 + 24);
+    const std::size_t hsize = std::max<std::size_t>(256, used + 8);           // the library's default header block; rest is a NIL message
+    const std::uint64_t h = alloc(16 + hsize);
+    const std::uint64_t raw = alloc(it.data.size() * 8);
+    std::memcpy(buf_.data() + raw, it.data.data(), it.data.size() * 8);
+    buf_[h] = 1;
+    put<std::uint16_t>(h + 2, 5);
+    put<std::uint32_t>(h + 4, 1);
+    put<std::uint32_t>(h + 8, static_cast<std::uint32_t>(hsize));
+    std::uint64_t o = h + 16;
+    auto msg = [&](std::uint16_t type, std::size_t size, unsigned char flags) { put<std::uint16_t>(o, type); put<std::uint16_t>(o + 2, static_cast<std::uint16_t>(size)); buf_[o + 4] = flags; o += 8; return o; };
+    std::uint64_t b = msg(0x0001, space, 0);          // dataspace v1 with maximum dimensions
+    buf_[b] = 1; buf_[b + 1] = static_cast<unsigned char>(rank); buf_[b + 2] = 1;
+    for (std::size_t d = 0; d < rank; ++d) { put<std::uint64_t>(b + 8 + 8 * d, it.shape[d]); put<std::uint64_t>(b + 8 + 8 * (rank + d), it.shape[d]); }
+    o += space;
+    b = msg(0x0003, 24, 1);                           // datatype: IEEE 754 binary64, little endian
+    static const unsigned char f64[20] = {0x11, 0x20, 0x3f, 0x00, 0x08, 0x00, 0x00, 0x00, 0x00, 0x00, 0x40, 0x00, 0x34, 0x0b, 0x00, 0x34, 0xff, 0x03, 0x00, 0x00};
+    std::memcpy(buf_.data() + b, f64, 20);
+    o += 24;
+    b = msg(0x0005, 8, 1);                            // fill value v2: allocate late, write if set, defined, size 0
+    buf_[b] = 2; buf_[b + 1] = 2; buf_[b + 2] = 2; buf_[b + 3] = 1;
+    o += 8;
+    b = msg(0x0008, 24, 0);                           // layout v3, contiguous
+    buf_[b] = 3; buf_[b + 1] = 1;
+    put<std::uint64_t>(b + 2, raw);
+    put<std::uint64_t>(b + 10, it.data.size() * 8);
+    o += 24;
+    msg(0x0000, hsize - used - 8, 0);                 // NIL message: the rest of the header block
+    return h;
+  }
+
+  Group root_;
+  std::vector<Item> items_;
+  std::vector<unsigned char> buf_;
+  std::size_t leafK_ = 4;
+};
 
 }  // namespace h5lite
 

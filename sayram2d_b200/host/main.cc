@@ -1,8 +1,8 @@
 // Stand-alone driver with the flow of the reference's source/main.cc:39-96: parameters ->
 // uniform (alpha0, log E) grid -> Mesh -> Equation case -> Solver -> time loop with
-// nplots + 1 snapshots.  Without libhdf5 the snapshots are written as NumPy files into
-// <output_path>/<run_id>_data/ (alpha0.npy [deg], logEN.npy, f_<k>.npy, t.npy - the datasets
-// /alpha0, /logEN, /f/<k>, /t of the reference's HDF5 file).
+// nplots + 1 snapshots.  The output is the reference's HDF5 file <output_path>/<run_id>_data.h5 with
+// /alpha0 [deg], /logEN, /f/<k>, /t (main.cc:58-67,74,83,87-89; written by h5lite::Writer, no libhdf5
+// needed, plot/cmp_ay.py reads it unchanged) plus the same arrays as NumPy files in <run_id>_data/.
 //
 //   sayram2d [p.ini] [--case AY|LC]     (the reference selects the case at compile time)
 #include <chrono>
@@ -51,18 +51,27 @@ int main(int argc, char** argv) {
     for (std::size_t j = 0; j < m.ny(); ++j) logEN[j] = m.y(j) - std::log(gE0);
     h5lite::write_npy(dir + "/alpha0.npy", alpha0.data(), {alpha0.size()});
     h5lite::write_npy(dir + "/logEN.npy", logEN.data(), {logEN.size()});
+    h5lite::Writer h5;
+    h5.add("/alpha0", alpha0.data(), {alpha0.size()});     // main.cc:63-66
+    h5.add("/logEN", logEN.data(), {logEN.size()});
 
     const clock_t c0 = clock();
     const auto w0 = std::chrono::steady_clock::now();
     h5lite::write_npy(dir + "/f_0.npy", solver.f().data(), {m.nx(), m.ny()});
+    h5.add("/f/0", solver.f().data(), {m.nx(), m.ny()});  // main.cc:74
     for (int tstep = 1; tstep <= paras.nsteps(); ++tstep) {
       solver.update();
-      if (tstep % paras.save_every_step() == 0)
-        h5lite::write_npy(dir + "/f_" + std::to_string(tstep / paras.save_every_step()) + ".npy", solver.f().data(), {m.nx(), m.ny()});
+      if (tstep % paras.save_every_step() == 0) {
+        const std::string k = std::to_string(tstep / paras.save_every_step());
+        h5lite::write_npy(dir + "/f_" + k + ".npy", solver.f().data(), {m.nx(), m.ny()});
+        h5.add("/f/" + k, solver.f().data(), {m.nx(), m.ny()});   // main.cc:83
+      }
     }
     std::vector<double> t(paras.nplots() + 1);
     for (int k = 0; k <= paras.nplots(); ++k) t[k] = paras.T() * k / paras.nplots();
     h5lite::write_npy(dir + "/t.npy", t.data(), {t.size()});
+    h5.add("/t", t.data(), {t.size()});                    // main.cc:87-89
+    h5.save(paras.output_path() + paras.run_id() + "_data.h5");
     const double cpu = double(clock() - c0) / CLOCKS_PER_SEC;
     const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - w0).count();
     std::cout << "CPU time used " << cpu << " seconds" << std::endl;  // the reference's line (main.cc:93)

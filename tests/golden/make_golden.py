@@ -17,6 +17,8 @@ Fixtures (all f64, (nx,ny) row-major j-fastest = reference layout):
   syn64x48.npz        : BASELINE config 3 tensor on a 64x48 grid, 10 steps.
   ens_members.npz     : BASELINE config 4 members 0, 63, 2047, 4095 after 500 steps.
   syn1024_sub.npz     : config 3 at 1024x1024, 3 steps, f sub-sampled every 8 cells.
+  td64.npz            : time-dependent user case (D(t), 1/tau(t), Dirichlet data(t); ref_driver.cc
+                        Time_Dependent) on a 64x64 grid, 60 steps, snapshots every 20 steps.
 """
 import json
 import os
@@ -85,6 +87,14 @@ def main():
             ens[f"f1_m{mth}"] = np.load(os.path.join(work, f"ens{mth}", "f_1.npy"))
             print("ens", mth, a, b, meta)
         np.savez_compressed(os.path.join(HERE, "ens_members.npz"), **ens)
+
+        open(os.path.join(work, "td.ini"), "w").write(ini_text("td64", 64, 64, 5))
+        meta = drive(work, "TD", "td.ini", "td", "--steps", 60, "--every", 20)
+        d = load(work, "td", ["x_edges", "y_edges", "G", "f_0", "f_1", "f_2", "f_3"])
+        np.savez_compressed(os.path.join(HERE, "td64.npz"), meta=json.dumps(meta), **d)
+        print("td64", meta)
+        if "--only-td" in sys.argv:
+            return
 
         open(os.path.join(work, "syn1024.ini"), "w").write(ini_text("syn1024", 1024, 1024, 5))
         meta = drive(work, "SYN", "syn1024.ini", "syn1024", "--steps", 3)

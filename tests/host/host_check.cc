@@ -67,6 +67,29 @@ int main(int argc, char** argv) {
     expect(p.alpha0_min() == 5 * gPI / 180 && p.logEmax() == std::log(5.0) && p.dID() == "X" && p.output_path() == "./output/q/", "derived values");
     return bad;
   }
+  if (argc >= 3 && !std::strcmp(argv[1], "h5write")) {
+    // h5write <file> [mirror]: "mirror" writes datasets with the names and shapes of D/AlbertYoung_chorus.h5
+    // (so the structures can be compared byte for byte with a file written by libhdf5); otherwise the
+    // layout of the reference's output file with 13 snapshots under /f (more than one default leaf node).
+    h5lite::Writer w;
+    auto ramp = [](std::size_t n, double a) { std::vector<double> v(n); for (std::size_t k = 0; k < n; ++k) v[k] = a + 0.5 * static_cast<double>(k); return v; };
+    if (argc >= 4 && !std::strcmp(argv[3], "mirror")) {
+      w.add("/alpha0", ramp(91, 0.0).data(), {91});
+      w.add("/E", ramp(49, 1.0).data(), {49});
+      w.add("/Daa", ramp(91 * 49, 2.0).data(), {91, 49});
+      w.add("/Dap", ramp(91 * 49, 3.0).data(), {91, 49});
+      w.add("/Dpp", ramp(91 * 49, 4.0).data(), {91, 49});
+    } else {
+      w.add("/alpha0", ramp(6, 5.0).data(), {6});
+      w.add("/logEN", ramp(4, -1.0).data(), {4});
+      for (int k = 0; k <= 12; ++k) w.add("/f/" + std::to_string(k), ramp(24, 100.0 * k).data(), {6, 4});
+      w.add("/t", ramp(13, 0.0).data(), {13});
+    }
+    w.save(argv[2]);
+    h5lite::File back(argv[2]);                      // this repo's C++ reader walks what the writer wrote
+    std::cout << "datasets " << back.datasets().size() << " f/12[23] " << (back.datasets().count("/f/12") ? back.read("/f/12")[23] : -1.0) << std::endl;
+    return 0;
+  }
   if (argc < 5 || std::strcmp(argv[1], "dump")) { std::cerr << "usage: host_check dump <AY|LC> <ini> <outdir> | errors | ini <file>" << std::endl; return 2; }
   const std::string kase = argv[2], out = argv[4];
   Parameters paras(argv[3]);

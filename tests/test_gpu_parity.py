@@ -312,6 +312,12 @@ def test_standalone_host_binary_full_run(tmp_path, case, ini, tag, run_id):
     for k in (0, 1, 5, 10):
         assert max_rel(np.load(d / f"f_{k}.npy"), g[f"f_{k}"]) < PARITY
     assert np.allclose(np.load(d / "t.npy"), np.linspace(0, 1, 11)) and np.load(d / "alpha0.npy").shape == (80,)
+    # the reference's output file (main.cc:58-89): /alpha0 [deg], /logEN, /f/0../f/10, /t as HDF5
+    import h5min
+    h5 = h5min.H5File(str(tmp_path / "output" / run_id / f"{run_id}_data.h5"))
+    assert sorted(h5.datasets) == sorted(["/alpha0", "/logEN", "/t"] + [f"/f/{k}" for k in range(11)])
+    assert np.array_equal(h5.read("/f/10"), np.load(d / "f_10.npy")) and np.array_equal(h5.read("/t"), np.load(d / "t.npy"))
+    assert np.allclose(h5.read("/alpha0"), np.degrees(0.5 * (g["x_edges"][1:] + g["x_edges"][:-1])), rtol=1e-14)
 
 
 @pytest.mark.parametrize("case,ini,tag,run_id", [("AY", "p.ini", "ay80", "AlbertYoung"), ("LC", "p_AlbertYoungLC.ini", "lc80", "AlbertYoungLC")])
@@ -328,6 +334,42 @@ def test_reference_main_with_gpu_solver_dropped_in(tmp_path, case, ini, tag, run
     d = tmp_path / "output" / run_id / f"{run_id}_data.h5.d"
     for k in (0, 1, 5, 10):
         assert max_rel(np.load(d / f"f_{k}.npy"), g[f"f_{k}"]) < PARITY
+
+
+def test_time_dependent_fields_and_boundary_data(tmp_path):
+    """Equation::update(t) (Solver.cc:286-289) through both routes: sy2d_set_coeffs / sy2d_set_bc called
+    before every step from Python, and the drop-in C++ Solver re-staging what eq.update(t) changed
+    (sayram2d_b200/examples/time_dependent_case.cc); reference: tests/golden/td64.npz."""
+    import math
+    import os
+    from conftest import ROOT
+    import h5min
+    import ppfv_oracle as O
+    g = load_golden("td64")
+    table = h5min.load_d_table(os.path.join(ROOT, "data", "D", "AlbertYoung_chorus.h5"))
+    kw = dict(nalpha0=64, nE=64, alpha0min=5, alpha0max=90, Emin=0.2, Emax=5, T=1.0, nplots=10, nsteps=500)
+    p, m, eq = O.build_case("TD", None, table, **kw)       # only the case DATA (fields, lines) come from the oracle
+    for engine, precond in ((1, 2), (2, 1)):
+        eng = sy.Engine(g["x_edges"], g["y_edges"], 0.002)
+        eng.set_options(engine=engine, precond=precond)
+        eng.set_f(g["f_0"])
+        for step in range(60):
+            t = step * 0.002
+            eq.update(t)
+            eng.set_coeffs(eq.G, eq.Dxx, eq.Dxy, eq.Dyy, eq.inv_tau)
+            eng.set_bc(eq.bc, *eq.dirichlet_lines(t))
+            st = eng.step(1)
+            assert st["negatives"] == 0
+            if (step + 1) % 20 == 0:
+                assert max_rel(eng.get_f()[0], g[f"f_{(step + 1) // 20}"]) < PARITY, (engine, step)
+        eng.close()
+    ini = tmp_path / "td.ini"
+    ini.write_text("[basic]\nrun_id = td64\nnalpha0 = 64\nnE = 64\nalpha0min = 5\nalpha0max = 90\nEmin = 0.2\nEmax = 5\nT = 1.0\n"
+                   "nsteps = 500\n[diagnostics]\nnplots = 10\n[diffusion_coefficients]\ndID = AlbertYoung_chorus\n")
+    out = _run_binary(os.path.join(ROOT, "sayram2d_b200", "bin", "sayram2d_td"), [str(ini), str(tmp_path), "60", "20"], tmp_path)
+    assert "negatives 0" in out
+    for k in (0, 1, 2, 3):
+        assert max_rel(np.load(tmp_path / f"f_{k}.npy"), g[f"f_{k}"]) < PARITY, k
 
 
 def _force_assembly(eng, variant):

@@ -73,3 +73,52 @@ def test_dropin_solver_compiles_against_both_header_sets():
         assert decl in text, decl   # the reference's public interface, source/Solver.h:20-25
     if os.path.isdir("/root/reference/source"):
         assert os.path.exists(os.path.join(ROOT, "oracle", "_ref", "sayram-2d_AY_dropin"))
+
+
+def test_hdf5_writer_round_trip_and_structures(host_check, tmp_path):
+    """h5lite::Writer (the /alpha0, /logEN, /f/<k>, /t output file of main.cc:58-89 without libhdf5):
+    (1) the file is read back by the independent Python reader (oracle/h5min.py, itself validated on a
+    file written by libhdf5) and by the C++ reader; (2) a "mirror" file with the names and shapes of
+    data/D/AlbertYoung_chorus.h5 has byte-identical superblock parameters, group structures and dataset
+    header messages as that libhdf5-written file, addresses aside."""
+    import struct
+    import h5min
+    out = tmp_path / "o.h5"
+    res = subprocess.run([host_check, "h5write", str(out)], capture_output=True, text=True)
+    assert res.returncode == 0 and "datasets 16 f/12[23] 1211.5" in res.stdout, res.stdout + res.stderr
+    h = h5min.H5File(str(out))
+    assert sorted(h.datasets) == sorted(["/alpha0", "/logEN", "/t"] + [f"/f/{k}" for k in range(13)])
+    assert np.array_equal(h.read("/alpha0"), 5.0 + 0.5 * np.arange(6)) and np.array_equal(h.read("/t"), 0.5 * np.arange(13))
+    for k in range(13):
+        assert np.array_equal(h.read(f"/f/{k}"), (100.0 * k + 0.5 * np.arange(24)).reshape(6, 4))
+    raw = out.read_bytes()
+    assert struct.unpack_from("<Q", raw, 40)[0] == len(raw)                  # end-of-file address
+    assert struct.unpack_from("<H", raw, 16)[0] == 7                         # leaf K raised for the 13-member group /f
+
+    mir = tmp_path / "m.h5"
+    assert subprocess.run([host_check, "h5write", str(mir), "mirror"], capture_output=True, text=True).returncode == 0
+    a = mir.read_bytes()
+    b = open(os.path.join(ROOT, "data", "D", "AlbertYoung_chorus.h5"), "rb").read()
+    assert a[:40] == b[:40] and a[48:64] == b[48:64]                         # superblock up to the EOF address, driver info, root name
+    ra, rb = struct.unpack_from("<Q", a, 64)[0], struct.unpack_from("<Q", b, 64)[0]
+    assert a[ra:ra + 24] == b[rb:rb + 24]                                    # root object header + symbol-table message head
+    bta, hpa = struct.unpack_from("<QQ", a, 80)
+    btb, hpb = struct.unpack_from("<QQ", b, 80)
+    assert a[bta:bta + 32] == b[btb:btb + 32]                                # B-tree node head and key 0
+    assert struct.unpack_from("<Q", a, bta + 40)[0] == struct.unpack_from("<Q", b, btb + 40)[0]   # key 1: offset of the largest name
+    da, db = struct.unpack_from("<Q", a, hpa + 24)[0], struct.unpack_from("<Q", b, hpb + 24)[0]
+    assert a[hpa:hpa + 8] == b[hpb:hpb + 8] and a[da:da + 48] == b[db:db + 48]                    # heap: names at the same offsets
+    sa, sb = struct.unpack_from("<Q", a, bta + 32)[0], struct.unpack_from("<Q", b, btb + 32)[0]
+    assert a[sa:sa + 8] == b[sb:sb + 8]                                      # SNOD head: version, 5 symbols
+    ha, hb = h5min.H5File(str(mir)), h5min.H5File(os.path.join(ROOT, "data", "D", "AlbertYoung_chorus.h5"))
+    assert sorted(ha.datasets) == sorted(hb.datasets)
+    for k in range(5):                                                       # entries in the same (name) order; dataset headers
+        ea, eb = sa + 8 + 40 * k, sb + 8 + 40 * k
+        assert a[ea:ea + 8] == b[eb:eb + 8] and a[ea + 16:ea + 40] == b[eb + 16:eb + 40]
+        oa, ob = struct.unpack_from("<Q", a, ea + 8)[0], struct.unpack_from("<Q", b, eb + 8)[0]
+        hdr_a, hdr_b = bytearray(a[oa:oa + 16 + 256]), bytearray(b[ob:ob + 16 + 256])
+        rank = hdr_a[16 + 8 + 1]
+        lay = 16 + (8 + 8 + 16 * rank) + (8 + 24) + (8 + 8) + 8 + 2           # offset of the layout message's data address
+        assert hdr_a[lay + 8:lay + 16] == hdr_b[lay + 8:lay + 16]            # same dataset size
+        hdr_a[lay:lay + 8] = hdr_b[lay:lay + 8] = b"\0" * 8                  # the raw-data address is the only difference
+        assert hdr_a == hdr_b, k

@@ -164,3 +164,17 @@ def test_reduces_to_five_point_backward_euler():
     assert np.allclose(op["W"][1:, :], -2.0 * hy / hx, rtol=1e-12)
     assert np.allclose(op["S"][:, 1:], -0.5 * hx / hy, rtol=1e-12)
     assert np.allclose(op["R"], hx * hy / 0.01 * f, rtol=1e-12)
+
+
+def test_time_dependent_case_matches_reference(d_table):
+    """Equation::update(t) path (Solver.cc:286-289): D(t), 1/tau(t) and the Dirichlet data(t) of the
+    Time_Dependent user case, against the reference's own Solver run on the same class."""
+    g = load_golden("td64")
+    kw = dict(nalpha0=64, nE=64, alpha0min=5, alpha0max=90, Emin=0.2, Emax=5, T=1.0, nplots=10)
+    p, m, eq = O.build_case("TD", None, d_table, nsteps=500, **kw)
+    s = O.Solver(m, eq)
+    assert max_rel(s.f, g["f_0"]) < 1e-13
+    for k in (1, 2, 3):
+        for _ in range(20):
+            s.update()
+        assert max_rel(s.f, g[f"f_{k}"]) < 1e-10, k
