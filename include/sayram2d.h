@@ -62,8 +62,8 @@ typedef struct {
   int use_graph;     /* 1: replay the iteration chunk as a CUDA graph; default 1 */
   int engine;        /* 0 auto (2 when nx*ny <= 16384, else 1), 1 lockstep multi-kernel,
                         2 one persistent CTA per problem (whole time loop in one launch) */
-  int mg_levels;     /* SY2D_PRECOND_MG: maximum number of grid levels (0 = default 5) */
-  int mg_coarse_sweeps; /* SY2D_PRECOND_MG: smoothing sweeps on the coarsest level (0 = default 4) */
+  int mg_levels;     /* SY2D_PRECOND_MG: maximum number of grid levels (0 = default: coarsen to <= 64 columns) */
+  int mg_coarse_sweeps; /* SY2D_PRECOND_MG: smoothing sweeps on the coarsest level (0 = default 2) */
   int reserved[3];   /* reserved[0]: force the one-thread-per-cell assembly (tests); reserved[1]: slab mode, fixed
                         iteration budget without a convergence error (bench) */
 } sy2d_options;

@@ -158,9 +158,12 @@ unsigned capped_blocks(const sy2d_ctx* c, size_t work_items_per_problem, int thr
 // 32 rows), pairs of columns on every level (ny a multiple of 4 gives at least two levels) and a single GPU.
 int mg_level_count(const sy2d_ctx* c) {
   if (c->slab || c->nx > 2048 || c->nx < 8 || c->ny % 4 != 0 || c->ny < 16) return 0;
-  const int want = c->opt.mg_levels > 0 ? std::min(c->opt.mg_levels, kMgMaxLevels) : 5;
+  // default: coarsen until a level has at most 64 columns (measured optimum from 128^2 to 2048^2: fewer levels cost
+  // iterations, more levels cost latency-bound launches), at least two levels; mg_levels > 0 caps the count instead.
+  // A level is only halved while its ny is a multiple of 4, so the coarsest level keeps an even ny >= 8.
+  const int cap = c->opt.mg_levels > 0 ? std::min(c->opt.mg_levels, kMgMaxLevels) : kMgMaxLevels;
   int nlev = 1, ny = c->ny;
-  while (nlev < want && ny % 4 == 0 && ny >= 16) { ny /= 2; ++nlev; }   // the coarsest level keeps an even ny >= 8
+  while (nlev < cap && ny % 4 == 0 && ny >= 16 && (c->opt.mg_levels > 0 || ny > 64 || nlev < 2)) { ny /= 2; ++nlev; }
   return nlev >= 2 ? nlev : 0;
 }
 int mg_coarse_sweeps(const sy2d_ctx* c) { return c->opt.mg_coarse_sweeps > 0 ? c->opt.mg_coarse_sweeps : kMgCoarseSweeps; }

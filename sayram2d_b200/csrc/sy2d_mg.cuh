@@ -22,7 +22,7 @@
 //   zc = V(rc)
 //   t  = r - A (z + P zc)                               k_mg_resid<prolong>
 //   z  = z + P zc + omega T^-1 t                        k_mg_line<MODE 1>
-// coarsest level: kCoarseSweeps damped line-Jacobi sweeps.
+// coarsest level (<= 64 columns by default): kMgCoarseSweeps damped line-Jacobi sweeps.
 // T = tridiag(wW, 1, wE) along i over the WHOLE column, solved exactly by a partitioned Thomas
 // algorithm: a thread owns kMgSeg consecutive rows of one column, runs both recurrences in registers
 // with carry-in 0, the per-segment affine maps (carry -> last value) are composed by a warp-shuffle
@@ -36,7 +36,7 @@ namespace sy2d {
 constexpr int kMgMaxLevels = 8;
 constexpr double kMgOmega = 0.7;   // line-Jacobi damping
 constexpr double kMgTheta = 0.5;   // rescaling of the inter-aggregate couplings
-constexpr int kMgCoarseSweeps = 4;  // default number of smoothing sweeps on the coarsest level
+constexpr int kMgCoarseSweeps = 2;  // default number of smoothing sweeps on the coarsest level
 
 struct MgLevel {
   const double *wW, *wE, *wS, *wN;  // unit-diagonal operator

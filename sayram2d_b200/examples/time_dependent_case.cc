@@ -8,8 +8,8 @@
 //
 // The case: Albert & Young with D(t) = D0 (1 + 0.5 sin(2 pi t / 0.1)), a loss term
 // 1/tau(t) = 3 sin^2(pi t / 0.05) day^-1 on the first quarter of the alpha0 rows, and the low-energy
-// Dirichlet line decaying like exp(-2 t).  oracle/ref_driver.cc holds the same class on the
-// reference's own headers; tests/golden/td64.npz is what the reference's CPU Solver produced for it.
+// Dirichlet line decaying like exp(-2 t).  The test suite runs the same class on the reference's own
+// headers and CPU Solver; tests/golden/td64.npz is what that produced.
 #include <cmath>
 #include <cstdlib>
 #include <iostream>

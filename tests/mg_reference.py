@@ -1,19 +1,20 @@
 """NumPy restatement of the multigrid V-cycle of sayram2d_b200/csrc/sy2d_mg.cuh (tests only).
 
 Same hierarchy (pairs along j, unit-diagonal levels with row weights om, theta = 1/2 rescaling of the
-inter-aggregate couplings), same cycle (V(1,1), damped whole-x-line Jacobi, omega = 0.7, 4 sweeps on
+inter-aggregate couplings), same cycle (V(1,1), damped whole-x-line Jacobi, omega = 0.7, 2 sweeps on
 the coarsest level); written with whole-array operations, so it shares no code and no evaluation
 order with the kernels.  Arrays are (nx, ny) for one problem."""
 import numpy as np
 
-OMEGA, THETA, COARSE_SWEEPS = 0.7, 0.5, 4
+OMEGA, THETA, COARSE_SWEEPS = 0.7, 0.5, 2
 
 
-def level_count(nx, ny, want=5):
+def level_count(nx, ny, want=0):
+    """The engine's rule: coarsen to <= 64 columns (at least two levels); want > 0 caps the count instead."""
     if nx > 2048 or nx < 8 or ny % 4 or ny < 16:
         return 0
-    nlev = 1
-    while nlev < want and ny % 4 == 0 and ny >= 16:
+    nlev, cap = 1, (want if want > 0 else 8)
+    while nlev < cap and ny % 4 == 0 and ny >= 16 and (want > 0 or ny > 64 or nlev < 2):
         ny //= 2
         nlev += 1
     return nlev if nlev >= 2 else 0
