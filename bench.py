@@ -466,6 +466,12 @@ def big_grid_object(n, device):
     peak, peak_src = measured_peak()
     out = {"workload": f"grid{n}", "l2": f"per-kernel inputs {n * n * 48 / 1e6:.0f}-{n * n * 104 / 1e6:.0f} MB >> 126 MB L2: DRAM-bound, no flush needed",
            "peak": peak, "unit": "GB/s", "peak_source": peak_src, "sustained": sustained_kernels(eng, n * n, peak, reps=10)}
+    # whole time steps at this size (multigrid-preconditioned BiCGSTAB; no CPU figure: the direct LU needs > 100 GB here)
+    eng.step(1)
+    st = eng.step(2)
+    out.update({"value": n * n * st["steps"] / st["seconds_device"], "value_unit": UNIT, "ms_per_step": 1e3 * st["seconds_device"] / st["steps"],
+                "iters_per_step": st["iters_total"] / st["steps"], "precond": PRECOND_NAMES.get(st.get("precond", 0), "?"),
+                "resid_last": st["resid_last"], "negatives": st["negatives"]})
     eng.close()
     return out
 

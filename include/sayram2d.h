@@ -45,7 +45,7 @@ enum { SY2D_DIRICHLET = 0, SY2D_ZEROFLUX = 1 };
 /* preconditioner inside the BiCGSTAB loop */
 enum {
   SY2D_PRECOND_AUTO = -1,  /* engine 2: XLINE where the grid fits (nx <= 80, ny <= 128), else JACOBI;
-                              engine 1: MG where the grid fits (nx <= 2048, ny a multiple of 4), else XLINE */
+                              engine 1: MG where the grid fits (nx <= 4096, ny a multiple of 4), else XLINE */
   SY2D_PRECOND_JACOBI = 0, /* the unit-diagonal scaling itself */
   SY2D_PRECOND_XLINE = 1,  /* right preconditioning by the tridiagonal along i (alpha0): ~4x fewer iterations
                               (engine 1: block-Jacobi with 16-row line segments) */

@@ -157,7 +157,7 @@ unsigned capped_blocks(const sy2d_ctx* c, size_t work_items_per_problem, int thr
 // Multigrid (sy2d_mg.cuh) needs whole columns inside one CTA of the line kernel (nx <= 64 segments of 16 or
 // 32 rows), pairs of columns on every level (ny a multiple of 4 gives at least two levels) and a single GPU.
 int mg_level_count(const sy2d_ctx* c) {
-  if (c->slab || c->nx > 2048 || c->nx < 8 || c->ny % 4 != 0 || c->ny < 16) return 0;
+  if (c->slab || c->nx > 4096 || c->nx < 8 || c->ny % 4 != 0 || c->ny < 16) return 0;
   // default: coarsen until a level has at most 64 columns (measured optimum from 128^2 to 2048^2: fewer levels cost
   // iterations, more levels cost latency-bound launches), at least two levels; mg_levels > 0 caps the count instead.
   // A level is only halved while its ny is a multiple of 4, so the coarsest level keeps an even ny >= 8.
@@ -349,7 +349,8 @@ void mg_setup(sy2d_ctx* c) {
 }
 
 // Shape of the line kernel: rows per thread (SEG) x columns per CTA (COLS); a CTA holds all nx / SEG
-// segments of its columns: nx <= 1024: 8 x 8 (up to 1024 threads of ~60 registers), else 16 x 4.
+// segments of its columns: nx <= 1024: 8 x 8 (up to 1024 threads of ~60 registers), nx <= 2048: 16 x 4,
+// nx <= 4096: 16 x 2 (512 threads; 16-byte row chunks - half-used sectors, still far ahead of the alternatives).
 template <int SEG, int COLS, int MODE>
 void mg_line_shape(sy2d_ctx* c, const MgLevel& lv, const double* zc) {
   const MgArgs a{c->scal, c->nx};
@@ -366,7 +367,8 @@ template <int MODE>
 void mg_line(sy2d_ctx* c, const MgLevel& lv, const double* zc) {
   Prof p(c, SY2D_K_MG_LINE);
   if (c->mg_seg == 8) mg_line_shape<8, 8, MODE>(c, lv, zc);
-  else mg_line_shape<16, 4, MODE>(c, lv, zc);
+  else if (c->nx <= 2048) mg_line_shape<16, 4, MODE>(c, lv, zc);
+  else mg_line_shape<16, 2, MODE>(c, lv, zc);
 }
 
 template <int KIND>
@@ -1156,7 +1158,7 @@ int sy2d_step(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
   const bool xl = lockstep_xline(c);
   if (c->opt.precond == SY2D_PRECOND_XLINE && !xl) return fail(c, SY2D_ERR_INVALID, "sy2d_step: the x-line preconditioner needs nx >= %d", kSeg);
   if (c->opt.precond == SY2D_PRECOND_MG && !mg)
-    return fail(c, SY2D_ERR_INVALID, "sy2d_step: the multigrid preconditioner needs engine 1 on one GPU, 8 <= nx <= 2048 and ny a multiple of 4, >= 16");
+    return fail(c, SY2D_ERR_INVALID, "sy2d_step: the multigrid preconditioner needs engine 1 on one GPU, 8 <= nx <= 4096 and ny a multiple of 4, >= 16");
   st.precond = mg ? SY2D_PRECOND_MG : (xl ? SY2D_PRECOND_XLINE : SY2D_PRECOND_JACOBI);
   if (xl) { rc = xl_alloc(c); if (rc) return rc; }
   if (mg) { rc = mg_alloc(c); if (rc) return rc; }
