@@ -402,6 +402,9 @@ def ours(args):
                             "note": "engine-2 kernel: achieved = streaming-equivalent bytes / time; the state is on-chip, so "
                                     "DRAM traffic is far below it and frac > 1 measures the residency, not HBM speed",
                             "peak_source": peak_src, "kernels": rows}
+        if traffic:   # what actually crosses HBM, from the ncu byte count and this run's kernel time
+            dram = traffic / (r["ms_total"] * 1e-3) / 1e9
+            line["roofline"].update({"dram_achieved": round(dram, 1), "dram_frac": round(dram / peak, 4)})
     eng.close()
 
     if rank == 0 and world == 1:
