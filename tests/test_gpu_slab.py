@@ -57,7 +57,7 @@ def test_two_gpu_slab_matches_single_gpu(tmp_path):
     Dxx, Dxy, Dyy, inv_tau = fields.synthetic_tensor(xe, ye)
     f0, bct, lines = fields.ay_init_and_bc(xe, ye)
     ref = sy.Engine(xe, ye, 0.002)
-    ref.set_options(engine=1)
+    ref.set_options(engine=1, precond=1)   # the same segmented x-line iteration as the slab ranks run (iteration counts are compared)
     ref.set_coeffs(fields.ay_G(xe, ye), Dxx, Dxy, Dyy, inv_tau)
     ref.set_bc(bct, *lines)
     ref.set_f(f0)
