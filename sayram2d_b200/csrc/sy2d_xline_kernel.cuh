@@ -117,21 +117,111 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
   for (int step = 0; step < a.nsteps; ++step) {
     // ------------- assembly of the scaled rows owned by this thread -------------
     double acc[2] = {0.0, 0.0};
-#pragma unroll
-    for (int m = 0; m < R; ++m) {
-      const int i = i0 + m, q = m * NT + tid;
-      double wW = 0.0, wE = 0.0, wS = 0.0, wN = 0.0, rh = 0.0;
-      if (FULL || (col_ok && i < nx)) {
-        const Scaled sc = assemble_scaled_cell(f, yprev, tx, ty, cxy, U, Ud, a.g, i, j);
-        wW = sc.wW; wE = sc.wE; wS = sc.wS; wN = sc.wN; rh = sc.rhs;
+    if (FULL) {
+      // Full 80 x 80 tile: every interior face is evaluated ONCE per CTA instead of once per adjacent cell.
+      // A thread owns rows i0 .. i0+R-1 of column j: it marches up its column, so the W face of a row is the
+      // E face it computed for the row below (11 x-faces per 10 cells); the S faces of its cells go through
+      // shared memory (the hat and 1/d regions are free during the assembly) and come back as the N faces
+      // of column j-1.  Vertices: the vertical lines j and j+1, 2 x 11 evaluations per 10 cells instead of
+      // 40.  Same per-face expressions as assemble_row (K/L roles, operand order), same accumulation order.
+      const Geometry& g = a.g;
+      double* SK_s = hat;    // A_K, A_L of the south face of slot q
+      double* SL_s = di_s;
+      auto vertex_at = [&](int vi, int vj) {
+        const int il = vi > 0 ? vi - 1 : 0, ih = vi < nx ? vi : nx - 1;
+        const int jl = vj > 0 ? vj - 1 : 0, jh = vj < ny ? vj : ny - 1;
+        return vertex_value(g, vi, vj, f[il * ny + jl], f[ih * ny + jl], f[il * ny + jh], f[ih * ny + jh]);
+      };
+      // Both passes are rolled loops (small code, no spills); the vertices of line j are stashed in the l
+      // region (slot m holds V(i0 + m, j) until row m overwrites it with its wW), the top one in a register.
+      double vprev = vertex_at(i0, j);
+#pragma unroll 1
+      for (int m = 0; m < R; ++m) {
+        const int n = (i0 + m) * ny + j;
+        const double vnext = vertex_at(i0 + m + 1, j);
+        double AK = 0.0, AL = 0.0;
+        if (j > 0) {   // south face: K = (i, j), L = (i, j-1)
+          const double tyP = ty[n], cP = cxy[n], t = ty[n - 1], c = cxy[n - 1];
+          const double aS_A = tyP + cP, aS_B = tyP - cP, lA = t + c, lB = t - c;
+          face_pair(aS_A * vprev + aS_B * vnext, aS_A + aS_B, f[n], lA * vnext + lB * vprev, lA + lB, f[n - 1], AK, AL);
+        }
+        SK_s[m * NT + tid] = AK;
+        SL_s[m * NT + tid] = AL;
+        l_s[m * NT + tid] = vprev;
+        vprev = vnext;
       }
-      l_s[q] = wW;   // raw wW, wE until the factorisation below turns them into l and wE/d
-      e_s[q] = wE;
-      wS_g[q] = wS; wN_g[q] = wN; rhs_g[q] = rh;
-      rs[m] = rh;
-      acc[0] += rh * rh;
-      acc[1] = fmax(acc[1], fabs(rh));
+      const double vtop = vprev;   // V(i0 + R, j)
+      __syncthreads();
+      const int jn = j + 1;
+      const int tidN = jn < ny ? (jn / kXlineCPW) * 32 + (jn % kXlineCPW) * NCH + k : tid;   // same rows, column j+1
+      double vNW = vertex_at(i0, jn);
+      double AKw = 0.0, ALw = 0.0;   // west face of the current row: K = current cell, L = the row below
+      if (i0 > 0) {
+        const int n = i0 * ny + j;
+        const double v0 = l_s[tid];
+        const double txP = tx[n], cP = cxy[n], t = tx[n - ny], c = cxy[n - ny];
+        const double aW_A = txP - cP, aW_B = txP + cP, lA = t - c, lB = t + c;
+        face_pair(aW_A * vNW + aW_B * v0, aW_A + aW_B, f[n], lA * v0 + lB * vNW, lA + lB, f[n - ny], AKw, ALw);
+      }
+#pragma unroll 1
+      for (int m = 0; m < R; ++m) {
+        const int i = i0 + m, n = i * ny + j, q = m * NT + tid;
+        const double vSW = l_s[q], vSE = m + 1 < R ? l_s[q + NT] : vtop, vNE = vertex_at(i + 1, jn);
+        const double txP = tx[n], tyP = ty[n], cP = cxy[n], f00 = f[n];
+        Row row;
+        double diag = 0.0, Rr = 0.0;
+        row.oW = 0.0; row.oE = 0.0; row.oS = 0.0; row.oN = 0.0;
+        if (i > 0) { diag += AKw; row.oW = -ALw; }
+        else if (g.bc[0] == 0) diag += dirichlet_face((txP - cP) * vNW + (txP + cP) * vSW, (txP - cP) + (txP + cP), f00, Rr);
+        double AKe = 0.0, ALe = 0.0;
+        if (i < nx - 1) {   // east face: K = (i+1, j), L = this cell
+          const double t = tx[n + ny], c = cxy[n + ny];
+          const double kA = t - c, kB = t + c, aE_A = txP - cP, aE_B = txP + cP;
+          face_pair(kA * vNE + kB * vSE, kA + kB, f[n + ny], aE_A * vSE + aE_B * vNE, aE_A + aE_B, f00, AKe, ALe);
+          diag += ALe;
+          row.oE = -AKe;
+        } else if (g.bc[1] == 0) {
+          diag += dirichlet_face((txP - cP) * vSE + (txP + cP) * vNE, (txP - cP) + (txP + cP), f00, Rr);
+        }
+        if (j > 0) { diag += SK_s[q]; row.oS = -SL_s[q]; }
+        else if (g.bc[2] == 0) diag += dirichlet_face((tyP + cP) * vSW + (tyP - cP) * vSE, (tyP + cP) + (tyP - cP), f00, Rr);
+        if (j < ny - 1) { diag += SL_s[m * NT + tidN]; row.oN = -SK_s[m * NT + tidN]; }
+        else if (g.bc[3] == 0) diag += dirichlet_face((tyP + cP) * vNE + (tyP - cP) * vNW, (tyP + cP) + (tyP - cP), f00, Rr);
+        diag += Ud[n];
+        Rr += U[n] * f00;
+        row.diag = diag; row.R = Rr; row.f00 = f00;
+        const int nW = i > 0 ? n - ny : n, nE = i < nx - 1 ? n + ny : n, nS = j > 0 ? n - 1 : n, nN = j < ny - 1 ? n + 1 : n;
+        row.fW = f[nW]; row.fE = f[nE]; row.fS = f[nS]; row.fN = f[nN];
+        Scaled sc;
+        scale_row(row, yprev[n], yprev[nW], yprev[nE], yprev[nS], yprev[nN], sc);
+        l_s[q] = sc.wW;   // raw wW, wE until the factorisation below turns them into l and wE/d
+        e_s[q] = sc.wE;
+        wS_g[q] = sc.wS; wN_g[q] = sc.wN; rhs_g[q] = sc.rhs;
+        acc[0] += sc.rhs * sc.rhs;
+        acc[1] = fmax(acc[1], fabs(sc.rhs));
+        AKw = AKe; ALw = ALe; vNW = vNE;
+      }
+#pragma unroll
+      for (int m = 0; m < R; ++m) rs[m] = rhs_g[m * NT + tid];   // this thread wrote them: visible to itself
+    } else {
+#pragma unroll
+      for (int m = 0; m < R; ++m) {
+        const int i = i0 + m, q = m * NT + tid;
+        double wW = 0.0, wE = 0.0, wS = 0.0, wN = 0.0, rh = 0.0;
+        if (col_ok && i < nx) {
+          const Scaled sc = assemble_scaled_cell(f, yprev, tx, ty, cxy, U, Ud, a.g, i, j);
+          wW = sc.wW; wE = sc.wE; wS = sc.wS; wN = sc.wN; rh = sc.rhs;
+        }
+        l_s[q] = wW;   // raw wW, wE until the factorisation below turns them into l and wE/d
+        e_s[q] = wE;
+        wS_g[q] = wS; wN_g[q] = wN; rhs_g[q] = rh;
+        rs[m] = rh;
+        acc[0] += rh * rh;
+        acc[1] = fmax(acc[1], fabs(rh));
+      }
     }
+    // (the reduction's barriers also separate the face exchange through the 1/d region from the factorisation)
+    cta_reduce_x<2>(acc, 1, red);
     // LU of T down each column: chain over the NCH lanes of the column
     {
       double dlast = 1.0, wElast = 0.0;
@@ -153,7 +243,6 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
         }
       }
     }
-    cta_reduce_x<2>(acc, 1, red);
     double rho = acc[0];
     rmax = acc[1];
     double alpha = 1.0, omega = 1.0, beta = 0.0;
