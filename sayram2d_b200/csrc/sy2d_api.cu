@@ -349,8 +349,11 @@ void mg_setup(sy2d_ctx* c) {
 }
 
 // Shape of the line kernel: rows per thread (SEG) x columns per CTA (COLS); a CTA holds all nx / SEG
-// segments of its columns: nx <= 1024: 8 x 8 (up to 1024 threads of ~60 registers), nx <= 2048: 16 x 4,
-// nx <= 4096: 16 x 2 (512 threads; 16-byte row chunks - half-used sectors, still far ahead of the alternatives).
+// segments of its columns.  SEG = 8 up to nx = 1024 (at most 1024 threads of ~60 registers), else 16 (512
+// threads).  COLS is chosen PER LEVEL: as many columns as the thread limit allows (8 at most: 64-byte row
+// chunks) on levels with enough columns to fill the GPU, fewer on the coarse levels, so that a level is always
+// spread over ~128 CTAs - a CTA streams its columns' factors through one SM's L1 (131 KB per phase with 8
+// columns at nx = 1024), and that per-SM streaming time, not DRAM, is what a coarse-level solve waits for.
 template <int SEG, int COLS, int MODE>
 void mg_line_shape(sy2d_ctx* c, const MgLevel& lv, const double* zc) {
   const MgArgs a{c->scal, c->nx};
@@ -363,12 +366,32 @@ void mg_line_shape(sy2d_ctx* c, const MgLevel& lv, const double* zc) {
   else k_mg_line<SEG, COLS, MODE, false><<<g, threads, smem, c->stream>>>(lv, zc, a);
 }
 
+template <int SEG>
+int mg_line_cols(const sy2d_ctx* c, const MgLevel& lv) {
+  const int nseg = (c->nx + SEG - 1) / SEG;
+  const int max_threads = SEG <= 8 ? 1024 : 512;
+  int cols = 8;
+  while (cols > 1 && nseg * cols > max_threads) cols /= 2;
+  // fewer columns per CTA while that brings the level closer to one CTA per SM (and a CTA keeps >= 2 warps)
+  while (cols > 1 && lv.ny * c->nbatch / cols < 128 && nseg * (cols / 2) >= 64) cols /= 2;
+  return cols;
+}
+
+template <int SEG, int MODE>
+void mg_line_seg(sy2d_ctx* c, const MgLevel& lv, const double* zc) {
+  switch (mg_line_cols<SEG>(c, lv)) {
+    case 8: mg_line_shape<SEG, 8, MODE>(c, lv, zc); break;
+    case 4: mg_line_shape<SEG, 4, MODE>(c, lv, zc); break;
+    case 2: mg_line_shape<SEG, 2, MODE>(c, lv, zc); break;
+    default: mg_line_shape<SEG, 1, MODE>(c, lv, zc); break;
+  }
+}
+
 template <int MODE>
 void mg_line(sy2d_ctx* c, const MgLevel& lv, const double* zc) {
   Prof p(c, SY2D_K_MG_LINE);
-  if (c->mg_seg == 8) mg_line_shape<8, 8, MODE>(c, lv, zc);
-  else if (c->nx <= 2048) mg_line_shape<16, 4, MODE>(c, lv, zc);
-  else mg_line_shape<16, 2, MODE>(c, lv, zc);
+  if (c->mg_seg == 8) mg_line_seg<8, MODE>(c, lv, zc);
+  else mg_line_seg<16, MODE>(c, lv, zc);
 }
 
 template <int KIND>
