@@ -64,15 +64,17 @@ typedef struct {
                         2 one persistent CTA per problem (whole time loop in one launch) */
   int mg_levels;     /* SY2D_PRECOND_MG: maximum number of grid levels (0 = default: coarsen to <= 64 columns) */
   int mg_coarse_sweeps; /* SY2D_PRECOND_MG: smoothing sweeps on the coarsest level (0 = default 2) */
-  int reserved[3];   /* reserved[0]: force the one-thread-per-cell assembly (tests); reserved[1]: slab mode, fixed
-                        iteration budget without a convergence error (bench) */
+  int reserved[3];   /* reserved[0]: 1 forces the one-thread-per-cell assembly, 2 the tile kernel without TMA (tests); reserved[1]: slab mode,
+                        fixed iteration budget without a convergence error (bench); reserved[2]: 1 makes the first attempt of every
+                        AUTO multigrid step count as failed, so the x-line fallback runs (tests) */
 } sy2d_options;
 
 typedef struct {
   long long steps;            /* time steps taken by the call */
   long long iters_total;      /* BiCGSTAB iterations summed over steps (max over the batch per step) */
   int iters_last;             /* iterations of the last step (max over the batch) */
-  int restarts_total;         /* true-residual restarts */
+  int restarts_total;         /* time steps redone with the x-line iteration after the multigrid-preconditioned solve
+                                 of an AUTO context stopped without converging */
   double resid_last;          /* max over batch and cells of |rhs - A x| after the last solve (true residual) */
   double fmin;                /* min f over batch and cells after the last step */
   long long negatives;        /* number of cells with f < 0 after the last step */

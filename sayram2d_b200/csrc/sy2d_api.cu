@@ -91,6 +91,7 @@ struct sy2d_ctx {
   cudaGraphExec_t chunk_exec = nullptr;
   cudaGraphExec_t one_exec = nullptr;   // multigrid: a single iteration + the convergence poll
   int mg_last_iters = 0;                // iterations of the previous time step (issue plan of the next one)
+  bool mg_off = false;                  // multigrid failed on the current step: it is being redone with the x-line iteration
   int chunk_iters = 0;
   int chunk_variant = -1;
   // profiling
@@ -168,6 +169,7 @@ int mg_level_count(const sy2d_ctx* c) {
 }
 int mg_coarse_sweeps(const sy2d_ctx* c) { return c->opt.mg_coarse_sweeps > 0 ? c->opt.mg_coarse_sweeps : kMgCoarseSweeps; }
 bool lockstep_mg(const sy2d_ctx* c) {
+  if (c->mg_off) return false;
   if (c->opt.precond != SY2D_PRECOND_AUTO && c->opt.precond != SY2D_PRECOND_MG) return false;
   return mg_level_count(c) > 0;
 }
@@ -482,7 +484,7 @@ int build_chunk_graph(sy2d_ctx* c) {
   if (lockstep_mg(c)) {
     CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
     launch_iteration(c);
-    CU(cudaMemcpyAsync(c->h_nactive, c->d_nactive, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_nactive, c->d_nactive, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamEndCapture(c->stream, &graph));
     CU(cudaGraphInstantiate(&c->one_exec, graph, 0));
     cudaGraphDestroy(graph);
@@ -490,7 +492,7 @@ int build_chunk_graph(sy2d_ctx* c) {
   }
   CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
   for (int it = 0; it < check_every; ++it) launch_iteration(c);
-  CU(cudaMemcpyAsync(c->h_nactive, c->d_nactive, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(c->h_nactive, c->d_nactive, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamEndCapture(c->stream, &graph));
   CU(cudaGraphInstantiate(&c->chunk_exec, graph, 0));
   cudaGraphDestroy(graph);
@@ -630,7 +632,7 @@ int step_slab(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
     int rc = slab_halo_exchange(c, c->f);
     if (!rc) rc = slab_halo_exchange(c, c->yprev);
     if (rc) return rc;
-    CU(cudaMemsetAsync(c->d_nactive, 0, sizeof(int), c->stream));
+    CU(cudaMemsetAsync(c->d_nactive, 0, 2 * sizeof(int), c->stream));
     AssembleOut o;
     std::memset(&o, 0, sizeof o);
     o.wW = c->wW; o.wE = c->wE; o.wS = c->wS; o.wN = c->wN; o.rhs = c->rhs; o.cs = c->cs;
@@ -642,7 +644,7 @@ int step_slab(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
     if (rc) return rc;
     if (xl) k_xl_factor<<<gs, kBlock, 0, c->stream>>>(xv, c->N);
     c->launches += 3;
-    CU(cudaMemcpyAsync(c->h_nactive, c->d_nactive, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_nactive, c->d_nactive, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     int done_its = 0;
     while (*c->h_nactive > 0 && done_its < c->opt.maxit + c->opt.check_every) {
@@ -671,7 +673,7 @@ int step_slab(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
         if ((rc = slab_reduce(c, 3, k))) return rc;
       }
       CU(cudaGetLastError());
-      CU(cudaMemcpyAsync(c->h_nactive, c->d_nactive, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaMemcpyAsync(c->h_nactive, c->d_nactive, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
       CU(cudaStreamSynchronize(c->stream));
       done_its += c->opt.check_every;
       c->launches += (long long)c->opt.check_every * 8;
@@ -808,8 +810,8 @@ static int create_impl(sy2d_ctx** out, int device, int nx, int ny, int nbatch, c
   }
   CUB(cudaMalloc(reinterpret_cast<void**>(&ctx->scal), nbatch * sizeof(Scal)));
   CUB(cudaMemset(ctx->scal, 0, nbatch * sizeof(Scal)));
-  CUB(cudaMalloc(reinterpret_cast<void**>(&ctx->d_nactive), sizeof(int)));
-  CUB(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_nactive), sizeof(int)));
+  CUB(cudaMalloc(reinterpret_cast<void**>(&ctx->d_nactive), 2 * sizeof(int)));
+  CUB(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_nactive), 2 * sizeof(int)));
   CUB(cudaMalloc(reinterpret_cast<void**>(&ctx->d_stats), sizeof(StepStats)));
   CUB(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_stats), sizeof(StepStats)));
   CUB(cudaEventCreate(&ctx->ev_call0));
@@ -1172,23 +1174,35 @@ int sy2d_step(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
   const dim3 g = grid_of(c);
   const Geometry geo = geometry(c);
   const bool graph = c->opt.use_graph && !c->profiling;
-  const int check_every = c->profiling ? 1 : effective_check_every(c);  // profiling: no zero-work launches
   c->launches = 0;
   sy2d_stats st;
   std::memset(&st, 0, sizeof st);
   st.engine = 1;
-  const bool mg = lockstep_mg(c);
-  const bool xl = lockstep_xline(c);
+  bool mg = lockstep_mg(c);
+  bool xl = lockstep_xline(c);
   if (c->opt.precond == SY2D_PRECOND_XLINE && !xl) return fail(c, SY2D_ERR_INVALID, "sy2d_step: the x-line preconditioner needs nx >= %d", kSeg);
   if (c->opt.precond == SY2D_PRECOND_MG && !mg)
     return fail(c, SY2D_ERR_INVALID, "sy2d_step: the multigrid preconditioner needs engine 1 on one GPU, 8 <= nx <= 4096 and ny a multiple of 4, >= 16");
-  st.precond = mg ? SY2D_PRECOND_MG : (xl ? SY2D_PRECOND_XLINE : SY2D_PRECOND_JACOBI);
-  if (xl) { rc = xl_alloc(c); if (rc) return rc; }
-  if (mg) { rc = mg_alloc(c); if (rc) return rc; }
-  if (graph) { rc = build_chunk_graph(c); if (rc) return rc; }
+  auto prepare = [&]() -> int {   // buffers and graphs of the preconditioner in force
+    mg = lockstep_mg(c);
+    xl = lockstep_xline(c);
+    st.precond = mg ? SY2D_PRECOND_MG : (xl ? SY2D_PRECOND_XLINE : SY2D_PRECOND_JACOBI);
+    int r = SY2D_OK;
+    if (xl) r = xl_alloc(c);
+    if (!r && mg) r = mg_alloc(c);
+    if (!r && graph) r = build_chunk_graph(c);
+    return r;
+  };
+  rc = prepare();
+  if (rc) return rc;
   CU(cudaEventRecord(c->ev_call0, c->stream));
   for (int step = 0; step < nsteps; ++step) {
-    CU(cudaMemsetAsync(c->d_nactive, 0, sizeof(int), c->stream));
+   // One attempt with the preconditioner in force; when the multigrid-preconditioned solve of an AUTO context stops
+   // without converging (maxit, breakdown), the step is redone from the same f with the segmented x-line iteration
+   // (f is only updated by k_finish below, after a successful solve).
+   for (int attempt = 0; attempt < 2; ++attempt) {
+    const int check_every = c->profiling ? 1 : effective_check_every(c);  // profiling: no zero-work launches
+    CU(cudaMemsetAsync(c->d_nactive, 0, 2 * sizeof(int), c->stream));
     c->cur_cells = (double)c->total;
     {
       Prof p(c, SY2D_K_ASSEMBLY);
@@ -1208,7 +1222,7 @@ int sy2d_step(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
     }
     if (mg) mg_setup(c);
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(c->h_nactive, c->d_nactive, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_nactive, c->d_nactive, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     c->launches += 1;
     int launched = 0;
@@ -1236,12 +1250,26 @@ int sy2d_step(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
       } else {
         for (int it = 0; it < check_every; ++it) launch_iteration(c);
         CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(c->h_nactive, c->d_nactive, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(c->h_nactive, c->d_nactive, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
       }
       CU(cudaStreamSynchronize(c->stream));
       launched += check_every;
       c->launches += (long long)check_every * kernels_per_iteration(c);
     }
+    const bool failed = c->h_nactive[0] > 0 || c->h_nactive[1] > 0 || (attempt == 0 && c->opt.reserved[2] == 1);  // reserved[2] = 1: test hook
+    if (!(failed && mg && attempt == 0 && c->opt.precond == SY2D_PRECOND_AUTO)) break;
+    c->mg_off = true;
+    st.restarts_total += 1;
+    rc = prepare();
+    if (rc) { c->mg_off = false; return rc; }
+   }
+   const int solved_by = st.precond;   // what solved this step
+   const bool fell_back = c->mg_off;
+   if (fell_back) {   // back to multigrid for the next step
+     c->mg_off = false;
+     rc = prepare();
+     if (rc) return rc;
+   }
     c->cur_cells = (double)c->total;
     // verification + finish
     StepStats init;
@@ -1268,7 +1296,8 @@ int sy2d_step(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
     st.iters_total += c->h_stats->it_max;
     st.iters_sum_all += (long long)c->h_stats->it_max * c->nbatch;
     st.iters_last = c->h_stats->it_max;
-    c->mg_last_iters = c->h_stats->it_max;
+    if (!fell_back) c->mg_last_iters = c->h_stats->it_max;
+    st.precond = solved_by;
     st.resid_last = c->h_stats->resid_max;
     st.fmin = c->h_stats->fmin;
     st.negatives = (long long)c->h_stats->negatives;
@@ -1359,7 +1388,7 @@ int sy2d_debug_vcycle(sy2d_ctx* c, const double* r, double* z, double* w4, doubl
   c->opt.precond = keep;
   if (!ok) return fail(c, SY2D_ERR_INVALID, "sy2d_debug_vcycle: multigrid does not support this grid");
   if (rc) return rc;
-  CU(cudaMemsetAsync(c->d_nactive, 0, sizeof(int), c->stream));
+  CU(cudaMemsetAsync(c->d_nactive, 0, 2 * sizeof(int), c->stream));
   CU(cudaMemsetAsync(c->scal, 0, c->nbatch * sizeof(Scal), c->stream));
   AssembleOut o;
   std::memset(&o, 0, sizeof o);
@@ -1416,7 +1445,7 @@ int sy2d_bench_kernel(sy2d_ctx* c, int which, int reps, double* ms_per_launch) {
   };
   if (which < SY2D_K_ASSEMBLY || which > SY2D_K_XR_UPDATE) return fail(c, SY2D_ERR_INVALID, "sy2d_bench_kernel: unknown kernel %d", which);
   // prime: operator + one full iteration so that every vector holds finite data
-  CU(cudaMemsetAsync(c->d_nactive, 0, sizeof(int), c->stream));
+  CU(cudaMemsetAsync(c->d_nactive, 0, 2 * sizeof(int), c->stream));
   CU(cudaMemsetAsync(c->scal, 0, c->nbatch * sizeof(Scal), c->stream));
   assemble();
   for (int w = SY2D_K_P_UPDATE; w <= SY2D_K_XR_UPDATE; ++w) launch(w);

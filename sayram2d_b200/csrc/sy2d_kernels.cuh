@@ -593,7 +593,7 @@ struct KrylovVecs {
   const double *wW, *wE, *wS, *wN, *rhs;
   double *x, *r, *p, *v, *s, *t;
   Scal* scal;
-  int* n_active;
+  int* n_active;   // [0] problems still iterating, [1] problems that stopped without converging (maxit / breakdown)
   double tol;
   int maxit;
   int freeze_state;  // sy2d_bench_kernel: keep every problem active whatever the residual does
@@ -623,6 +623,7 @@ __device__ __forceinline__ void xr_finish_iteration(Scal* sc, const KrylovVecs& 
   if (state != 0 && !k.freeze_state) {
     sc->state = state;
     atomicSub(k.n_active, 1);
+    if (state >= 2) atomicAdd(k.n_active + 1, 1);   // n_active[1]: problems that stopped without converging
   }
 }
 

@@ -77,3 +77,47 @@ def test_mg_levels_option_and_unsupported_grids():
     eng.set_options(engine=1, precond=-1)       # AUTO falls back to the segmented x-line preconditioner
     assert eng.step(1)["precond"] == 1
     eng.close()
+
+
+@pytest.mark.parametrize("case,nx,ny,stretch", [("AY", 160, 96, 0.6), ("LC", 128, 128, 0.0), ("SYN", 192, 64, -0.4)])
+def test_mg_time_steps_match_the_oracle_on_mid_size_grids(case, nx, ny, stretch):
+    """Multigrid-preconditioned engine 1 against the oracle's direct solve (SciPy SuperLU) at sizes between the
+    reference's 80 x 80 fixtures and the 1024 x 1024 sub-sampled one: warped (non-uniform) grids, the loss-cone
+    case with its zero-flux alpha0 = 0 boundary and 49 decades of f, the synthetic tensor with cross terms."""
+    import os
+    from conftest import ROOT
+    import h5min
+    import ppfv_oracle as O
+    table = h5min.load_d_table(os.path.join(ROOT, "data", "D", "AlbertYoung_chorus.h5"))
+    kw = dict(nalpha0=nx, nE=ny, alpha0min=0 if case == "LC" else 5, alpha0max=90, Emin=0.2, Emax=5, T=1.0, nplots=10, nsteps=500)
+    p, m, eq = O.build_case(case, None, table, stretch=stretch, **kw)
+    ref = O.Solver(m, eq)
+    eng = sy.Engine(m.x_edges, m.y_edges, m.dt)
+    eng.set_options(engine=1, precond=2)
+    eng.set_coeffs(eq.G, eq.Dxx, eq.Dxy, eq.Dyy, eq.inv_tau)
+    eng.set_bc(eq.bc, *eq.dirichlet_lines(0.0))
+    eng.set_f(ref.f)
+    for _ in range(6):
+        ref.update()
+    st = eng.step(6)
+    assert st["precond"] == 2 and st["negatives"] == 0 and st["iters_last"] <= 30
+    assert max_rel(eng.get_f()[0], ref.f) < 1e-9
+    eng.close()
+
+
+def test_failed_multigrid_step_is_redone_with_the_xline_iteration():
+    """AUTO contexts: a multigrid-preconditioned solve that stops without converging is redone from the same f
+    with the segmented x-line iteration (reserved[2] = 1 makes every first attempt count as failed)."""
+    a = synthetic_engine(128, 128)            # AUTO -> multigrid
+    b = synthetic_engine(128, 128)
+    o = b.options(); o.engine = 1; o.reserved[2] = 1
+    b._check(b.lib.sy2d_set_options(b._ctx, o)); b._opt = o
+    sa, sb = a.step(3), b.step(3)
+    assert sa["precond"] == 2 and sa["restarts_total"] == 0
+    assert sb["precond"] == 1 and sb["restarts_total"] == 3 and sb["iters_last"] > 3 * sa["iters_last"]
+    assert max_rel(a.get_f(), b.get_f()) < 1e-10 and sb["negatives"] == 0
+    o.reserved[2] = 0
+    b._check(b.lib.sy2d_set_options(b._ctx, o))
+    sc = b.step(1)                            # back to multigrid on the next call
+    assert sc["precond"] == 2 and sc["restarts_total"] == 0 and sc["iters_last"] <= sa["iters_last"] + 3
+    a.close(); b.close()
