@@ -186,7 +186,7 @@ def main():
             levels = [fine]
             while levels[-1].d.shape[1] > 1 and levels[-1].d.shape[1] % 2 == 0:
                 levels.append(coarsen(levels[-1], theta))
-            for kind, omg, nu in (("jacobi", 0.7, 1),):
+            for kind, omg, nu in (("segjacobi", 0.7, 1),):
                 for depth in (5,):
                     lv = levels[:depth]
                     t0 = time.time()

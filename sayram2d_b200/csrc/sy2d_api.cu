@@ -157,8 +157,11 @@ unsigned capped_blocks(const sy2d_ctx* c, size_t work_items_per_problem, int thr
 
 // Multigrid (sy2d_mg.cuh) needs whole columns inside one CTA of the line kernel (nx <= 64 segments of 16 or
 // 32 rows), pairs of columns on every level (ny a multiple of 4 gives at least two levels) and a single GPU.
+// rows the multigrid kernels work on: the owned rows of a slab context (its lines end at the slab)
+int mg_rows(const sy2d_ctx* c) { return c->slab ? c->nx - 2 : c->nx; }
+
 int mg_level_count(const sy2d_ctx* c) {
-  if (c->slab || c->nx > 4096 || c->nx < 8 || c->ny % 4 != 0 || c->ny < 16) return 0;
+  if (mg_rows(c) > 8192 || mg_rows(c) < 8 || c->ny % 4 != 0 || c->ny < 16) return 0;
   // default: coarsen until a level has at most 64 columns (measured optimum from 128^2 to 2048^2: fewer levels cost
   // iterations, more levels cost latency-bound launches), at least two levels; mg_levels > 0 caps the count instead.
   // A level is only halved while its ny is a multiple of 4, so the coarsest level keeps an even ny >= 8.
@@ -309,28 +312,34 @@ int mg_alloc(sy2d_ctx* c) {
     c->mg_bufs.push_back(*out);
     return SY2D_OK;
   };
-  c->mg_seg = c->nx <= 1024 ? 8 : 16;
+  // Slab contexts: every level array carries one halo row on each side (like the fine-grid arrays); the level
+  // pointers address the first OWNED row, so the kernels index rows 0 .. rows-1 and the residual kernels reach
+  // the halo rows at -1 and rows.
+  const int rows = mg_rows(c), halo_rows = c->slab ? 2 : 0;
+  c->mg_seg = rows <= 1024 ? 8 : 16;
   std::memset(&c->mg, 0, sizeof c->mg);
   c->mg.nlev = nlev;
   double* t0 = nullptr;
   if ((rc = grab(c->total, &c->mg_om0)) || (rc = grab(c->total, &c->mg_shat)) || (rc = grab(c->total, &t0))) return rc;
+  const size_t off0 = c->slab ? (size_t)c->ny : 0;
   MgLevel& l0 = c->mg.lv[0];
-  l0.wW = c->wW; l0.wE = c->wE; l0.wS = c->wS; l0.wN = c->wN; l0.om = c->mg_om0;
-  l0.l = c->xl_l; l0.dinv = c->xl_dinv; l0.e = c->xl_e;
-  l0.r = nullptr; l0.z = nullptr; l0.t = t0;
-  l0.ny = c->ny; l0.N = c->N;
+  l0.wW = c->wW + off0; l0.wE = c->wE + off0; l0.wS = c->wS + off0; l0.wN = c->wN + off0; l0.om = c->mg_om0 + off0;
+  l0.l = c->xl_l + off0; l0.dinv = c->xl_dinv + off0; l0.e = c->xl_e + off0;
+  l0.r = nullptr; l0.z = nullptr; l0.t = t0 + off0;
+  l0.ny = c->ny; l0.N = (size_t)rows * c->ny;
   int ny = c->ny;
   for (int k = 1; k < nlev; ++k) {
     ny /= 2;
-    const size_t n = (size_t)c->nx * ny * c->nbatch;
+    const size_t n = (size_t)(rows + halo_rows) * ny * c->nbatch;
+    const size_t off = c->slab ? (size_t)ny : 0;
     double* a[11];
     for (double*& q : a) if ((rc = grab(n, &q))) return rc;
     MgLevel& lv = c->mg.lv[k];
-    lv.wW = a[0]; lv.wE = a[1]; lv.wS = a[2]; lv.wN = a[3]; lv.om = a[4];
-    lv.l = a[5]; lv.dinv = a[6]; lv.e = a[7];
-    lv.r = a[8]; c->mg_rc[k] = a[8];
-    lv.z = a[9]; lv.t = a[10];
-    lv.ny = ny; lv.N = (size_t)c->nx * ny;
+    lv.wW = a[0] + off; lv.wE = a[1] + off; lv.wS = a[2] + off; lv.wN = a[3] + off; lv.om = a[4] + off;
+    lv.l = a[5] + off; lv.dinv = a[6] + off; lv.e = a[7] + off;
+    lv.r = a[8] + off; c->mg_rc[k] = a[8] + off;
+    lv.z = a[9] + off; lv.t = a[10] + off;
+    lv.ny = ny; lv.N = (size_t)rows * ny;
   }
   c->mg_nlev = nlev;
   return SY2D_OK;
@@ -344,9 +353,9 @@ void mg_setup(sy2d_ctx* c) {
     const MgLevel& g = c->mg.lv[k + 1];
     k_mg_coarsen<<<dim3(capped_blocks(c, g.N, kBlock), (unsigned)c->nbatch, 1), kBlock, 0, c->stream>>>(
         f, const_cast<double*>(g.wW), const_cast<double*>(g.wE), const_cast<double*>(g.wS), const_cast<double*>(g.wN),
-        const_cast<double*>(g.om), c->nx);
+        const_cast<double*>(g.om), mg_rows(c));
   }
-  k_mg_factor<<<dim3((unsigned)((c->ny + 63) / 64), (unsigned)c->nbatch, (unsigned)c->mg_nlev), 64, 0, c->stream>>>(c->mg, c->nx);
+  k_mg_factor<<<dim3((unsigned)((c->ny + 63) / 64), (unsigned)c->nbatch, (unsigned)c->mg_nlev), 64, 0, c->stream>>>(c->mg, mg_rows(c));
   c->launches += c->mg_nlev;
 }
 
@@ -358,19 +367,20 @@ void mg_setup(sy2d_ctx* c) {
 // columns at nx = 1024), and that per-SM streaming time, not DRAM, is what a coarse-level solve waits for.
 template <int SEG, int COLS, int MODE>
 void mg_line_shape(sy2d_ctx* c, const MgLevel& lv, const double* zc) {
-  const MgArgs a{c->scal, c->nx};
-  const int nseg = (c->nx + SEG - 1) / SEG;
+  const int rows = mg_rows(c);
+  const MgArgs a{c->scal, rows, c->slab ? 1 : 0};
+  const int nseg = (rows + SEG - 1) / SEG;
   const int threads = (nseg * COLS + 31) / 32 * 32;
   const size_t smem = (size_t)3 * COLS * (nseg + 1) * sizeof(double);
   const dim3 g((unsigned)((lv.ny + COLS - 1) / COLS), (unsigned)c->nbatch, 1);
-  const bool full = c->nx % SEG == 0 && lv.ny % COLS == 0 && nseg * COLS == threads;
+  const bool full = rows % SEG == 0 && lv.ny % COLS == 0 && nseg * COLS == threads;
   if (full) k_mg_line<SEG, COLS, MODE, true><<<g, threads, smem, c->stream>>>(lv, zc, a);
   else k_mg_line<SEG, COLS, MODE, false><<<g, threads, smem, c->stream>>>(lv, zc, a);
 }
 
 template <int SEG>
 int mg_line_cols(const sy2d_ctx* c, const MgLevel& lv) {
-  const int nseg = (c->nx + SEG - 1) / SEG;
+  const int nseg = (mg_rows(c) + SEG - 1) / SEG;
   const int max_threads = SEG <= 8 ? 1024 : 512;
   int cols = 8;
   while (cols > 1 && nseg * cols > max_threads) cols /= 2;
@@ -399,34 +409,49 @@ void mg_line(sy2d_ctx* c, const MgLevel& lv, const double* zc) {
 template <int KIND>
 void mg_resid(sy2d_ctx* c, const MgLevel& lv, const double* zc, const double* omc, double* rc) {
   Prof p(c, SY2D_K_MG_RESID);
-  const MgArgs a{c->scal, c->nx};
+  const MgArgs a{c->scal, mg_rows(c), c->slab ? 1 : 0};
   k_mg_resid<KIND><<<dim3(capped_blocks(c, lv.N / 2, kBlock), (unsigned)c->nbatch, 1), kBlock, 0, c->stream>>>(lv, zc, omc, rc, a);
 }
 
-// z = V(r): one V(1,1) cycle on the fine grid; r and z are [nbatch][nx][ny] device vectors
-void mg_vcycle(sy2d_ctx* c, const double* r, double* z) {
+int slab_halo_exchange_n(sy2d_ctx* c, double* a, int ny_l);
+
+// z = V(r): one V(1,1) cycle on the fine grid; r and z are [nbatch][nx][ny] device vectors (local arrays incl. the
+// halo rows on a slab context).  Slab contexts exchange one halo row of the iterate with both neighbours before
+// every residual that reads it (10 small ncclSend/Recv pairs per cycle); the caller exchanges the halo of z.
+int mg_vcycle(sy2d_ctx* c, const double* r, double* z) {
   const int L = c->mg_nlev;
+  const size_t off0 = c->slab ? (size_t)c->ny : 0;
   MgLevel lv0 = c->mg.lv[0];
-  lv0.r = r; lv0.z = z;
+  lv0.r = r + off0; lv0.z = z + off0;
   auto level = [&](int k) -> const MgLevel& { return k == 0 ? lv0 : c->mg.lv[k]; };
+  auto halo = [&](int k) -> int {   // the iterate of level k
+    if (!c->slab) return SY2D_OK;
+    const MgLevel& lv = level(k);
+    return slab_halo_exchange_n(c, lv.z - lv.ny, lv.ny);
+  };
+  int rc = SY2D_OK;
   const double scale0 = c->cur_cells;
   for (int k = 0; k + 1 < L; ++k) {
     c->cur_cells = scale0 / (double)(1 << k);
     mg_line<0>(c, level(k), nullptr);
+    if ((rc = halo(k))) return rc;
     mg_resid<1>(c, level(k), nullptr, c->mg.lv[k + 1].om, c->mg_rc[k + 1]);
   }
   c->cur_cells = scale0 / (double)(1 << (L - 1));
   mg_line<0>(c, level(L - 1), nullptr);
   for (int sweep = 1; sweep < mg_coarse_sweeps(c); ++sweep) {
+    if ((rc = halo(L - 1))) return rc;
     mg_resid<0>(c, level(L - 1), nullptr, nullptr, nullptr);
     mg_line<2>(c, level(L - 1), nullptr);
   }
   for (int k = L - 2; k >= 0; --k) {
     c->cur_cells = scale0 / (double)(1 << k);
+    if ((rc = halo(k + 1))) return rc;   // the correction; the halo of z_k is still the one exchanged on the way down
     mg_resid<2>(c, level(k), c->mg.lv[k + 1].z, nullptr, nullptr);
     mg_line<1>(c, level(k), c->mg.lv[k + 1].z);
   }
   c->cur_cells = scale0;
+  return SY2D_OK;
 }
 int mg_kernels_per_vcycle(const sy2d_ctx* c) { return 4 * (c->mg_nlev - 1) + 1 + 2 * (mg_coarse_sweeps(c) - 1); }
 
@@ -583,9 +608,9 @@ void slab_comm_destroy(sy2d_ctx* c) {
 
 // One line (ny doubles) to each neighbour: my first owned row -> bottom halo of rank-1, my last owned
 // row -> top halo of rank+1.  Contiguous 8*ny bytes over NVLink.
-int slab_halo_exchange(sy2d_ctx* c, double* a) {
+int slab_halo_exchange_n(sy2d_ctx* c, double* a, int ny_l) {
   ncclComm_t comm = static_cast<ncclComm_t>(c->comm);
-  const size_t ny = (size_t)c->ny;
+  const size_t ny = (size_t)ny_l;
   const int rows = c->nx - 2;
   NC(nccl().GroupStart());
   if (c->rank > 0) {
@@ -599,6 +624,7 @@ int slab_halo_exchange(sy2d_ctx* c, double* a) {
   NC(nccl().GroupEnd());
   return SY2D_OK;
 }
+int slab_halo_exchange(sy2d_ctx* c, double* a) { return slab_halo_exchange_n(c, a, c->ny); }
 
 // accumulators of every rank -> scalars on every rank (identical summation order everywhere)
 int slab_reduce(sy2d_ctx* c, int phase, const KrylovVecs& k) {
@@ -620,9 +646,14 @@ int step_slab(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
   sy2d_stats st;
   std::memset(&st, 0, sizeof st);
   st.engine = 1;
+  const bool mg = lockstep_mg(c);
   const bool xl = lockstep_xline(c);
-  st.precond = xl ? SY2D_PRECOND_XLINE : SY2D_PRECOND_JACOBI;
+  if (c->opt.precond == SY2D_PRECOND_MG && !mg)
+    return fail(c, SY2D_ERR_INVALID, "sy2d_step (slab): the multigrid preconditioner needs 8 <= rows per rank <= 8192 and ny a multiple of 4, >= 16");
+  st.precond = mg ? SY2D_PRECOND_MG : (xl ? SY2D_PRECOND_XLINE : SY2D_PRECOND_JACOBI);
   if (xl) { int rc0 = xl_alloc(c); if (rc0) return rc0; }
+  if (mg) { int rc0 = mg_alloc(c); if (rc0) return rc0; }
+  const int check_every = effective_check_every(c);
   const XlVecs xv = xl_vecs(c);
   const int nseg = (rows + kSeg - 1) / kSeg;
   const dim3 gs(capped_blocks(c, (size_t)nseg * c->ny, kSweepThreads), 1, 1);
@@ -637,18 +668,40 @@ int step_slab(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
     std::memset(&o, 0, sizeof o);
     o.wW = c->wW; o.wE = c->wE; o.wS = c->wS; o.wN = c->wN; o.rhs = c->rhs; o.cs = c->cs;
     o.scal = c->scal; o.n_active = c->d_nactive; o.tol = c->opt.tol; o.local_rows = c->nx;
+    if (mg) o.om = c->mg_om0;
     k_assemble_tiled<<<dim3(capped_blocks(c, (size_t)tiles_i * tiles_j, 1), 1, 1), kTI * kTJ, 0, c->stream>>>(
         c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud, geo, o, tiles_j, c->i_lo - 1, 1, rows + 1, 1);
     CU(cudaGetLastError());
     rc = slab_reduce(c, 0, k);
     if (rc) return rc;
     if (xl) k_xl_factor<<<gs, kBlock, 0, c->stream>>>(xv, c->N);
+    if (mg) mg_setup(c);   // coarse operators and line LU of the owned rows: local, the lines end at the slab
     c->launches += 3;
     CU(cudaMemcpyAsync(c->h_nactive, c->d_nactive, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     int done_its = 0;
-    while (*c->h_nactive > 0 && done_its < c->opt.maxit + c->opt.check_every) {
-      for (int it = 0; it < c->opt.check_every && xl; ++it) {
+    while (*c->h_nactive > 0 && done_its < c->opt.maxit + check_every) {
+      for (int it = 0; it < check_every && mg; ++it) {
+        // right-preconditioned BiCGSTAB, one V-cycle per preconditioner application; the smoother's lines end at
+        // the slab (block Jacobi across ranks), every residual uses the neighbours' rows (halo exchange)
+        double* phat = c->xl_hat;
+        double* shat = c->mg_shat;
+        k_p_update2<<<g2, kBlock, 0, c->stream>>>(k, c->N);
+        if ((rc = mg_vcycle(c, c->p, phat))) return rc;
+        if ((rc = slab_halo_exchange(c, phat))) return rc;
+        KrylovVecs kv = k;
+        kv.p = phat;
+        k_spmv_v2<<<g2, kBlock, 0, c->stream>>>(kv, c->N, c->ny);
+        if ((rc = slab_reduce(c, 1, k))) return rc;
+        k_s_update2<<<g2, kBlock, 0, c->stream>>>(k, c->N);
+        if ((rc = mg_vcycle(c, c->s, shat))) return rc;
+        if ((rc = slab_halo_exchange(c, shat))) return rc;
+        k_mg_spmv_t<<<g2, kBlock, 0, c->stream>>>(k, shat, c->N, c->ny);
+        if ((rc = slab_reduce(c, 2, k))) return rc;
+        k_mg_xr<<<g2, kBlock, 0, c->stream>>>(k, phat, shat, c->N);
+        if ((rc = slab_reduce(c, 3, k))) return rc;
+      }
+      for (int it = 0; it < check_every && xl; ++it) {
         k_xl_sweep<0><<<gs, kSweepThreads, 0, c->stream>>>(xv, c->N);
         if ((rc = slab_halo_exchange(c, c->xl_hat))) return rc;
         k_xl_spmv_v<2><<<gc, kBlock, 0, c->stream>>>(xv, c->N);
@@ -660,7 +713,7 @@ int step_slab(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
         k_xl_xr<2><<<gc, kBlock, 0, c->stream>>>(xv, c->N);
         if ((rc = slab_reduce(c, 3, k))) return rc;
       }
-      for (int it = 0; it < c->opt.check_every && !xl; ++it) {
+      for (int it = 0; it < check_every && !xl && !mg; ++it) {
         k_p_update2<<<g2, kBlock, 0, c->stream>>>(k, c->N);
         if ((rc = slab_halo_exchange(c, c->p))) return rc;
         k_spmv_v2<<<g2, kBlock, 0, c->stream>>>(k, c->N, c->ny);
@@ -675,8 +728,8 @@ int step_slab(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
       CU(cudaGetLastError());
       CU(cudaMemcpyAsync(c->h_nactive, c->d_nactive, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
       CU(cudaStreamSynchronize(c->stream));
-      done_its += c->opt.check_every;
-      c->launches += (long long)c->opt.check_every * 8;
+      done_its += check_every;
+      c->launches += (long long)check_every * (mg ? kernels_per_iteration(c) : 8);
     }
     StepStats init;
     std::memset(&init, 0, sizeof init);
@@ -1182,7 +1235,7 @@ int sy2d_step(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
   bool xl = lockstep_xline(c);
   if (c->opt.precond == SY2D_PRECOND_XLINE && !xl) return fail(c, SY2D_ERR_INVALID, "sy2d_step: the x-line preconditioner needs nx >= %d", kSeg);
   if (c->opt.precond == SY2D_PRECOND_MG && !mg)
-    return fail(c, SY2D_ERR_INVALID, "sy2d_step: the multigrid preconditioner needs engine 1 on one GPU, 8 <= nx <= 4096 and ny a multiple of 4, >= 16");
+    return fail(c, SY2D_ERR_INVALID, "sy2d_step: the multigrid preconditioner needs engine 1, 8 <= nx <= 8192 (rows per rank) and ny a multiple of 4, >= 16");
   auto prepare = [&]() -> int {   // buffers and graphs of the preconditioner in force
     mg = lockstep_mg(c);
     xl = lockstep_xline(c);

@@ -50,7 +50,11 @@ struct MgLevel {
 
 struct MgArgs {
   const Scal* scal;   // converged problems skip all work
-  int nx;
+  int nx;             // rows of the (local) grid the kernels work on
+  int halo;           // row-slab mode: the level arrays carry one halo row below row 0 and one above row nx-1 (the
+                      // pointers address the first OWNED row), filled by the host with the neighbour ranks' rows:
+                      // the residual kernels read them instead of clamping.  The line solves never look at them -
+                      // a rank's lines end at its slab (block-Jacobi smoothing across ranks).
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -295,15 +299,16 @@ __global__ void __launch_bounds__(kBlock) k_mg_resid(MgLevel lv, const double* _
   const double* __restrict__ zcp = KIND == 2 ? zc + bc : nullptr;
   for (size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < Nc; n += (size_t)gridDim.x * blockDim.x) {
     const int i = (int)(n / nyc), J = (int)(n - (size_t)i * nyc);
-    const size_t p = (size_t)i * ny + 2 * J;          // in-problem index of cell a
-    const size_t pW = i > 0 ? p - ny : p, pE = i < nx - 1 ? p + ny : p;
-    const size_t pS = J > 0 ? p - 1 : p, pN = J < nyc - 1 ? p + 2 : p + 1;
+    const ptrdiff_t p = (ptrdiff_t)i * ny + 2 * J;    // in-problem index of cell a
+    const ptrdiff_t pW = (i > 0 || a.halo) ? p - ny : p, pE = (i < nx - 1 || a.halo) ? p + ny : p;
+    const ptrdiff_t pS = J > 0 ? p - 1 : p, pN = J < nyc - 1 ? p + 2 : p + 1;
     double2 zz = ld2(z + p), zW = ld2(z + pW), zE = ld2(z + pE);
     double zS = z[pS], zN = z[pN];
     if (KIND == 2) {
-      const double c0 = zcp[n];
+      const ptrdiff_t q = (ptrdiff_t)n;
+      const double c0 = zcp[q];
       zz.x += c0; zz.y += c0;
-      const double cW = zcp[i > 0 ? n - nyc : n], cE = zcp[i < nx - 1 ? n + nyc : n];
+      const double cW = zcp[(i > 0 || a.halo) ? q - nyc : q], cE = zcp[(i < nx - 1 || a.halo) ? q + nyc : q];
       zW.x += cW; zW.y += cW; zE.x += cE; zE.y += cE;
       zS += zcp[J > 0 ? n - 1 : n];
       zN += zcp[J < nyc - 1 ? n + 1 : n];
@@ -337,7 +342,7 @@ __global__ void __launch_bounds__(kBlock) k_mg_spmv_t(KrylovVecs k, const double
   const size_t stride = 2 * (size_t)gridDim.x * blockDim.x;
   const size_t base = (size_t)blockIdx.y * N;
   double ts = 0.0, tt = 0.0;
-  for (size_t n = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); n < N; n += stride) {
+  for (size_t n = k.n_begin + 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); n < k.n_end; n += stride) {
     const size_t g = base + n;
     const double* h = shat + base;
     double t0, t1;
@@ -352,7 +357,7 @@ __global__ void __launch_bounds__(kBlock) k_mg_spmv_t(KrylovVecs k, const double
   if (threadIdx.x == 0) {
     atomicAdd(&sc->acc_ts, sums[0]);
     atomicAdd(&sc->acc_tt, sums[1]);
-    if (last_block_done(sc, gridDim.x)) {
+    if (last_block_done(sc, gridDim.x) && !k.defer) {
       const double a = sc->acc_ts, b = sc->acc_tt;
       sc->acc_ts = 0.0;
       sc->acc_tt = 0.0;
@@ -371,7 +376,7 @@ __global__ void __launch_bounds__(kBlock) k_mg_xr(KrylovVecs k, const double* __
   double dot = 0.0, rabs = 0.0;
   const double alpha = sc->alpha, omega = sc->omega;
   const bool first = sc->first;
-  for (size_t n = 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); n < N; n += stride) {
+  for (size_t n = k.n_begin + 2 * ((size_t)blockIdx.x * blockDim.x + threadIdx.x); n < k.n_end; n += stride) {
     const size_t g = (size_t)blockIdx.y * N + n;
     const double2 s = ld2(k.s + g), ph = ld2(phat + g), sh = ld2(shat + g), t = ld2(k.t + g), rh = ld2(k.rhs + g);
     double2 x = make_double2(0.0, 0.0);
@@ -388,7 +393,7 @@ __global__ void __launch_bounds__(kBlock) k_mg_xr(KrylovVecs k, const double* __
   if (threadIdx.x == 0) {
     atomicAdd(&sc->acc_rho, sums[0]);
     atomicMax(&sc->acc_rmax, (unsigned long long)__double_as_longlong(bmax));
-    if (last_block_done(sc, gridDim.x)) xr_finish_iteration(sc, k);
+    if (last_block_done(sc, gridDim.x) && !k.defer) xr_finish_iteration(sc, k);
   }
 }
 
