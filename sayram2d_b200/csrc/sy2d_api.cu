@@ -1055,11 +1055,18 @@ static bool xline_shape(const sy2d_ctx* c, int* R, int* NT, int* S, int* HS, siz
   const int ny_pad = (c->ny + kXlineCPW - 1) / kXlineCPW * kXlineCPW;
   const int nt = ny_pad * kXlineNCH;
   if (nt > 1024) return false;
-  int hs = c->ny;  // smallest stride >= ny with r*hs = 4 (mod 16): conflict-free hat accesses (not solvable for r = 8)
-  for (int t = c->ny; t < c->ny + 16; ++t)
-    if ((r * t) % 16 == 4) { hs = t; break; }
-  if (hs == c->ny && (r * hs) % 16 != 4) hs = c->ny + 1;
-  const size_t bytes = ((size_t)c->nx * hs + 3 * (size_t)r * nt + 128) * sizeof(double);
+  // Row stride of hat.  A 64-bit shared access is served per HALF-warp (16 lanes, 16 eight-byte slots): lanes
+  // 0-15 are (jj, k) = (0..1, 0..7) and hit slots (k*r*hs + jj) mod 16, so r*hs = 2 (mod 16) makes the 16 distinct
+  // (ncu: every hat access was a 2-way conflict with the earlier rule r*hs = 4, which only spreads a full warp).
+  // Not solvable for r = 4 and r = 8 (r*hs is then a multiple of 4): fall back to 4 (mod 16), then to ny + 1.
+  int hs = 0;
+  for (int want : {2, 4}) {
+    for (int t = c->ny; t < c->ny + 16 && !hs; ++t)
+      if ((r * t) % 16 == want) hs = t;
+    if (hs) break;
+  }
+  if (!hs) hs = c->ny + 1;
+  const size_t bytes = ((size_t)c->nx * hs + 3 * (size_t)r * nt + 192) * sizeof(double)   /* + three 64-double reduction buffers */;
   if (bytes > 232448) return false;
   *R = r; *NT = nt; *S = r * nt; *HS = hs; *smem = bytes;
   return true;
@@ -1074,8 +1081,8 @@ static cudaError_t launch_xline(const XlineArgs& xa, int nbatch, size_t smem, cu
 }
 
 static cudaError_t dispatch_xline(const XlineArgs& xa, int R, int nbatch, size_t smem, cudaStream_t stream) {
-  if (R == 10 && xa.NT == 640 && xa.hs == 82 && xa.a.g.nx == 80 && xa.a.g.ny == 80)
-    return launch_xline<10, 640, 640, 82>(xa, nbatch, smem, stream);   // 80 x 80: the production shape, everything compile-time
+  if (R == 10 && xa.NT == 640 && xa.hs == 85 && xa.a.g.nx == 80 && xa.a.g.ny == 80)
+    return launch_xline<10, 640, 640, 85>(xa, nbatch, smem, stream);   // 80 x 80: the production shape, everything compile-time
   if (R == 10 && xa.NT == 640) return launch_xline<10, 640, 640>(xa, nbatch, smem, stream);
   const bool small = xa.NT <= 640;
   switch (R) {

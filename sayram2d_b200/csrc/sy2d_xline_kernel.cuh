@@ -9,8 +9,9 @@
 // accuracy of f - exactly those of the unpreconditioned engine; iterations drop ~4x
 // (80x80 AY: 59 -> 14.5 per step).
 //
-// Bank conflicts: lane (k, jj) touches hat[(k*R + m)*hs + j]; with R*hs = 4 (mod 16) the eight
-// lanes of a column land 8 words apart and a warp covers all 32 banks exactly once.
+// Bank conflicts: lane (k, jj) touches hat[(k*R + m)*hs + j]; 64-bit accesses are served per half-warp
+// (lanes 0-15 = columns jj, jj+1 x the eight k), so with R*hs = 2 (mod 16) the 16 lanes of a half-warp
+// land on 16 distinct eight-byte slots (hs = 85 for the 80 x 80 instance).
 //
 // Thread layout: a warp owns CPW = 32/NCH columns j; the NCH lanes of a column own R consecutive
 // rows each (lane = jj*NCH + k, rows k*R .. k*R+R-1).  A Thomas sweep is then a chain over the
@@ -21,8 +22,9 @@
 //   registers : r/s and p of the owned cells (resident), phat/shat, t, v (transient)
 //   shared    : hat (phat/shat, natural (i,j) layout, row stride ny+1: the S/N neighbour exchange),
 //               l, 1/d, wE/d (sweep coefficients, private layout, conflict-free)
-//   L2        : wS, wN, v, x, rhs (private layout => fully coalesced 128 B lines per warp)
-// Algorithmic traffic per cell and iteration: 12 L2 accesses (96 B) + 16 shared accesses.
+//   L2        : wS, wN, v, y, rhs (private layout => fully coalesced 128 B lines per warp)
+// Traffic per cell and iteration: 10 L2 accesses (80 B: v r/w, wS wN twice, rhat twice, y r/w) + 16 shared
+// accesses (two Thomas solves of 5, two publishes, four neighbour reads).
 #pragma once
 #include "sy2d_problem_kernel.cuh"
 
@@ -39,7 +41,9 @@ struct XlineArgs {
   int hs;            // row stride of hat in shared memory (>= ny)
 };
 
-template <int NV>
+// TRAIL = false drops the trailing barrier: the caller must then not reuse `red` before every thread has
+// passed a later barrier (the iteration loop rotates over three buffers).
+template <int NV, bool TRAIL = true>
 __device__ __forceinline__ void cta_reduce_x(double (&v)[NV], int nsum, double* red) {
   // first nsum entries are sums, the rest maxima; all threads get the result
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -55,7 +59,7 @@ __device__ __forceinline__ void cta_reduce_x(double (&v)[NV], int nsum, double* 
     const double y = lane < nw ? red[k * 32 + lane] : 0.0;   // maxima here are of non-negative values
     v[k] = k < nsum ? warp_sum(y) : warp_max(y);
   }
-  __syncthreads();
+  if (TRAIL) __syncthreads();
 }
 
 // one scaled row; kept out of line so that the R-times unrolled assembly loop stays small
@@ -107,7 +111,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
   double* f = a.f + base;
   double* yprev = a.yprev + base;
   double* scr = xa.scratch + (size_t)prob * 5 * S;
-  double* wS_g = scr; double* wN_g = scr + S; double* v_g = scr + 2 * S; double* x_g = scr + 3 * S; double* rhs_g = scr + 4 * S;
+  double* wS_g = scr; double* wN_g = scr + S; double* v_g = scr + 2 * S; double* y_g = scr + 3 * S; double* rhs_g = scr + 4 * S;
   const unsigned full = 0xffffffffu;
 
   double rs[R], p[R], z[R];
@@ -330,16 +334,11 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
         v_g[q] = val;
         a1[0] += rhs_g[q] * val;
       }
-      cta_reduce_x<1>(a1, 1, red);
+      cta_reduce_x<1, false>(a1, 1, red);
       alpha = a1[0] != 0.0 ? rho / a1[0] : 0.0;
-      // s = r - alpha v (in place) ; x += alpha phat
+      // s = r - alpha v (in place)
 #pragma unroll
-      for (int m = 0; m < R; ++m) {
-        const int i = i0 + m, q = m * NT + tid;
-        rs[m] -= alpha * vv[m];
-        const double ph = (FULL || (col_ok && i < nx)) ? hat[i * hs + j] : 0.0;
-        x_g[q] = (first ? 0.0 : x_g[q]) + alpha * ph;
-      }
+      for (int m = 0; m < R; ++m) rs[m] -= alpha * vv[m];
       tsolve(rs);
       publish();
       // t = s + wS shat_S + wN shat_N ; (t,s), (t,t)
@@ -353,20 +352,20 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
         a2[0] += val * rs[m];
         a2[1] += val * val;
       }
-      cta_reduce_x<2>(a2, 2, red);
+      cta_reduce_x<2, false>(a2, 2, red + 64);
       omega = a2[1] > 0.0 ? a2[0] / a2[1] : 0.0;
-      // x += omega shat ; r = s - omega t ; (rhat, r), max|r|
+      // y += alpha p + omega s (x = T^-1 y is formed once, after the loop: x = sum alpha phat + omega shat and
+      // T^-1 is linear) ; r = s - omega t ; (rhat, r), max|r|
       double a3[2] = {0.0, 0.0};
 #pragma unroll
       for (int m = 0; m < R; ++m) {
-        const int i = i0 + m, q = m * NT + tid;
-        const double sh = (FULL || (col_ok && i < nx)) ? hat[i * hs + j] : 0.0;
-        x_g[q] += omega * sh;
+        const int q = m * NT + tid;
+        y_g[q] = (first ? 0.0 : y_g[q]) + (alpha * p[m] + omega * rs[m]);
         rs[m] -= omega * vv[m];
         a3[0] += rhs_g[q] * rs[m];
         a3[1] = fmax(a3[1], fabs(rs[m]));
       }
-      cta_reduce_x<2>(a3, 1, red);
+      cta_reduce_x<2, false>(a3, 1, red + 128);
       const double rho_new = a3[0];
       rmax = a3[1];
       ++it;
@@ -378,15 +377,22 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
       rho = rho_new;
     }
     it_total += it;
+    // x = T^-1 y  (left in z; p is free from here on)
+    if (it > 0) {
+#pragma unroll
+      for (int m = 0; m < R; ++m) p[m] = y_g[m * NT + tid];
+      tsolve(p);
+    } else {
+#pragma unroll
+      for (int m = 0; m < R; ++m) z[m] = 0.0;
+    }
 
     // ------------- f^{n+1} = c (1 + d) ; predictor ; true residual of the last step -------------
     const bool last = step == a.nsteps - 1;
     if (last) {
       // true residual with the FULL operator: rhs - (d + wW d_W + wE d_E + wS d_S + wN d_N); wW, wE
       // are recovered from the factors: wE = (wE/d) * d, wW = l * d_prev
-#pragma unroll
-      for (int m = 0; m < R; ++m) z[m] = it > 0 ? x_g[m * NT + tid] : 0.0;
-      __syncthreads();
+      __syncthreads();   // every thread is past its last read of shat
       publish();
       double mres = 0.0;
 #pragma unroll
@@ -419,7 +425,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
         const int n = i * ny + j;
         const double fold = f[n];
         const double yp = yprev[n];
-        const double d = it > 0 ? x_g[m * NT + tid] : 0.0;
+        const double d = z[m];
         const double fnew = (fold * yp) * (1.0 + d);
         f[n] = fnew;
         if (a.predictor) {
