@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -35,6 +36,10 @@ struct sy2d_ctx {
   long long istep = 0;
   cudaStream_t stream = nullptr;
   int sm_count = 148;
+  // grid caps of the grid-stride kernels (tuning: SY2D_CTAS_PER_SM, SY2D_ASM_CTAS_PER_SM).  6 = the CTAs of 256 threads x 40
+  // registers that are resident on an SM at once: one full wave, no tail (profiles/sweep_caps_steps.py: 1024^2 4.98 -> 4.81 ms
+  // per step against 16, 2048^2 15.2 -> 14.9, 4096^2 equal; 8 is worse everywhere - a partial second wave)
+  int ctas_per_sm = 6, asm_ctas_per_sm = 4;
   std::string err;
   sy2d_options opt;
   bool have_coeffs = false, have_bc = false, have_f = false;
@@ -147,11 +152,11 @@ KrylovVecs krylov(const sy2d_ctx* c) {
 
 dim3 grid_of(const sy2d_ctx* c) { return dim3((unsigned)((c->N + kBlock - 1) / kBlock), (unsigned)c->nbatch, 1); }
 
-// Grid-stride kernels: at most ~16 resident CTAs per SM over the whole batch, so that a problem
+// Grid-stride kernels: one resident wave of CTAs over the whole batch (6 per SM), so that a problem
 // costs a few hundred block-level atomics per reduction instead of one per 256 cells.
 unsigned capped_blocks(const sy2d_ctx* c, size_t work_items_per_problem, int threads) {
   const size_t need = (work_items_per_problem + threads - 1) / threads;
-  const size_t cap = std::max<size_t>(1, (size_t)c->sm_count * 16 / (size_t)c->nbatch);
+  const size_t cap = std::max<size_t>(1, (size_t)c->sm_count * c->ctas_per_sm / (size_t)c->nbatch);
   return (unsigned)std::min(need, cap);
 }
 
@@ -288,7 +293,7 @@ void launch_assembly(sy2d_ctx* c, const Geometry& geo, const AssembleOut& o, int
   const bool tiled = c->nx >= 2 * kTI && c->ny >= kTJ && variant != 1;
   if (tiled && c->have_tma && variant == 0) {
     const int ntiles = tiles_i * tiles_j;
-    const unsigned ctas = (unsigned)std::min<size_t>((size_t)ntiles, std::max<size_t>(1, (size_t)c->sm_count * 4 / (size_t)c->nbatch));
+    const unsigned ctas = (unsigned)std::min<size_t>((size_t)ntiles, std::max<size_t>(1, (size_t)c->sm_count * c->asm_ctas_per_sm / (size_t)c->nbatch));
     k_assemble_tma<<<dim3(ctas, (unsigned)c->nbatch, 1), kTI * kTJ, kTmaSmemBytes, c->stream>>>(c->d_tma_maps, geo, o, tiles_j, ntiles);
   } else if (tiled) {
     k_assemble_tiled<<<dim3(capped_blocks(c, (size_t)tiles_i * tiles_j, 1), (unsigned)c->nbatch, 1), kTI * kTJ, 0, c->stream>>>(
@@ -842,6 +847,8 @@ static int create_impl(sy2d_ctx** out, int device, int nx, int ny, int nbatch, c
   CUB(cudaSetDevice(device));
   CUB(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   CUB(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
+  if (const char* e = std::getenv("SY2D_CTAS_PER_SM")) ctx->ctas_per_sm = std::max(1, std::min(32, std::atoi(e)));
+  if (const char* e = std::getenv("SY2D_ASM_CTAS_PER_SM")) ctx->asm_ctas_per_sm = std::max(1, std::min(4, std::atoi(e)));
   const HostGeometry hg = make_host_geometry(nx, ny, xe, ye);
   const std::vector<double>&wxL = hg.wxL, &wxR = hg.wxR, &wyB = hg.wyB, &wyT = hg.wyT, &dx = hg.dx, &dy = hg.dy;
   struct Up { double** dst; const std::vector<double>* src; } ups[] = {
