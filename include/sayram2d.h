@@ -66,7 +66,8 @@ typedef struct {
   int mg_coarse_sweeps; /* SY2D_PRECOND_MG: smoothing sweeps on the coarsest level (0 = default 2) */
   int reserved[3];   /* reserved[0]: 1 forces the one-thread-per-cell assembly, 2 the tile kernel without TMA (tests); reserved[1]: slab mode,
                         fixed iteration budget without a convergence error (bench); reserved[2]: 1 makes the first attempt of every
-                        AUTO multigrid step count as failed, so the x-line fallback runs (tests) */
+                        AUTO multigrid step count as failed, so the x-line fallback runs (tests); 2 (slab mode, multigrid): the smoother's
+                        lines end at the slab instead of being coupled across ranks by the spike correction (comparison runs) */
 } sy2d_options;
 
 typedef struct {

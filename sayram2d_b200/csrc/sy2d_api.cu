@@ -63,6 +63,13 @@ struct sy2d_ctx {
   MgLevels mg;
   double* mg_rc[kMgMaxLevels] = {};   // writable right-hand sides of the coarse levels
   double *mg_om0 = nullptr, *mg_shat = nullptr;
+  // row-slab mode, exact lines across ranks (spike correction, sy2d_mg.cuh): per level the damped spikes of the
+  // own rows and the gathered spike tips [nranks][4][ny_l]; per solve the tips [2][ny] / gathered [nranks][2][ny] / coefficients
+  double* mg_spW[kMgMaxLevels] = {};
+  double* mg_spV[kMgMaxLevels] = {};
+  double* mg_sp_all[kMgMaxLevels] = {};
+  double *mg_tips = nullptr, *mg_tips_all = nullptr, *mg_coef = nullptr;
+  bool mg_spike = false;   // spikes of the current operator are set up: line solves are corrected
   std::vector<double*> mg_bufs;
   // TMA-staged assembly (sy2d_assemble_tma.cuh): tensor maps of f, yprev, tx, ty, cxy, U, Ud
   bool have_tma = false;
@@ -346,6 +353,19 @@ int mg_alloc(sy2d_ctx* c) {
     lv.z = a[9] + off; lv.t = a[10] + off;
     lv.ny = ny; lv.N = (size_t)rows * ny;
   }
+  if (c->slab) {
+    if (c->nranks > kMgMaxRanks) return fail(c, SY2D_ERR_INVALID, "multigrid in slab mode: at most %d ranks", kMgMaxRanks);
+    int nyl = c->ny;
+    for (int k = 0; k < nlev; ++k, nyl /= 2) {
+      const size_t n = (size_t)(rows + halo_rows) * nyl;
+      double *w = nullptr, *v = nullptr;
+      if ((rc = grab(n, &w)) || (rc = grab(n, &v)) || (rc = grab((size_t)c->nranks * 4 * nyl, &c->mg_sp_all[k]))) return rc;
+      c->mg_spW[k] = w + nyl; c->mg_spV[k] = v + nyl;   // first owned row, like the level arrays
+    }
+    if ((rc = grab((size_t)6 * c->ny, &c->mg_tips)) || (rc = grab((size_t)c->nranks * 2 * c->ny, &c->mg_tips_all)) ||
+        (rc = grab((size_t)2 * c->ny, &c->mg_coef)))
+      return rc;
+  }
   c->mg_nlev = nlev;
   return SY2D_OK;
 }
@@ -373,7 +393,7 @@ void mg_setup(sy2d_ctx* c) {
 template <int SEG, int COLS, int MODE>
 void mg_line_shape(sy2d_ctx* c, const MgLevel& lv, const double* zc) {
   const int rows = mg_rows(c);
-  const MgArgs a{c->scal, rows, c->slab ? 1 : 0};
+  const MgArgs a{c->scal, rows, c->slab ? 1 : 0, c->slab ? c->mg_tips : nullptr};
   const int nseg = (rows + SEG - 1) / SEG;
   const int threads = (nseg * COLS + 31) / 32 * 32;
   const size_t smem = (size_t)3 * COLS * (nseg + 1) * sizeof(double);
@@ -404,17 +424,58 @@ void mg_line_seg(sy2d_ctx* c, const MgLevel& lv, const double* zc) {
   }
 }
 
+int slab_gather(sy2d_ctx* c, const double* src, double* dst, size_t count);
+
+// Row-slab mode: turns the local line solutions just written to lv.z into the solutions of the global lines
+// (sy2d_mg.cuh, "exact x-lines across ranks"): all-gather of the tips, reduced system per column, one correction pass.
+int mg_spike_fix(sy2d_ctx* c, const MgLevel& lv, int k) {
+  int rc = slab_gather(c, c->mg_tips, c->mg_tips_all, (size_t)2 * lv.ny);
+  if (rc) return rc;
+  k_mg_spike_reduced<<<(unsigned)((lv.ny + 127) / 128), 128, 0, c->stream>>>(c->mg_tips_all, c->mg_sp_all[k], c->mg_coef, c->scal, c->rank, c->nranks, lv.ny);
+  k_mg_spike_apply<<<capped_blocks(c, lv.N / 2, kBlock), kBlock, 0, c->stream>>>(lv.z, c->mg_spW[k], c->mg_spV[k], c->mg_coef, c->scal, mg_rows(c), lv.ny);
+  CU(cudaGetLastError());
+  return SY2D_OK;
+}
+
 template <int MODE>
-void mg_line(sy2d_ctx* c, const MgLevel& lv, const double* zc) {
+int mg_line(sy2d_ctx* c, const MgLevel& lv, const double* zc, int k) {
   Prof p(c, SY2D_K_MG_LINE);
   if (c->mg_seg == 8) mg_line_seg<8, MODE>(c, lv, zc);
   else mg_line_seg<16, MODE>(c, lv, zc);
+  if (c->slab && c->mg_spike) return mg_spike_fix(c, lv, k);
+  return SY2D_OK;
+}
+
+// Row-slab mode, once per time step after mg_setup: the two spikes of every level (damped like the smoother's
+// output, so that the correction pass needs no extra factor) and the all-gathered spike tips.
+int mg_spike_setup(sy2d_ctx* c) {
+  c->mg_spike = false;   // the spike solves themselves are plain local solves
+  for (int k = 0; k < c->mg_nlev; ++k) {
+    MgLevel lv = c->mg.lv[k];
+    const int rows = mg_rows(c);
+    double* rhs = lv.t;   // free at setup time
+    for (int which = 0; which < 2; ++which) {
+      k_mg_spike_rhs<<<capped_blocks(c, lv.N, kBlock), kBlock, 0, c->stream>>>(rhs, which == 0 ? lv.wW : lv.wE, which, rows, lv.ny);
+      MgLevel sv = lv;
+      sv.r = rhs; sv.z = which == 0 ? c->mg_spW[k] : c->mg_spV[k];
+      int rc = mg_line<0>(c, sv, nullptr, k);
+      if (rc) return rc;
+      // tips of the undamped spike: [2][ny_l] -> slots (2 which, 2 which + 1) of the local [4][ny_l] block
+      CU(cudaMemcpyAsync(c->mg_tips + (size_t)(2 + 2 * which) * lv.ny, c->mg_tips, (size_t)2 * lv.ny * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    // local block [4][ny_l] sits at mg_tips + 2 ny_l (behind the [2][ny_l] the line kernel writes)
+    int rc = slab_gather(c, c->mg_tips + (size_t)2 * lv.ny, c->mg_sp_all[k], (size_t)4 * lv.ny);
+    if (rc) return rc;
+  }
+  CU(cudaGetLastError());
+  c->mg_spike = true;
+  return SY2D_OK;
 }
 
 template <int KIND>
 void mg_resid(sy2d_ctx* c, const MgLevel& lv, const double* zc, const double* omc, double* rc) {
   Prof p(c, SY2D_K_MG_RESID);
-  const MgArgs a{c->scal, mg_rows(c), c->slab ? 1 : 0};
+  const MgArgs a{c->scal, mg_rows(c), c->slab ? 1 : 0, nullptr};
   k_mg_resid<KIND><<<dim3(capped_blocks(c, lv.N / 2, kBlock), (unsigned)c->nbatch, 1), kBlock, 0, c->stream>>>(lv, zc, omc, rc, a);
 }
 
@@ -438,22 +499,22 @@ int mg_vcycle(sy2d_ctx* c, const double* r, double* z) {
   const double scale0 = c->cur_cells;
   for (int k = 0; k + 1 < L; ++k) {
     c->cur_cells = scale0 / (double)(1 << k);
-    mg_line<0>(c, level(k), nullptr);
+    if ((rc = mg_line<0>(c, level(k), nullptr, k))) return rc;
     if ((rc = halo(k))) return rc;
     mg_resid<1>(c, level(k), nullptr, c->mg.lv[k + 1].om, c->mg_rc[k + 1]);
   }
   c->cur_cells = scale0 / (double)(1 << (L - 1));
-  mg_line<0>(c, level(L - 1), nullptr);
+  if ((rc = mg_line<0>(c, level(L - 1), nullptr, L - 1))) return rc;
   for (int sweep = 1; sweep < mg_coarse_sweeps(c); ++sweep) {
     if ((rc = halo(L - 1))) return rc;
     mg_resid<0>(c, level(L - 1), nullptr, nullptr, nullptr);
-    mg_line<2>(c, level(L - 1), nullptr);
+    if ((rc = mg_line<2>(c, level(L - 1), nullptr, L - 1))) return rc;
   }
   for (int k = L - 2; k >= 0; --k) {
     c->cur_cells = scale0 / (double)(1 << k);
     if ((rc = halo(k + 1))) return rc;   // the correction; the halo of z_k is still the one exchanged on the way down
     mg_resid<2>(c, level(k), c->mg.lv[k + 1].z, nullptr, nullptr);
-    mg_line<1>(c, level(k), c->mg.lv[k + 1].z);
+    if ((rc = mg_line<1>(c, level(k), c->mg.lv[k + 1].z, k))) return rc;
   }
   c->cur_cells = scale0;
   return SY2D_OK;
@@ -631,6 +692,12 @@ int slab_halo_exchange_n(sy2d_ctx* c, double* a, int ny_l) {
 }
 int slab_halo_exchange(sy2d_ctx* c, double* a) { return slab_halo_exchange_n(c, a, c->ny); }
 
+// count doubles of every rank -> [nranks][count] on every rank
+int slab_gather(sy2d_ctx* c, const double* src, double* dst, size_t count) {
+  NC(nccl().AllGather(src, dst, count, ncclDouble, static_cast<ncclComm_t>(c->comm), c->stream));
+  return SY2D_OK;
+}
+
 // accumulators of every rank -> scalars on every rank (identical summation order everywhere)
 int slab_reduce(sy2d_ctx* c, int phase, const KrylovVecs& k) {
   ncclComm_t comm = static_cast<ncclComm_t>(c->comm);
@@ -680,7 +747,11 @@ int step_slab(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
     rc = slab_reduce(c, 0, k);
     if (rc) return rc;
     if (xl) k_xl_factor<<<gs, kBlock, 0, c->stream>>>(xv, c->N);
-    if (mg) mg_setup(c);   // coarse operators and line LU of the owned rows: local, the lines end at the slab
+    if (mg) {
+      mg_setup(c);   // coarse operators and line LU of the owned rows (local) ...
+      if (c->opt.reserved[2] != 2 && (rc = mg_spike_setup(c))) return rc;   // ... and the spikes that couple the ranks' lines
+      if (c->opt.reserved[2] == 2) c->mg_spike = false;   // reserved[2] = 2: lines end at the slab (block Jacobi across ranks; tests / bench comparison)
+    }
     c->launches += 3;
     CU(cudaMemcpyAsync(c->h_nactive, c->d_nactive, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));

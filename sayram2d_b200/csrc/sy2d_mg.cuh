@@ -54,7 +54,9 @@ struct MgArgs {
   int halo;           // row-slab mode: the level arrays carry one halo row below row 0 and one above row nx-1 (the
                       // pointers address the first OWNED row), filled by the host with the neighbour ranks' rows:
                       // the residual kernels read them instead of clamping.  The line solves never look at them -
-                      // a rank's lines end at its slab (block-Jacobi smoothing across ranks).
+                      // The line kernel solves the rank's OWN rows; the coupling to the neighbour ranks' rows is
+                      // restored afterwards by the spike correction below (exact global lines).
+  double* tips;       // row-slab mode: [2][ny] - first and last value of every local line solution (before damping)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -258,6 +260,15 @@ __global__ void __launch_bounds__(SEG <= 8 ? 1024 : 512, 1) k_mg_line(MgLevel lv
 #pragma unroll
     for (int m = SEG - 1; m >= 0; --m) { q = -c[m] * q; y[m] += q; }
   }
+  if (a.tips && live) {   // interface values of the local solution (spike correction, row-slab mode)
+    if (r0 == 0) a.tips[j] = y[0];
+    if (r0 + cnt == nx) {
+      double yl = y[0];
+#pragma unroll
+      for (int m = 1; m < SEG; ++m) yl = (m < cnt) ? y[m] : yl;
+      a.tips[ny + j] = yl;
+    }
+  }
   // all loads of the update before the first store (z is read and written through the same pointer)
   double* pz = lv.z + n0;
   if (MODE != 0) {
@@ -278,6 +289,77 @@ __global__ void __launch_bounds__(SEG <= 8 ? 1024 : 512, 1) k_mg_line(MgLevel lv
   for (int m = 0; m < SEG; ++m) {
     if (FULL || m < cnt) *pz = MODE == 0 ? kMgOmega * y[m] : c[m] + kMgOmega * y[m];
     pz += ny;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row-slab mode: exact x-lines across ranks (SPIKE).  Rank r owns rows [0, n) of every global line; with
+// T_r its own tridiagonal block, bot_{r-1} the line's value on the last row of rank r-1 and top_{r+1} the one on
+// the first row of rank r+1,
+//     x_r = g_r - W_r bot_{r-1} - V_r top_{r+1},    g_r = T_r^-1 b_r,
+//     W_r = T_r^-1 (wW_0 e_0),  V_r = T_r^-1 (wE_{n-1} e_{n-1})          (the "spikes": once per time step).
+// The interface values solve a 2P x 2P system per column whose data are the tips (first, last entry) of g, W, V
+// of every rank: all-gathered (2 ny doubles per rank and solve), solved redundantly by every rank with a block
+// forward elimination / back substitution over the ranks, then x_r is corrected in one streaming pass.  The
+// preconditioner is then the one of the single-GPU engine up to round-off, so the iteration counts do not grow
+// with the number of slabs.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMgMaxRanks = 16;
+
+// right-hand side of a spike solve: which = 0: wW of the first row on row 0; 1: wE of the last row on row nx-1
+__global__ void __launch_bounds__(kBlock) k_mg_spike_rhs(double* __restrict__ t, const double* __restrict__ w, int which, int nx, int ny) {
+  const size_t N = (size_t)nx * ny;
+  const size_t hot = which == 0 ? 0 : (size_t)(nx - 1) * ny;
+  for (size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (size_t)gridDim.x * blockDim.x)
+    t[n] = (n >= hot && n < hot + ny) ? w[n] : 0.0;
+}
+
+// tips_all: [P][2][ny] (g first, g last); sp_all: [P][4][ny] (W first, W last, V first, V last);
+// coef: [2][ny] = (bot_{rank-1}, top_{rank+1}) of the corrected lines.  One thread per column.
+__global__ void __launch_bounds__(128) k_mg_spike_reduced(const double* __restrict__ tips_all, const double* __restrict__ sp_all,
+                                                          double* __restrict__ coef, const Scal* scal, int rank, int P, int ny) {
+  if (scal[0].state != 0) return;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= ny) return;
+  double al[kMgMaxRanks], be[kMgMaxRanks], ga[kMgMaxRanks], de[kMgMaxRanks];
+  double ap = 0.0, bp = 0.0;
+  for (int r = 0; r < P; ++r) {
+    const double g0 = tips_all[((size_t)r * 2 + 0) * ny + j], g1 = tips_all[((size_t)r * 2 + 1) * ny + j];
+    const double W0 = sp_all[((size_t)r * 4 + 0) * ny + j], W1 = sp_all[((size_t)r * 4 + 1) * ny + j];
+    const double V0 = sp_all[((size_t)r * 4 + 2) * ny + j], V1 = sp_all[((size_t)r * 4 + 3) * ny + j];
+    const double inv = 1.0 / (1.0 + W0 * bp);
+    ga[r] = (g0 - W0 * ap) * inv;
+    de[r] = -V0 * inv;
+    al[r] = g1 - W1 * ap - W1 * bp * ga[r];
+    be[r] = -W1 * bp * de[r] - V1;
+    ap = al[r]; bp = be[r];
+  }
+  double tnext = 0.0, t_after_me = 0.0, b_before_me = 0.0;
+  for (int r = P - 1; r >= 0; --r) {
+    const double tr = ga[r] + de[r] * tnext;
+    const double br = al[r] + be[r] * tnext;
+    if (r == rank + 1) t_after_me = tr;
+    if (r == rank - 1) b_before_me = br;
+    tnext = tr;
+  }
+  coef[j] = b_before_me;
+  coef[ny + j] = t_after_me;
+}
+
+// z -= spW * bot_{rank-1} + spV * top_{rank+1}   (spW, spV already carry the damping omega of the smoother)
+__global__ void __launch_bounds__(kBlock) k_mg_spike_apply(double* __restrict__ z, const double* __restrict__ spW, const double* __restrict__ spV,
+                                                           const double* __restrict__ coef, const Scal* scal, int nx, int ny) {
+  if (scal[0].state != 0) return;
+  const size_t N2 = (size_t)nx * ny / 2;
+  const int ny2 = ny >> 1;
+  for (size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < N2; n += (size_t)gridDim.x * blockDim.x) {
+    const int j2 = (int)(n % ny2);
+    const double2 a = ld2(coef + 2 * j2), b = ld2(coef + ny + 2 * j2);
+    const double2 w = ld2(spW + 2 * n), v = ld2(spV + 2 * n);
+    double2 zz = ld2(z + 2 * n);
+    zz.x -= w.x * a.x + v.x * b.x;
+    zz.y -= w.y * a.y + v.y * b.y;
+    st2(z + 2 * n, zz.x, zz.y);
   }
 }
 

@@ -12,7 +12,7 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, precond, outdir, nx, ny):
+def _worker(rank, world, port, precond, outdir, nx, ny, tol):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -30,7 +30,7 @@ def _worker(rank, world, port, precond, outdir, nx, ny):
     G = fields.ay_G(xe, ye)
     f0, bct, lines = fields.ay_init_and_bc(xe, ye)
     eng = sy.Engine(xe, ye, 0.002, device=rank, slab=(rank, world, ids[0]))
-    eng.set_options(precond=precond)
+    eng.set_options(precond=precond, tol=tol, check_every=1 if precond == 2 else 16)   # exact iteration counts for the multigrid runs
     lo, hi = eng.i_lo, eng.i_hi
     eng.set_coeffs(G[lo:hi], Dxx[lo:hi], Dxy[lo:hi], Dyy[lo:hi], inv_tau[lo:hi])
     eng.set_bc(bct, *lines)
@@ -43,10 +43,10 @@ def _worker(rank, world, port, precond, outdir, nx, ny):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("precond,nx,ny", [(1, 256, 64), (2, 256, 64), (2, 1024, 256)])
-def test_two_gpu_slab_matches_single_gpu(tmp_path, precond, nx, ny):
+@pytest.mark.parametrize("precond,nx,ny,tol", [(1, 256, 64, 1e-14), (2, 256, 64, 1e-14), (2, 1024, 256, 1e-14), (2, 1024, 256, 1e-10)])
+def test_two_gpu_slab_matches_single_gpu(tmp_path, precond, nx, ny, tol):
     """precond 1: segmented x-line iteration on both sides (same iteration, same counts); precond 2: multigrid - the
-    slab ranks' smoothing lines end at the slab (block Jacobi across ranks), so the counts differ, the result does not."""
+    slab ranks' whole-line smoother is made exact across the ranks by the spike correction: same counts again."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -54,12 +54,12 @@ def test_two_gpu_slab_matches_single_gpu(tmp_path, precond, nx, ny):
     import sayram2d_b200 as sy
     from sayram2d_b200 import fields
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    mp.spawn(_worker, args=(2, port, precond, str(tmp_path), nx, ny), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, precond, str(tmp_path), nx, ny, tol), nprocs=2, join=True)
     xe, ye = fields.uniform_edges(nx, ny)
     Dxx, Dxy, Dyy, inv_tau = fields.synthetic_tensor(xe, ye)
     f0, bct, lines = fields.ay_init_and_bc(xe, ye)
     ref = sy.Engine(xe, ye, 0.002)
-    ref.set_options(engine=1, precond=precond)   # the same preconditioner as the slab ranks run
+    ref.set_options(engine=1, precond=precond, tol=tol)   # the same preconditioner as the slab ranks run
     ref.set_coeffs(fields.ay_G(xe, ye), Dxx, Dxy, Dyy, inv_tau)
     ref.set_bc(bct, *lines)
     ref.set_f(f0)
@@ -72,11 +72,15 @@ def test_two_gpu_slab_matches_single_gpu(tmp_path, precond, nx, ny):
         f = np.load(tmp_path / f"f_{r}.npy")
         lo, hi = int(lo), int(hi)
         assert f.shape == (hi - lo, ny)
-        assert np.max(np.abs(f - fref[lo:hi]) / np.abs(fref[lo:hi])) < 1e-10
-        assert neg == 0 and res < 1e-13 and int(pc) == precond
+        assert np.max(np.abs(f - fref[lo:hi]) / np.abs(fref[lo:hi])) < max(1e-10, 100 * tol)
+        assert neg == 0 and res <= tol and int(pc) == precond
         if precond == 1:
             assert abs(its - st["iters_total"]) <= 0.2 * st["iters_total"]
         else:
-            assert its <= 6 * st["iters_total"] and its <= 3 * 80   # one cut line per column costs ~3-4x the iterations
+            # the spike correction couples the ranks' line solves: the preconditioner is the single-GPU one up to
+            # round-off (lines that end at the slab cost 3-4x the iterations here, 8x at 16384^2)
+            print(f"rank {r}: {int(its)} iterations in 3 steps, single GPU {st['iters_total']}")
+            # (at tol = 1e-14 the last iterations sit on the round-off floor and the count depends on the summation order)
+            assert abs(its - st["iters_total"]) <= (1 if tol > 1e-12 else 3)
         rows += hi - lo
     assert rows == nx
