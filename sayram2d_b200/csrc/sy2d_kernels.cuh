@@ -884,6 +884,7 @@ __global__ void __launch_bounds__(kBlock) k_xr_update2(KrylovVecs k, size_t N) {
 // 3 after the x, r update.
 __global__ void k_slab_scalars(int phase, Scal* sc, const double* __restrict__ gathered, int nranks, KrylovVecs k) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (phase != 0 && sc->state != 0) return;   // stopped: the rest of the polling chunk must not count iterations or touch rmax
   double rv = 0.0, ts = 0.0, tt = 0.0, rho = 0.0, rmax = 0.0;
   for (int r = 0; r < nranks; ++r) {
     const double* q = gathered + 5 * r;
