@@ -73,6 +73,29 @@ def shard(n, rank, world):
     return shard_range(n, rank, world)
 
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Run this rank (and first-touch its pinned host buffers) on the CPUs of the NUMA node its GPU hangs off: with
+    one rank per GPU the end-to-end loop moves 2 x 26-210 MB per step and rank over PCIe, and buffers on the far
+    socket make that cross the inter-socket link.  Best effort: returns the node or None."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        dev = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{dev}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -314,6 +337,7 @@ def ours(args):
         raise SystemExit("bench.py: no CUDA device - the engine has no CPU path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_node = bind_to_gpu_numa_node(torch, local_rank)
 
     def barrier():
         torch.cuda.synchronize()
@@ -375,7 +399,8 @@ def ours(args):
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     clocks = sampler.stop() if sampler else None
     e2e = {"value": cells_total * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": cells_total * 8,
-           "d2h_bytes_per_step": cells_total * 8, "ms_per_step": 1e3 * e2e_s / args.steps}
+           "d2h_bytes_per_step": cells_total * 8, "ms_per_step": 1e3 * e2e_s / args.steps,
+           "host_buffers": "pinned" + (f", rank bound to the GPU's NUMA node ({numa_node})" if numa_node is not None else "")}
 
     # ---- per-kernel roofline (separate profiled pass, CUDA events around every launch) ----
     prof, pst = profile_pass(eng, 2)
