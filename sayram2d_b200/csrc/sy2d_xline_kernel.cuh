@@ -4,7 +4,15 @@
 //
 //   phat = T^-1 p   (Thomas sweeps along i),   v = A phat = p + wS phat_S + wN phat_N
 // (T phat = p holds by construction, so the W/E couplings never have to be applied again and
-// wW, wE are needed only as the LU factors l, 1/d, wE/d of T).  Same for s.  Right
+// wW, wE are needed only as the LU factors of T).  Same for s.
+//
+// Pivot scaling: the rows of the system are divided once per time step by the pivots d_i of T's LU,
+//   A' = D^-1 A,  rhs' = D^-1 rhs,  T' = D^-1 T = (I + L')(I + U'),  l'_i = wW_i / d_i,  e_i = wE_i / d_i,
+// so both triangular factors have a UNIT diagonal: a solve is z_i = b_i - l'_i z_{i-1}, x_i = z_i - e_i x_{i+1}
+// (two factor arrays and two FMAs per row instead of three and three), wS' = wS / d and wN' = wN / d carry the
+// scaling, and the shared-memory array that held 1/d holds the search direction p instead, which with r/s and
+// the Thomas work vector does not fit in the 96 registers of a 640-thread CTA.  0 < d <= 1 (M-matrix), so the
+// stopping rule max|r'| <= tol on the scaled residual r' = r / d is at least as strict as the one on r.  Right
 // preconditioning leaves the residual - and therefore the stopping rule max|r| <= tol and the
 // accuracy of f - exactly those of the unpreconditioned engine; iterations drop ~4x
 // (80x80 AY: 59 -> 14.5 per step).
@@ -19,12 +27,12 @@
 // sweep, every warp sweeps its own columns independently.
 //
 // Placement per problem (N = nx*ny cells, S = R*NT slots in thread-private [m][tid] layout):
-//   registers : r/s and p of the owned cells (resident), phat/shat, t, v (transient)
-//   shared    : hat (phat/shat, natural (i,j) layout, row stride ny+1: the S/N neighbour exchange),
-//               l, 1/d, wE/d (sweep coefficients, private layout, conflict-free)
+//   registers : r/s of the owned cells (resident), phat/shat, t, v (transient)
+//   shared    : hat (phat/shat, natural (i,j) layout: the S/N neighbour exchange),
+//               l', e (sweep coefficients) and p, private layout, conflict-free
 //   L2        : wS, wN, v, y, rhs (private layout => fully coalesced 128 B lines per warp)
-// Traffic per cell and iteration: 10 L2 accesses (80 B: v r/w, wS wN twice, rhat twice, y r/w) + 16 shared
-// accesses (two Thomas solves of 5, two publishes, four neighbour reads).
+// Traffic per cell and iteration: 10 L2 accesses (80 B: v r/w, wS wN twice, rhat twice, y r/w) + 18 shared
+// accesses (two Thomas solves of 4, two publishes, four neighbour reads, p written once and read three times).
 #pragma once
 #include "sy2d_problem_kernel.cuh"
 
@@ -98,8 +106,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
   const int hs = HSC > 0 ? HSC : xa.hs;   // hat row stride, chosen on the host so that the NCH lanes of a column hit distinct banks
   double* hat = sm;
   double* l_s = hat + nx * hs;
-  double* di_s = l_s + S;
-  double* e_s = di_s + S;
+  double* p_s = l_s + S;     // the search direction p; during the assembly: face exchange, then 1/d of the factorisation
+  double* e_s = p_s + S;
   double* red = e_s + S;
   const int prob = a.order ? a.order[blockIdx.x] : blockIdx.x;
   const size_t base = (size_t)prob * N;
@@ -114,7 +122,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
   double* wS_g = scr; double* wN_g = scr + S; double* v_g = scr + 2 * S; double* y_g = scr + 3 * S; double* rhs_g = scr + 4 * S;
   const unsigned full = 0xffffffffu;
 
-  double rs[R], p[R], z[R];
+  double rs[R], z[R];
   int it_total = 0, it = 0, state = 1;
   double rmax = 0.0, res_true = 0.0;
 
@@ -130,7 +138,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
       // 40.  Same per-face expressions as assemble_row (K/L roles, operand order), same accumulation order.
       const Geometry& g = a.g;
       double* SK_s = hat;    // A_K, A_L of the south face of slot q
-      double* SL_s = di_s;
+      double* SL_s = p_s;
       auto vertex_at = [&](int vi, int vj) {
         const int il = vi > 0 ? vi - 1 : 0, ih = vi < nx ? vi : nx - 1;
         const int jl = vj > 0 ? vj - 1 : 0, jh = vj < ny ? vj : ny - 1;
@@ -201,12 +209,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
         l_s[q] = sc.wW;   // raw wW, wE until the factorisation below turns them into l and wE/d
         e_s[q] = sc.wE;
         wS_g[q] = sc.wS; wN_g[q] = sc.wN; rhs_g[q] = sc.rhs;
-        acc[0] += sc.rhs * sc.rhs;
-        acc[1] = fmax(acc[1], fabs(sc.rhs));
         AKw = AKe; ALw = ALe; vNW = vNE;
       }
-#pragma unroll
-      for (int m = 0; m < R; ++m) rs[m] = rhs_g[m * NT + tid];   // this thread wrote them: visible to itself
     } else {
 #pragma unroll
       for (int m = 0; m < R; ++m) {
@@ -219,34 +223,43 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
         l_s[q] = wW;   // raw wW, wE until the factorisation below turns them into l and wE/d
         e_s[q] = wE;
         wS_g[q] = wS; wN_g[q] = wN; rhs_g[q] = rh;
-        rs[m] = rh;
-        acc[0] += rh * rh;
-        acc[1] = fmax(acc[1], fabs(rh));
       }
     }
-    // (the reduction's barriers also separate the face exchange through the 1/d region from the factorisation)
-    cta_reduce_x<2>(acc, 1, red);
-    // LU of T down each column: chain over the NCH lanes of the column
+    __syncthreads();   // the face exchange through the p region is over: the factorisation writes 1/d there
+    // LU of T down each column: chain over the NCH lanes of the column.  d_i = 1 - wW_i e_{i-1} (e = wE / d), so only
+    // e is handed from row to row and from lane to lane; l' = wW / d, e = wE / d, 1/d parked in the p region.
     {
-      double dlast = 1.0, wElast = 0.0;
+      double elast = 0.0;
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c) {
-        const double din = __shfl_up_sync(full, dlast, 1, NCH);
-        const double win = __shfl_up_sync(full, wElast, 1, NCH);
+        const double ein = __shfl_up_sync(full, elast, 1, NCH);
         if (k == c) {
-          double dprev = k == 0 ? 1.0 : din, wEprev = k == 0 ? 0.0 : win;
+          double eprev = k == 0 ? 0.0 : ein;   // wW of the first row of a column is 0
 #pragma unroll
           for (int m = 0; m < R; ++m) {
             const int q = m * NT + tid;
             const double wW = l_s[q], wE = e_s[q];
-            const XlineFactor fc = xline_factor(wW, wEprev, dprev, k == 0 && m == 0);
-            l_s[q] = fc.l; di_s[q] = fc.dinv; e_s[q] = wE * fc.dinv;
-            dprev = fc.d; wEprev = wE;
+            const double dinv = sy2d_div(1.0, 1.0 - wW * eprev);
+            eprev = wE * dinv;
+            l_s[q] = wW * dinv; p_s[q] = dinv; e_s[q] = eprev;
           }
-          dlast = dprev; wElast = wEprev;
+          elast = eprev;
         }
       }
     }
+    // pivot scaling of the rest of the row (thread-private slots: no barrier needed), r0 = rhs', rho0, max|r0|
+#pragma unroll
+    for (int m = 0; m < R; ++m) {
+      const int q = m * NT + tid;
+      const double dinv = p_s[q];
+      wS_g[q] *= dinv; wN_g[q] *= dinv;
+      const double rh = rhs_g[q] * dinv;
+      rhs_g[q] = rh;
+      rs[m] = rh;
+      acc[0] += rh * rh;
+      acc[1] = fmax(acc[1], fabs(rh));
+    }
+    cta_reduce_x<2>(acc, 1, red);
     double rho = acc[0];
     rmax = acc[1];
     double alpha = 1.0, omega = 1.0, beta = 0.0;
@@ -259,12 +272,12 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
     // the multipliers, i.e. its chunk as an affine map  carry_out = A + B * carry_in.  The maps
     // of the NCH lanes of a column are composed with a 3-step shuffle scan, and a second pass adds
     // (product up to row m) * carry_in.  All lanes work concurrently - no serial hand-off.
-    auto tsolve = [&](const double (&b)[R]) {
+    auto tsolve = [&](auto bget) {   // bget(m): right-hand side of owned row m (called once per row, in order)
       double A = 0.0, B = 1.0;
 #pragma unroll
       for (int m = 0; m < R; ++m) {
         const double lm = l_s[m * NT + tid];
-        A = b[m] - lm * A;
+        A = bget(m) - lm * A;
         z[m] = A;
         B = -lm * B;
       }
@@ -281,12 +294,12 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
         P = -l_s[m * NT + tid] * P;
         z[m] += P * cin;
       }
-      // backward: y_m = z_m / d_m - (wE_m / d_m) y_{m+1}
+      // backward (unit diagonal): x_m = z_m - e_m x_{m+1}
       A = 0.0; B = 1.0;
 #pragma unroll
       for (int m = R - 1; m >= 0; --m) {
         const double em = e_s[m * NT + tid];
-        A = z[m] * di_s[m * NT + tid] - em * A;
+        A = z[m] - em * A;
         z[m] = A;
         B = -em * B;
       }
@@ -316,10 +329,13 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
     const int jS = j > 0 ? j - 1 : j, jN = j < ny - 1 ? j + 1 : j;
 
     while (state == 0) {
-      // p = r + beta (p - omega v)
-#pragma unroll
-      for (int m = 0; m < R; ++m) p[m] = first ? rs[m] : rs[m] + beta * (p[m] - omega * v_g[m * NT + tid]);
-      tsolve(p);
+      // p = r + beta (p - omega v), formed row by row as the right-hand side of the first sweep
+      tsolve([&](int m) {
+        const int q = m * NT + tid;
+        const double pm = first ? rs[m] : rs[m] + beta * (p_s[q] - omega * v_g[q]);
+        p_s[q] = pm;
+        return pm;
+      });
       publish();
       // v = p + wS phat_S + wN phat_N ; (rhat, v).  z is dead from here on (the thread re-reads its own
       // phat from hat), so v and later t reuse its registers: peak live arrays are rs, p and one more.
@@ -329,7 +345,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
       for (int m = 0; m < R; ++m) {
         const int i = i0 + m, q = m * NT + tid;
         double val = 0.0;
-        if (FULL || (col_ok && i < nx)) val = p[m] + (wS_g[q] * hat[i * hs + jS] + wN_g[q] * hat[i * hs + jN]);
+        if (FULL || (col_ok && i < nx)) val = p_s[q] + (wS_g[q] * hat[i * hs + jS] + wN_g[q] * hat[i * hs + jN]);
         vv[m] = val;
         v_g[q] = val;
         a1[0] += rhs_g[q] * val;
@@ -339,7 +355,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
       // s = r - alpha v (in place)
 #pragma unroll
       for (int m = 0; m < R; ++m) rs[m] -= alpha * vv[m];
-      tsolve(rs);
+      tsolve([&](int m) { return rs[m]; });
       publish();
       // t = s + wS shat_S + wN shat_N ; (t,s), (t,t)
       double a2[2] = {0.0, 0.0};
@@ -360,7 +376,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
 #pragma unroll
       for (int m = 0; m < R; ++m) {
         const int q = m * NT + tid;
-        y_g[q] = (first ? 0.0 : y_g[q]) + (alpha * p[m] + omega * rs[m]);
+        y_g[q] = (first ? 0.0 : y_g[q]) + (alpha * p_s[q] + omega * rs[m]);
         rs[m] -= omega * vv[m];
         a3[0] += rhs_g[q] * rs[m];
         a3[1] = fmax(a3[1], fabs(rs[m]));
@@ -377,11 +393,9 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
       rho = rho_new;
     }
     it_total += it;
-    // x = T^-1 y  (left in z; p is free from here on)
+    // x = T^-1 y  (left in z)
     if (it > 0) {
-#pragma unroll
-      for (int m = 0; m < R; ++m) p[m] = y_g[m * NT + tid];
-      tsolve(p);
+      tsolve([&](int m) { return y_g[m * NT + tid]; });
     } else {
 #pragma unroll
       for (int m = 0; m < R; ++m) z[m] = 0.0;
@@ -390,8 +404,10 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
     // ------------- f^{n+1} = c (1 + d) ; predictor ; true residual of the last step -------------
     const bool last = step == a.nsteps - 1;
     if (last) {
-      // true residual with the FULL operator: rhs - (d + wW d_W + wE d_E + wS d_S + wN d_N); wW, wE
-      // are recovered from the factors: wE = (wE/d) * d, wW = l * d_prev
+      // true residual with the FULL operator, row by row in the pivot-scaled form
+      //   r'_i = rhs'_i - (l'_i x_W + (1/d_i) x_i + e_i x_E + wS'_i x_S + wN'_i x_N),   1/d_i = 1 + l'_i e_{i-1},
+      // reported unscaled: |r_i| = d_i |r'_i| (the quantity the lockstep engine reports).  e_{i-1} lives in the
+      // previous slot of this thread or in the last slot of lane k-1.
       __syncthreads();   // every thread is past its last read of shat
       publish();
       double mres = 0.0;
@@ -399,18 +415,16 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
       for (int m = 0; m < R; ++m) {
         const int i = i0 + m, q = m * NT + tid;
         if (FULL || (col_ok && i < nx)) {
-          const double d_i = 1.0 / di_s[q];
-          const double wE = e_s[q] * d_i;
-          // d_prev: 1/d of the row above (i-1) lives in the previous slot of this thread or in lane k-1
-          double wWv = 0.0;
+          const double lp = l_s[q];
+          double dinv_i = 1.0;
           if (i > 0) {
             const int kp = (i - 1) / R, mp = (i - 1) - kp * R;
             const int tp = tid - (k - kp);
-            wWv = l_s[q] / di_s[mp * NT + tp];
+            dinv_i = 1.0 + lp * e_s[mp * NT + tp];
           }
           const double dW = i > 0 ? hat[(i - 1) * hs + j] : 0.0, dE = i < nx - 1 ? hat[(i + 1) * hs + j] : 0.0;
-          const double ax = z[m] + ((wWv * dW + wE * dE) + (wS_g[q] * hat[i * hs + jS] + wN_g[q] * hat[i * hs + jN]));
-          mres = fmax(mres, fabs(rhs_g[q] - ax));
+          const double ax = dinv_i * z[m] + ((lp * dW + e_s[q] * dE) + (wS_g[q] * hat[i * hs + jS] + wN_g[q] * hat[i * hs + jN]));
+          mres = fmax(mres, fabs(rhs_g[q] - ax) / dinv_i);
         }
       }
       double mm[1] = {mres};
