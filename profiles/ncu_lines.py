@@ -35,7 +35,7 @@ for r in rows:
         a = agg[key]
         a['samples'] += f(d['# Samples']); a['inst'] += f(d['Instructions Executed'])
         a['shw'] += f(d['L1 Wavefronts Shared']); a['shx'] += f(d['L1 Wavefronts Shared Excessive'])
-        a['gtag'] += f(d['L1 Tag Requests Global']); a['loc'] += f(d['L2 Theoretical Sectors Local'])
+        a['gtag'] += f(d.get('L1 Tag Requests Global', 0)); a['loc'] += f(d.get('L2 Theoretical Sectors Local', 0))
         for k in KEYS:
             a[k] += f(d[k])
 tot = sum(a['samples'] for a in agg.values())
