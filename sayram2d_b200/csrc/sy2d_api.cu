@@ -40,7 +40,7 @@ struct sy2d_ctx {
   // registers that are resident on an SM at once: one full wave, no tail (profiles/sweep_caps_steps.py: 1024^2 4.98 -> 4.81 ms
   // per step against 16, 2048^2 15.2 -> 14.9, 4096^2 equal; 8 is worse everywhere - a partial second wave)
   int ctas_per_sm = 6, asm_ctas_per_sm = 4;
-  int pipe_max = 32;   // sy2d_step_host: at most this many pipelined sub-batches (tuning: SY2D_PIPE_CHUNKS)
+  int pipe_max = 32, pipe_forced = 0;   // sy2d_step_host: at most pipe_max pipelined sub-batches (SY2D_PIPE_CHUNKS forces a count)
   std::string err;
   sy2d_options opt;
   bool have_coeffs = false, have_bc = false, have_f = false;
@@ -920,7 +920,7 @@ static int create_impl(sy2d_ctx** out, int device, int nx, int ny, int nbatch, c
   CUB(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   CUB(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
   if (const char* e = std::getenv("SY2D_CTAS_PER_SM")) ctx->ctas_per_sm = std::max(1, std::min(32, std::atoi(e)));
-  if (const char* e = std::getenv("SY2D_PIPE_CHUNKS")) ctx->pipe_max = std::max(1, std::min(64, std::atoi(e)));
+  if (const char* e = std::getenv("SY2D_PIPE_CHUNKS")) ctx->pipe_forced = std::max(1, std::min(64, std::atoi(e)));
   if (const char* e = std::getenv("SY2D_ASM_CTAS_PER_SM")) ctx->asm_ctas_per_sm = std::max(1, std::min(4, std::atoi(e)));
   const HostGeometry hg = make_host_geometry(nx, ny, xe, ye);
   const std::vector<double>&wxL = hg.wxL, &wxR = hg.wxR, &wyB = hg.wyB, &wyT = hg.wyT, &dx = hg.dx, &dy = hg.dy;
@@ -1175,11 +1175,16 @@ static cudaError_t dispatch_xline(const XlineArgs& xa, int R, int nbatch, size_t
 
 // Engine 2: the whole call (nsteps time steps of every problem) is ONE kernel launch.
 // Number of sub-batches a host-buffer call is pipelined over (and within which problems are sorted
-// by cost): at least half a wave of CTAs per sub-batch (the tail of a sub-batch is filled by the next
-// one's CTAs, the streams run concurrently), at most 32 - what is exposed of the copies is the upload of
-// the first sub-batch and the download of the last one (measured, 4096 members: 8 sub-batches 9.07 ms per
-// end-to-end step, 16: 8.55, 27: 8.41 against 8.2 ms device-resident).
-static int pipe_chunks(const sy2d_ctx* c) { return std::max(1, std::min(c->pipe_max, 2 * c->nbatch / c->sm_count)); }
+// by cost): one wave of CTAs per sub-batch (half a wave while that gives at most 6; the tail of a sub-batch is
+// filled by the next one's CTAs, the streams run concurrently), at most 32 - what is exposed of the copies is
+// the upload of the first sub-batch and the download of the last one (measured, 4096 members: 8 sub-batches
+// 9.07 ms per end-to-end step, 16: 8.55, 27: 8.41, 55: 8.38 against 8.2 ms device-resident; 512 members: 3
+// sub-batches 1.50 ms, 6: 1.46 against 1.13).
+static int pipe_chunks(const sy2d_ctx* c) {
+  if (c->pipe_forced > 0) return std::max(1, std::min(c->pipe_forced, c->nbatch));
+  const int waves = c->nbatch / c->sm_count, half_waves = 2 * c->nbatch / c->sm_count;
+  return std::max(1, std::min(c->pipe_max, std::max(waves, std::min(6, half_waves))));
+}
 
 // Engine 2: nsteps time steps of every problem in ONE kernel launch per sub-batch.  With host
 // buffers (h_in / h_out non-NULL) the batch is cut into pipe_chunks() contiguous sub-batches on
