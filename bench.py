@@ -575,8 +575,10 @@ def slab_object(n, iters, rank, world, local_rank, dist, torch):
 
 def main():
     global NB_TOTAL
-    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"   # NCCL prints its version banner on stdout, where the JSON line goes
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        # NCCL prints its version banner on stdout, where the JSON line goes (the level may also come from an nccl.conf,
+        # which an explicit environment value overrides); a level the user set explicitly is left alone
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
