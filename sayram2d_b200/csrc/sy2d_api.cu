@@ -170,7 +170,8 @@ unsigned capped_blocks(const sy2d_ctx* c, size_t work_items_per_problem, int thr
 
 // Multigrid (sy2d_mg.cuh) needs whole columns inside one CTA of the line kernel (nx <= 64 segments of 16 or
 // 32 rows), pairs of columns on every level (ny a multiple of 4 gives at least two levels) and a single GPU.
-// rows the multigrid kernels work on: the owned rows of a slab context (its lines end at the slab)
+// rows the multigrid kernels work on: the owned rows of a slab context (the line kernel solves them locally, the spike
+// correction couples them to the neighbour ranks' rows)
 int mg_rows(const sy2d_ctx* c) { return c->slab ? c->nx - 2 : c->nx; }
 
 int mg_level_count(const sy2d_ctx* c) {
@@ -759,8 +760,8 @@ int step_slab(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
     int done_its = 0;
     while (*c->h_nactive > 0 && done_its < c->opt.maxit + check_every) {
       for (int it = 0; it < check_every && mg; ++it) {
-        // right-preconditioned BiCGSTAB, one V-cycle per preconditioner application; the smoother's lines end at
-        // the slab (block Jacobi across ranks), every residual uses the neighbours' rows (halo exchange)
+        // right-preconditioned BiCGSTAB, one V-cycle per preconditioner application; the smoother's line solves are made
+        // exact across the ranks by mg_spike_fix, every residual uses the neighbours' rows (halo exchange)
         double* phat = c->xl_hat;
         double* shat = c->mg_shat;
         k_p_update2<<<g2, kBlock, 0, c->stream>>>(k, c->N);
