@@ -33,7 +33,12 @@ typedef enum {
   SY2D_OK = 0,
   SY2D_ERR_INVALID = -1,       /* bad argument (sizes, NULL, non-increasing edges: Grid2D.h:44-67) */
   SY2D_ERR_CUDA = -2,          /* CUDA runtime failure or no device */
-  SY2D_ERR_NOT_CONVERGED = -3, /* Krylov solve hit maxit (the reference's direct LU cannot fail this way) */
+  SY2D_ERR_NOT_CONVERGED = -3, /* Krylov solve stopped without converging (maxit, breakdown, NaN) or its true residual
+                                  exceeds 1000 tol (the reference's direct LU cannot fail this way).  The failing time step is
+                                  NOT committed: f, the predictor state and the step counter stay those of the last completed
+                                  step, so the call may be retried with other options.  Engine 2 (batches): a failed member keeps
+                                  its last completed step while the others finish the call; stats.steps and the step counter
+                                  advance by what EVERY member completed. */
   SY2D_ERR_STATE = -4,         /* call order: coefficients / BCs / f not set yet */
   SY2D_ERR_BC = -5             /* Dirichlet side without data: "Dirichlet BC: missing value." (Solver.cc:393) */
 } sy2d_status;
@@ -45,7 +50,7 @@ enum { SY2D_DIRICHLET = 0, SY2D_ZEROFLUX = 1 };
 /* preconditioner inside the BiCGSTAB loop */
 enum {
   SY2D_PRECOND_AUTO = -1,  /* engine 2: XLINE where the grid fits (nx <= 80, ny <= 128), else JACOBI;
-                              engine 1: MG where the grid fits (nx <= 4096, ny a multiple of 4), else XLINE */
+                              engine 1: MG where the grid fits (8 <= rows per context <= 8192, ny a multiple of 4 and >= 16), else XLINE */
   SY2D_PRECOND_JACOBI = 0, /* the unit-diagonal scaling itself */
   SY2D_PRECOND_XLINE = 1,  /* right preconditioning by the tridiagonal along i (alpha0): ~4x fewer iterations
                               (engine 1: block-Jacobi with 16-row line segments) */
@@ -136,7 +141,22 @@ int sy2d_set_coeffs_dev(sy2d_ctx* ctx, const double* G, const double* Dxx, const
 int sy2d_set_bc(sy2d_ctx* ctx, const int bc_type[4], const double* xmin, const double* xmax,
                 const double* ymin, const double* ymax);
 
-/* Solver::init f_ = eq.init_f (Solver.cc:38-42); [nbatch][nx][ny]. Resets the step counter. */
+/* Asynchronous flavours for time-dependent cases (Equation::update(t) followed by update_Lambda / update_vertex_f,
+ * Solver.cc:286-289): the arrays are copied into pinned staging owned by the context (they are free again on return),
+ * uploaded and folded on a separate copy stream into a SECOND set of device buffers while a time step may be running,
+ * and become the active set at the start of the NEXT sy2d_step / sy2d_step_host call, whose kernels wait for the upload
+ * on the device - the host never does.  These two calls (and only these) may be made from another host thread while
+ * sy2d_step is executing on the same context.  A later call before the next step overwrites an earlier one; a
+ * synchronous sy2d_set_coeffs / sy2d_set_bc supersedes a pending asynchronous one.  Not available on slab contexts. */
+int sy2d_set_coeffs_async(sy2d_ctx* ctx, const double* G, const double* Dxx, const double* Dxy,
+                          const double* Dyy, const double* inv_tau);
+int sy2d_set_bc_async(sy2d_ctx* ctx, const int bc_type[4], const double* xmin, const double* xmax,
+                      const double* ymin, const double* ymax);
+long long sy2d_stage_swaps(const sy2d_ctx* ctx);   /* asynchronously staged sets swapped in so far */
+
+/* Solver::init f_ = eq.init_f (Solver.cc:38-42); [nbatch][nx][ny]. Resets the step counter.
+ * f must be finite and > 0 in every cell (SY2D_ERR_INVALID otherwise): the engine solves for the per-cell ratio
+ * f^{n+1}/f^n.  The reference's cases add gEPS to f0 (Albert_Young.h:39) and the PPFV scheme keeps f positive. */
 int sy2d_set_f(sy2d_ctx* ctx, const double* f);
 int sy2d_set_f_dev(sy2d_ctx* ctx, const double* f_dev);
 /* Overwrites f from the host WITHOUT resetting the step counter or the predictor state:
@@ -192,6 +212,28 @@ int sy2d_nccl_unique_id(void* id_out /* 128 bytes */);
 int sy2d_create_slab(sy2d_ctx** out, int device, int nx_global, int ny, int rank, int nranks, const void* nccl_id,
                      const double* x_edges /* nx_global+1 */, const double* y_edges /* ny+1 */, double dt);
 int sy2d_slab_rows(const sy2d_ctx* ctx, int* i_lo, int* i_hi);
+
+/* The same decomposition with an IN-PROCESS transport instead of NCCL: the nranks slab contexts live in one process
+ * (one host thread per context; all on one device, or on several), halo lines and the small gathered vectors move with
+ * cudaMemcpyAsync between the contexts' buffers, ordered by CUDA events and a host barrier.  Kernels, spike-coupled
+ * multigrid and reduction order are exactly those of the NCCL contexts, so a single-GPU box can run and test the slab
+ * path at 2..16 ranks.  Every collective call (sy2d_set_coeffs, sy2d_step ...) must be made by all ranks concurrently,
+ * each from its own thread.  Destroy the contexts before the group. */
+typedef struct sy2d_local_group sy2d_local_group;
+int sy2d_local_group_create(sy2d_local_group** out, int nranks);
+void sy2d_local_group_destroy(sy2d_local_group* group);
+int sy2d_create_slab_local(sy2d_ctx** out, int device, int nx_global, int ny, int rank, int nranks, sy2d_local_group* group,
+                           const double* x_edges /* nx_global+1 */, const double* y_edges /* ny+1 */, double dt);
+
+/* Measured bandwidths of the units the kernels are bound by (copy micro-kernels with 8 / 16-byte accesses, best of 5):
+ * the denominators of bench.py's rooflines.  smem_gbs: shared memory / L1TEX data pipe, loads + stores, all SMs;
+ * l2_gbs: copy inside the L2 (32 MB -> 32 MB), reads + writes; hbm_gbs: copy of 1 GB -> 1 GB. */
+typedef struct {
+  double smem_gbs, l2_gbs, hbm_gbs;
+  int sm_count;
+  double sm_clock_mhz;   /* the device's nominal maximum SM clock */
+} sy2d_peaks;
+int sy2d_measure_peaks(int device, sy2d_peaks* out);
 
 /* Build/device facts: "sm_100a;cuda=12.9;..." */
 const char* sy2d_build_info(void);

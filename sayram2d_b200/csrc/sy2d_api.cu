@@ -11,6 +11,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -21,6 +23,7 @@
 #include "sy2d_xline_lockstep.cuh"
 #include "sy2d_mg.cuh"
 #include "sy2d_assemble_tma.cuh"
+#include "sy2d_peaks.cuh"
 
 using namespace sy2d;
 
@@ -28,6 +31,8 @@ namespace {
 thread_local std::string g_create_error;
 
 }  // namespace
+
+namespace { struct SlabTransport; }
 
 struct sy2d_ctx {
   int device = 0, nx = 0, ny = 0, nbatch = 0;
@@ -76,24 +81,45 @@ struct sy2d_ctx {
   bool have_tma = false;
   AsmMaps tma_maps;
   AsmMaps* d_tma_maps = nullptr;   // device copy read by the TMA unit
+  // Asynchronous staging (sy2d_set_coeffs_async / sy2d_set_bc_async): a second set of coefficient arrays and boundary
+  // lines is filled on `copy_stream` from pinned staging while the step in flight computes with the active set; the
+  // sets are swapped at the start of the next time step (stage_mu guards the hand-over: the setters may be called
+  // from another host thread while sy2d_step runs).
+  std::mutex stage_mu;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t coeffs_ready = nullptr, bc_ready = nullptr;
+  bool coeffs_pending = false, bc_pending = false;
+  double *tx2 = nullptr, *ty2 = nullptr, *cxy2 = nullptr, *U2 = nullptr, *Ud2 = nullptr;   // the inactive set
+  double* raw_dev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // G, Dxx, Dxy, Dyy, inv_tau as uploaded
+  double* raw_pin[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // pinned host staging
+  AsmMaps* d_tma_maps2 = nullptr;   // tensor maps of the inactive set
+  double* d_bc2[4] = {nullptr, nullptr, nullptr, nullptr};
+  double* bc_pin = nullptr;         // pinned: 2 (ny + 1) + 2 (nx + 1)
+  int bc2[4] = {SY2D_ZEROFLUX, SY2D_ZEROFLUX, SY2D_ZEROFLUX, SY2D_ZEROFLUX};
+  long long swaps = 0;              // buffer-set swaps done so far (tests)
   Scal* scal = nullptr;
   int* d_nactive = nullptr;
   int* h_nactive = nullptr;  // pinned
   StepStats* d_stats = nullptr;
   StepStats* h_stats = nullptr;  // pinned
-  double* stage = nullptr;      // unused staging pointer (kept for destroy)
-  size_t stage_elems = 0;
   // engine 2 / x-line: per-problem scratch in thread-private layout, allocated on first use
   // row-slab mode (sy2d_create_slab): this context holds rows [i_lo, i_hi) of an nx_glob x ny grid in
   // local arrays of nx = (i_hi - i_lo) + 2 rows (one halo row on each side)
   bool slab = false;
   int rank = 0, nranks = 1, nx_glob = 0, i_lo = 0, i_hi = 0;
-  void* comm = nullptr;          // ncclComm_t
+  SlabTransport* tp = nullptr;   // NCCL (one process per GPU) or the in-process transport (tests, single-GPU boxes)
   double* d_gather = nullptr;    // [nranks][5]
   int* d_order = nullptr;       // engine 2 scheduling: problems sorted by last call's cost, longest first
   int* d_cost = nullptr;
   std::vector<int> h_cost, h_order;
-  bool have_order = false;
+  int order_age = 0, order_calls = 0, order_C = -1;   // calls since the issue order was last rebuilt from the measured costs; sub-batch count it was built for
+  size_t xl_scratch_slots = 0;
+  // engine 2 work queues (sy2d_xline_kernel.cuh): control words per sub-batch launch, ticket slots, steps done per problem
+  XlineQueue* d_qctl = nullptr;
+  int* d_slots = nullptr;
+  size_t slots_cap = 0;
+  int* d_steps_done = nullptr;
+  int xl_chunk = 1;              // time steps per work item (SY2D_XLINE_CHUNK; 0 = all steps of a call: one CTA per problem)
   std::vector<cudaStream_t> pipe_streams;   // sy2d_step_host: one stream per sub-batch
   std::vector<cudaEvent_t> pipe_events;
   cudaEvent_t pipe_start = nullptr;
@@ -261,8 +287,21 @@ void launch_iteration_xline(sy2d_ctx* c) {
 // halo boxes of 36 x 10 cells and interior boxes of 32 x 8 cells, out-of-bounds elements zero-filled.
 // cuTensorMapEncodeTiled is a driver entry point; it is resolved through the runtime, so the library
 // keeps linking against libcudart only.
+bool tma_encode_maps(sy2d_ctx* c, AsmMaps* host_maps, double* tx, double* ty, double* cxy, double* U, double* Ud);
+
 bool tma_build_maps(sy2d_ctx* c) {
   if (c->slab || c->ny % 2 != 0 || c->nx < 2 * kTI || c->ny < kTJ) return false;
+  if (!tma_encode_maps(c, &c->tma_maps, c->tx, c->ty, c->cxy, c->U, c->Ud)) return false;
+  if (cudaFuncSetAttribute(k_assemble_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&c->d_tma_maps), sizeof(AsmMaps)) != cudaSuccess ||
+      cudaMemcpy(c->d_tma_maps, &c->tma_maps, sizeof(AsmMaps), cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return true;
+}
+
+bool tma_encode_maps(sy2d_ctx* c, AsmMaps* host_maps, double* tx, double* ty, double* cxy, double* U, double* Ud) {
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
@@ -274,23 +313,17 @@ bool tma_build_maps(sy2d_ctx* c) {
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
   EncodeFn encode = reinterpret_cast<EncodeFn>(fn);
-  double* arrs[7] = {c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud};
+  double* arrs[7] = {c->f, c->yprev, tx, ty, cxy, U, Ud};
   const cuuint64_t dims[3] = {(cuuint64_t)c->ny, (cuuint64_t)c->nx, (cuuint64_t)c->nbatch};
   const cuuint64_t strides[2] = {(cuuint64_t)c->ny * sizeof(double), (cuuint64_t)c->N * sizeof(double)};
   const cuuint32_t estr[3] = {1, 1, 1};
   for (int k = 0; k < 7; ++k) {
     const cuuint32_t box[3] = {(cuuint32_t)(k < 5 ? kTmaHaloJ : kTJ), (cuuint32_t)(k < 5 ? kTmaHaloI : kTI), 1};
-    const CUresult r = encode(&c->tma_maps.m[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, arrs[k], dims, strides, box, estr,
+    const CUresult r = encode(&host_maps->m[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, arrs[k], dims, strides, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,  // (L2 promotion raises an illegal-instruction fault with these boxes on B200 / driver 580: profiles/tma_probe.cu)
                              
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return false;
-  }
-  if (cudaFuncSetAttribute(k_assemble_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes) != cudaSuccess ||
-      cudaMalloc(reinterpret_cast<void**>(&c->d_tma_maps), sizeof(AsmMaps)) != cudaSuccess ||
-      cudaMemcpy(c->d_tma_maps, &c->tma_maps, sizeof(AsmMaps), cudaMemcpyHostToDevice) != cudaSuccess) {
-    cudaGetLastError();
-    return false;
   }
   return true;
 }
@@ -523,13 +556,14 @@ int mg_vcycle(sy2d_ctx* c, const double* r, double* z) {
 }
 int mg_kernels_per_vcycle(const sy2d_ctx* c) { return 4 * (c->mg_nlev - 1) + 1 + 2 * (mg_coarse_sweeps(c) - 1); }
 
-void launch_iteration_mg(sy2d_ctx* c) {
+int launch_iteration_mg(sy2d_ctx* c) {
+  int rc = SY2D_OK;
   KrylovVecs k = krylov(c);
   const dim3 g2(capped_blocks(c, c->N / 2, kBlock), (unsigned)c->nbatch, 1);
   double* phat = c->xl_hat;
   double* shat = c->mg_shat;
   { Prof p(c, SY2D_K_P_UPDATE); k_p_update2<<<g2, kBlock, 0, c->stream>>>(k, c->N); }
-  mg_vcycle(c, c->p, phat);
+  if ((rc = mg_vcycle(c, c->p, phat))) return rc;
   {
     Prof p(c, SY2D_K_SPMV_V);
     KrylovVecs kv = k;
@@ -537,14 +571,15 @@ void launch_iteration_mg(sy2d_ctx* c) {
     k_spmv_v2<<<g2, kBlock, 0, c->stream>>>(kv, c->N, c->ny);
   }
   { Prof p(c, SY2D_K_S_UPDATE); k_s_update2<<<g2, kBlock, 0, c->stream>>>(k, c->N); }
-  mg_vcycle(c, c->s, shat);
+  if ((rc = mg_vcycle(c, c->s, shat))) return rc;
   { Prof p(c, SY2D_K_SPMV_T); k_mg_spmv_t<<<g2, kBlock, 0, c->stream>>>(k, shat, c->N, c->ny); }
   { Prof p(c, SY2D_K_XR_UPDATE); k_mg_xr<<<g2, kBlock, 0, c->stream>>>(k, phat, shat, c->N); }
+  return SY2D_OK;
 }
 
-void launch_iteration(sy2d_ctx* c) {
-  if (lockstep_mg(c)) { launch_iteration_mg(c); return; }
-  if (lockstep_xline(c)) { launch_iteration_xline(c); return; }
+int launch_iteration(sy2d_ctx* c) {
+  if (lockstep_mg(c)) return launch_iteration_mg(c);
+  if (lockstep_xline(c)) { launch_iteration_xline(c); return SY2D_OK; }
   const KrylovVecs k = krylov(c);
   if (c->ny % 2 == 0) {  // two cells per thread, 16-byte accesses
     const dim3 g2(capped_blocks(c, c->N / 2, kBlock), (unsigned)c->nbatch, 1);
@@ -553,7 +588,7 @@ void launch_iteration(sy2d_ctx* c) {
     { Prof p(c, SY2D_K_S_UPDATE); k_s_update2<<<g2, kBlock, 0, c->stream>>>(k, c->N); }
     { Prof p(c, SY2D_K_SPMV_T); k_spmv_t2<<<g2, kBlock, 0, c->stream>>>(k, c->N, c->ny); }
     { Prof p(c, SY2D_K_XR_UPDATE); k_xr_update2<<<g2, kBlock, 0, c->stream>>>(k, c->N); }
-    return;
+    return SY2D_OK;
   }
   const dim3 g = grid_of(c);
   { Prof p(c, SY2D_K_P_UPDATE); k_p_update<<<g, kBlock, 0, c->stream>>>(k, c->N); }
@@ -561,6 +596,7 @@ void launch_iteration(sy2d_ctx* c) {
   { Prof p(c, SY2D_K_S_UPDATE); k_s_update<<<g, kBlock, 0, c->stream>>>(k, c->N); }
   { Prof p(c, SY2D_K_SPMV_T); k_spmv_t<<<g, kBlock, 0, c->stream>>>(k, c->N, c->ny); }
   { Prof p(c, SY2D_K_XR_UPDATE); k_xr_update<<<g, kBlock, 0, c->stream>>>(k, c->N); }
+  return SY2D_OK;
 }
 int kernels_per_iteration(const sy2d_ctx* c) { return lockstep_mg(c) ? 5 + 2 * mg_kernels_per_vcycle(c) : 5; }
 // with multigrid an iteration is ~50 launches and a solve ~15 iterations: poll more often
@@ -576,17 +612,20 @@ int build_chunk_graph(sy2d_ctx* c) {
   cudaGraph_t graph = nullptr;
   if (lockstep_mg(c)) {
     CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-    launch_iteration(c);
+    int rci = launch_iteration(c);
     CU(cudaMemcpyAsync(c->h_nactive, c->d_nactive, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamEndCapture(c->stream, &graph));
+    if (rci) { cudaGraphDestroy(graph); return rci; }
     CU(cudaGraphInstantiate(&c->one_exec, graph, 0));
     cudaGraphDestroy(graph);
     graph = nullptr;
   }
   CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-  for (int it = 0; it < check_every; ++it) launch_iteration(c);
+  int rcc = SY2D_OK;
+  for (int it = 0; it < check_every && !rcc; ++it) rcc = launch_iteration(c);
   CU(cudaMemcpyAsync(c->h_nactive, c->d_nactive, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamEndCapture(c->stream, &graph));
+  if (rcc) { cudaGraphDestroy(graph); return rcc; }
   CU(cudaGraphInstantiate(&c->chunk_exec, graph, 0));
   cudaGraphDestroy(graph);
   c->chunk_iters = check_every;
@@ -634,6 +673,7 @@ struct NcclApi {
   decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
   decltype(&ncclCommInitRank) CommInitRank = nullptr;
   decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclCommAbort) CommAbort = nullptr;
   decltype(&ncclAllGather) AllGather = nullptr;
   decltype(&ncclSend) Send = nullptr;
   decltype(&ncclRecv) Recv = nullptr;
@@ -656,6 +696,7 @@ NcclApi& nccl() {
   SY2D_NCCL_SYM(GetUniqueId) SY2D_NCCL_SYM(CommInitRank) SY2D_NCCL_SYM(CommDestroy) SY2D_NCCL_SYM(AllGather)
   SY2D_NCCL_SYM(Send) SY2D_NCCL_SYM(Recv) SY2D_NCCL_SYM(GroupStart) SY2D_NCCL_SYM(GroupEnd) SY2D_NCCL_SYM(GetErrorString)
 #undef SY2D_NCCL_SYM
+  api.CommAbort = reinterpret_cast<decltype(api.CommAbort)>(dlsym(h, "ncclCommAbort"));   // optional
   api.ok = true;
   return api;
 }
@@ -669,48 +710,172 @@ NcclApi& nccl() {
 double* own_ptr(const sy2d_ctx* c, double* a) { return c->slab ? a + c->ny : a; }
 size_t own_elems(const sy2d_ctx* c) { return c->slab ? (size_t)(c->nx - 2) * c->ny : c->total; }
 
+// ---- transports: how the slabs of one grid exchange halo lines and small vectors ----
+// halo(a, ny_l): one line of ny_l doubles with each neighbour - my first owned row -> the bottom halo of rank-1, my last
+//   owned row -> the top halo of rank+1 (a = local array incl. the halo rows; contiguous 8 ny_l bytes).
+// gather(src, dst, count): count doubles of every rank -> dst[nranks][count] on every rank.
+// abort(): this rank gives up (CUDA / transport failure); the peers must not wait for it for ever.
+// Convergence decisions are taken from all-gathered scalars reduced in rank order, i.e. they are IDENTICAL on every rank:
+// SY2D_ERR_NOT_CONVERGED is returned by all ranks of a step together, only hard failures can separate the ranks.
+struct SlabTransport {
+  virtual ~SlabTransport() {}
+  virtual int halo(sy2d_ctx* c, double* a, int ny_l) = 0;
+  virtual int gather(sy2d_ctx* c, const double* src, double* dst, size_t count) = 0;
+  virtual void abort(sy2d_ctx* c) = 0;
+  virtual const char* name() const = 0;
+};
+
+// NCCL over NVLink / NVSwitch: one process (or thread) per GPU.
+struct NcclTransport : SlabTransport {
+  ncclComm_t comm = nullptr;
+  ~NcclTransport() override { if (comm && nccl().ok) nccl().CommDestroy(comm); }
+  int halo(sy2d_ctx* c, double* a, int ny_l) override {
+    const size_t ny = (size_t)ny_l;
+    const int rows = c->nx - 2;
+    NC(nccl().GroupStart());
+    if (c->rank > 0) {
+      NC(nccl().Send(a + ny, ny, ncclDouble, c->rank - 1, comm, c->stream));
+      NC(nccl().Recv(a, ny, ncclDouble, c->rank - 1, comm, c->stream));
+    }
+    if (c->rank < c->nranks - 1) {
+      NC(nccl().Send(a + (size_t)rows * ny, ny, ncclDouble, c->rank + 1, comm, c->stream));
+      NC(nccl().Recv(a + (size_t)(rows + 1) * ny, ny, ncclDouble, c->rank + 1, comm, c->stream));
+    }
+    NC(nccl().GroupEnd());
+    return SY2D_OK;
+  }
+  int gather(sy2d_ctx* c, const double* src, double* dst, size_t count) override {
+    NC(nccl().AllGather(src, dst, count, ncclDouble, comm, c->stream));
+    return SY2D_OK;
+  }
+  void abort(sy2d_ctx*) override {
+    if (comm && nccl().CommAbort) { nccl().CommAbort(comm); comm = nullptr; }   // frees this rank's resources without a collective teardown
+  }
+  const char* name() const override { return "nccl"; }
+};
+}  // namespace
+
+// In-process transport: the P slab contexts live in ONE process (one host thread per context, on one device or on
+// several), lines and small vectors move with cudaMemcpyAsync between the contexts' buffers, ordered by CUDA events
+// and a host barrier.  This is what lets a single-GPU box run - and test - the slab decomposition at P = 2, 4, 8:
+// the kernels, the spike-coupled multigrid and the reduction order are exactly those of the NCCL runs.
+struct sy2d_local_group {
+  int nranks = 0;
+  std::mutex mu;
+  std::condition_variable cv;
+  int arrived = 0;
+  unsigned long long gen = 0;
+  bool aborted = false;
+  int attached = 0;
+  std::vector<const double*> ptr;
+  std::vector<int> rows;
+  std::vector<cudaEvent_t> ready, done;
+  // false once the group was aborted: the caller must fail instead of waiting for a rank that gave up
+  bool barrier() {
+    std::unique_lock<std::mutex> lk(mu);
+    if (aborted) return false;
+    const unsigned long long g0 = gen;
+    if (++arrived == nranks) {
+      arrived = 0;
+      ++gen;
+      cv.notify_all();
+      return true;
+    }
+    cv.wait(lk, [&] { return gen != g0 || aborted; });
+    return gen != g0;
+  }
+  void abort() {
+    std::lock_guard<std::mutex> lk(mu);
+    aborted = true;
+    cv.notify_all();
+  }
+};
+
+namespace {
+struct LocalTransport : SlabTransport {
+  sy2d_local_group* g = nullptr;
+  int rank = 0;
+  ~LocalTransport() override {
+    if (!g) return;
+    if (g->ready[rank]) cudaEventDestroy(g->ready[rank]);
+    if (g->done[rank]) cudaEventDestroy(g->done[rank]);
+    g->ready[rank] = g->done[rank] = nullptr;
+    std::lock_guard<std::mutex> lk(g->mu);
+    g->attached -= 1;
+  }
+  int halo(sy2d_ctx* c, double* a, int ny_l) override {
+    const size_t ny = (size_t)ny_l;
+    const int r = rank, P = g->nranks, rows = c->nx - 2;
+    g->ptr[r] = a;
+    g->rows[r] = rows;
+    CU(cudaEventRecord(g->ready[r], c->stream));
+    if (!g->barrier()) return fail(c, SY2D_ERR_CUDA, "slab group aborted by another rank");
+    if (r > 0) {
+      CU(cudaStreamWaitEvent(c->stream, g->ready[r - 1], 0));
+      CU(cudaMemcpyAsync(a, g->ptr[r - 1] + (size_t)g->rows[r - 1] * ny, ny * sizeof(double), cudaMemcpyDefault, c->stream));
+    }
+    if (r < P - 1) {
+      CU(cudaStreamWaitEvent(c->stream, g->ready[r + 1], 0));
+      CU(cudaMemcpyAsync(a + (size_t)(rows + 1) * ny, g->ptr[r + 1] + ny, ny * sizeof(double), cudaMemcpyDefault, c->stream));
+    }
+    CU(cudaEventRecord(g->done[r], c->stream));
+    if (!g->barrier()) return fail(c, SY2D_ERR_CUDA, "slab group aborted by another rank");
+    // my owned rows may only be overwritten once the neighbours have copied them
+    if (r > 0) CU(cudaStreamWaitEvent(c->stream, g->done[r - 1], 0));
+    if (r < P - 1) CU(cudaStreamWaitEvent(c->stream, g->done[r + 1], 0));
+    return SY2D_OK;
+  }
+  int gather(sy2d_ctx* c, const double* src, double* dst, size_t count) override {
+    const int r = rank, P = g->nranks;
+    g->ptr[r] = src;
+    CU(cudaEventRecord(g->ready[r], c->stream));
+    if (!g->barrier()) return fail(c, SY2D_ERR_CUDA, "slab group aborted by another rank");
+    for (int q = 0; q < P; ++q) {
+      if (q != r) CU(cudaStreamWaitEvent(c->stream, g->ready[q], 0));
+      CU(cudaMemcpyAsync(dst + (size_t)q * count, g->ptr[q], count * sizeof(double), cudaMemcpyDefault, c->stream));
+    }
+    CU(cudaEventRecord(g->done[r], c->stream));
+    if (!g->barrier()) return fail(c, SY2D_ERR_CUDA, "slab group aborted by another rank");
+    for (int q = 0; q < P; ++q)
+      if (q != r) CU(cudaStreamWaitEvent(c->stream, g->done[q], 0));
+    return SY2D_OK;
+  }
+  void abort(sy2d_ctx*) override { g->abort(); }
+  const char* name() const override { return "local"; }
+};
+
 void slab_comm_destroy(sy2d_ctx* c) {
-  if (c->comm && nccl().ok) nccl().CommDestroy(static_cast<ncclComm_t>(c->comm));
-  c->comm = nullptr;
+  delete c->tp;
+  c->tp = nullptr;
 }
 
-// One line (ny doubles) to each neighbour: my first owned row -> bottom halo of rank-1, my last owned
-// row -> top halo of rank+1.  Contiguous 8*ny bytes over NVLink.
-int slab_halo_exchange_n(sy2d_ctx* c, double* a, int ny_l) {
-  ncclComm_t comm = static_cast<ncclComm_t>(c->comm);
-  const size_t ny = (size_t)ny_l;
-  const int rows = c->nx - 2;
-  NC(nccl().GroupStart());
-  if (c->rank > 0) {
-    NC(nccl().Send(a + ny, ny, ncclDouble, c->rank - 1, comm, c->stream));
-    NC(nccl().Recv(a, ny, ncclDouble, c->rank - 1, comm, c->stream));
-  }
-  if (c->rank < c->nranks - 1) {
-    NC(nccl().Send(a + (size_t)rows * ny, ny, ncclDouble, c->rank + 1, comm, c->stream));
-    NC(nccl().Recv(a + (size_t)(rows + 1) * ny, ny, ncclDouble, c->rank + 1, comm, c->stream));
-  }
-  NC(nccl().GroupEnd());
-  return SY2D_OK;
-}
-int slab_halo_exchange(sy2d_ctx* c, double* a) { return slab_halo_exchange_n(c, a, c->ny); }
-
-// count doubles of every rank -> [nranks][count] on every rank
-int slab_gather(sy2d_ctx* c, const double* src, double* dst, size_t count) {
-  NC(nccl().AllGather(src, dst, count, ncclDouble, static_cast<ncclComm_t>(c->comm), c->stream));
-  return SY2D_OK;
-}
+int slab_halo_exchange_n(sy2d_ctx* c, double* a, int ny_l) { return c->tp->halo(c, a, ny_l); }
+int slab_halo_exchange(sy2d_ctx* c, double* a) { return c->tp->halo(c, a, c->ny); }
+int slab_gather(sy2d_ctx* c, const double* src, double* dst, size_t count) { return c->tp->gather(c, src, dst, count); }
 
 // accumulators of every rank -> scalars on every rank (identical summation order everywhere)
 int slab_reduce(sy2d_ctx* c, int phase, const KrylovVecs& k) {
-  ncclComm_t comm = static_cast<ncclComm_t>(c->comm);
-  NC(nccl().AllGather(&c->scal->acc_rv, c->d_gather, 5, ncclDouble, comm, c->stream));
+  int rc = slab_gather(c, &c->scal->acc_rv, c->d_gather, 5);
+  if (rc) return rc;
   k_slab_scalars<<<1, 32, 0, c->stream>>>(phase, c->scal, c->d_gather, c->nranks, k);
   CU(cudaGetLastError());
   return SY2D_OK;
 }
 
+int step_slab_impl(sy2d_ctx* c, int nsteps, sy2d_stats* stats);
+
+// A hard failure (CUDA, transport) on this rank must not leave the peers waiting in the next collective: the transport
+// is aborted (in-process group: the peers' calls fail at once; NCCL: the communicator is torn down without a collective).
+// SY2D_ERR_NOT_CONVERGED is not such a failure - every rank returns it for the same step.
 int step_slab(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
+  const int rc = step_slab_impl(c, nsteps, stats);
+  if (rc == SY2D_ERR_CUDA && c->tp) c->tp->abort(c);
+  return rc;
+}
+
+int step_slab_impl(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
   if (c->ny % 2) return fail(c, SY2D_ERR_INVALID, "slab mode needs an even ny");
+  const bool budget = c->opt.reserved[1] != 0;   // fixed iteration budget without a convergence error (bench)
   const Geometry geo = geometry(c);
   const KrylovVecs k = krylov(c);
   const int rows = c->nx - 2;
@@ -814,26 +979,40 @@ int step_slab(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
     init.fmin = 1.0e300;
     *c->h_stats = init;
     CU(cudaMemcpyAsync(c->d_stats, c->h_stats, sizeof(StepStats), cudaMemcpyHostToDevice, c->stream));
-    const dim3 gf((unsigned)((own + kBlock - 1) / kBlock), 1, 1);
-    k_finish<<<gf, kBlock, 0, c->stream>>>(c->x + c->ny, c->cs + c->ny, c->f + c->ny, c->yprev + c->ny, c->scal, own, c->opt.predictor, c->d_stats);
+    // h_nactive comes from scalars that are identical on every rank, so all ranks take this branch together
+    const bool solve_failed = (c->h_nactive[0] > 0 || c->h_nactive[1] > 0) && !budget;
+    if (solve_failed) {
+      k_fail_stats<<<1, 32, 0, c->stream>>>(c->scal, 1, c->d_stats);
+    } else {
+      // true residual max|rhs - A d| over the whole grid: own rows with the neighbours' halo rows of d, then the max over
+      // the ranks (all-gathered, so the commit decision of k_finish is the same everywhere)
+      if ((rc = slab_halo_exchange(c, c->x))) return rc;
+      k_true_residual<<<grid_of(c), kBlock, 0, c->stream>>>(k, c->N, c->ny, &c->d_stats->resid_max);
+      if ((rc = slab_gather(c, &c->d_stats->resid_max, c->d_gather, 1))) return rc;
+      k_slab_max<<<1, 32, 0, c->stream>>>(c->d_gather, c->nranks, &c->d_stats->resid_max);
+      const dim3 gf((unsigned)((own + kBlock - 1) / kBlock), 1, 1);
+      k_finish<<<gf, kBlock, 0, c->stream>>>(c->x + c->ny, c->cs + c->ny, c->f + c->ny, c->yprev + c->ny, c->scal, own, c->opt.predictor, c->d_stats,
+                                             budget ? 1.0e300 : 1000.0 * c->opt.tol);
+    }
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(StepStats), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    c->istep += 1;
-    st.steps += 1;
+    const bool bad = solve_failed || (c->h_stats->n_bad > 0 && !budget);
+    if (!bad) {
+      c->istep += 1;
+      st.steps += 1;
+    }
     st.iters_total += c->h_stats->it_max;
     st.iters_sum_all += c->h_stats->it_max;
     st.iters_last = c->h_stats->it_max;
     st.fmin = c->h_stats->fmin;                      // of this rank's rows
     st.negatives = (long long)c->h_stats->negatives;  // of this rank's rows
     st.kernel_launches = c->launches;
-    Scal hs;
-    CU(cudaMemcpy(&hs, c->scal, sizeof(Scal), cudaMemcpyDeviceToHost));
-    st.resid_last = hs.rmax;                         // recursive residual (global max-norm)
-    if ((c->h_stats->n_bad > 0 || *c->h_nactive > 0) && !c->opt.reserved[1]) {  // reserved[1]: fixed iteration budget (bench)
+    st.resid_last = c->h_stats->resid_max;           // true residual, max over all ranks
+    if (bad) {
       if (stats) *stats = st;
-      return fail(c, SY2D_ERR_NOT_CONVERGED, "sy2d_step (slab): BiCGSTAB did not converge at step %lld (%d iterations, max|r|=%.3e)",
-                  c->istep, c->h_stats->it_max, hs.rmax);
+      return fail(c, SY2D_ERR_NOT_CONVERGED, "sy2d_step (slab): step %lld not committed (%s; %d iterations, true residual %.3e)",
+                  c->istep + 1, solve_failed ? "BiCGSTAB did not converge" : "true residual above 1000 x tol", c->h_stats->it_max, c->h_stats->resid_max);
     }
   }
   CU(cudaEventRecord(c->ev_call1, c->stream));
@@ -923,6 +1102,7 @@ static int create_impl(sy2d_ctx** out, int device, int nx, int ny, int nbatch, c
   if (const char* e = std::getenv("SY2D_CTAS_PER_SM")) ctx->ctas_per_sm = std::max(1, std::min(32, std::atoi(e)));
   if (const char* e = std::getenv("SY2D_PIPE_CHUNKS")) ctx->pipe_forced = std::max(1, std::min(64, std::atoi(e)));
   if (const char* e = std::getenv("SY2D_ASM_CTAS_PER_SM")) ctx->asm_ctas_per_sm = std::max(1, std::min(4, std::atoi(e)));
+  if (const char* e = std::getenv("SY2D_XLINE_CHUNK")) ctx->xl_chunk = std::max(0, std::atoi(e));
   const HostGeometry hg = make_host_geometry(nx, ny, xe, ye);
   const std::vector<double>&wxL = hg.wxL, &wxR = hg.wxR, &wyB = hg.wyB, &wyT = hg.wyT, &dx = hg.dx, &dy = hg.dy;
   struct Up { double** dst; const std::vector<double>* src; } ups[] = {
@@ -970,16 +1150,30 @@ void sy2d_destroy(sy2d_ctx* c) {
   if (c->one_exec) cudaGraphExecDestroy(c->one_exec);
   double* bufs[] = {c->d_wxL, c->d_wxR, c->d_wyB, c->d_wyT, c->d_dx, c->d_dy, c->d_bc[0], c->d_bc[1], c->d_bc[2], c->d_bc[3],
                     c->tx, c->ty, c->cxy, c->U, c->Ud, c->f, c->yprev, c->cs, c->wW, c->wE, c->wS, c->wN, c->rhs,
-                    c->x, c->r, c->p, c->v, c->s, c->t, c->stage, c->xl_scratch, c->xl_l, c->xl_dinv, c->xl_e, c->xl_hat};
+                    c->x, c->r, c->p, c->v, c->s, c->t, c->xl_scratch, c->xl_l, c->xl_dinv, c->xl_e, c->xl_hat};
   for (double* b : bufs) if (b) cudaFree(b);
   if (c->scal) cudaFree(c->scal);
   for (double* b : c->mg_bufs) cudaFree(b);
   if (c->d_tma_maps) cudaFree(c->d_tma_maps);
+  if (c->d_tma_maps2) cudaFree(c->d_tma_maps2);
+  if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+  if (c->coeffs_ready) cudaEventDestroy(c->coeffs_ready);
+  if (c->bc_ready) cudaEventDestroy(c->bc_ready);
+  {
+    double* more[] = {c->tx2, c->ty2, c->cxy2, c->U2, c->Ud2, c->raw_dev[0], c->raw_dev[1], c->raw_dev[2], c->raw_dev[3], c->raw_dev[4],
+                      c->d_bc2[0], c->d_bc2[1], c->d_bc2[2], c->d_bc2[3]};
+    for (double* b : more) if (b) cudaFree(b);
+    for (double* b : c->raw_pin) if (b) cudaFreeHost(b);
+    if (c->bc_pin) cudaFreeHost(c->bc_pin);
+  }
   for (cudaStream_t sk : c->pipe_streams) if (sk) { cudaStreamSynchronize(sk); cudaStreamDestroy(sk); }
   for (cudaEvent_t ek : c->pipe_events) if (ek) cudaEventDestroy(ek);
   if (c->pipe_start) cudaEventDestroy(c->pipe_start);
   if (c->d_order) cudaFree(c->d_order);
   if (c->d_cost) cudaFree(c->d_cost);
+  if (c->d_qctl) cudaFree(c->d_qctl);
+  if (c->d_slots) cudaFree(c->d_slots);
+  if (c->d_steps_done) cudaFree(c->d_steps_done);
   if (c->d_gather) cudaFree(c->d_gather);
   slab_comm_destroy(c);
   if (c->d_nactive) cudaFree(c->d_nactive);
@@ -999,7 +1193,13 @@ int sy2d_set_options(sy2d_ctx* c, const sy2d_options* o) {
     return fail(c, SY2D_ERR_INVALID, "sy2d_set_options: tol, maxit and check_every must be positive");
   if (o->precond < SY2D_PRECOND_AUTO || o->precond > SY2D_PRECOND_MG)
     return fail(c, SY2D_ERR_INVALID, "sy2d_set_options: unknown preconditioner %d", o->precond);
+  // the captured iteration graphs hold tol and maxit by value (KrylovVecs is a kernel argument): rebuild them on change
+  if (o->tol != c->opt.tol || o->maxit != c->opt.maxit) {
+    if (c->chunk_exec) { cudaGraphExecDestroy(c->chunk_exec); c->chunk_exec = nullptr; }
+    if (c->one_exec) { cudaGraphExecDestroy(c->one_exec); c->one_exec = nullptr; }
+  }
   c->opt = *o;
+  if (c->slab) c->opt.use_graph = 0;
   return SY2D_OK;
 }
 
@@ -1007,6 +1207,10 @@ int sy2d_set_coeffs_dev(sy2d_ctx* c, const double* G, const double* Dxx, const d
   if (!c) return SY2D_ERR_INVALID;
   if (!G || !Dxx || !Dxy || !Dyy) return fail(c, SY2D_ERR_INVALID, "sy2d_set_coeffs: NULL field");
   CU(cudaSetDevice(c->device));
+  {
+    std::lock_guard<std::mutex> lk(c->stage_mu);   // a synchronous set supersedes fields staged asynchronously before it
+    c->coeffs_pending = false;
+  }
   if (c->slab) {  // inputs are the owned rows [i_lo, i_hi); outputs go to local rows 1..; dx is indexed globally
     const int rows = c->nx - 2, off = c->ny;
     const dim3 g((unsigned)(((size_t)rows * c->ny + kBlock - 1) / kBlock), 1, 1);
@@ -1038,6 +1242,111 @@ int sy2d_set_coeffs(sy2d_ctx* c, const double* G, const double* Dxx, const doubl
   return sy2d_set_coeffs_dev(c, dst[0], dst[1], dst[2], dst[3], inv_tau ? dst[4] : nullptr);
 }
 
+}  // extern "C"
+
+// ---- asynchronous staging of the next step's fields (Solver.cc:286-289 without stalling the step in flight) ----
+static int stage_alloc(sy2d_ctx* c) {
+  if (c->copy_stream) return SY2D_OK;
+  CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  CU(cudaEventCreateWithFlags(&c->coeffs_ready, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&c->bc_ready, cudaEventDisableTiming));
+  double** dev[] = {&c->tx2, &c->ty2, &c->cxy2, &c->U2, &c->Ud2, &c->raw_dev[0], &c->raw_dev[1], &c->raw_dev[2], &c->raw_dev[3], &c->raw_dev[4]};
+  for (double** d : dev) CU(cudaMalloc(reinterpret_cast<void**>(d), c->total * sizeof(double)));
+  for (double*& h : c->raw_pin) CU(cudaMallocHost(reinterpret_cast<void**>(&h), c->total * sizeof(double)));
+  for (int k = 0; k < 4; ++k) {
+    const size_t n = (k < 2 ? c->ny : c->nx) + 1;
+    CU(cudaMalloc(reinterpret_cast<void**>(&c->d_bc2[k]), n * sizeof(double)));
+    CU(cudaMemset(c->d_bc2[k], 0, n * sizeof(double)));
+  }
+  CU(cudaMallocHost(reinterpret_cast<void**>(&c->bc_pin), (size_t)(2 * (c->ny + 1) + 2 * (c->nx + 1)) * sizeof(double)));
+  if (c->have_tma) {
+    AsmMaps m2;
+    if (!tma_encode_maps(c, &m2, c->tx2, c->ty2, c->cxy2, c->U2, c->Ud2)) return fail(c, SY2D_ERR_CUDA, "cuTensorMapEncodeTiled failed for the second coefficient set");
+    CU(cudaMalloc(reinterpret_cast<void**>(&c->d_tma_maps2), sizeof(AsmMaps)));
+    CU(cudaMemcpy(c->d_tma_maps2, &m2, sizeof(AsmMaps), cudaMemcpyHostToDevice));
+  }
+  return SY2D_OK;
+}
+
+// Start of a time step: fields staged asynchronously since the last step become the active set (the compute stream
+// waits for their upload; the host does not).
+static int stage_swap_in(sy2d_ctx* c) {
+  std::lock_guard<std::mutex> lk(c->stage_mu);
+  if (c->coeffs_pending) {
+    CU(cudaStreamWaitEvent(c->stream, c->coeffs_ready, 0));
+    std::swap(c->tx, c->tx2); std::swap(c->ty, c->ty2); std::swap(c->cxy, c->cxy2); std::swap(c->U, c->U2); std::swap(c->Ud, c->Ud2);
+    std::swap(c->d_tma_maps, c->d_tma_maps2);
+    c->coeffs_pending = false;
+    c->have_coeffs = true;
+    c->swaps += 1;
+  }
+  if (c->bc_pending) {
+    CU(cudaStreamWaitEvent(c->stream, c->bc_ready, 0));
+    for (int k = 0; k < 4; ++k) { std::swap(c->d_bc[k], c->d_bc2[k]); std::swap(c->bc[k], c->bc2[k]); }
+    c->bc_pending = false;
+    c->have_bc = true;
+    c->swaps += 1;
+  }
+  return SY2D_OK;
+}
+
+extern "C" {
+
+int sy2d_set_coeffs_async(sy2d_ctx* c, const double* G, const double* Dxx, const double* Dxy, const double* Dyy, const double* inv_tau) {
+  if (!c) return SY2D_ERR_INVALID;
+  if (!G || !Dxx || !Dxy || !Dyy) return fail(c, SY2D_ERR_INVALID, "sy2d_set_coeffs_async: NULL field");
+  if (c->slab) return fail(c, SY2D_ERR_INVALID, "sy2d_set_coeffs_async: not available on a slab context (use sy2d_set_coeffs)");
+  CU(cudaSetDevice(c->device));
+  std::lock_guard<std::mutex> lk(c->stage_mu);
+  int rc = stage_alloc(c);
+  if (rc) return rc;
+  // a set staged earlier and not yet swapped in is overwritten (the last call before a step wins); its upload must be over
+  // before the pinned staging is reused
+  CU(cudaStreamSynchronize(c->copy_stream));
+  const double* src[5] = {G, Dxx, Dxy, Dyy, inv_tau};
+  for (int k = 0; k < 5; ++k) {
+    if (!src[k]) continue;
+    std::memcpy(c->raw_pin[k], src[k], c->total * sizeof(double));   // the caller's arrays are free again on return
+    CU(cudaMemcpyAsync(c->raw_dev[k], c->raw_pin[k], c->total * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
+  }
+  k_prepare_coeffs<<<grid_of(c), kBlock, 0, c->copy_stream>>>(c->raw_dev[0], c->raw_dev[1], c->raw_dev[2], c->raw_dev[3], inv_tau ? c->raw_dev[4] : nullptr,
+                                                             c->d_dx, c->d_dy, c->dt, c->nx, c->ny, c->tx2, c->ty2, c->cxy2, c->U2, c->Ud2);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(c->coeffs_ready, c->copy_stream));
+  c->coeffs_pending = true;
+  return SY2D_OK;
+}
+
+int sy2d_set_bc_async(sy2d_ctx* c, const int bc_type[4], const double* xmin, const double* xmax, const double* ymin, const double* ymax) {
+  if (!c || !bc_type) return SY2D_ERR_INVALID;
+  if (c->slab) return fail(c, SY2D_ERR_INVALID, "sy2d_set_bc_async: not available on a slab context (use sy2d_set_bc)");
+  const double* lines[4] = {xmin, xmax, ymin, ymax};
+  for (int k = 0; k < 4; ++k) {
+    if (bc_type[k] != SY2D_DIRICHLET && bc_type[k] != SY2D_ZEROFLUX) return fail(c, SY2D_ERR_INVALID, "sy2d_set_bc_async: unknown BCType %d", bc_type[k]);
+    if (bc_type[k] == SY2D_DIRICHLET && !lines[k]) return fail(c, SY2D_ERR_BC, "Dirichlet BC: missing value.");
+  }
+  CU(cudaSetDevice(c->device));
+  std::lock_guard<std::mutex> lk(c->stage_mu);
+  int rc = stage_alloc(c);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(c->copy_stream));
+  double* pin = c->bc_pin;
+  for (int k = 0; k < 4; ++k) {
+    const size_t n = (k < 2 ? c->ny : c->nx) + 1;
+    c->bc2[k] = bc_type[k];
+    if (lines[k]) {
+      std::memcpy(pin, lines[k], n * sizeof(double));
+      CU(cudaMemcpyAsync(c->d_bc2[k], pin, n * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream));
+    }
+    pin += n;
+  }
+  CU(cudaEventRecord(c->bc_ready, c->copy_stream));
+  c->bc_pending = true;
+  return SY2D_OK;
+}
+
+long long sy2d_stage_swaps(const sy2d_ctx* c) { return c ? c->swaps : 0; }
+
 int sy2d_set_bc(sy2d_ctx* c, const int bc_type[4], const double* xmin, const double* xmax, const double* ymin, const double* ymax) {
   if (!c || !bc_type) return SY2D_ERR_INVALID;
   const double* lines[4] = {xmin, xmax, ymin, ymax};
@@ -1046,6 +1355,10 @@ int sy2d_set_bc(sy2d_ctx* c, const int bc_type[4], const double* xmin, const dou
     if (bc_type[k] == SY2D_DIRICHLET && !lines[k]) return fail(c, SY2D_ERR_BC, "Dirichlet BC: missing value.");
   }
   CU(cudaSetDevice(c->device));
+  {
+    std::lock_guard<std::mutex> lk(c->stage_mu);
+    c->bc_pending = false;
+  }
   for (int k = 0; k < 4; ++k) {
     c->bc[k] = bc_type[k];
     const size_t n = (k < 2 ? c->ny : (c->slab ? c->nx_glob : c->nx)) + 1;
@@ -1053,6 +1366,23 @@ int sy2d_set_bc(sy2d_ctx* c, const int bc_type[4], const double* xmin, const dou
   }
   CU(cudaStreamSynchronize(c->stream));
   c->have_bc = true;
+  return SY2D_OK;
+}
+
+// f must be finite and > 0 in every cell (k_check_f); on failure the context has no usable f
+static int check_f_input(sy2d_ctx* c, const char* who) {
+  unsigned long long* d_bad = &c->d_stats->negatives;
+  CU(cudaMemsetAsync(d_bad, 0, sizeof(unsigned long long), c->stream));
+  const size_t n = own_elems(c);
+  k_check_f<<<(unsigned)std::min<size_t>((n + kBlock - 1) / kBlock, (size_t)c->sm_count * 8), kBlock, 0, c->stream>>>(own_ptr(c, c->f), n, d_bad);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(&c->h_stats->negatives, d_bad, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (c->h_stats->negatives > 0) {
+    c->have_f = false;
+    return fail(c, SY2D_ERR_INVALID, "%s: f must be finite and > 0 in every cell (%llu cells are not): the engine solves for the per-cell ratio "
+                "f^{n+1}/f^n; the reference's cases add gEPS to f0 for the same reason (Albert_Young.h:39)", who, c->h_stats->negatives);
+  }
   return SY2D_OK;
 }
 
@@ -1069,6 +1399,8 @@ int sy2d_set_f_dev(sy2d_ctx* c, const double* f) {
   if (!c || !f) return SY2D_ERR_INVALID;
   CU(cudaSetDevice(c->device));
   CU(cudaMemcpyAsync(own_ptr(c, c->f), f, own_elems(c) * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  int rc = check_f_input(c, "sy2d_set_f_dev");
+  if (rc) return rc;
   c->have_f = true;
   return reset_state(c);
 }
@@ -1077,6 +1409,8 @@ int sy2d_set_f(sy2d_ctx* c, const double* f) {
   if (!c || !f) return SY2D_ERR_INVALID;
   CU(cudaSetDevice(c->device));
   CU(cudaMemcpyAsync(own_ptr(c, c->f), f, own_elems(c) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  int rc = check_f_input(c, "sy2d_set_f");
+  if (rc) return rc;
   c->have_f = true;
   return reset_state(c);
 }
@@ -1086,7 +1420,7 @@ int sy2d_put_f(sy2d_ctx* c, const double* f) {
   if (!c->have_f) return sy2d_set_f(c, f);
   CU(cudaSetDevice(c->device));
   CU(cudaMemcpyAsync(own_ptr(c, c->f), f, own_elems(c) * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  return SY2D_OK;
+  return check_f_input(c, "sy2d_put_f");   // synchronises: the caller's buffer is free again on return
 }
 
 int sy2d_get_f(sy2d_ctx* c, double* out) {
@@ -1147,18 +1481,25 @@ static bool xline_shape(const sy2d_ctx* c, int* R, int* NT, int* S, int* HS, siz
     if (hs) break;
   }
   if (!hs) hs = c->ny + 1;
-  const size_t bytes = ((size_t)c->nx * hs + 3 * (size_t)r * nt + 192) * sizeof(double)   /* + three 64-double reduction buffers */;
+  const size_t bytes = ((size_t)c->nx * hs + 3 * (size_t)r * nt + 194) * sizeof(double)   /* + three 64-double reduction buffers + the work-item word */;
   if (bytes > 232448) return false;
   *R = r; *NT = nt; *S = r * nt; *HS = hs; *smem = bytes;
   return true;
 }
 
 template <int R, int MAXT, int NTC, int HSC = 0>
-static cudaError_t launch_xline(const XlineArgs& xa, int nbatch, size_t smem, cudaStream_t stream) {
+static cudaError_t launch_xline(const XlineArgs& xa, int nctas, size_t smem, cudaStream_t stream) {
   cudaError_t e = cudaFuncSetAttribute(k_problem_xline<R, MAXT, NTC, HSC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_problem_xline<R, MAXT, NTC, HSC><<<nbatch, xa.NT, smem, stream>>>(xa);
+  k_problem_xline<R, MAXT, NTC, HSC><<<nctas, xa.NT, smem, stream>>>(xa);
   return cudaGetLastError();
+}
+
+// slots[0 .. nprob) = the problems of the launch in issue order, the rest "not yet pushed"; control words
+__global__ void k_xline_queue_init(XlineQueue* q, int* __restrict__ slots, const int* __restrict__ order, int nprob, int nchunks) {
+  const int total = nprob * nchunks;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) slots[t] = t < nprob ? order[t] : -1;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { q->head = 0; q->tail = nprob; q->total = total; q->pad = 0; }
 }
 
 static cudaError_t dispatch_xline(const XlineArgs& xa, int R, int nbatch, size_t smem, cudaStream_t stream) {
@@ -1191,16 +1532,31 @@ static int pipe_chunks(const sy2d_ctx* c) {
 // buffers (h_in / h_out non-NULL) the batch is cut into pipe_chunks() contiguous sub-batches on
 // separate streams, so that the H2D copy of sub-batch k+1, the kernel of sub-batch k and the D2H
 // copy of sub-batch k-1 overlap (and the tail wave of one kernel is filled by the next one).
+// x-line kernel: persistent CTAs (one per SM) pull (problem, chunk of steps) items from a device-side queue.
+static int build_issue_order(sy2d_ctx* c, int C) {
+  // inside every sub-batch, most expensive problems (iterations of the last measured call) first
+  for (int b = 0; b < c->nbatch; ++b) c->h_order[b] = b;
+  for (int k = 0; k < C; ++k) {
+    const int b0 = (int)((long long)c->nbatch * k / C), b1 = (int)((long long)c->nbatch * (k + 1) / C);
+    std::stable_sort(c->h_order.begin() + b0, c->h_order.begin() + b1, [&](int x, int y) { return c->h_cost[x] > c->h_cost[y]; });
+  }
+  CU(cudaMemcpyAsync(c->d_order, c->h_order.data(), c->nbatch * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  c->order_C = C;
+  c->order_age = 0;
+  return SY2D_OK;
+}
+
 static int step_per_problem(sy2d_ctx* c, int nsteps, sy2d_stats* stats, const double* h_in, double* h_out) {
   sy2d_stats st;
   std::memset(&st, 0, sizeof st);
   st.engine = 2;
   if (nsteps == 0) { if (stats) *stats = st; return SY2D_OK; }
   const bool piped = (h_in || h_out) && !c->profiling;
-  const int C = pipe_chunks(c);
+  const int C = piped ? pipe_chunks(c) : 1;
   StepStats init;
   std::memset(&init, 0, sizeof init);
   init.fmin = 1.0e300;
+  init.steps_min = nsteps;
   *c->h_stats = init;
   CU(cudaEventRecord(c->ev_call0, c->stream));
   CU(cudaMemcpyAsync(c->d_stats, c->h_stats, sizeof(StepStats), cudaMemcpyHostToDevice, c->stream));
@@ -1214,12 +1570,19 @@ static int step_per_problem(sy2d_ctx* c, int nsteps, sy2d_stats* stats, const do
   if (!c->d_order) {
     CU(cudaMalloc(reinterpret_cast<void**>(&c->d_order), c->nbatch * sizeof(int)));
     CU(cudaMalloc(reinterpret_cast<void**>(&c->d_cost), c->nbatch * sizeof(int)));
+    CU(cudaMalloc(reinterpret_cast<void**>(&c->d_steps_done), c->nbatch * sizeof(int)));
+    CU(cudaMalloc(reinterpret_cast<void**>(&c->d_qctl), 64 * sizeof(XlineQueue)));
     c->h_cost.assign(c->nbatch, 0);
     c->h_order.resize(c->nbatch);
-    for (int b = 0; b < c->nbatch; ++b) c->h_order[b] = b;
-    CU(cudaMemcpyAsync(c->d_order, c->h_order.data(), c->nbatch * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    c->order_C = -1;
   }
+  // The issue order is rebuilt from the measured costs on the first calls, when the sub-batch partition changes (the
+  // order must keep every problem inside its own sub-batch: the copies are per sub-batch) and every 16th call after that.
+  if (c->order_C != C || c->order_age >= 16 || c->order_calls < 2) { int rc0 = build_issue_order(c, C); if (rc0) return rc0; }
+  c->order_age += 1;
+  c->order_calls += 1;
   a.cost = c->d_cost;
+  CU(cudaMemsetAsync(c->d_cost, 0, c->nbatch * sizeof(int), c->stream));
   c->cur_cells = (double)c->total * nsteps;
   int R = 0, NT = 0, S = 0, HS = 0;
   size_t smem = 0;
@@ -1227,20 +1590,48 @@ static int step_per_problem(sy2d_ctx* c, int nsteps, sy2d_stats* stats, const do
   if (c->opt.precond == SY2D_PRECOND_XLINE && !xline)
     return fail(c, SY2D_ERR_INVALID, "sy2d_step: the x-line preconditioner needs nx <= 80, ny <= 128 and engine 2");
   st.precond = xline ? SY2D_PRECOND_XLINE : SY2D_PRECOND_JACOBI;
-  if (xline && (!c->xl_scratch || c->xl_S != S)) {
-    if (c->xl_scratch) cudaFree(c->xl_scratch);
-    c->xl_scratch = nullptr;
-    CU(cudaMalloc(reinterpret_cast<void**>(&c->xl_scratch), (size_t)c->nbatch * 5 * S * sizeof(double)));
-    c->xl_S = S;
-  }
-  auto launch = [&](int b0, int b1, cudaStream_t stream) -> cudaError_t {
-    ProblemArgs aa = a;
-    aa.order = c->d_order + b0;   // CTA b of this launch works on problem order[b0 + b]
-    if (xline) {
-      XlineArgs xa;
-      xa.a = aa; xa.scratch = c->xl_scratch; xa.NT = NT; xa.S = S; xa.hs = HS;
-      return dispatch_xline(xa, R, b1 - b0, smem, stream);
+  // x-line kernel: work items of `chunk` time steps (default 1; SY2D_XLINE_CHUNK=0: the whole call, i.e. one CTA per problem)
+  const int chunk = c->xl_chunk > 0 ? std::min(c->xl_chunk, nsteps) : nsteps;
+  const int nchunks = (nsteps + chunk - 1) / chunk;
+  // co-resident CTAs of a launch: one per SM when the CTA needs more than half of an SM's shared memory (always for the
+  // production shape), else what fits; never more than the problems of the launch
+  const int ctas_per_sm = smem > 113 * 1024 ? 1 : (int)std::min<size_t>(2, (227 * 1024) / std::max<size_t>(smem, 1));
+  if (xline) {
+    const size_t scratch_slots = (size_t)std::min(c->nbatch, C * c->sm_count * ctas_per_sm);
+    if (!c->xl_scratch || c->xl_S != S || c->xl_scratch_slots < scratch_slots) {
+      if (c->xl_scratch) cudaFree(c->xl_scratch);
+      c->xl_scratch = nullptr;
+      CU(cudaMalloc(reinterpret_cast<void**>(&c->xl_scratch), scratch_slots * 5 * S * sizeof(double)));
+      c->xl_S = S;
+      c->xl_scratch_slots = scratch_slots;
     }
+    const size_t need = (size_t)c->nbatch * nchunks;
+    if (c->slots_cap < need) {
+      if (c->d_slots) cudaFree(c->d_slots);
+      c->d_slots = nullptr;
+      CU(cudaMalloc(reinterpret_cast<void**>(&c->d_slots), need * sizeof(int)));
+      c->slots_cap = need;
+    }
+    CU(cudaMemsetAsync(c->d_steps_done, 0, c->nbatch * sizeof(int), c->stream));
+  }
+  int scratch_next = 0;   // first free scratch slot (launches of one call use disjoint slots)
+  auto launch = [&](int k, int b0, int b1, cudaStream_t stream) -> cudaError_t {
+    ProblemArgs aa = a;
+    if (xline) {
+      const int nprob = b1 - b0;
+      const int nctas = std::min(nprob, c->sm_count * ctas_per_sm);
+      XlineArgs xa;
+      xa.a = aa; xa.NT = NT; xa.S = S; xa.hs = HS;
+      xa.scratch = c->xl_scratch + (size_t)scratch_next * 5 * S;
+      scratch_next += nctas;
+      xa.q = c->d_qctl + k;
+      xa.slots = c->d_slots + (size_t)b0 * nchunks;
+      xa.steps_done = c->d_steps_done;
+      xa.chunk = chunk; xa.nchunks = nchunks;
+      k_xline_queue_init<<<std::max(1, std::min(64, (nprob * nchunks + 255) / 256)), 256, 0, stream>>>(xa.q, xa.slots, c->d_order + b0, nprob, nchunks);
+      return dispatch_xline(xa, R, nctas, smem, stream);
+    }
+    aa.order = c->d_order + b0;   // CTA b of this launch works on problem order[b0 + b]
     k_problem_steps<<<b1 - b0, kProblemThreads, 0, stream>>>(aa);
     return cudaGetLastError();
   };
@@ -1248,19 +1639,20 @@ static int step_per_problem(sy2d_ctx* c, int nsteps, sy2d_stats* stats, const do
     if (h_in) CU(cudaMemcpyAsync(c->f, h_in, c->total * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     {
       Prof p(c, SY2D_K_PROBLEM_STEPS);
-      CU(launch(0, c->nbatch, c->stream));
+      CU(launch(0, 0, c->nbatch, c->stream));
     }
     if (h_out) CU(cudaMemcpyAsync(h_out, c->f, c->total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    st.kernel_launches = 1;
+    st.kernel_launches = xline ? 2 : 1;
   } else {
-    if (c->pipe_streams.empty()) {
+    if ((int)c->pipe_streams.size() < C) {
+      const size_t have = c->pipe_streams.size();
       c->pipe_streams.resize(C);
       c->pipe_events.resize(C);
-      for (int k = 0; k < C; ++k) {
+      for (size_t k = have; k < (size_t)C; ++k) {
         CU(cudaStreamCreateWithFlags(&c->pipe_streams[k], cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&c->pipe_events[k], cudaEventDisableTiming));
       }
-      CU(cudaEventCreateWithFlags(&c->pipe_start, cudaEventDisableTiming));
+      if (!c->pipe_start) CU(cudaEventCreateWithFlags(&c->pipe_start, cudaEventDisableTiming));
     }
     CU(cudaEventRecord(c->pipe_start, c->stream));  // stats initialised, order uploaded
     for (int k = 0; k < C; ++k) {
@@ -1269,12 +1661,12 @@ static int step_per_problem(sy2d_ctx* c, int nsteps, sy2d_stats* stats, const do
       cudaStream_t sk = c->pipe_streams[k];
       CU(cudaStreamWaitEvent(sk, c->pipe_start, 0));
       if (h_in) CU(cudaMemcpyAsync(c->f + off, h_in + off, bytes, cudaMemcpyHostToDevice, sk));
-      CU(launch(b0, b1, sk));
+      CU(launch(k, b0, b1, sk));
       if (h_out) CU(cudaMemcpyAsync(h_out + off, c->f + off, bytes, cudaMemcpyDeviceToHost, sk));
       CU(cudaEventRecord(c->pipe_events[k], sk));
     }
     for (int k = 0; k < C; ++k) CU(cudaStreamWaitEvent(c->stream, c->pipe_events[k], 0));
-    st.kernel_launches = C;
+    st.kernel_launches = (xline ? 2 : 1) * C;
   }
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(StepStats), cudaMemcpyDeviceToHost, c->stream));
@@ -1283,19 +1675,14 @@ static int step_per_problem(sy2d_ctx* c, int nsteps, sy2d_stats* stats, const do
   CU(cudaStreamSynchronize(c->stream));
   float ms = 0.f;
   CU(cudaEventElapsedTime(&ms, c->ev_call0, c->ev_call1));
-  if (c->nbatch > 1) {  // issue order for the next call: inside every sub-batch, most expensive problems first
-    for (int b = 0; b < c->nbatch; ++b) c->h_order[b] = b;
-    for (int k = 0; k < C; ++k) {
-      const int b0 = (int)((long long)c->nbatch * k / C), b1 = (int)((long long)c->nbatch * (k + 1) / C);
-      std::stable_sort(c->h_order.begin() + b0, c->h_order.begin() + b1, [&](int x, int y) { return c->h_cost[x] > c->h_cost[y]; });
-    }
-    CU(cudaMemcpyAsync(c->d_order, c->h_order.data(), c->nbatch * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-  }
   int rc = collect_profile(c);
   if (rc) return rc;
   const StepStats& h = *c->h_stats;
-  c->istep += nsteps;
-  st.steps = nsteps;
+  // a failed problem keeps the f of the last time step it completed (nothing of the failing step is committed) while the
+  // others finish the call: the context's clock advances by what EVERY problem completed
+  const int steps_all = h.n_bad > 0 ? std::min(h.steps_min, nsteps) : nsteps;
+  c->istep += steps_all;
+  st.steps = steps_all;
   st.iters_total = h.it_total_max;
   st.iters_last = h.it_max;
   st.iters_sum_all = (long long)h.it_sum_all;
@@ -1305,8 +1692,10 @@ static int step_per_problem(sy2d_ctx* c, int nsteps, sy2d_stats* stats, const do
   st.seconds_device = ms * 1e-3;
   if (stats) *stats = st;
   if (h.n_bad > 0)
-    return fail(c, SY2D_ERR_NOT_CONVERGED, "sy2d_step: BiCGSTAB did not converge (%d problems, up to %d iterations in a step)",
-                h.n_bad, h.it_max);
+    return fail(c, SY2D_ERR_NOT_CONVERGED, "sy2d_step: BiCGSTAB did not converge (%d problems, up to %d iterations in a step; every problem "
+                "completed %d of %d time steps, a failed problem keeps the f of its last completed step)", h.n_bad, h.it_max, steps_all, nsteps);
+  if (!(h.resid_max <= 1000.0 * c->opt.tol))
+    return fail(c, SY2D_ERR_NOT_CONVERGED, "sy2d_step: true residual %.3e after the last step exceeds 1000 x tol", h.resid_max);
   return SY2D_OK;
 }
 
@@ -1314,9 +1703,11 @@ extern "C" {
 
 int sy2d_step(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
   if (!c || nsteps < 0) return SY2D_ERR_INVALID;
-  int rc = ready(c, "sy2d_step");
-  if (rc) return rc;
   CU(cudaSetDevice(c->device));
+  int rc = stage_swap_in(c);   // fields staged with sy2d_set_coeffs_async / sy2d_set_bc_async since the last call
+  if (rc) return rc;
+  rc = ready(c, "sy2d_step");
+  if (rc) return rc;
   if (c->slab) return step_slab(c, nsteps, stats);
   if (engine_of(c) == 2) return step_per_problem(c, nsteps, stats, nullptr, nullptr);
   const dim3 g = grid_of(c);
@@ -1396,7 +1787,7 @@ int sy2d_step(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
       if (graph) {
         CU(cudaGraphLaunch(c->chunk_exec, c->stream));
       } else {
-        for (int it = 0; it < check_every; ++it) launch_iteration(c);
+        for (int it = 0; it < check_every; ++it) { rc = launch_iteration(c); if (rc) return rc; }
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(c->h_nactive, c->d_nactive, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
       }
@@ -1425,36 +1816,50 @@ int sy2d_step(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
     init.fmin = 1.0e300;
     *c->h_stats = init;
     CU(cudaMemcpyAsync(c->d_stats, c->h_stats, sizeof(StepStats), cudaMemcpyHostToDevice, c->stream));
-    {
-      Prof p(c, SY2D_K_OTHER);
-      k_true_residual<<<g, kBlock, 0, c->stream>>>(krylov(c), c->N, c->ny, &c->d_stats->resid_max);
+    // A solve that stopped without converging (maxit, breakdown, NaN) commits NOTHING: f, yprev and the step counter stay
+    // those of t^n, so the caller may retry with other options.  A converged solve is committed by k_finish only when its
+    // TRUE residual (k_true_residual) is finite and <= 1000 tol - the recursive BiCGSTAB residual alone can drift.
+    const bool solve_failed = c->h_nactive[0] > 0 || c->h_nactive[1] > 0;
+    if (solve_failed) {
+      k_fail_stats<<<1, 256, 0, c->stream>>>(c->scal, c->nbatch, c->d_stats);
+      c->launches += 1;
+    } else {
+      {
+        Prof p(c, SY2D_K_OTHER);
+        k_true_residual<<<g, kBlock, 0, c->stream>>>(krylov(c), c->N, c->ny, &c->d_stats->resid_max);
+      }
+      {
+        Prof p(c, SY2D_K_FINISH);
+        k_finish<<<g, kBlock, 0, c->stream>>>(c->x, c->cs, c->f, c->yprev, c->scal, c->N, c->opt.predictor, c->d_stats, 1000.0 * c->opt.tol);
+      }
+      c->launches += 2;
     }
-    {
-      Prof p(c, SY2D_K_FINISH);
-      k_finish<<<g, kBlock, 0, c->stream>>>(c->x, c->cs, c->f, c->yprev, c->scal, c->N, c->opt.predictor, c->d_stats);
-    }
-    c->launches += 2;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(StepStats), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     rc = collect_profile(c);
     if (rc) return rc;
-    c->istep += 1;
-    st.steps += 1;
+    const bool bad = solve_failed || c->h_stats->n_bad > 0;
+    if (!bad) {
+      c->istep += 1;
+      st.steps += 1;
+    }
     st.iters_total += c->h_stats->it_max;
     st.iters_sum_all += (long long)c->h_stats->it_max * c->nbatch;
     st.iters_last = c->h_stats->it_max;
-    if (!fell_back) c->mg_last_iters = c->h_stats->it_max;
+    if (!fell_back && !bad) c->mg_last_iters = c->h_stats->it_max;
     st.precond = solved_by;
     st.resid_last = c->h_stats->resid_max;
     st.fmin = c->h_stats->fmin;
     st.negatives = (long long)c->h_stats->negatives;
     st.kernel_launches = c->launches;
-    if (c->h_stats->n_bad > 0 || *c->h_nactive > 0) {
+    if (bad) {
       if (stats) *stats = st;
-      collect_profile(c);
-      return fail(c, SY2D_ERR_NOT_CONVERGED, "sy2d_step: BiCGSTAB did not converge at step %lld (%d problems, %d iterations, max|r|=%.3e)",
-                  c->istep, c->h_stats->n_bad, c->h_stats->it_max, c->h_stats->resid_max);
+      if (solve_failed)
+        return fail(c, SY2D_ERR_NOT_CONVERGED, "sy2d_step: BiCGSTAB did not converge at step %lld (%d problems, %d iterations); the step was not committed",
+                    c->istep + 1, c->h_stats->n_bad, c->h_stats->it_max);
+      return fail(c, SY2D_ERR_NOT_CONVERGED, "sy2d_step: step %lld not committed: true residual %.3e exceeds 1000 x tol (or f is not finite)",
+                  c->istep + 1, c->h_stats->resid_max);
     }
   }
   CU(cudaEventRecord(c->ev_call1, c->stream));
@@ -1470,9 +1875,11 @@ int sy2d_step(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
 int sy2d_step_host(sy2d_ctx* c, const double* f_in, double* f_out, int nsteps, sy2d_stats* stats) {
   if (!c || nsteps < 0) return SY2D_ERR_INVALID;
   if (f_in && !c->have_f) { int rc0 = sy2d_set_f(c, f_in); if (rc0) return rc0; }
-  int rc = ready(c, "sy2d_step_host");
-  if (rc) return rc;
   CU(cudaSetDevice(c->device));
+  int rc = stage_swap_in(c);
+  if (rc) return rc;
+  rc = ready(c, "sy2d_step_host");
+  if (rc) return rc;
   if (!c->slab && engine_of(c) == 2) return step_per_problem(c, nsteps, stats, f_in, f_out);
   if (f_in) { rc = sy2d_put_f(c, f_in); if (rc) return rc; }
   rc = sy2d_step(c, nsteps, stats);
@@ -1548,7 +1955,8 @@ int sy2d_debug_vcycle(sy2d_ctx* c, const double* r, double* z, double* w4, doubl
   mg_setup(c);
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(c->p, r, c->total * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  mg_vcycle(c, c->p, c->xl_hat);
+  rc = mg_vcycle(c, c->p, c->xl_hat);
+  if (rc) return rc;
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(z, c->xl_hat, c->total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   if (w4) {
@@ -1615,6 +2023,72 @@ int sy2d_bench_kernel(sy2d_ctx* c, int which, int reps, double* ms_per_launch) {
   return SY2D_OK;
 }
 
+int sy2d_measure_peaks(int device, sy2d_peaks* out) {
+  sy2d_ctx* c = nullptr;
+  if (!out) return SY2D_ERR_INVALID;
+  std::memset(out, 0, sizeof *out);
+  CU(cudaSetDevice(device));
+  int sms = 0, khz = 0;
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  CU(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device));
+  out->sm_count = sms;
+  out->sm_clock_mhz = khz * 1e-3;
+  cudaStream_t st = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  double *a = nullptr, *b = nullptr, *sink = nullptr;
+  int rc = SY2D_OK;
+  auto body = [&]() -> int {
+    CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    const size_t big = (size_t)1 << 27;   // doubles: 1 GB per buffer
+    CU(cudaMalloc(reinterpret_cast<void**>(&a), big * sizeof(double)));
+    CU(cudaMalloc(reinterpret_cast<void**>(&b), big * sizeof(double)));
+    CU(cudaMalloc(reinterpret_cast<void**>(&sink), (size_t)sms * 2 * sizeof(double)));
+    CU(cudaMemsetAsync(a, 0, big * sizeof(double), st));
+    CU(cudaMemsetAsync(b, 0, big * sizeof(double), st));
+    auto timed = [&](auto&& launch, int reps, double* best_ms) -> int {
+      *best_ms = 1e30;
+      for (int trial = 0; trial < 5; ++trial) {
+        CU(cudaEventRecord(e0, st));
+        for (int r = 0; r < reps; ++r) launch();
+        CU(cudaEventRecord(e1, st));
+        CU(cudaEventSynchronize(e1));
+        CU(cudaGetLastError());
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        *best_ms = std::min(*best_ms, (double)ms / reps);
+      }
+      return SY2D_OK;
+    };
+    double ms = 0.0;
+    // shared memory: 2 CTAs of 1024 threads per SM, 96 KB each
+    const int smem_bytes = kPeakSmemDoubles * (int)sizeof(double), smem_reps = 400;
+    CU(cudaFuncSetAttribute(k_peak_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    int r0 = timed([&] { k_peak_smem<<<sms * 2, 1024, smem_bytes, st>>>(sink, smem_reps); }, 1, &ms);
+    if (r0) return r0;
+    out->smem_gbs = (double)sms * 2 * smem_reps * (kPeakSmemDoubles / 2) * 8.0 * 4.0 / (ms * 1e-3) / 1e9;
+    // L2: 32 MB -> 32 MB, resident after the first pass
+    const size_t l2n = (size_t)1 << 22;   // doubles: 32 MB
+    r0 = timed([&] { k_peak_copy<<<sms * 8, 256, 0, st>>>(reinterpret_cast<const double2*>(a), reinterpret_cast<double2*>(b), l2n / 2); }, 20, &ms);
+    if (r0) return r0;
+    out->l2_gbs = 2.0 * l2n * 8.0 / (ms * 1e-3) / 1e9;
+    // HBM: 1 GB -> 1 GB
+    r0 = timed([&] { k_peak_copy<<<sms * 8, 256, 0, st>>>(reinterpret_cast<const double2*>(a), reinterpret_cast<double2*>(b), big / 2); }, 2, &ms);
+    if (r0) return r0;
+    out->hbm_gbs = 2.0 * big * 8.0 / (ms * 1e-3) / 1e9;
+    return SY2D_OK;
+  };
+  rc = body();
+  if (a) cudaFree(a);
+  if (b) cudaFree(b);
+  if (sink) cudaFree(sink);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  if (st) cudaStreamDestroy(st);
+  return rc;
+}
+
 int sy2d_set_profiling(sy2d_ctx* c, int on) {
   if (!c) return SY2D_ERR_INVALID;
   c->profiling = on != 0;
@@ -1638,15 +2112,35 @@ int sy2d_nccl_unique_id(void* id_out) {
   return SY2D_OK;
 }
 
+static int slab_check_shape(int nx_global, int ny, int rank, int nranks) {
+  sy2d_ctx* c = nullptr;
+  if (nranks < 2 || rank < 0 || rank >= nranks) return fail(c, SY2D_ERR_INVALID, "sy2d_create_slab: need nranks >= 2 and 0 <= rank < nranks");
+  if (nx_global / nranks < 2 * kTI) return fail(c, SY2D_ERR_INVALID, "sy2d_create_slab: at least %d rows per rank", 2 * kTI);
+  if (ny % 2 || ny < kTJ) return fail(c, SY2D_ERR_INVALID, "sy2d_create_slab: ny must be even and >= %d", kTJ);
+  return SY2D_OK;
+}
+
+static int slab_finish_create(sy2d_ctx** out, SlabTransport* tp) {
+  sy2d_ctx* c = *out;
+  c->tp = tp;
+  if (cudaMalloc(reinterpret_cast<void**>(&c->d_gather), (size_t)c->nranks * 8 * sizeof(double)) != cudaSuccess) {
+    g_create_error = "cudaMalloc failed";
+    sy2d_destroy(c);
+    *out = nullptr;
+    return SY2D_ERR_CUDA;
+  }
+  c->opt.use_graph = 0;
+  return SY2D_OK;
+}
+
 int sy2d_create_slab(sy2d_ctx** out, int device, int nx_global, int ny, int rank, int nranks, const void* nccl_id,
                      const double* x_edges, const double* y_edges, double dt) {
   sy2d_ctx* c = nullptr;
   if (!out || !nccl_id) return fail(c, SY2D_ERR_INVALID, "sy2d_create_slab: NULL argument");
-  if (nranks < 2 || rank < 0 || rank >= nranks) return fail(c, SY2D_ERR_INVALID, "sy2d_create_slab: need nranks >= 2 and 0 <= rank < nranks");
-  if (nx_global / nranks < 2 * kTI) return fail(c, SY2D_ERR_INVALID, "sy2d_create_slab: at least %d rows per rank", 2 * kTI);
-  if (ny % 2 || ny < kTJ) return fail(c, SY2D_ERR_INVALID, "sy2d_create_slab: ny must be even and >= %d", kTJ);
+  int rc = slab_check_shape(nx_global, ny, rank, nranks);
+  if (rc) return rc;
   if (!nccl().ok) return fail(c, SY2D_ERR_CUDA, "sy2d_create_slab: %s", nccl().why.c_str());
-  int rc = create_impl(out, device, nx_global, ny, 1, x_edges, y_edges, dt, rank, nranks);
+  rc = create_impl(out, device, nx_global, ny, 1, x_edges, y_edges, dt, rank, nranks);
   if (rc) return rc;
   c = *out;
   ncclUniqueId id;
@@ -1659,15 +2153,64 @@ int sy2d_create_slab(sy2d_ctx** out, int device, int nx_global, int ny, int rank
     *out = nullptr;
     return SY2D_ERR_CUDA;
   }
-  c->comm = comm;
-  if (cudaMalloc(reinterpret_cast<void**>(&c->d_gather), (size_t)nranks * 5 * sizeof(double)) != cudaSuccess) {
-    g_create_error = "cudaMalloc failed";
+  NcclTransport* tp = new NcclTransport;
+  tp->comm = comm;
+  return slab_finish_create(out, tp);
+}
+
+int sy2d_local_group_create(sy2d_local_group** out, int nranks) {
+  sy2d_ctx* c = nullptr;
+  if (!out || nranks < 2 || nranks > kMgMaxRanks) return fail(c, SY2D_ERR_INVALID, "sy2d_local_group_create: 2 <= nranks <= %d", kMgMaxRanks);
+  sy2d_local_group* g = new sy2d_local_group;
+  g->nranks = nranks;
+  g->ptr.assign(nranks, nullptr);
+  g->rows.assign(nranks, 0);
+  g->ready.assign(nranks, nullptr);
+  g->done.assign(nranks, nullptr);
+  *out = g;
+  return SY2D_OK;
+}
+
+void sy2d_local_group_destroy(sy2d_local_group* g) {
+  if (!g) return;
+  {
+    std::lock_guard<std::mutex> lk(g->mu);
+    if (g->attached > 0) return;   // contexts still attached: destroy them first (the group is leaked rather than freed under them)
+  }
+  delete g;
+}
+
+int sy2d_create_slab_local(sy2d_ctx** out, int device, int nx_global, int ny, int rank, int nranks, sy2d_local_group* group,
+                           const double* x_edges, const double* y_edges, double dt) {
+  sy2d_ctx* c = nullptr;
+  if (!out || !group) return fail(c, SY2D_ERR_INVALID, "sy2d_create_slab_local: NULL argument");
+  if (group->nranks != nranks) return fail(c, SY2D_ERR_INVALID, "sy2d_create_slab_local: the group was created for %d ranks", group->nranks);
+  int rc = slab_check_shape(nx_global, ny, rank, nranks);
+  if (rc) return rc;
+  {
+    std::lock_guard<std::mutex> lk(group->mu);
+    if (group->ready[rank]) return fail(c, SY2D_ERR_INVALID, "sy2d_create_slab_local: rank %d is already attached", rank);
+  }
+  rc = create_impl(out, device, nx_global, ny, 1, x_edges, y_edges, dt, rank, nranks);
+  if (rc) return rc;
+  c = *out;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (cudaEventCreateWithFlags(&e0, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&e1, cudaEventDisableTiming) != cudaSuccess) {
+    g_create_error = "cudaEventCreate failed";
     sy2d_destroy(c);
     *out = nullptr;
     return SY2D_ERR_CUDA;
   }
-  c->opt.use_graph = 0;
-  return SY2D_OK;
+  LocalTransport* tp = new LocalTransport;
+  tp->g = group;
+  tp->rank = rank;
+  {
+    std::lock_guard<std::mutex> lk(group->mu);
+    group->ready[rank] = e0;
+    group->done[rank] = e1;
+    group->attached += 1;
+  }
+  return slab_finish_create(out, tp);
 }
 
 int sy2d_slab_rows(const sy2d_ctx* c, int* i_lo, int* i_hi) {

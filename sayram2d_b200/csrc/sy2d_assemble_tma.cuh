@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(kTI * kTJ, 4) k_assemble_tma(const AsmMaps* __
       o.cs[c0] = cs0;
       if (o.om) o.om[c0] = om;
       rr += rhs * rhs;
-      rabs = fmax(rabs, fabs(rhs));
+      rabs = nmax(rabs, fabs(rhs));
     }
 #undef H
     __syncthreads();  // vs / face arrays and this stage are rewritten from here on

@@ -71,6 +71,9 @@ __host__ __device__ __forceinline__ double sy2d_div(double a, double b) {
 #endif
 }
 
+// max that PROPAGATES NaN (fmax drops it): a residual reduction must not turn a NaN iterate into "max|r| = 0 => converged"
+__host__ __device__ __forceinline__ double nmax(double a, double b) { return (b != b || b > a) ? b : a; }
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -78,7 +81,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 __device__ __forceinline__ double warp_max(double v) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  for (int o = 16; o > 0; o >>= 1) v = nmax(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
 __device__ __forceinline__ double warp_min(double v) {
@@ -552,7 +555,7 @@ __global__ void __launch_bounds__(kTI * kTJ, 4) k_assemble_tiled(const double* _
       o.cs[c0] = cs0;
       if (o.om) o.om[c0] = om;
       rr += rhs * rhs;
-      rabs = fmax(rabs, fabs(rhs));
+      rabs = nmax(rabs, fabs(rhs));
     }
     __syncthreads();  // the tile's shared arrays are rewritten by the next tile
   }
@@ -616,7 +619,7 @@ __device__ __forceinline__ void xr_finish_iteration(Scal* sc, const KrylovVecs& 
   sc->first = 0;
   int state = 0;
   if (rmax <= k.tol) state = 1;
-  else if (!(rmax == rmax) || rho_new == 0.0 || sc->omega == 0.0) state = 3;  // NaN / breakdown
+  else if (!(rmax == rmax) || !(rho_new == rho_new) || rho_new == 0.0 || sc->omega == 0.0) state = 3;  // NaN / breakdown
   else if (sc->it >= k.maxit) state = 2;
   sc->beta = (rho_new / sc->rho) * (sc->alpha / sc->omega);
   sc->rho = rho_new;
@@ -865,7 +868,7 @@ __global__ void __launch_bounds__(kBlock) k_xr_update2(KrylovVecs k, size_t N) {
     const double r0 = s.x - omega * t.x, r1 = s.y - omega * t.y;
     st2(k.r + g, r0, r1);
     dot += rh.x * r0 + rh.y * r1;
-    rabs = fmax(rabs, fmax(fabs(r0), fabs(r1)));
+    rabs = nmax(rabs, nmax(fabs(r0), fabs(r1)));
   }
   double sums[1] = {dot};
   block_sums<1>(sums, red);
@@ -889,7 +892,7 @@ __global__ void k_slab_scalars(int phase, Scal* sc, const double* __restrict__ g
   for (int r = 0; r < nranks; ++r) {
     const double* q = gathered + 5 * r;
     rv += q[0]; ts += q[1]; tt += q[2]; rho += q[3];
-    rmax = fmax(rmax, __longlong_as_double(__double_as_longlong(q[4])));  // raw bits of a non-negative double
+    rmax = nmax(rmax, __longlong_as_double(__double_as_longlong(q[4])));  // raw bits of a non-negative double
   }
   sc->acc_rv = 0.0; sc->acc_ts = 0.0; sc->acc_tt = 0.0;
   if (phase == 0) {
@@ -911,6 +914,14 @@ __global__ void k_slab_scalars(int phase, Scal* sc, const double* __restrict__ g
   }
 }
 
+// max over the ranks' all-gathered values (non-negative doubles; NaN propagates)
+__global__ void k_slab_max(const double* __restrict__ gathered, int nranks, double* out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double m = 0.0;
+  for (int r = 0; r < nranks; ++r) m = nmax(m, gathered[r]);
+  *out = m;
+}
+
 // True residual max|rhs - A x| per problem (verification of the recursive residual).
 __global__ void __launch_bounds__(kBlock) k_true_residual(KrylovVecs k, size_t N, int ny, double* out_max) {
   __shared__ double red[32];
@@ -918,7 +929,7 @@ __global__ void __launch_bounds__(kBlock) k_true_residual(KrylovVecs k, size_t N
   const size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t base = (size_t)blockIdx.y * N;
   double rabs = 0.0;
-  if (n < N) {
+  if (n >= k.n_begin && n < k.n_end) {
     const size_t g = base + n;
     double ax = 0.0;
     if (sc->it > 0) {
@@ -939,29 +950,36 @@ struct StepStats {  // device-resident, copied back with the step result
   int it_max;
   int n_bad;  // problems that ended in state 2/3
   int it_total_max;                // engine B: max over problems of iterations summed over the call's steps
-  int pad_;
+  int steps_min;                   // engine B: smallest number of time steps of the call a problem completed (< nsteps only after a failure)
   unsigned long long it_sum_all;   // engine B: iterations summed over problems and steps
 };
 
 // KF: f^{n+1} = c (1 + d); yprev = clamp(f^{n+1}/f^n); statistics.           40 B/cell
+// The step is COMMITTED only when the true residual of the solve (st->resid_max, written by k_true_residual
+// earlier on the stream; the max over the batch) is finite and <= resid_limit: otherwise f and yprev are left
+// untouched and every problem counts as bad (the recursive BiCGSTAB residual alone can drift from the true one).
 __global__ void __launch_bounds__(kBlock) k_finish(const double* __restrict__ x, const double* __restrict__ cs,
                                                    double* __restrict__ f, double* __restrict__ yprev,
                                                    const Scal* __restrict__ scal, size_t N, int predictor,
-                                                   StepStats* st) {
+                                                   StepStats* st, double resid_limit) {
   const Scal* sc = scal + blockIdx.y;
   const size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool commit = st->resid_max <= resid_limit;   // false for NaN
   double fmin = 1.0e300;
   int neg = 0;
   if (n < N) {
     const size_t g = (size_t)blockIdx.y * N + n;
     const double d = sc->it > 0 ? x[g] : 0.0;
     const double fold = f[g];
-    const double fnew = cs[g] * (1.0 + d);
-    f[g] = fnew;
-    if (predictor) {
-      double y = fnew / fold;
-      y = ::fmin(::fmax(y, kPredMin), kPredMax);
-      yprev[g] = (y == y) ? y : 1.0;
+    const double fnew = commit ? cs[g] * (1.0 + d) : fold;
+    if (commit) {
+      f[g] = fnew;
+      if (predictor) {
+        double y = fnew / fold;
+        y = ::fmin(::fmax(y, kPredMin), kPredMax);
+        yprev[g] = (y == y) ? y : 1.0;
+      }
+      if (!(fabs(fnew) <= 1.0e300)) atomicAdd(&st->n_bad, 1);   // non-finite f (cannot happen after a verified solve of finite data)
     }
     fmin = fnew;
     neg = fnew < 0.0;
@@ -988,10 +1006,30 @@ __global__ void __launch_bounds__(kBlock) k_finish(const double* __restrict__ x,
       }
       if (blockIdx.x == 0) {
         atomicMax(&st->it_max, sc->it);
-        if (sc->state >= 2) atomicAdd(&st->n_bad, 1);
+        if (sc->state >= 2 || !commit) atomicAdd(&st->n_bad, 1);
       }
     }
   }
+}
+
+// A solve that stopped without converging commits nothing: only the statistics of the failure are collected.
+__global__ void k_fail_stats(const Scal* __restrict__ scal, int nbatch, StepStats* st) {
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < nbatch; b += gridDim.x * blockDim.x) {
+    atomicMax(&st->it_max, scal[b].it);
+    if (scal[b].state != 1) atomicAdd(&st->n_bad, 1);
+  }
+}
+
+// Input check of sy2d_set_f / sy2d_put_f: the engine solves for the per-cell ratio f^{n+1} / (f^n yprev), so f must be
+// finite and strictly positive (the reference's initial conditions add gEPS for the same reason - Albert_Young.h:39 - and
+// the PPFV scheme keeps f positive).  Counts the offending cells.
+__global__ void __launch_bounds__(kBlock) k_check_f(const double* __restrict__ f, size_t n_total, unsigned long long* bad) {
+  unsigned long long mine = 0;
+  for (size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < n_total; n += (size_t)gridDim.x * blockDim.x) {
+    const double v = f[n];
+    mine += !(v > 0.0 && v <= 1.0e300);
+  }
+  if (mine) atomicAdd(bad, mine);
 }
 
 }  // namespace sy2d

@@ -467,7 +467,7 @@ __global__ void __launch_bounds__(kBlock) k_mg_xr(KrylovVecs k, const double* __
     const double r0 = s.x - omega * t.x, r1 = s.y - omega * t.y;
     st2(k.r + g, r0, r1);
     dot += rh.x * r0 + rh.y * r1;
-    rabs = fmax(rabs, fmax(fabs(r0), fabs(r1)));
+    rabs = nmax(rabs, nmax(fabs(r0), fabs(r1)));
   }
   double sums[1] = {dot};
   block_sums<1>(sums, red);

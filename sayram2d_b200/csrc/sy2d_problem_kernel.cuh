@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(kProblemThreads, 1) k_problem_steps(ProblemArg
   double* rhs = a.rhs + base; double* x = a.x + base; double* r = a.r + base; double* p = a.p + base;
   double* v = a.v + base; double* s = a.s + base; double* t = a.t + base;
 
-  int it_total = 0, it = 0, state = 1;
+  int it_total = 0, it = 0, state = 1, steps_ok = 0;
   double rmax = 0.0, res_true = 0.0;
   for (int step = 0; step < a.nsteps; ++step) {
     // ---------------- assembly (Solver.cc:167-267 fused with :292-422) ----------------
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(kProblemThreads, 1) k_problem_steps(ProblemArg
       scale_row(row, yprev[n], yprev[nW], yprev[nE], yprev[nS], yprev[nN], sc);
       wW[n] = sc.wW; wE[n] = sc.wE; wS[n] = sc.wS; wN[n] = sc.wN; rhs[n] = sc.rhs; cs[n] = sc.cs;
       acc[0] += sc.rhs * sc.rhs;
-      acc[1] = fmax(acc[1], fabs(sc.rhs));
+      acc[1] = nmax(acc[1], fabs(sc.rhs));
     }
     cta_allreduce<1, true>(acc, red);
     double rho = acc[0];
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(kProblemThreads, 1) k_problem_steps(ProblemArg
         const double rn = sn - omega * t[n];
         r[n] = rn;
         a3[0] += rhs[n] * rn;
-        a3[1] = fmax(a3[1], fabs(rn));
+        a3[1] = nmax(a3[1], fabs(rn));
       }
       cta_allreduce<1, true>(a3, red);
       const double rho_new = a3[0];
@@ -142,13 +142,14 @@ __global__ void __launch_bounds__(kProblemThreads, 1) k_problem_steps(ProblemArg
       rho = rho_new;
     }
     it_total += it;
+    if (state >= 2) break;   // stopped without converging (maxit, breakdown, NaN): f and yprev stay those of t^n
     // ---------------- true residual of the accepted solution ----------------
     const bool last = step == a.nsteps - 1;
     if (last) {
       double m = 0.0;
       for (int n = tid; n < N; n += kProblemThreads) {
         const double ax = it > 0 ? stencil_apply(x, (size_t)n, (size_t)N, ny, x[n], wW[n], wE[n], wS[n], wN[n]) : 0.0;
-        m = fmax(m, fabs(rhs[n] - ax));
+        m = nmax(m, fabs(rhs[n] - ax));
       }
       double mm[1] = {m};
       cta_allreduce<0, true>(mm, red);
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(kProblemThreads, 1) k_problem_steps(ProblemArg
       }
     }
     __syncthreads();  // f complete before the next step's assembly reads neighbours
-    if (state >= 2) break;
+    steps_ok = step + 1;
   }
   if (tid == 0) {
     Scal* sc = a.scal + prob;
@@ -197,7 +198,8 @@ __global__ void __launch_bounds__(kProblemThreads, 1) k_problem_steps(ProblemArg
     atomicMax(&a.stats->it_total_max, it_total);
     atomicAdd(&a.stats->it_sum_all, (unsigned long long)it_total);
     atomicMax(reinterpret_cast<unsigned long long*>(&a.stats->resid_max), (unsigned long long)__double_as_longlong(res_true));
-    if (state >= 2) atomicAdd(&a.stats->n_bad, 1);
+    atomicMin(&a.stats->steps_min, steps_ok);
+    if (state >= 2 || !(res_true == res_true)) atomicAdd(&a.stats->n_bad, 1);
   }
 }
 

@@ -41,13 +41,39 @@ namespace sy2d {
 constexpr int kXlineNCH = 8;          // lanes per column
 constexpr int kXlineCPW = 32 / kXlineNCH;
 
+// Work queue of one launch.  An item is "the next `chunk` time steps of problem p"; the persistent CTAs (one per SM)
+// pop tickets from `head`, wait until the ticket's slot holds a problem, run the chunk and - when the problem has steps
+// left - append it at `tail`.  The first nprob slots are filled by the host in issue order (most expensive problems
+// first), so the queue is a round robin over the problems: nprob * nsteps / chunk work units over the SMs instead of
+// nprob units of nsteps steps each - with 512 members on 148 SMs (the per-GPU share of the 4096-member ensemble on 8
+// GPUs) the last, partly filled wave costs 1 / 70 of the call instead of 0.54 / 4.  A problem is worked on by one CTA
+// at a time; its state between steps is f and yprev in global memory, handed over with a release store of the slot /
+// an acquire load by the popping thread followed by the CTA barrier.
+struct XlineQueue {
+  int head, tail, total, pad;
+};
+
 struct XlineArgs {
   ProblemArgs a;
-  double* scratch;   // [nbatch][5][S]
+  double* scratch;   // [CTAs of the launch][5][S]: per-step temporaries of the CTA (not of the problem)
   int NT;            // threads per CTA = ny_pad * NCH
   int S;             // R * NT
   int hs;            // row stride of hat in shared memory (>= ny)
+  XlineQueue* q;     // control words of this launch
+  int* slots;        // [nprob * chunks_per_problem] problem ids (local to the launch's first problem), -1 = not yet pushed
+  int* steps_done;   // [nbatch] time steps of the call completed per problem (zeroed by the host)
+  int chunk;         // time steps per work item
+  int nchunks;       // work items per problem = ceil(nsteps / chunk)
 };
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 // TRAIL = false drops the trailing barrier: the caller must then not reuse `red` before every thread has
 // passed a later barrier (the iteration loop rotates over three buffers).
@@ -109,7 +135,28 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
   double* p_s = l_s + S;     // the search direction p; during the assembly: face exchange, then 1/d of the factorisation
   double* e_s = p_s + S;
   double* red = e_s + S;
-  const int prob = a.order ? a.order[blockIdx.x] : blockIdx.x;
+  int* s_item = reinterpret_cast<int*>(red + 192);
+  double* scr = xa.scratch + (size_t)blockIdx.x * 5 * S;
+  double* wS_g = scr; double* wN_g = scr + S; double* v_g = scr + 2 * S; double* y_g = scr + 3 * S; double* rhs_g = scr + 4 * S;
+  const unsigned full = 0xffffffffu;
+
+  double rs[R], z[R];
+
+ for (;;) {   // work items: (problem, chunk of time steps)
+  if (tid == 0) {
+    const int ticket = atomicAdd(&xa.q->head, 1);
+    int item = -1;
+    while (ticket < ld_acquire_gpu(&xa.q->total)) {   // total shrinks when a problem fails: its remaining items never come
+      item = ld_acquire_gpu(xa.slots + ticket);
+      if (item >= 0) break;
+      __nanosleep(200);
+    }
+    s_item[0] = item;
+  }
+  __syncthreads();
+  const int item = s_item[0];
+  if (item < 0) break;
+  const int prob = item;
   const size_t base = (size_t)prob * N;
   const double* __restrict__ tx = a.tx + base;
   const double* __restrict__ ty = a.ty + base;
@@ -118,15 +165,12 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
   const double* __restrict__ Ud = a.Ud + base;
   double* f = a.f + base;
   double* yprev = a.yprev + base;
-  double* scr = xa.scratch + (size_t)prob * 5 * S;
-  double* wS_g = scr; double* wN_g = scr + S; double* v_g = scr + 2 * S; double* y_g = scr + 3 * S; double* rhs_g = scr + 4 * S;
-  const unsigned full = 0xffffffffu;
-
-  double rs[R], z[R];
-  int it_total = 0, it = 0, state = 1;
+  const int step_begin = xa.steps_done[prob];
+  const int step_end = min(step_begin + xa.chunk, a.nsteps);
+  int it_total = 0, it = 0, state = 1, steps_ok = step_begin;   // steps_ok: time steps of the call this problem has completed
   double rmax = 0.0, res_true = 0.0;
 
-  for (int step = 0; step < a.nsteps; ++step) {
+  for (int step = step_begin; step < step_end; ++step) {
     // ------------- assembly of the scaled rows owned by this thread -------------
     double acc[2] = {0.0, 0.0};
     if (FULL) {
@@ -257,7 +301,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
       rhs_g[q] = rh;
       rs[m] = rh;
       acc[0] += rh * rh;
-      acc[1] = fmax(acc[1], fabs(rh));
+      acc[1] = nmax(acc[1], fabs(rh));
     }
     cta_reduce_x<2>(acc, 1, red);
     double rho = acc[0];
@@ -379,7 +423,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
         y_g[q] = (first ? 0.0 : y_g[q]) + (alpha * p_s[q] + omega * rs[m]);
         rs[m] -= omega * vv[m];
         a3[0] += rhs_g[q] * rs[m];
-        a3[1] = fmax(a3[1], fabs(rs[m]));
+        a3[1] = nmax(a3[1], fabs(rs[m]));
       }
       cta_reduce_x<2, false>(a3, 1, red + 128);
       const double rho_new = a3[0];
@@ -424,13 +468,14 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
           }
           const double dW = i > 0 ? hat[(i - 1) * hs + j] : 0.0, dE = i < nx - 1 ? hat[(i + 1) * hs + j] : 0.0;
           const double ax = dinv_i * z[m] + ((lp * dW + e_s[q] * dE) + (wS_g[q] * hat[i * hs + jS] + wN_g[q] * hat[i * hs + jN]));
-          mres = fmax(mres, fabs(rhs_g[q] - ax) / dinv_i);
+          mres = nmax(mres, fabs(rhs_g[q] - ax) / dinv_i);
         }
       }
       double mm[1] = {mres};
       cta_reduce_x<1>(mm, 0, red);
       res_true = mm[0];
     }
+    if (state >= 2) break;   // the solve stopped without converging (maxit, breakdown, NaN): f and yprev stay those of t^n
     double fneg = 0.0, fmin_neg = -1.0e300;
 #pragma unroll
     for (int m = 0; m < R; ++m) {
@@ -448,7 +493,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
           yprev[n] = (y == y) ? y : 1.0;
         }
         fneg += fnew < 0.0 ? 1.0 : 0.0;
-        fmin_neg = ::fmax(fmin_neg, -fnew);
+        fmin_neg = nmax(fmin_neg, -fnew);
       }
     }
     if (last) {
@@ -457,6 +502,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
       cta_reduce_x<2>(mm, 1, red);
       if (tid == 0) {
         if (mm[0] > 0.0) atomicAdd(&a.stats->negatives, (unsigned long long)mm[0]);
+        if (!(mm[1] == mm[1]) || !(res_true == res_true)) atomicAdd(&a.stats->n_bad, 1);   // non-finite f or residual
         const double mn = -(mm[1] - 1.0e300);
         unsigned long long* addr = reinterpret_cast<unsigned long long*>(&a.stats->fmin);
         unsigned long long old = *addr;
@@ -468,20 +514,35 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
       }
     }
     __syncthreads();  // f and yprev complete before the next step's assembly reads neighbours
-    if (state >= 2) break;
+    steps_ok = step + 1;
   }
+  __syncthreads();   // (the failure path leaves the step loop without the barrier above)
   if (tid == 0) {
     Scal* sc = a.scal + prob;
-    if (a.cost) a.cost[prob] = it_total;
+    const int cost = (a.cost ? a.cost[prob] : 0) + it_total;
+    if (a.cost) a.cost[prob] = cost;
     sc->it = it;
     sc->state = state;
     sc->rmax = rmax;
     atomicMax(&a.stats->it_max, it);
-    atomicMax(&a.stats->it_total_max, it_total);
     atomicAdd(&a.stats->it_sum_all, (unsigned long long)it_total);
-    atomicMax(reinterpret_cast<unsigned long long*>(&a.stats->resid_max), (unsigned long long)__double_as_longlong(res_true));
-    if (state >= 2) atomicAdd(&a.stats->n_bad, 1);
+    xa.steps_done[prob] = steps_ok;
+    if (state >= 2) {   // failed: nothing of the failing step was committed, the problem leaves the queue
+      atomicAdd(&a.stats->n_bad, 1);
+      atomicMin(&a.stats->steps_min, steps_ok);
+      atomicMax(&a.stats->it_total_max, cost);
+      const int item_no = step_begin / xa.chunk;                     // chunks start at multiples of `chunk`
+      atomicSub(&xa.q->total, xa.nchunks - 1 - item_no);              // its later items will never be pushed
+    } else if (step_end < a.nsteps) {
+      const int u = atomicAdd(&xa.q->tail, 1);
+      st_release_gpu(xa.slots + u, prob);   // f, yprev, steps_done of this problem are visible to whoever pops it
+    } else {
+      atomicMin(&a.stats->steps_min, steps_ok);
+      atomicMax(&a.stats->it_total_max, cost);
+      atomicMax(reinterpret_cast<unsigned long long*>(&a.stats->resid_max), (unsigned long long)__double_as_longlong(res_true));
+    }
   }
+ }
 }
 
 }  // namespace sy2d

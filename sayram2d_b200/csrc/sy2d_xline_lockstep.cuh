@@ -246,14 +246,14 @@ __global__ void __launch_bounds__(kBlock) k_xl_xr(XlVecs x, size_t N) {
       const double r0 = s.x - omega * t.x, r1 = s.y - omega * t.y;
       st2(x.k.r + g, r0, r1);
       dot += rh.x * r0 + rh.y * r1;
-      rabs = fmax(rabs, fmax(fabs(r0), fabs(r1)));
+      rabs = nmax(rabs, nmax(fabs(r0), fabs(r1)));
     } else {
       const double s = x.k.s[g];
       x.k.x[g] += omega * x.hat[g];
       const double r = s - omega * x.k.t[g];
       x.k.r[g] = r;
       dot += x.k.rhs[g] * r;
-      rabs = fmax(rabs, fabs(r));
+      rabs = nmax(rabs, fabs(r));
     }
   }
   double sums[1] = {dot};

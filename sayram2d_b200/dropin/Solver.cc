@@ -2,6 +2,8 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <exception>
+#include <future>
 #include <stdexcept>
 #include <string>
 
@@ -15,6 +17,18 @@ template <class E>
 auto equation_is_static(const E& e, int) -> decltype(e.is_static()) { return e.is_static(); }
 template <class E>
 bool equation_is_static(const E&, long) { return false; }
+
+// Equation::fields_version() / bc_version() (this directory's Equation.h, not the reference's): counters a time-dependent
+// case bumps whenever update(t) really changed its fields / boundary data - the dirty flag that replaces gathering and
+// comparing 5 N values per step.  Without them (an unmodified reference Equation) every step is treated as dirty.
+template <class E>
+auto equation_fields_version(const E& e, int) -> decltype(e.fields_version()) { return e.fields_version(); }
+template <class E>
+long long equation_fields_version(const E&, long) { return -1; }
+template <class E>
+auto equation_bc_version(const E& e, int) -> decltype(e.bc_version()) { return e.bc_version(); }
+template <class E>
+long long equation_bc_version(const E&, long) { return -1; }
 
 int default_device() {
   const char* s = std::getenv("SY2D_DEVICE");
@@ -45,9 +59,7 @@ void Solver::create_context(int device) {
   if (rc != SY2D_OK) throw std::runtime_error(sy2d_last_error(nullptr));
   if (ctx_) sy2d_destroy(ctx_);
   ctx_ = c;
-  G_.clear();
-  for (auto& l : bc_lines_) l.clear();
-  stage(true);                                        // update_Lambda + update_vertex_f at t = 0 (Solver.cc:44-45)
+  stage(t(), true, false);                            // update_Lambda + update_vertex_f at t = 0 (Solver.cc:44-45)
   check(sy2d_set_f(ctx_, f_.data()));
   f_stale_ = false;
 }
@@ -58,32 +70,33 @@ void Solver::set_device(int device) {
 }
 
 // Equation fields through the per-cell accessors (Equation.h:44-50); Lambda = G*D is formed
-// on the device (Solver.cc:57-65).
-bool Solver::gather_coefficients() {
+// on the device (Solver.cc:57-65).  Returns false when the Equation's dirty counter says nothing changed.
+bool Solver::gather_coefficients(bool force) {
+  const long long ver = equation_fields_version(eq, 0);
+  if (!force && ver >= 0 && ver == fields_ver_) return false;
+  fields_ver_ = ver;
   const std::size_t nx = m.nx(), ny = m.ny(), N = nx * ny;
-  std::vector<double> g(N), dxx(N), dxy(N), dyy(N), it(N);
+  G_.resize(N); Dxx_.resize(N); Dxy_.resize(N); Dyy_.resize(N); itau_.resize(N);
   for (std::size_t i = 0; i < nx; ++i)
     for (std::size_t j = 0; j < ny; ++j) {
       const Ind c{i, j};
       const std::size_t n = i * ny + j;
-      g[n] = eq.G(c); dxx[n] = eq.Dxx(c); dxy[n] = eq.Dxy(c); dyy[n] = eq.Dyy(c); it[n] = eq.inv_tau(c);
+      G_[n] = eq.G(c); Dxx_[n] = eq.Dxx(c); Dxy_[n] = eq.Dxy(c); Dyy_[n] = eq.Dyy(c); itau_[n] = eq.inv_tau(c);
     }
-  const bool same = G_.size() == N && !std::memcmp(g.data(), G_.data(), N * 8) && !std::memcmp(dxx.data(), Dxx_.data(), N * 8) &&
-                    !std::memcmp(dxy.data(), Dxy_.data(), N * 8) && !std::memcmp(dyy.data(), Dyy_.data(), N * 8) &&
-                    !std::memcmp(it.data(), itau_.data(), N * 8);
-  if (same) return false;
-  G_.swap(g); Dxx_.swap(dxx); Dxy_.swap(dxy); Dyy_.swap(dyy); itau_.swap(it);
   return true;
 }
 
 // Boundary types and Dirichlet vertex lines at time t (Solver.cc:385-422).
-bool Solver::gather_boundaries(double tt) {
+bool Solver::gather_boundaries(double tt, bool force) {
+  const long long ver = equation_bc_version(eq, 0);
+  if (!force && ver >= 0 && ver == bc_ver_) return false;
+  bc_ver_ = ver;
   const std::size_t nx = m.nx(), ny = m.ny();
   const BoundaryID sides[4] = {BoundaryID::XMIN, BoundaryID::XMAX, BoundaryID::YMIN, BoundaryID::YMAX};
-  bool changed = false;
   for (int s = 0; s < 4; ++s) {
     const int type = eq.bc_type(sides[s]) == BCType::Dirichlet ? SY2D_DIRICHLET : SY2D_ZEROFLUX;
-    std::vector<double> line;
+    std::vector<double>& line = bc_lines_[s];
+    line.clear();
     if (type == SY2D_DIRICHLET) {
       const std::size_t n = (s < 2 ? ny : nx) + 1;
       line.resize(n);
@@ -95,35 +108,64 @@ bool Solver::gather_boundaries(double tt) {
         line[k] = u;
       }
     }
-    if (type != bc_types_[s] || line != bc_lines_[s]) changed = true;
     bc_types_[s] = type;
-    bc_lines_[s].swap(line);
   }
-  return changed;
+  return true;
 }
 
-void Solver::stage(bool force) {
-  if (gather_coefficients() || force)
-    check(sy2d_set_coeffs(ctx_, G_.data(), Dxx_.data(), Dxy_.data(), Dyy_.data(), itau_.data()));
-  if (gather_boundaries(t()) || force) {
+// update_Lambda + update_vertex_f of the reference (Solver.cc:57-65, 292-422) for time tt: gather what changed and hand
+// it to the library - blocking (first staging) or asynchronously into the second buffer set (every later step).
+void Solver::stage(double tt, bool force, bool async) {
+  if (gather_coefficients(force)) {
+    if (async) check(sy2d_set_coeffs_async(ctx_, G_.data(), Dxx_.data(), Dxy_.data(), Dyy_.data(), itau_.data()));
+    else check(sy2d_set_coeffs(ctx_, G_.data(), Dxx_.data(), Dxy_.data(), Dyy_.data(), itau_.data()));
+  }
+  if (gather_boundaries(tt, force)) {
     const double* lines[4];
     for (int s = 0; s < 4; ++s) lines[s] = bc_lines_[s].empty() ? nullptr : bc_lines_[s].data();
-    check(sy2d_set_bc(ctx_, bc_types_, lines[0], lines[1], lines[2], lines[3]));
+    if (async) check(sy2d_set_bc_async(ctx_, bc_types_, lines[0], lines[1], lines[2], lines[3]));
+    else check(sy2d_set_bc(ctx_, bc_types_, lines[0], lines[1], lines[2], lines[3]));
   }
 }
 
-void Solver::update() {
-  sy2d_stats st;
-  check(sy2d_step(ctx_, 1, &st));                     // assemble + solve (Solver.cc:271-284)
+void Solver::account(const sy2d_stats& st) {
   iters_last_ = st.iters_last;
   iters_total_ += st.iters_total;
   resid_last_ = st.resid_last;
   negatives_last_ = st.negatives;
   seconds_device_ += st.seconds_device;
   f_stale_ = true;
-  istep_ += 1;                                        // Solver.cc:286
-  eq.update(t());                                     // Solver.cc:287
-  if (!static_eq_) stage(false);                      // update_Lambda + update_vertex_f (Solver.cc:288-289)
+}
+
+void Solver::update() {
+  sy2d_stats st;
+  if (static_eq_ || !async_staging_) {
+    check(sy2d_step(ctx_, 1, &st));                   // assemble + solve (Solver.cc:271-284)
+    account(st);
+    istep_ += 1;                                      // Solver.cc:286
+    eq.update(t());                                   // Solver.cc:287
+    if (!static_eq_) stage(t(), false, false);        // update_Lambda + update_vertex_f (Solver.cc:288-289)
+    return;
+  }
+  // Time-dependent case: the fields and boundary data of t^{n+1} do not depend on the solve of step n, so
+  // Equation::update(t^{n+1}), the gathering through the accessors and the upload (a second device buffer set filled
+  // on a copy stream) run on this thread WHILE the GPU advances step n on a helper thread; the new set is swapped in at
+  // the start of step n+1.  The reference's order of effects (Solver.cc:286-289) is kept for everything the Solver's
+  // result depends on; the only visible difference: eq.update(t^{n+1}) has already run if step n throws.
+  std::future<int> step = std::async(std::launch::async, [&] { return sy2d_step(ctx_, 1, &st); });
+  std::exception_ptr err;
+  try {
+    const double tnext = static_cast<double>(istep_ + 1) * m.dt();
+    eq.update(tnext);
+    stage(tnext, false, true);
+  } catch (...) {
+    err = std::current_exception();
+  }
+  const int rc = step.get();
+  if (err) std::rethrow_exception(err);
+  check(rc);
+  account(st);
+  istep_ += 1;
 }
 
 void Solver::update(int nsteps) {
@@ -134,12 +176,7 @@ void Solver::update(int nsteps) {
   }
   sy2d_stats st;
   check(sy2d_step(ctx_, nsteps, &st));
-  iters_last_ = st.iters_last;
-  iters_total_ += st.iters_total;
-  resid_last_ = st.resid_last;
-  negatives_last_ = st.negatives;
-  seconds_device_ += st.seconds_device;
-  f_stale_ = true;
+  account(st);
   istep_ += static_cast<std::size_t>(nsteps);
   eq.update(t());
 }

@@ -21,8 +21,7 @@
 #include "Equation.h"
 #include "Mesh.h"
 #include "common.h"
-
-struct sy2d_ctx;
+#include "sayram2d.h"
 
 class Solver {
  public:
@@ -39,6 +38,7 @@ class Solver {
   // ---- extensions (not in the reference) ----
   void update(int nsteps);                         // nsteps steps without leaving the device; needs a static Equation
   void set_static_equation(bool is_static) { static_eq_ = is_static; }  // skip the per-step re-staging check
+  void set_async_staging(bool on) { async_staging_ = on; }  // time-dependent cases: stage t^{n+1} while step n runs (default on)
   void set_device(int device);                     // before the first update(); default 0 or $SY2D_DEVICE
   long long iterations_last() const { return iters_last_; }
   long long iterations_total() const { return iters_total_; }
@@ -52,20 +52,23 @@ class Solver {
   std::size_t istep_ = 0;
   sy2d_ctx* ctx_ = nullptr;
   bool static_eq_ = false;
+  bool async_staging_ = true;
+  long long fields_ver_ = -2, bc_ver_ = -2;            // Equation dirty counters at the last staging (-1: the Equation has none)
 
   mutable Xtensor2d f_;
   mutable bool f_stale_ = false;
 
-  std::vector<double> G_, Dxx_, Dxy_, Dyy_, itau_;     // last staged fields (to detect changes)
+  std::vector<double> G_, Dxx_, Dxy_, Dyy_, itau_;     // gathered fields (host staging)
   std::vector<double> bc_lines_[4];
   int bc_types_[4] = {1, 1, 1, 1};
   long long iters_last_ = 0, iters_total_ = 0, negatives_last_ = 0;
   double resid_last_ = 0.0, seconds_device_ = 0.0;
 
   void create_context(int device);
-  bool gather_coefficients();   // true if anything changed since the last staging
-  bool gather_boundaries(double t);
-  void stage(bool force);
+  bool gather_coefficients(bool force);   // false: the Equation's dirty counter says nothing changed
+  bool gather_boundaries(double t, bool force);
+  void stage(double t, bool force, bool async);
+  void account(const sy2d_stats& st);
   void check(int rc) const;
 };
 

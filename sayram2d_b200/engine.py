@@ -36,6 +36,11 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class Peaks(C.Structure):
+    _fields_ = [("smem_gbs", C.c_double), ("l2_gbs", C.c_double), ("hbm_gbs", C.c_double), ("sm_count", C.c_int),
+                ("sm_clock_mhz", C.c_double)]
+
+
 class Profile(C.Structure):
     _fields_ = [("ms", C.c_double * len(K_NAMES)), ("launches", C.c_longlong * len(K_NAMES)),
                 ("cells", C.c_double * len(K_NAMES))]
@@ -65,6 +70,9 @@ def load_library():
         "sy2d_set_coeffs": (C.c_int, [vp, dp, dp, dp, dp, dp]),
         "sy2d_set_coeffs_dev": (C.c_int, [vp, vp, vp, vp, vp, vp]),
         "sy2d_set_bc": (C.c_int, [vp, ip, dp, dp, dp, dp]),
+        "sy2d_set_coeffs_async": (C.c_int, [vp, dp, dp, dp, dp, dp]),
+        "sy2d_set_bc_async": (C.c_int, [vp, ip, dp, dp, dp, dp]),
+        "sy2d_stage_swaps": (C.c_longlong, [vp]),
         "sy2d_set_f": (C.c_int, [vp, dp]),
         "sy2d_set_f_dev": (C.c_int, [vp, vp]),
         "sy2d_put_f": (C.c_int, [vp, dp]),
@@ -82,7 +90,11 @@ def load_library():
         "sy2d_nccl_unique_id": (C.c_int, [C.c_char_p]),
         "sy2d_create_slab": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p, dp, dp, C.c_double]),
         "sy2d_slab_rows": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+        "sy2d_local_group_create": (C.c_int, [C.POINTER(vp), C.c_int]),
+        "sy2d_local_group_destroy": (None, [vp]),
+        "sy2d_create_slab_local": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, dp, dp, C.c_double]),
         "sy2d_bench_kernel": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_double)]),
+        "sy2d_measure_peaks": (C.c_int, [C.c_int, C.POINTER(Peaks)]),
         "sy2d_build_info": (C.c_char_p, []),
         "sy2d_device_count": (C.c_int, []),
     }
@@ -101,6 +113,58 @@ def nccl_unique_id():
     if rc != 0:
         raise Sy2dError(rc, lib.sy2d_last_error(None).decode())
     return buf.raw
+
+
+class LocalGroup:
+    """In-process slab transport (sy2d_local_group): nranks slab Engines in ONE process, one host thread each."""
+
+    def __init__(self, nranks):
+        self.lib = load_library()
+        self.nranks = int(nranks)
+        self._g = C.c_void_p()
+        rc = self.lib.sy2d_local_group_create(C.byref(self._g), self.nranks)
+        if rc != 0:
+            raise Sy2dError(rc, self.lib.sy2d_last_error(None).decode())
+
+    def close(self):
+        if getattr(self, "_g", None):
+            self.lib.sy2d_local_group_destroy(self._g)
+            self._g = None
+
+
+def run_local_slabs(nranks, fn, device=0):
+    """Runs fn(rank, group) on nranks host threads (one slab context each; ctypes releases the GIL inside the
+    library, so the ranks' collective calls meet).  Returns the list of results; re-raises the first exception."""
+    import threading
+    group = LocalGroup(nranks)
+    out, err = [None] * nranks, [None] * nranks
+
+    def work(r):
+        try:
+            out[r] = fn(r, group)
+        except BaseException as ex:  # noqa: BLE001
+            err[r] = ex
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(nranks)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    group.close()
+    for e in err:
+        if e is not None:
+            raise e
+    return out
+
+
+def measure_peaks(device=0):
+    """Measured shared-memory / L2 / HBM copy bandwidths (GB/s) of the device: roofline denominators."""
+    lib = load_library()
+    p = Peaks()
+    rc = lib.sy2d_measure_peaks(int(device), C.byref(p))
+    if rc != 0:
+        raise Sy2dError(rc, lib.sy2d_last_error(None).decode())
+    return {k: getattr(p, k) for k, _ in p._fields_}
 
 
 def _dp(a):
@@ -124,8 +188,8 @@ class Engine:
     for nbatch independent problems sharing one mesh and one set of BCs."""
 
     def __init__(self, x_edges, y_edges, dt, nbatch=1, device=0, slab=None):
-        """slab = (rank, nranks, nccl_id_bytes): this engine holds one row slab of the grid
-        (sy2d_create_slab); field arguments are then the owned rows [i_lo:i_hi]."""
+        """slab = (rank, nranks, nccl_id_bytes | LocalGroup): this engine holds one row slab of the grid
+        (sy2d_create_slab / sy2d_create_slab_local); field arguments are then the owned rows [i_lo:i_hi]."""
         self.lib = load_library()
         xe = _f64(x_edges)
         ye = _f64(y_edges)
@@ -135,8 +199,12 @@ class Engine:
             rc = self.lib.sy2d_create(C.byref(self._ctx), int(device), self.nx, self.ny, self.nbatch, _dp(xe), _dp(ye), self.dt)
         else:
             rank, nranks, nccl_id = slab
-            rc = self.lib.sy2d_create_slab(C.byref(self._ctx), int(device), self.nx, self.ny, int(rank), int(nranks),
-                                           bytes(nccl_id), _dp(xe), _dp(ye), self.dt)
+            if isinstance(nccl_id, LocalGroup):
+                rc = self.lib.sy2d_create_slab_local(C.byref(self._ctx), int(device), self.nx, self.ny, int(rank), int(nranks),
+                                                     nccl_id._g, _dp(xe), _dp(ye), self.dt)
+            else:
+                rc = self.lib.sy2d_create_slab(C.byref(self._ctx), int(device), self.nx, self.ny, int(rank), int(nranks),
+                                               bytes(nccl_id), _dp(xe), _dp(ye), self.dt)
         if rc != 0:
             msg = self.lib.sy2d_last_error(None).decode()
             self._ctx = None
@@ -190,6 +258,20 @@ class Engine:
         lines = [_f64(xmin, (self.ny + 1,), "xmin"), _f64(xmax, (self.ny + 1,), "xmax"),
                  _f64(ymin, (self.nx + 1,), "ymin"), _f64(ymax, (self.nx + 1,), "ymax")]
         self._check(self.lib.sy2d_set_bc(self._ctx, t, *[_dp(a) for a in lines]))
+
+    def set_coeffs_async(self, G, Dxx, Dxy, Dyy, inv_tau=None):
+        """Stage the NEXT step's fields without waiting for the step in flight (sy2d_set_coeffs_async)."""
+        arrs = [_f64(a, self.shape, n) for a, n in ((G, "G"), (Dxx, "Dxx"), (Dxy, "Dxy"), (Dyy, "Dyy"), (inv_tau, "inv_tau"))]
+        self._check(self.lib.sy2d_set_coeffs_async(self._ctx, *[_dp(a) for a in arrs]))
+
+    def set_bc_async(self, bc_type, xmin=None, xmax=None, ymin=None, ymax=None):
+        t = (C.c_int * 4)(*[int(b) for b in bc_type])
+        lines = [_f64(xmin, (self.ny + 1,), "xmin"), _f64(xmax, (self.ny + 1,), "xmax"),
+                 _f64(ymin, (self.nx + 1,), "ymin"), _f64(ymax, (self.nx + 1,), "ymax")]
+        self._check(self.lib.sy2d_set_bc_async(self._ctx, t, *[_dp(a) for a in lines]))
+
+    def stage_swaps(self):
+        return self.lib.sy2d_stage_swaps(self._ctx)
 
     def set_f(self, f):
         self._check(self.lib.sy2d_set_f(self._ctx, _dp(_f64(f, self.shape, "f"))))

@@ -1,8 +1,9 @@
 // A user-defined TIME-DEPENDENT case on the reference's Equation interface (the extension point the
 // reference documents in README.md:148-177: "update(t) is where G, D and the BCs are updated"), run
-// with the GPU Solver.  After every step the drop-in Solver calls eq.update(t), compares the fields
-// and the Dirichlet vertex lines with what the device holds and re-stages only what changed
-// (Solver.cc:286-289 of the reference: eq.update(t), update_Lambda, update_vertex_f).
+// with the GPU Solver.  While the GPU advances step n, the drop-in Solver calls eq.update(t^{n+1}), gathers the
+// fields and the Dirichlet vertex lines and uploads them into the library's second buffer set, which becomes
+// active at step n+1 (Solver.cc:286-289 of the reference: eq.update(t), update_Lambda, update_vertex_f);
+// SY2D_SYNC_STAGING=1 selects the blocking route (stage after the step) instead.
 //
 //   sayram2d_td <ini> <outdir> <nsteps> <every>
 //
@@ -62,6 +63,7 @@ int main(int argc, char** argv) {
     Mesh m(grid, paras.dt());
     Time_Dependent eq(paras, m);
     Solver solver(m, &eq);
+    if (const char* e = std::getenv("SY2D_SYNC_STAGING")) solver.set_async_staging(std::atoi(e) == 0);
     h5lite::write_npy(out + "/f_0.npy", solver.f().data(), {m.nx(), m.ny()});
     long iters = 0;
     for (long k = 1; k <= nsteps; ++k) {
@@ -69,7 +71,8 @@ int main(int argc, char** argv) {
       iters += solver.iterations_last();
       if (k % every == 0) h5lite::write_npy(out + "/f_" + std::to_string(k / every) + ".npy", solver.f().data(), {m.nx(), m.ny()});
     }
-    std::cout << "steps " << nsteps << " t " << solver.t() << " iterations " << iters << " negatives " << solver.negatives_last() << std::endl;
+    std::cout << "steps " << nsteps << " t " << solver.t() << " iterations " << iters << " negatives " << solver.negatives_last()
+              << " device_seconds " << solver.seconds_device() << std::endl;
   } catch (const std::exception& e) {
     std::cerr << "error: " << e.what() << std::endl;
     return 1;

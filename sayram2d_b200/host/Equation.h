@@ -34,6 +34,12 @@ class Equation {
   // on t says so, and the GPU Solver then never re-stages them.
   virtual bool is_static() const { return false; }
 
+  // Extension: dirty counters for time-dependent cases.  A case that bumps fields_version() / bc_version() exactly when
+  // update(t) changed its fields / Dirichlet data lets the GPU Solver skip the gathering of unchanged data; the default
+  // (-1) means "unknown": the Solver then re-stages after every update(t), overlapped with the running time step.
+  virtual long long fields_version() const { return -1; }
+  virtual long long bc_version() const { return -1; }
+
   // whole fields, for staging to the device in one copy
   const Xtensor2d& G_field() const { return G_; }
   const Xtensor2d& Dxx_field() const { return Dxx_; }

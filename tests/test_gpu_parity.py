@@ -363,13 +363,43 @@ def test_time_dependent_fields_and_boundary_data(tmp_path):
             if (step + 1) % 20 == 0:
                 assert max_rel(eng.get_f()[0], g[f"f_{(step + 1) // 20}"]) < PARITY, (engine, step)
         eng.close()
+    # the asynchronous route: the fields of step n+1 are staged into the second buffer set while step n runs on another
+    # host thread (sy2d_set_coeffs_async / sy2d_set_bc_async), and swapped in at the start of step n+1
+    import threading
+    for engine, precond in ((1, 2), (2, 1)):
+        eng = sy.Engine(g["x_edges"], g["y_edges"], 0.002)
+        eng.set_options(engine=engine, precond=precond)
+        eng.set_f(g["f_0"])
+        eq.update(0.0)
+        eng.set_coeffs_async(eq.G, eq.Dxx, eq.Dxy, eq.Dyy, eq.inv_tau)      # also the very first set may come this way
+        eng.set_bc_async(eq.bc, *eq.dirichlet_lines(0.0))
+        for step in range(60):
+            res = {}
+            th = threading.Thread(target=lambda: res.update(st=eng.step(1)))
+            th.start()
+            tn = (step + 1) * 0.002
+            eq.update(tn)
+            eng.set_coeffs_async(eq.G, eq.Dxx, eq.Dxy, eq.Dyy, eq.inv_tau)
+            eng.set_bc_async(eq.bc, *eq.dirichlet_lines(tn))
+            th.join()
+            assert res["st"]["negatives"] == 0
+            if (step + 1) % 20 == 0:
+                assert max_rel(eng.get_f()[0], g[f"f_{(step + 1) // 20}"]) < PARITY, (engine, step)
+        assert eng.stage_swaps() == 2 * 60
+        eng.close()
     ini = tmp_path / "td.ini"
     ini.write_text("[basic]\nrun_id = td64\nnalpha0 = 64\nnE = 64\nalpha0min = 5\nalpha0max = 90\nEmin = 0.2\nEmax = 5\nT = 1.0\n"
                    "nsteps = 500\n[diagnostics]\nnplots = 10\n[diffusion_coefficients]\ndID = AlbertYoung_chorus\n")
-    out = _run_binary(os.path.join(ROOT, "sayram2d_b200", "bin", "sayram2d_td"), [str(ini), str(tmp_path), "60", "20"], tmp_path)
-    assert "negatives 0" in out
-    for k in (0, 1, 2, 3):
-        assert max_rel(np.load(tmp_path / f"f_{k}.npy"), g[f"f_{k}"]) < PARITY, k
+    for sync in ("0", "1"):   # the drop-in C++ Solver: asynchronous staging (default) and the blocking route
+        os.environ["SY2D_SYNC_STAGING"] = sync
+        try:
+            out = _run_binary(os.path.join(ROOT, "sayram2d_b200", "bin", "sayram2d_td"), [str(ini), str(tmp_path), "60", "20"], tmp_path)
+        finally:
+            del os.environ["SY2D_SYNC_STAGING"]
+        assert "negatives 0" in out
+        for k in (0, 1, 2, 3):
+            assert max_rel(np.load(tmp_path / f"f_{k}.npy"), g[f"f_{k}"]) < PARITY, (sync, k)
+            os.remove(tmp_path / f"f_{k}.npy")
 
 
 def _force_assembly(eng, variant):
