@@ -189,27 +189,42 @@ def make_grid(n, device):
 BYTES_PER_CELL_XLINE = {"p_update": 64, "spmv_v": 48, "s_update": 80, "spmv_t": 40, "xr_update": 56}
 
 
-def roofline_from_profile(prof, only=None, stats=None, cells_per_problem=None):
-    """achieved = algorithmic bytes / CUDA-event time per kernel.  The engine-2 kernel does whole
-    time steps; its "algorithmic bytes" are what the same arithmetic moves when every array streams
-    through memory once per use (the lockstep engine's accounting): (assembly 104 + finish 40) per
-    cell-step + one 56 B/cell true-residual pass + per cell-iteration 216 B (Jacobi) or 288 B (x-line:
-    two sweep pairs 48+72 and 40+64, x/r update 64).  The kernel keeps that traffic in registers /
-    shared memory / L2, so `achieved` above the HBM peak is the point, and `hbm_bytes_min` (what must
-    cross HBM: coefficients and f in, f and yprev out = 72 B per cell-step) is listed beside it."""
+# The engine-2 x-line kernel (k_problem_xline) keeps a problem's state on chip: what it moves goes through the L1TEX data
+# pipe of its SM (shared memory + the L2-backed thread-private scratch), not through HBM.  Algorithmic bytes, counted
+# from the kernel source ("engine 2"): per cell and BiCGSTAB iteration 18 shared-memory accesses
+# (two Thomas solves of 4, two publishes, four neighbour reads, p written once and read three times) + 10 L2-backed
+# accesses (v r/w, wS and wN twice, rhat twice, y r/w), 8 bytes each = 224 B; per cell and time step (assembly of
+# the row incl. the face exchange, factorisation, pivot scaling, final solve and update) 76 accesses = 608 B.
+XLINE_L1_BYTES_PER_CELL_ITER = 224
+XLINE_L1_BYTES_PER_CELL_STEP = 608
+HBM_COMPULSORY_BYTES_PER_CELL_STEP = 72   # tx, ty, cxy, U, Ud, f, yprev in; f, yprev out
+
+
+def roofline_from_profile(prof, only=None, stats=None, cells_per_problem=None, peaks=None):
+    """achieved = algorithmic bytes / CUDA-event time per kernel, against the measured peak of the unit that bounds it:
+    HBM for the streaming kernels of the lockstep engine, the L1TEX data pipe (shared memory) for the engine-2 kernel."""
     peak, peak_src = measured_peak()
     rows = {}
     for name, p in prof.items():
         if p["launches"] == 0 or p["ms"] <= 0:
             continue
         if name == "problem_steps":
-            per_iter = 288 if stats.get("precond", 0) == 1 else 216
-            nbytes = p["cells"] * 144 + per_iter * cells_per_problem * stats["iters_sum_all"] + 56 * p["cells"] / max(stats["steps"], 1)
-            gbs = nbytes / (p["ms"] * 1e-3) / 1e9
-            rows[name] = {"achieved": round(gbs, 1), "frac": round(gbs / peak, 4), "ms_total": round(p["ms"], 3),
-                          "launches": p["launches"], "bytes_total": nbytes, "bytes_per_cell_iteration": per_iter,
-                          "hbm_bytes_min": p["cells"] * 72, "precond": "xline" if per_iter == 288 else "jacobi",
-                          "mean_iters_per_step": stats["iters_sum_all"] * cells_per_problem / p["cells"]}
+            xline = stats.get("precond", 0) == 1
+            cell_iters = cells_per_problem * stats["iters_sum_all"]
+            sec = p["ms"] * 1e-3
+            hbm = HBM_COMPULSORY_BYTES_PER_CELL_STEP * p["cells"] / sec / 1e9
+            row = {"ms_total": round(p["ms"], 3), "launches": p["launches"], "precond": "xline" if xline else "jacobi",
+                   "mean_iters_per_step": cell_iters / p["cells"], "cell_steps": p["cells"], "cell_iterations": cell_iters,
+                   "hbm_compulsory": {"bytes_per_cell_step": HBM_COMPULSORY_BYTES_PER_CELL_STEP, "achieved": round(hbm, 1),
+                                      "frac": round(hbm / peak, 4), "peak": peak, "unit": "GB/s"}}
+            if xline:
+                nbytes = XLINE_L1_BYTES_PER_CELL_STEP * p["cells"] + XLINE_L1_BYTES_PER_CELL_ITER * cell_iters
+                gbs = nbytes / sec / 1e9
+                l1peak = (peaks or {}).get("smem_gbs")
+                row.update({"bound": "l1tex", "achieved": round(gbs, 1), "peak": round(l1peak, 1) if l1peak else None,
+                            "frac": round(gbs / l1peak, 4) if l1peak else None, "unit": "GB/s", "bytes_total": nbytes,
+                            "bytes_per_cell_iteration": XLINE_L1_BYTES_PER_CELL_ITER, "bytes_per_cell_step": XLINE_L1_BYTES_PER_CELL_STEP})
+            rows[name] = row
             continue
         bpc = BYTES_PER_CELL.get(name)
         if stats and stats.get("precond", 0) == 1 and stats.get("engine", 0) == 1:
@@ -225,6 +240,14 @@ def roofline_from_profile(prof, only=None, stats=None, cells_per_problem=None):
     cand = {k: v for k, v in rows.items() if only is None or k in only or k == "problem_steps"}
     dom = max(cand, key=lambda k: cand[k]["ms_total"]) if cand else None
     return rows, dom, peak, peak_src
+
+
+def sy_measure_peaks(device):
+    import sayram2d_b200 as sy
+    try:
+        return sy.measure_peaks(device)
+    except Exception as ex:  # noqa: BLE001
+        return {"error": str(ex)[:200]}
 
 
 def profile_pass(eng, steps):
@@ -257,28 +280,28 @@ def cpu_baseline_ensemble(members=(0, 2047, 4095), steps=400):
     in its sources and Eigen's SparseLU is sequential - BASELINE.md section 2)."""
     from sayram2d_b200 import fields
     if not os.path.exists(REF_DRIVER):
-        return {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": "oracle/_ref/ref_driver missing"}
+        return {"value": None, "unit": UNIT, "cores": 1, "kind": "reference+shim-LU", "sample": "oracle/_ref/ref_driver missing"}
     wall, cells = 0.0, 0
     for m in members:
         a, b = fields.ensemble_scales(m)
         r = run_ref_driver("ENS", LC_INI, steps, 0, ("--member", repr(float(a)), repr(float(b))))
         wall += r["loop_wall_s"]
         cells += r["nx"] * r["ny"] * r["timed_steps"]
-    return {"value": cells / wall, "unit": UNIT, "cores": 1, "kind": "reference",
+    return {"value": cells / wall, "unit": UNIT, "cores": 1, "kind": "reference+shim-LU",
             "sample": f"members {list(members)} x {steps} steps of the 4096-member ensemble, sequentially on 1 core "
                       f"({wall:.1f} s of oracle/_ref/ref_driver = reference Solver.cc + shim LU)"}
 
 
 def cpu_baseline_grid(n, steps=1):
     if not os.path.exists(REF_DRIVER):
-        return {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": "oracle/_ref/ref_driver missing"}
+        return {"value": None, "unit": UNIT, "cores": 1, "kind": "reference+shim-LU", "sample": "oracle/_ref/ref_driver missing"}
     with tempfile.TemporaryDirectory() as d:
         ini = os.path.join(d, "syn.ini")
         open(ini, "w").write(f"[basic]\nrun_id = syn{n}\nnalpha0 = {n}\nnE = {n}\nalpha0min = 5\nalpha0max = 90\nEmin = 0.2\n"
                              f"Emax = 5\nT = 1.0\nnsteps = 500\n[diagnostics]\nnplots = 10\n[diffusion_coefficients]\n"
                              f"dID = AlbertYoung_chorus\n")
         r = run_ref_driver("SYN", ini, steps, 0)
-    return {"value": r["nx"] * r["ny"] * r["timed_steps"] / r["loop_wall_s"], "unit": UNIT, "cores": 1, "kind": "reference",
+    return {"value": r["nx"] * r["ny"] * r["timed_steps"] / r["loop_wall_s"], "unit": UNIT, "cores": 1, "kind": "reference+shim-LU",
             "sample": f"{steps} time step(s) of the {n}x{n} grid ({r['loop_wall_s']:.1f} s; LU factor {r['lu_factor_s']:.1f} s, "
                       f"nnz(L+U)={r['nnz_LU']})"}
 
@@ -317,7 +340,7 @@ def reference_arm(args):
     value = procs * NX * NY * args.steps * REF_SUBSTEPS / wall
     line["config"]["sample_per_step"] = f"{REF_SUBSTEPS} time steps of {procs} members (one per host core)"
     line.update(value=value, ms_per_step=1e3 * wall / args.steps,
-                cpu_baseline={"value": value, "unit": UNIT, "cores": procs, "kind": "reference",
+                cpu_baseline={"value": value, "unit": UNIT, "cores": procs, "kind": "reference+shim-LU",
                               "sample": f"{procs} of the 4096 members (one oracle/_ref/ref_driver process per core, "
                                         f"({args.warmup}+{args.steps}) x {REF_SUBSTEPS} time steps each; the direct LU costs the same "
                                         f"every step); total wall {time.perf_counter() - t0:.1f} s"},
@@ -401,11 +424,35 @@ def ours(args):
     e2e = {"value": cells_total * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": cells_total * 8,
            "d2h_bytes_per_step": cells_total * 8, "ms_per_step": 1e3 * e2e_s / args.steps,
            "host_buffers": "pinned" + (f", rank bound to the GPU's NUMA node ({numa_node})" if numa_node is not None else "")}
+    # The host-side ceiling of that loop: the same bytes per step and rank, pinned host <-> device in both directions at
+    # once on two streams, all ranks concurrently, NO kernels.  An end-to-end step cannot be faster than this; on a box
+    # whose ranks share one host memory system / PCIe root it, not the GPU, is what the N-GPU end-to-end number runs into.
+    d_buf = torch.empty((nb, NX, NY), dtype=torch.float64, device=dev)
+    d_buf2 = torch.empty((nb, NX, NY), dtype=torch.float64, device=dev)
+    s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    def copy_step():
+        with torch.cuda.stream(s_up):
+            d_buf.copy_(pin_in, non_blocking=True)
+        with torch.cuda.stream(s_dn):
+            pin_out.copy_(d_buf2, non_blocking=True)
+    for _ in range(3):
+        copy_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        copy_step()
+    barrier()
+    copy_s = max_over_ranks(time.perf_counter() - t0)
+    e2e["copy_ceiling"] = {"ms_per_step": 1e3 * copy_s / args.steps, "value": cells_total * args.steps / copy_s, "unit": UNIT,
+                           "aggregate_GBps_each_way": cells_total * 8 * args.steps / copy_s / 1e9,
+                           "what": "pinned H2D + D2H of one step's f per rank, both directions concurrently, all ranks at once, no kernels"}
+    del d_buf, d_buf2
 
     # ---- per-kernel roofline (separate profiled pass, CUDA events around every launch) ----
+    peaks = sy_measure_peaks(local_rank) if rank == 0 else None
     prof, pst = profile_pass(eng, 2)
     rows, dom, peak, peak_src = roofline_from_profile(prof, only=("p_update", "spmv_v", "s_update", "spmv_t", "xr_update", "assembly"),
-                                                      stats=pst, cells_per_problem=NX * NY)
+                                                      stats=pst, cells_per_problem=NX * NY, peaks=peaks)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
@@ -415,33 +462,48 @@ def ours(args):
                        "l2": f"working set {nb * NX * NY * 8 * 19 / 1e6:.0f} MB per GPU > 126 MB L2: no flush needed"},
             "iters_per_step": iters, "iters_per_step_mean": iters_mean, "engine": st["engine"], "negatives": int(negatives), "wall_ms_per_step": 1e3 * wall_s / args.steps,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
-    if dom:
+    if dom and rank == 0:
         r = rows[dom]
-        traffic, traffic_src = None, None
-        try:  # DRAM bytes per launch from the committed ncu --set full capture, scaled to this launch's cell-steps
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-            if dom == "problem_steps" and pst.get("precond", 0) == 1:
-                traffic = tj["k_problem_xline"]["dram_bytes_per_cell_step"] * prof[dom]["cells"]
-                traffic_src = tj["k_problem_xline"]["source"]
-        except Exception:
-            pass
-        line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": r["achieved"], "peak": peak, "unit": "GB/s",
-                            "frac": r["frac"], "traffic": traffic, "traffic_source": traffic_src,
-                            "note": "engine-2 kernel: achieved = streaming-equivalent bytes / time; the state is on-chip, so "
-                                    "DRAM traffic is far below it and frac > 1 measures the residency, not HBM speed",
-                            "peak_source": peak_src, "kernels": rows}
-        if traffic:   # what actually crosses HBM, from the ncu byte count and this run's kernel time
-            dram = traffic / (r["ms_total"] * 1e-3) / 1e9
-            line["roofline"].update({"dram_achieved": round(dram, 1), "dram_frac": round(dram / peak, 4)})
+        if dom == "problem_steps" and r.get("bound") == "l1tex":
+            # the dominant kernel is bound by the L1TEX data pipe (ncu: l1tex throughput is the top unit, DRAM ~4 %):
+            # achieved = algorithmic shared-memory + L2-backed bytes / kernel time, peak = the measured shared-memory
+            # copy bandwidth of this device (sy2d_measure_peaks); what crosses HBM is listed beside it
+            traffic, traffic_src = None, None
+            try:  # L1TEX bytes per launch from the committed ncu --set full capture, scaled to this launch's work
+                tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))["k_problem_xline"]
+                traffic = tj["l1tex_bytes_per_cell_iteration"] * r["cell_iterations"] / r["launches"]
+                traffic_src = tj["source"]
+            except Exception:
+                pass
+            line["roofline"] = {"bound": "l1tex", "kernel": "k_problem_xline", "achieved": r["achieved"], "peak": r["peak"],
+                                "unit": "GB/s", "frac": r["frac"], "traffic": traffic, "traffic_source": traffic_src,
+                                "bytes_per_launch": r["bytes_total"] / r["launches"], "ms_per_launch": r["ms_total"] / r["launches"],
+                                "model": f"{XLINE_L1_BYTES_PER_CELL_STEP} B per cell-step + {XLINE_L1_BYTES_PER_CELL_ITER} B per cell-iteration through "
+                                         "the L1TEX data pipe (18 shared + 10 L2-backed 8-byte accesses per cell and iteration)",
+                                "peak_source": "measured: sy2d_measure_peaks shared-memory copy (8-byte accesses, loads + stores, all SMs)",
+                                "hbm_compulsory": r["hbm_compulsory"], "measured_peaks": peaks, "kernels": {"ensemble_xline": r}}
+        else:
+            line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": r.get("achieved"), "peak": peak, "unit": "GB/s",
+                                "frac": r.get("frac"), "traffic": None, "peak_source": peak_src, "measured_peaks": peaks, "kernels": rows}
     eng.close()
 
     if rank == 0 and world == 1:
         if not args.no_grid1024:
             line["grid1024"] = grid_object(1024, local_rank, args, torch)
             line["grid4096"] = big_grid_object(4096, local_rank)
+            if "roofline" in line:   # the north-star target's kernels, next to the dominant kernel of the headline workload
+                line["roofline"]["kernels"].update(north_star_rows(line["grid1024"], line["grid4096"], peak))
         line["cpu_baseline"] = cpu_baseline_ensemble() if not args.no_cpu else None
     if world > 1 and args.slab_n > 0:
         slab = slab_object(args.slab_n, args.slab_iters, rank, world, local_rank, dist, torch)
+        try:
+            par = slab_parity(4096, 2, rank, world, local_rank, dist, torch)
+            if par:
+                slab["parity"] = par
+                slab["parity_max_rel"] = par["parity_max_rel"]
+                slab["iters"] = {"slab": par["iters_slab"], "single": par["iters_single"]}
+        except Exception as ex:  # noqa: BLE001
+            slab["parity"] = {"unavailable": str(ex)[:200]}
         line["slab"] = slab
     if rank == 0:
         print(json.dumps(line), flush=True)
@@ -462,6 +524,7 @@ def grid_object(n, device, args, torch):
         flush.zero_(); torch.cuda.synchronize()
         st = eng.step(1)
         dev_s += st["seconds_device"]; iters += st["iters_total"]
+    flush.zero_(); torch.cuda.synchronize()
     prof, pst = profile_pass(eng, 1)
     rows, dom, peak, peak_src = roofline_from_profile(prof, stats=pst, cells_per_problem=n * n)
     out = {"workload": f"grid{n}", "value": n * n * steps / dev_s, "unit": UNIT, "steps": steps, "ms_per_step": 1e3 * dev_s / steps,
@@ -470,10 +533,101 @@ def grid_object(n, device, args, torch):
            "kernel_launches_per_step": st["kernel_launches"],
            "l2": "256 MB flush between timed steps; the working set (~25 fine-grid arrays, 210 MB, plus the coarse levels) cycles through L2 within a step",
            "roofline": {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src, "dominant": dom, "kernels": rows}}
+    # The event bracket around a launch (record, kernel, record on a plain stream) is longer than the kernel's slot in the
+    # real step, which replays CUDA graphs: the difference per launch, measured here as
+    #   (sum of all brackets of the profiled step - device time of the graph-replayed step) / launches,
+    # is taken off every bracket, so that the in-step times add up to the real step (both sides CUDA events, same run).
+    tot_ms = sum(r["ms_total"] for r in rows.values())
+    tot_launches = sum(r["launches"] for r in rows.values())
+    step_ms = 1e3 * dev_s / steps
+    over_us = max(0.0, 1e3 * (tot_ms - step_ms) / max(tot_launches, 1))
+    out["roofline"]["bracket"] = {"sum_of_brackets_ms": round(tot_ms, 3), "graph_step_ms": round(step_ms, 3), "launches": tot_launches,
+                                  "overhead_us_per_launch": round(over_us, 2),
+                                  "what": "us_per_launch = bracketed CUDA-event time - overhead_us_per_launch; the in-step times then add up to graph_step_ms"}
+    for name, r in rows.items():
+        if "us_per_launch" not in r:
+            continue
+        r["us_per_launch_bracketed"] = r["us_per_launch"]
+        r["us_per_launch"] = round(max(r["us_per_launch"] - over_us, 0.1), 2)
+        r["achieved_bracketed"], r["frac_bracketed"] = r["achieved"], r["frac"]
+        gbs = r["achieved_bracketed"] * r["us_per_launch_bracketed"] / r["us_per_launch"]
+        r["achieved"], r["frac"] = round(gbs, 1), round(gbs / peak, 4)
     out["roofline"]["sustained"] = sustained_kernels(eng, n * n, peak)
+    out["time_dependent"] = time_dependent_leg(eng, n, torch)
     eng.close()
     if not args.no_cpu and not args.no_grid_cpu:
         out["cpu_baseline"] = cpu_baseline_grid(n, 1)
+    return out
+
+
+# the figures the north-star roofline target is quoted with - assembly 96 B per cell (104 with the
+# predictor's yprev, 112 with the multigrid row weights: what the kernel really moves), SpMV 56 B per cell
+SURVEY_BYTES = {"assembly": 96, "spmv_v": 56, "spmv_t": 56}
+
+
+def north_star_rows(grid1024, grid4096, peak):
+    """The kernels BASELINE.json's roofline target names (PPFV assembly, stencil SpMV) on the 1024^2 grid it is quoted on:
+    IN-STEP (CUDA events around every launch of a real time step, L2 flushed before the step - the bracket includes the
+    launch gap) and SUSTAINED (back-to-back launches; at 1024^2 the SpMV working set fits the 126 MB L2), with the
+    DRAM-bound 4096^2 figures alongside.  frac uses SURVEY 8(d)'s bytes, frac_moved what the kernel really moves."""
+    rows = {}
+    for gname, g in (("grid1024", grid1024), ("grid4096", grid4096)):
+        if not g:
+            continue
+        cells = int(gname[4:]) ** 2
+        ins = (g.get("roofline") or {}).get("kernels", {})
+        sus = (g.get("roofline") or {}).get("sustained", {}) if gname == "grid1024" else g.get("sustained", {})
+        for k, sb in SURVEY_BYTES.items():
+            for mode, src in (("in_step", ins), ("sustained", sus)):
+                r = src.get(k)
+                if not r or not r.get("us_per_launch"):
+                    continue
+                us = r["us_per_launch"]
+                gbs = cells * sb / (us * 1e-6) / 1e9
+                rows[f"{gname}_{k}_{mode}"] = {"us_per_launch": us, "bytes_per_cell": sb, "achieved": round(gbs, 1), "peak": peak, "unit": "GB/s",
+                                               "frac": round(gbs / peak, 4), "bytes_per_cell_moved": r["bytes_per_cell"],
+                                               "frac_moved": r["frac"], "launches": r.get("launches")}
+                if "us_per_launch_bracketed" in r:
+                    rows[f"{gname}_{k}_{mode}"].update({"us_per_launch_bracketed": r["us_per_launch_bracketed"],
+                                                        "frac_bracketed": round(cells * sb / (r["us_per_launch_bracketed"] * 1e-6) / 1e9 / peak, 4)})
+    return rows
+
+
+def time_dependent_leg(eng, n, torch, steps=6):
+    """Equation::update(t) on the device (Solver.cc:286-289): per step new D fields and Dirichlet data.  Blocking route:
+    sy2d_set_coeffs + sy2d_set_bc then the step.  Overlapped route: the NEXT step's fields go through
+    sy2d_set_coeffs_async / sy2d_set_bc_async (second buffer set, copy stream) from this thread while the step runs on
+    another host thread.  Host-side evaluation of the fields is excluded (two precomputed field sets alternate)."""
+    from sayram2d_b200 import fields
+    xe, ye = fields.uniform_edges(n, n)
+    G = fields.ay_G(xe, ye)
+    Dxx, Dxy, Dyy, inv_tau = fields.synthetic_tensor(xe, ye)
+    _, bct, lines = fields.ay_init_and_bc(xe, ye)
+    sets = [(G, Dxx * a, Dxy * a, Dyy * a, inv_tau) for a in (1.0, 1.02)]
+    out = {}
+    try:
+        eng.step(1)
+        t0 = time.perf_counter()
+        for k in range(steps):
+            eng.set_coeffs(*sets[k % 2]); eng.set_bc(bct, *lines)
+            eng.step(1)
+        out["blocking_ms_per_step"] = 1e3 * (time.perf_counter() - t0) / steps
+        eng.set_coeffs_async(*sets[0]); eng.set_bc_async(bct, *lines)
+        eng.step(1)
+        t0 = time.perf_counter()
+        for k in range(steps):
+            def stage_next(k=k):
+                eng.set_coeffs_async(*sets[(k + 1) % 2]); eng.set_bc_async(bct, *lines)
+            eng.step_overlapped(stage_next)
+        out["overlapped_ms_per_step"] = 1e3 * (time.perf_counter() - t0) / steps
+        eng.set_coeffs(*sets[0]); eng.set_bc(bct, *lines)
+        t0 = time.perf_counter()
+        eng.step(steps)
+        out["static_ms_per_step"] = 1e3 * (time.perf_counter() - t0) / steps
+        out["staged_bytes_per_step"] = 5 * n * n * 8
+        out["note"] = "wall clock per time step incl. staging 5 fields + 4 boundary lines from pageable host arrays"
+    except Exception as ex:  # noqa: BLE001
+        out["unavailable"] = str(ex)[:200]
     return out
 
 
@@ -570,6 +724,56 @@ def slab_object(n, iters, rank, world, local_rank, dist, torch):
     except Exception as ex:  # e.g. rows per rank beyond what the line kernel covers
         out["solved"] = {"unavailable": str(ex)[:200]}
     eng.close()
+    return out
+
+
+def slab_parity(n, steps, rank, world, local_rank, dist, torch):
+    """Parity certificate of the slab path: `steps` time steps of the n x n grid as `world` row slabs
+    over NCCL against the SAME steps in one context on rank 0; max relative difference of f over the whole grid."""
+    import sayram2d_b200 as sy
+    from sayram2d_b200 import fields
+    from sayram2d_b200.shard import slab_range
+    dev = f"cuda:{local_rank}"
+    ids = [sy.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    xe, ye = fields.uniform_edges(n, n)
+    lo, hi = slab_range(n, rank, world)
+    eng = sy.Engine(xe, ye, DT, device=local_rank, slab=(rank, world, ids[0]))
+    eng.set_options(precond=2, check_every=1)
+    Dxx, Dxy, Dyy, inv_tau = fields.synthetic_tensor(xe, ye, rows=(lo, hi))
+    eng.set_coeffs(fields.ay_G(xe, ye, rows=(lo, hi)), Dxx, Dxy, Dyy, inv_tau)
+    f0, bct, lines = fields.ay_init_and_bc(xe, ye, rows=(lo, hi))
+    eng.set_bc(bct, *lines)
+    eng.set_f(f0)
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    st = eng.step(steps)
+    rows_max = -(-n // world)
+    mine = torch.zeros((rows_max, n), dtype=torch.float64, device=dev)
+    mine[: hi - lo] = torch.from_numpy(eng.get_f()[0]).to(dev)
+    eng.close()
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    out = None
+    if rank == 0:
+        f = np.empty((n, n))
+        for r in range(world):
+            l, h = slab_range(n, r, world)
+            f[l:h] = parts[r][: h - l].cpu().numpy()
+        ref = sy.Engine(xe, ye, DT, device=local_rank)
+        ref.set_options(engine=1, precond=2, check_every=1)
+        D = fields.synthetic_tensor(xe, ye)
+        ref.set_coeffs(fields.ay_G(xe, ye), *D)
+        f0g, bct, lines = fields.ay_init_and_bc(xe, ye)
+        ref.set_bc(bct, *lines)
+        ref.set_f(f0g)
+        rs = ref.step(steps)
+        fr = ref.get_f()[0]
+        ref.close()
+        out = {"grid": n, "steps": steps, "parity_max_rel": float(np.max(np.abs(f - fr) / np.abs(fr))),
+               "iters_slab": st["iters_total"], "iters_single": rs["iters_total"], "resid_slab": st["resid_last"], "resid_single": rs["resid_last"],
+               "ms_per_step_slab": 1e3 * st["seconds_device"] / steps, "ms_per_step_single": 1e3 * rs["seconds_device"] / steps,
+               "what": f"{steps} time steps of {n}x{n} as {world} NCCL row slabs against one context on rank 0 (multigrid-preconditioned BiCGSTAB on both)"}
+    dist.barrier()
     return out
 
 

@@ -69,7 +69,7 @@ typedef struct {
                         2 one persistent CTA per problem (whole time loop in one launch) */
   int mg_levels;     /* SY2D_PRECOND_MG: maximum number of grid levels (0 = default: coarsen to <= 64 columns) */
   int mg_coarse_sweeps; /* SY2D_PRECOND_MG: smoothing sweeps on the coarsest level (0 = default 2) */
-  int reserved[3];   /* reserved[0]: 1 forces the one-thread-per-cell assembly, 2 the tile kernel without TMA (tests); reserved[1]: slab mode,
+  int reserved[3];   /* reserved[0]: assembly kernel of engine 1 - 0 default, 1 one thread per cell, 2 tile kernel with plain loads, 3 warp-marching kernel, 4 TMA-staged tiles (tests); reserved[1]: slab mode,
                         fixed iteration budget without a convergence error (bench); reserved[2]: 1 makes the first attempt of every
                         AUTO multigrid step count as failed, so the x-line fallback runs (tests); 2 (slab mode, multigrid): the smoother's
                         lines end at the slab instead of being coupled across ranks by the spike correction (comparison runs) */
@@ -153,6 +153,10 @@ int sy2d_set_coeffs_async(sy2d_ctx* ctx, const double* G, const double* Dxx, con
 int sy2d_set_bc_async(sy2d_ctx* ctx, const int bc_type[4], const double* xmin, const double* xmax,
                       const double* ymin, const double* ymax);
 long long sy2d_stage_swaps(const sy2d_ctx* ctx);   /* asynchronously staged sets swapped in so far */
+/* Number of sy2d_step / sy2d_step_host calls that have passed their swap-in point.  A thread that stages the fields of
+ * step n+1 while another thread runs step n must not stage before step n has taken ITS fields: read the counter before
+ * starting the step thread and wait until it has advanced (dropin/Solver.cc does exactly this). */
+long long sy2d_steps_begun(sy2d_ctx* ctx);
 
 /* Solver::init f_ = eq.init_f (Solver.cc:38-42); [nbatch][nx][ny]. Resets the step counter.
  * f must be finite and > 0 in every cell (SY2D_ERR_INVALID otherwise): the engine solves for the per-cell ratio
@@ -183,6 +187,11 @@ long long sy2d_step_count(const sy2d_ctx* ctx);
 int sy2d_dump_operator(sy2d_ctx* ctx, double* diags, double* rhs);
 /* vertex_f_ (Solver.cc:292-422) for the current f: [nbatch][nx+1][ny+1]. For parity tests. */
 int sy2d_dump_vertex_f(sy2d_ctx* ctx, double* vf);
+
+/* Test hook: the scaled unit-diagonal system A d = rhs of the current f as the lockstep engine
+ * assembles it, by the assembly kernel options.reserved[0] selects: w4 = [4][nbatch][nx][ny] = wW, wE, wS, wN;
+ * rhs, cs = [nbatch][nx][ny] (cs may be NULL).  The kernels must agree bit for bit.  Does not advance time. */
+int sy2d_dump_scaled_operator(sy2d_ctx* ctx, double* w4, double* rhs, double* cs);
 
 /* Test hook for the multigrid preconditioner (SY2D_PRECOND_MG): assembles the scaled operator of the
  * current f, builds the hierarchy and applies ONE V-cycle to r -> z ([nbatch][nx][ny], host).  w4 (may be

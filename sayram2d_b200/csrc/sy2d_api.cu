@@ -23,6 +23,7 @@
 #include "sy2d_xline_lockstep.cuh"
 #include "sy2d_mg.cuh"
 #include "sy2d_assemble_tma.cuh"
+#include "sy2d_assemble_march.cuh"
 #include "sy2d_peaks.cuh"
 
 using namespace sy2d;
@@ -44,7 +45,8 @@ struct sy2d_ctx {
   // grid caps of the grid-stride kernels (tuning: SY2D_CTAS_PER_SM, SY2D_ASM_CTAS_PER_SM).  6 = the CTAs of 256 threads x 40
   // registers that are resident on an SM at once: one full wave, no tail (profiles/sweep_caps_steps.py: 1024^2 4.98 -> 4.81 ms
   // per step against 16, 2048^2 15.2 -> 14.9, 4096^2 equal; 8 is worse everywhere - a partial second wave)
-  int ctas_per_sm = 6, asm_ctas_per_sm = 4;
+  int ctas_per_sm = 6, asm_ctas_per_sm = 4, march_ctas_per_sm = 4;
+  int asm_kernel = 0;   // default fast assembly: 0 TMA-staged tiles, 1 warp-marching (SY2D_ASM_KERNEL)
   int pipe_max = 32, pipe_forced = 0;   // sy2d_step_host: at most pipe_max pipelined sub-batches (SY2D_PIPE_CHUNKS forces a count)
   std::string err;
   sy2d_options opt;
@@ -97,6 +99,7 @@ struct sy2d_ctx {
   double* bc_pin = nullptr;         // pinned: 2 (ny + 1) + 2 (nx + 1)
   int bc2[4] = {SY2D_ZEROFLUX, SY2D_ZEROFLUX, SY2D_ZEROFLUX, SY2D_ZEROFLUX};
   long long swaps = 0;              // buffer-set swaps done so far (tests)
+  long long steps_begun = 0;        // sy2d_step / sy2d_step_host calls that have passed their swap-in point (guarded by stage_mu)
   Scal* scal = nullptr;
   int* d_nactive = nullptr;
   int* h_nactive = nullptr;  // pinned
@@ -119,6 +122,9 @@ struct sy2d_ctx {
   int* d_slots = nullptr;
   size_t slots_cap = 0;
   int* d_steps_done = nullptr;
+  int host_io_direct = 0;        // sy2d_step_host, SY2D_HOST_IO=direct: the x-line kernel reads / writes pinned host buffers itself instead of
+                                 // the copy engines (measured SLOWER on B200 / PCIe: 9.9 against 8.5 ms per end-to-end step at 4096
+                                 // members - the loads an SM issues to system memory run at ~1 GB/s per SM; kept as an experiment)
   int xl_chunk = 1;              // time steps per work item (SY2D_XLINE_CHUNK; 0 = all steps of a call: one CTA per problem)
   std::vector<cudaStream_t> pipe_streams;   // sy2d_step_host: one stream per sub-batch
   std::vector<cudaEvent_t> pipe_events;
@@ -283,14 +289,14 @@ void launch_iteration_xline(sy2d_ctx* c) {
 }
 
 
-// Tensor maps for the TMA-staged assembly: [nbatch][nx][ny] fp64 arrays seen as 3-D tensors (ny fastest),
-// halo boxes of 36 x 10 cells and interior boxes of 32 x 8 cells, out-of-bounds elements zero-filled.
+// Tensor maps for the TMA-staged assembly: [nbatch][local rows][ny] fp64 arrays seen as 3-D tensors (ny fastest),
+// halo boxes of 36 x 10 cells, out-of-bounds elements zero-filled.
 // cuTensorMapEncodeTiled is a driver entry point; it is resolved through the runtime, so the library
 // keeps linking against libcudart only.
 bool tma_encode_maps(sy2d_ctx* c, AsmMaps* host_maps, double* tx, double* ty, double* cxy, double* U, double* Ud);
 
 bool tma_build_maps(sy2d_ctx* c) {
-  if (c->slab || c->ny % 2 != 0 || c->nx < 2 * kTI || c->ny < kTJ) return false;
+  if (c->ny % 2 != 0 || mg_rows(c) < 2 * kTI || c->ny < kTJ) return false;
   if (!tma_encode_maps(c, &c->tma_maps, c->tx, c->ty, c->cxy, c->U, c->Ud)) return false;
   if (cudaFuncSetAttribute(k_assemble_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes) != cudaSuccess ||
       cudaMalloc(reinterpret_cast<void**>(&c->d_tma_maps), sizeof(AsmMaps)) != cudaSuccess ||
@@ -313,12 +319,13 @@ bool tma_encode_maps(sy2d_ctx* c, AsmMaps* host_maps, double* tx, double* ty, do
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
   EncodeFn encode = reinterpret_cast<EncodeFn>(fn);
-  double* arrs[7] = {c->f, c->yprev, tx, ty, cxy, U, Ud};
+  (void)U; (void)Ud;   // no halo, used once per cell: loaded directly by the kernel
+  double* arrs[5] = {c->f, c->yprev, tx, ty, cxy};
   const cuuint64_t dims[3] = {(cuuint64_t)c->ny, (cuuint64_t)c->nx, (cuuint64_t)c->nbatch};
   const cuuint64_t strides[2] = {(cuuint64_t)c->ny * sizeof(double), (cuuint64_t)c->N * sizeof(double)};
   const cuuint32_t estr[3] = {1, 1, 1};
-  for (int k = 0; k < 7; ++k) {
-    const cuuint32_t box[3] = {(cuuint32_t)(k < 5 ? kTmaHaloJ : kTJ), (cuuint32_t)(k < 5 ? kTmaHaloI : kTI), 1};
+  for (int k = 0; k < 5; ++k) {
+    const cuuint32_t box[3] = {(cuuint32_t)kTmaHaloJ, (cuuint32_t)kTmaHaloI, 1};
     const CUresult r = encode(&host_maps->m[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, arrs[k], dims, strides, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,  // (L2 promotion raises an illegal-instruction fault with these boxes on B200 / driver 580: profiles/tma_probe.cu)
                              
@@ -328,15 +335,27 @@ bool tma_encode_maps(sy2d_ctx* c, AsmMaps* host_maps, double* tx, double* ty, do
   return true;
 }
 
-// Engine-1 assembly of the whole batch: TMA-staged tiles where available, else the tiled / per-cell kernels.
-// variant: 0 auto, 1 per-cell kernel, 2 tiled kernel without TMA (tests compare the three).
+// Warp-marching assembly of local rows [li_begin, li_end) (sy2d_assemble_march.cuh): one warp per 16 x 30 strip.
+void launch_march(sy2d_ctx* c, const Geometry& geo, const AssembleOut& o, int gi0, int li_begin, int li_end, int defer) {
+  const int strips_i = (li_end - li_begin + kMarchRows - 1) / kMarchRows, strips_j = (c->ny + kMarchCols - 1) / kMarchCols;
+  const int nstrips = strips_i * strips_j;
+  const size_t need = ((size_t)nstrips + kMarchWarps - 1) / kMarchWarps;
+  const size_t cap = std::max<size_t>(1, (size_t)c->sm_count * c->march_ctas_per_sm / (size_t)c->nbatch);
+  k_assemble_march<<<dim3((unsigned)std::min(need, cap), (unsigned)c->nbatch, 1), kMarchWarps * 32, kMarchSmemBytes, c->stream>>>(
+      c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud, geo, o, strips_j, nstrips, gi0, li_begin, li_end, defer);
+}
+
+// Engine-1 assembly of the whole batch.  variant: 0 auto (SY2D_ASM_KERNEL = march | tma picks the default fast kernel),
+// 1 per-cell kernel, 2 tiled kernel without TMA, 3 warp-marching kernel, 4 TMA-staged tiles (tests compare them).
 void launch_assembly(sy2d_ctx* c, const Geometry& geo, const AssembleOut& o, int variant) {
   const int tiles_i = (c->nx + kTI - 1) / kTI, tiles_j = (c->ny + kTJ - 1) / kTJ;
   const bool tiled = c->nx >= 2 * kTI && c->ny >= kTJ && variant != 1;
-  if (tiled && c->have_tma && variant == 0) {
+  if (tiled && (variant == 3 || (variant == 0 && c->asm_kernel == 1))) {
+    launch_march(c, geo, o, 0, 0, c->nx, 0);
+  } else if (tiled && c->have_tma && (variant == 0 || variant == 4)) {
     const int ntiles = tiles_i * tiles_j;
     const unsigned ctas = (unsigned)std::min<size_t>((size_t)ntiles, std::max<size_t>(1, (size_t)c->sm_count * c->asm_ctas_per_sm / (size_t)c->nbatch));
-    k_assemble_tma<<<dim3(ctas, (unsigned)c->nbatch, 1), kTI * kTJ, kTmaSmemBytes, c->stream>>>(c->d_tma_maps, geo, o, tiles_j, ntiles);
+    k_assemble_tma<<<dim3(ctas, (unsigned)c->nbatch, 1), kTI * kTJ, kTmaSmemBytes, c->stream>>>(c->d_tma_maps, c->U, c->Ud, geo, o, tiles_j, ntiles, 0, 0, c->nx, 0);
   } else if (tiled) {
     k_assemble_tiled<<<dim3(capped_blocks(c, (size_t)tiles_i * tiles_j, 1), (unsigned)c->nbatch, 1), kTI * kTJ, 0, c->stream>>>(
         c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud, geo, o, tiles_j, 0, 0, c->nx, 0);
@@ -908,8 +927,16 @@ int step_slab_impl(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
     o.wW = c->wW; o.wE = c->wE; o.wS = c->wS; o.wN = c->wN; o.rhs = c->rhs; o.cs = c->cs;
     o.scal = c->scal; o.n_active = c->d_nactive; o.tol = c->opt.tol; o.local_rows = c->nx;
     if (mg) o.om = c->mg_om0;
-    k_assemble_tiled<<<dim3(capped_blocks(c, (size_t)tiles_i * tiles_j, 1), 1, 1), kTI * kTJ, 0, c->stream>>>(
-        c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud, geo, o, tiles_j, c->i_lo - 1, 1, rows + 1, 1);
+    if (c->opt.reserved[0] == 3 || (c->opt.reserved[0] == 0 && c->asm_kernel == 1)) {
+      launch_march(c, geo, o, c->i_lo - 1, 1, rows + 1, 1);
+    } else if (c->have_tma && (c->opt.reserved[0] == 0 || c->opt.reserved[0] == 4)) {
+      const int ntiles = tiles_i * tiles_j;
+      const unsigned ctas = (unsigned)std::min<size_t>((size_t)ntiles, (size_t)c->sm_count * c->asm_ctas_per_sm);
+      k_assemble_tma<<<dim3(ctas, 1, 1), kTI * kTJ, kTmaSmemBytes, c->stream>>>(c->d_tma_maps, c->U, c->Ud, geo, o, tiles_j, ntiles, c->i_lo - 1, 1, rows + 1, 1);
+    } else {
+      k_assemble_tiled<<<dim3(capped_blocks(c, (size_t)tiles_i * tiles_j, 1), 1, 1), kTI * kTJ, 0, c->stream>>>(
+          c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud, geo, o, tiles_j, c->i_lo - 1, 1, rows + 1, 1);
+    }
     CU(cudaGetLastError());
     rc = slab_reduce(c, 0, k);
     if (rc) return rc;
@@ -988,7 +1015,7 @@ int step_slab_impl(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
       // the ranks (all-gathered, so the commit decision of k_finish is the same everywhere)
       if ((rc = slab_halo_exchange(c, c->x))) return rc;
       k_true_residual<<<grid_of(c), kBlock, 0, c->stream>>>(k, c->N, c->ny, &c->d_stats->resid_max);
-      if ((rc = slab_gather(c, &c->d_stats->resid_max, c->d_gather, 1))) return rc;
+      if ((rc = slab_gather(c, &c->d_stats->resid_max, c->d_gather, 2))) return rc;   // resid_max, resid_rel_max are adjacent
       k_slab_max<<<1, 32, 0, c->stream>>>(c->d_gather, c->nranks, &c->d_stats->resid_max);
       const dim3 gf((unsigned)((own + kBlock - 1) / kBlock), 1, 1);
       k_finish<<<gf, kBlock, 0, c->stream>>>(c->x + c->ny, c->cs + c->ny, c->f + c->ny, c->yprev + c->ny, c->scal, own, c->opt.predictor, c->d_stats,
@@ -1012,7 +1039,7 @@ int step_slab_impl(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
     if (bad) {
       if (stats) *stats = st;
       return fail(c, SY2D_ERR_NOT_CONVERGED, "sy2d_step (slab): step %lld not committed (%s; %d iterations, true residual %.3e)",
-                  c->istep + 1, solve_failed ? "BiCGSTAB did not converge" : "true residual above 1000 x tol", c->h_stats->it_max, c->h_stats->resid_max);
+                  c->istep + 1, solve_failed ? "BiCGSTAB did not converge" : "componentwise backward error of the true residual above 1000 x tol", c->h_stats->it_max, c->h_stats->resid_max);
     }
   }
   CU(cudaEventRecord(c->ev_call1, c->stream));
@@ -1103,6 +1130,9 @@ static int create_impl(sy2d_ctx** out, int device, int nx, int ny, int nbatch, c
   if (const char* e = std::getenv("SY2D_PIPE_CHUNKS")) ctx->pipe_forced = std::max(1, std::min(64, std::atoi(e)));
   if (const char* e = std::getenv("SY2D_ASM_CTAS_PER_SM")) ctx->asm_ctas_per_sm = std::max(1, std::min(4, std::atoi(e)));
   if (const char* e = std::getenv("SY2D_XLINE_CHUNK")) ctx->xl_chunk = std::max(0, std::atoi(e));
+  if (const char* e = std::getenv("SY2D_HOST_IO")) ctx->host_io_direct = std::string(e) == "direct" ? 1 : 0;
+  if (const char* e = std::getenv("SY2D_ASM_KERNEL")) ctx->asm_kernel = std::string(e) == "march" ? 1 : 0;
+  if (const char* e = std::getenv("SY2D_MARCH_CTAS_PER_SM")) ctx->march_ctas_per_sm = std::max(1, std::min(16, std::atoi(e)));
   const HostGeometry hg = make_host_geometry(nx, ny, xe, ye);
   const std::vector<double>&wxL = hg.wxL, &wxR = hg.wxR, &wyB = hg.wyB, &wyT = hg.wyT, &dx = hg.dx, &dy = hg.dy;
   struct Up { double** dst; const std::vector<double>* src; } ups[] = {
@@ -1287,6 +1317,7 @@ static int stage_swap_in(sy2d_ctx* c) {
     c->have_bc = true;
     c->swaps += 1;
   }
+  c->steps_begun += 1;
   return SY2D_OK;
 }
 
@@ -1346,6 +1377,12 @@ int sy2d_set_bc_async(sy2d_ctx* c, const int bc_type[4], const double* xmin, con
 }
 
 long long sy2d_stage_swaps(const sy2d_ctx* c) { return c ? c->swaps : 0; }
+
+long long sy2d_steps_begun(sy2d_ctx* c) {
+  if (!c) return 0;
+  std::lock_guard<std::mutex> lk(c->stage_mu);
+  return c->steps_begun;
+}
 
 int sy2d_set_bc(sy2d_ctx* c, const int bc_type[4], const double* xmin, const double* xmax, const double* ymin, const double* ymax) {
   if (!c || !bc_type) return SY2D_ERR_INVALID;
@@ -1551,7 +1588,23 @@ static int step_per_problem(sy2d_ctx* c, int nsteps, sy2d_stats* stats, const do
   std::memset(&st, 0, sizeof st);
   st.engine = 2;
   if (nsteps == 0) { if (stats) *stats = st; return SY2D_OK; }
-  const bool piped = (h_in || h_out) && !c->profiling;
+  // Host buffers the device can address (pinned / registered memory under UVA) are read and written by the x-line kernel
+  // itself; anything else goes through the copy engines, pipelined over sub-batches.
+  auto device_view = [&](const void* h) -> double* {
+    if (!h) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, h) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+    return static_cast<double*>(at.devicePointer);
+  };
+  int R = 0, NT = 0, S = 0, HS = 0;
+  size_t smem = 0;
+  const bool xline = c->opt.precond != SY2D_PRECOND_JACOBI && xline_shape(c, &R, &NT, &S, &HS, &smem);
+  double* d_hin = c->host_io_direct && xline ? device_view(h_in) : nullptr;
+  double* d_hout = c->host_io_direct && xline ? device_view(h_out) : nullptr;
+  const bool direct = (h_in || h_out) && (!h_in || d_hin) && (!h_out || d_hout) && !c->profiling;
+  if (!direct) d_hin = d_hout = nullptr;
+  const bool piped = (h_in || h_out) && !c->profiling && !direct;
   const int C = piped ? pipe_chunks(c) : 1;
   StepStats init;
   std::memset(&init, 0, sizeof init);
@@ -1584,9 +1637,6 @@ static int step_per_problem(sy2d_ctx* c, int nsteps, sy2d_stats* stats, const do
   a.cost = c->d_cost;
   CU(cudaMemsetAsync(c->d_cost, 0, c->nbatch * sizeof(int), c->stream));
   c->cur_cells = (double)c->total * nsteps;
-  int R = 0, NT = 0, S = 0, HS = 0;
-  size_t smem = 0;
-  const bool xline = c->opt.precond != SY2D_PRECOND_JACOBI && xline_shape(c, &R, &NT, &S, &HS, &smem);
   if (c->opt.precond == SY2D_PRECOND_XLINE && !xline)
     return fail(c, SY2D_ERR_INVALID, "sy2d_step: the x-line preconditioner needs nx <= 80, ny <= 128 and engine 2");
   st.precond = xline ? SY2D_PRECOND_XLINE : SY2D_PRECOND_JACOBI;
@@ -1628,6 +1678,7 @@ static int step_per_problem(sy2d_ctx* c, int nsteps, sy2d_stats* stats, const do
       xa.slots = c->d_slots + (size_t)b0 * nchunks;
       xa.steps_done = c->d_steps_done;
       xa.chunk = chunk; xa.nchunks = nchunks;
+      xa.hin = d_hin; xa.hout = d_hout;
       k_xline_queue_init<<<std::max(1, std::min(64, (nprob * nchunks + 255) / 256)), 256, 0, stream>>>(xa.q, xa.slots, c->d_order + b0, nprob, nchunks);
       return dispatch_xline(xa, R, nctas, smem, stream);
     }
@@ -1636,12 +1687,12 @@ static int step_per_problem(sy2d_ctx* c, int nsteps, sy2d_stats* stats, const do
     return cudaGetLastError();
   };
   if (!piped) {
-    if (h_in) CU(cudaMemcpyAsync(c->f, h_in, c->total * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (h_in && !direct) CU(cudaMemcpyAsync(c->f, h_in, c->total * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     {
       Prof p(c, SY2D_K_PROBLEM_STEPS);
       CU(launch(0, 0, c->nbatch, c->stream));
     }
-    if (h_out) CU(cudaMemcpyAsync(h_out, c->f, c->total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (h_out && !direct) CU(cudaMemcpyAsync(h_out, c->f, c->total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     st.kernel_launches = xline ? 2 : 1;
   } else {
     if ((int)c->pipe_streams.size() < C) {
@@ -1694,8 +1745,9 @@ static int step_per_problem(sy2d_ctx* c, int nsteps, sy2d_stats* stats, const do
   if (h.n_bad > 0)
     return fail(c, SY2D_ERR_NOT_CONVERGED, "sy2d_step: BiCGSTAB did not converge (%d problems, up to %d iterations in a step; every problem "
                 "completed %d of %d time steps, a failed problem keeps the f of its last completed step)", h.n_bad, h.it_max, steps_all, nsteps);
-  if (!(h.resid_max <= 1000.0 * c->opt.tol))
-    return fail(c, SY2D_ERR_NOT_CONVERGED, "sy2d_step: true residual %.3e after the last step exceeds 1000 x tol", h.resid_max);
+  if (!(h.resid_rel_max <= 1000.0 * c->opt.tol))
+    return fail(c, SY2D_ERR_NOT_CONVERGED, "sy2d_step: true residual after the last step (%.3e, componentwise backward error %.3e) exceeds 1000 x tol",
+                h.resid_max, h.resid_rel_max);
   return SY2D_OK;
 }
 
@@ -1858,8 +1910,8 @@ int sy2d_step(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
       if (solve_failed)
         return fail(c, SY2D_ERR_NOT_CONVERGED, "sy2d_step: BiCGSTAB did not converge at step %lld (%d problems, %d iterations); the step was not committed",
                     c->istep + 1, c->h_stats->n_bad, c->h_stats->it_max);
-      return fail(c, SY2D_ERR_NOT_CONVERGED, "sy2d_step: step %lld not committed: true residual %.3e exceeds 1000 x tol (or f is not finite)",
-                  c->istep + 1, c->h_stats->resid_max);
+      return fail(c, SY2D_ERR_NOT_CONVERGED, "sy2d_step: step %lld not committed: true residual %.3e (componentwise backward error %.3e) exceeds 1000 x tol, or f is not finite",
+                  c->istep + 1, c->h_stats->resid_max, c->h_stats->resid_rel_max);
     }
   }
   CU(cudaEventRecord(c->ev_call1, c->stream));
@@ -1903,6 +1955,35 @@ int sy2d_dump_operator(sy2d_ctx* c, double* diags, double* rhs) {
   for (int k = 0; k < 5; ++k)
     CU(cudaMemcpyAsync(diags + (size_t)k * c->total, src[k], c->total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CU(cudaMemcpyAsync(rhs, c->t, c->total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return SY2D_OK;
+}
+
+// Test hook: the SCALED unit-diagonal system A d = rhs of the current f exactly as the next sy2d_step of the lockstep
+// engine would assemble it, with the assembly kernel selected by options.reserved[0]:
+// w4 = [4][nbatch][nx][ny] (wW, wE, wS, wN), rhs and cs = [nbatch][nx][ny] (cs may be NULL).  Does not advance time.
+int sy2d_dump_scaled_operator(sy2d_ctx* c, double* w4, double* rhs, double* cs) {
+  if (!c || !w4 || !rhs) return SY2D_ERR_INVALID;
+  CU(cudaSetDevice(c->device));
+  int rc = ready(c, "sy2d_dump_scaled_operator");
+  if (rc) return rc;
+  if (c->slab) return fail(c, SY2D_ERR_INVALID, "sy2d_dump_scaled_operator: not available on a slab context");
+  CU(cudaMemsetAsync(c->d_nactive, 0, 2 * sizeof(int), c->stream));
+  CU(cudaMemsetAsync(c->scal, 0, c->nbatch * sizeof(Scal), c->stream));
+  AssembleOut o;
+  std::memset(&o, 0, sizeof o);
+  o.wW = c->wW; o.wE = c->wE; o.wS = c->wS; o.wN = c->wN; o.rhs = c->rhs; o.cs = c->cs;
+  o.scal = c->scal; o.n_active = c->d_nactive; o.tol = -1.0;
+  o.local_rows = c->nx;
+  launch_assembly(c, geometry(c), o, c->opt.reserved[0]);
+  CU(cudaGetLastError());
+  double* src[4] = {c->wW, c->wE, c->wS, c->wN};
+  for (int k = 0; k < 4; ++k)
+    CU(cudaMemcpyAsync(w4 + (size_t)k * c->total, src[k], c->total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(rhs, c->rhs, c->total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (cs) CU(cudaMemcpyAsync(cs, c->cs, c->total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaMemsetAsync(c->scal, 0, c->nbatch * sizeof(Scal), c->stream));
   CU(cudaStreamSynchronize(c->stream));
   return SY2D_OK;
 }

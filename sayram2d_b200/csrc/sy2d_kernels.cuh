@@ -915,38 +915,50 @@ __global__ void k_slab_scalars(int phase, Scal* sc, const double* __restrict__ g
 }
 
 // max over the ranks' all-gathered values (non-negative doubles; NaN propagates)
-__global__ void k_slab_max(const double* __restrict__ gathered, int nranks, double* out) {
+__global__ void k_slab_max(const double* __restrict__ gathered, int nranks, double* out) {   // pairs (absolute, relative)
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double m = 0.0;
-  for (int r = 0; r < nranks; ++r) m = nmax(m, gathered[r]);
-  *out = m;
+  double m0 = 0.0, m1 = 0.0;
+  for (int r = 0; r < nranks; ++r) { m0 = nmax(m0, gathered[2 * r]); m1 = nmax(m1, gathered[2 * r + 1]); }
+  out[0] = m0;
+  out[1] = m1;
 }
 
-// True residual max|rhs - A x| per problem (verification of the recursive residual).
+// True residual of the accepted solution (verification of the recursive BiCGSTAB residual), two max-norms over batch
+// and cells: out_max[0] = max |rhs - A d| (reported), out_max[1] = max |rhs - A d|_K / (1 + |d_K| + sum_L |w_KL d_L|),
+// the componentwise backward error the commit decision uses - when a cell jumps by orders of magnitude in one step
+// (|d| >> 1: a tiny cell next to O(1) Dirichlet data) round-off alone puts |rhs - A d| at eps |A| |d| >> tol.
 __global__ void __launch_bounds__(kBlock) k_true_residual(KrylovVecs k, size_t N, int ny, double* out_max) {
   __shared__ double red[32];
   const Scal* sc = k.scal + blockIdx.y;
   const size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t base = (size_t)blockIdx.y * N;
-  double rabs = 0.0;
+  double rabs = 0.0, rrel = 0.0;
   if (n >= k.n_begin && n < k.n_end) {
     const size_t g = base + n;
-    double ax = 0.0;
+    double ax = 0.0, scale = 1.0;
     if (sc->it > 0) {
       const double* x = k.x + base;
-      ax = stencil_apply(x, n, N, ny, x[n], k.wW[g], k.wE[g], k.wS[g], k.wN[g]);
+      const double xW = x[n >= (size_t)ny ? n - ny : n], xE = x[n + ny < N ? n + ny : n], xS = x[n > 0 ? n - 1 : n], xN = x[n + 1 < N ? n + 1 : n];
+      const double wW = k.wW[g], wE = k.wE[g], wS = k.wS[g], wN = k.wN[g];
+      ax = x[n] + ((wW * xW + wE * xE) + (wS * xS + wN * xN));   // stencil_apply
+      scale += fabs(x[n]) + ((fabs(wW * xW) + fabs(wE * xE)) + (fabs(wS * xS) + fabs(wN * xN)));
     }
     rabs = fabs(k.rhs[g] - ax);
+    rrel = rabs / scale;
   }
   const double bmax = block_max(rabs, red);
-  if (threadIdx.x == 0)
+  const double bmax_rel = block_max(rrel, red);
+  if (threadIdx.x == 0) {
     atomicMax(reinterpret_cast<unsigned long long*>(out_max), (unsigned long long)__double_as_longlong(bmax));
+    atomicMax(reinterpret_cast<unsigned long long*>(out_max + 1), (unsigned long long)__double_as_longlong(bmax_rel));
+  }
 }
 
 struct StepStats {  // device-resident, copied back with the step result
   double fmin;
   unsigned long long negatives;
-  double resid_max;
+  double resid_max;      // max |rhs - A d| (true residual, absolute)
+  double resid_rel_max;  // max componentwise backward error |rhs - A d|_K / (1 + |d_K| + sum |w d|): what a step is committed on
   int it_max;
   int n_bad;  // problems that ended in state 2/3
   int it_total_max;                // engine B: max over problems of iterations summed over the call's steps
@@ -955,8 +967,8 @@ struct StepStats {  // device-resident, copied back with the step result
 };
 
 // KF: f^{n+1} = c (1 + d); yprev = clamp(f^{n+1}/f^n); statistics.           40 B/cell
-// The step is COMMITTED only when the true residual of the solve (st->resid_max, written by k_true_residual
-// earlier on the stream; the max over the batch) is finite and <= resid_limit: otherwise f and yprev are left
+// The step is COMMITTED only when the true residual of the solve (st->resid_rel_max, the componentwise backward error
+// written by k_true_residual earlier on the stream; the max over the batch) is finite and <= resid_limit: otherwise f and yprev are left
 // untouched and every problem counts as bad (the recursive BiCGSTAB residual alone can drift from the true one).
 __global__ void __launch_bounds__(kBlock) k_finish(const double* __restrict__ x, const double* __restrict__ cs,
                                                    double* __restrict__ f, double* __restrict__ yprev,
@@ -964,7 +976,7 @@ __global__ void __launch_bounds__(kBlock) k_finish(const double* __restrict__ x,
                                                    StepStats* st, double resid_limit) {
   const Scal* sc = scal + blockIdx.y;
   const size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool commit = st->resid_max <= resid_limit;   // false for NaN
+  const bool commit = st->resid_rel_max <= resid_limit;   // false for NaN
   double fmin = 1.0e300;
   int neg = 0;
   if (n < N) {

@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(kProblemThreads, 1) k_problem_steps(ProblemArg
   double* v = a.v + base; double* s = a.s + base; double* t = a.t + base;
 
   int it_total = 0, it = 0, state = 1, steps_ok = 0;
-  double rmax = 0.0, res_true = 0.0;
+  double rmax = 0.0, res_true = 0.0, res_rel = 0.0;
   for (int step = 0; step < a.nsteps; ++step) {
     // ---------------- assembly (Solver.cc:167-267 fused with :292-422) ----------------
     double acc[2] = {0.0, 0.0};
@@ -146,14 +146,24 @@ __global__ void __launch_bounds__(kProblemThreads, 1) k_problem_steps(ProblemArg
     // ---------------- true residual of the accepted solution ----------------
     const bool last = step == a.nsteps - 1;
     if (last) {
-      double m = 0.0;
+      double m = 0.0, mr = 0.0;   // absolute, and componentwise-relative (k_true_residual) true residual
       for (int n = tid; n < N; n += kProblemThreads) {
-        const double ax = it > 0 ? stencil_apply(x, (size_t)n, (size_t)N, ny, x[n], wW[n], wE[n], wS[n], wN[n]) : 0.0;
-        m = nmax(m, fabs(rhs[n] - ax));
+        double ax = 0.0, scale = 1.0;
+        if (it > 0) {
+          const double xW = x[n >= ny ? n - ny : n], xE = x[n + ny < N ? n + ny : n], xS = x[n > 0 ? n - 1 : n], xN = x[n + 1 < N ? n + 1 : n];
+          ax = x[n] + ((wW[n] * xW + wE[n] * xE) + (wS[n] * xS + wN[n] * xN));
+          scale += fabs(x[n]) + ((fabs(wW[n] * xW) + fabs(wE[n] * xE)) + (fabs(wS[n] * xS) + fabs(wN[n] * xN)));
+        }
+        const double ra = fabs(rhs[n] - ax);
+        m = nmax(m, ra);
+        mr = nmax(mr, ra / scale);
       }
       double mm[1] = {m};
       cta_allreduce<0, true>(mm, red);
       res_true = mm[0];
+      mm[0] = mr;
+      cta_allreduce<0, true>(mm, red);
+      res_rel = mm[0];
     }
     // ---------------- f^{n+1} = c (1 + d), predictor, statistics ----------------
     double fmin_l = 1.0e300;
@@ -198,8 +208,9 @@ __global__ void __launch_bounds__(kProblemThreads, 1) k_problem_steps(ProblemArg
     atomicMax(&a.stats->it_total_max, it_total);
     atomicAdd(&a.stats->it_sum_all, (unsigned long long)it_total);
     atomicMax(reinterpret_cast<unsigned long long*>(&a.stats->resid_max), (unsigned long long)__double_as_longlong(res_true));
+    atomicMax(reinterpret_cast<unsigned long long*>(&a.stats->resid_rel_max), (unsigned long long)__double_as_longlong(res_rel));
     atomicMin(&a.stats->steps_min, steps_ok);
-    if (state >= 2 || !(res_true == res_true)) atomicAdd(&a.stats->n_bad, 1);
+    if (state >= 2 || !(res_rel == res_rel)) atomicAdd(&a.stats->n_bad, 1);
   }
 }
 

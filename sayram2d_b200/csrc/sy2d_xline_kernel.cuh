@@ -64,6 +64,12 @@ struct XlineArgs {
   int* steps_done;   // [nbatch] time steps of the call completed per problem (zeroed by the host)
   int chunk;         // time steps per work item
   int nchunks;       // work items per problem = ceil(nsteps / chunk)
+  // Host-resident f without copy engines (sy2d_step_host with pinned, device-accessible buffers): the CTA that starts a
+  // problem's first item pulls its f straight from host memory over PCIe / C2C, the CTA that finishes its last item
+  // pushes the result back - in the queue's issue order (most expensive problems first), so that no problem waits for
+  // the upload of a sub-batch it happens to sit in and nothing is left to download when the last CTA ends.
+  const double* hin;   // [nbatch][N] device-accessible host pointer or NULL
+  double* hout;        // [nbatch][N] device-accessible host pointer or NULL
 };
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
@@ -94,6 +100,44 @@ __device__ __forceinline__ void cta_reduce_x(double (&v)[NV], int nsum, double* 
     v[k] = k < nsum ? warp_sum(y) : warp_max(y);
   }
   if (TRAIL) __syncthreads();
+}
+
+// Two sums with ONE shuffle tree: after the first exchange the lower half-warp carries the partial sums of a, the upper
+// half-warp those of b, and the remaining four steps reduce a single double (a 64-bit shuffle is two SHFL instructions,
+// so two sums cost 10 + 4 of them per phase instead of 20).  No trailing barrier: the caller rotates its buffers.
+__device__ __forceinline__ void cta_reduce_pair(double& a, double& b, double* red /* >= 64 */) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const bool up = (lane & 16) != 0;
+  double keep = up ? b : a;
+  keep += __shfl_xor_sync(full, up ? a : b, 16);
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) keep += __shfl_xor_sync(full, keep, o);
+  if ((lane & 15) == 0) red[(up ? 32 : 0) + w] = keep;
+  __syncthreads();
+  const double xa = lane < nw ? red[lane] : 0.0, xb = lane < nw ? red[32 + lane] : 0.0;
+  keep = up ? xb : xa;
+  keep += __shfl_xor_sync(full, up ? xa : xb, 16);
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) keep += __shfl_xor_sync(full, keep, o);
+  a = __shfl_sync(full, keep, 0);
+  b = __shfl_sync(full, keep, 16);
+}
+
+// One sum and the maximum of non-negative values.  The maximum goes through REDUX on the upper 32 bits of the doubles
+// (non-negative doubles order like their bit patterns; NaN - upper word 0x7ff8.... - wins, as it must): one instruction
+// per phase instead of a five-step tree, and the result is an UPPER bound (lower word all ones, relative excess
+// < 2^-20), so the stopping test max|r| <= tol it feeds can only become stricter.
+__device__ __forceinline__ void cta_reduce_sum_max(double& sum, double& mx, double* red /* >= 64 */) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  sum = warp_sum(sum);
+  unsigned hi = __reduce_max_sync(full, (unsigned)__double2hiint(mx));
+  if (lane == 0) { red[w] = sum; reinterpret_cast<unsigned*>(red + 32)[w] = hi; }
+  __syncthreads();
+  sum = warp_sum(lane < nw ? red[lane] : 0.0);
+  hi = __reduce_max_sync(full, lane < nw ? reinterpret_cast<const unsigned*>(red + 32)[lane] : 0u);
+  mx = __hiloint2double((int)hi, (int)0xffffffffu);
 }
 
 // one scaled row; kept out of line so that the R-times unrolled assembly loop stays small
@@ -167,8 +211,17 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
   double* yprev = a.yprev + base;
   const int step_begin = xa.steps_done[prob];
   const int step_end = min(step_begin + xa.chunk, a.nsteps);
+  if (xa.hin && step_begin == 0) {   // first item of the problem: f from the host buffer (coalesced 16-byte loads over PCIe)
+    const double* src = xa.hin + base;
+    if ((N & 1) == 0) {
+      for (int n = tid; n < N / 2; n += NT) reinterpret_cast<double2*>(f)[n] = reinterpret_cast<const double2*>(src)[n];
+    } else {
+      for (int n = tid; n < N; n += NT) f[n] = src[n];
+    }
+    __syncthreads();
+  }
   int it_total = 0, it = 0, state = 1, steps_ok = step_begin;   // steps_ok: time steps of the call this problem has completed
-  double rmax = 0.0, res_true = 0.0;
+  double rmax = 0.0, res_true = 0.0, res_rel = 0.0;
 
   for (int step = step_begin; step < step_end; ++step) {
     // ------------- assembly of the scaled rows owned by this thread -------------
@@ -412,7 +465,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
         a2[0] += val * rs[m];
         a2[1] += val * val;
       }
-      cta_reduce_x<2, false>(a2, 2, red + 64);
+      cta_reduce_pair(a2[0], a2[1], red + 64);
       omega = a2[1] > 0.0 ? a2[0] / a2[1] : 0.0;
       // y += alpha p + omega s (x = T^-1 y is formed once, after the loop: x = sum alpha phat + omega shat and
       // T^-1 is linear) ; r = s - omega t ; (rhat, r), max|r|
@@ -425,13 +478,13 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
         a3[0] += rhs_g[q] * rs[m];
         a3[1] = nmax(a3[1], fabs(rs[m]));
       }
-      cta_reduce_x<2, false>(a3, 1, red + 128);
+      cta_reduce_sum_max(a3[0], a3[1], red + 128);
       const double rho_new = a3[0];
       rmax = a3[1];
       ++it;
       first = false;
       if (rmax <= a.tol) state = 1;
-      else if (!(rmax == rmax) || rho_new == 0.0 || omega == 0.0) state = 3;
+      else if (!(rmax == rmax) || !(rho_new == rho_new) || rho_new == 0.0 || omega == 0.0) state = 3;
       else if (it >= a.maxit) state = 2;
       beta = (rho_new / rho) * (alpha / omega);
       rho = rho_new;
@@ -454,7 +507,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
       // previous slot of this thread or in the last slot of lane k-1.
       __syncthreads();   // every thread is past its last read of shat
       publish();
-      double mres = 0.0;
+      double mres = 0.0, mrel = 0.0;   // absolute, and componentwise-relative (k_true_residual) true residual
 #pragma unroll
       for (int m = 0; m < R; ++m) {
         const int i = i0 + m, q = m * NT + tid;
@@ -467,13 +520,17 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
             dinv_i = 1.0 + lp * e_s[mp * NT + tp];
           }
           const double dW = i > 0 ? hat[(i - 1) * hs + j] : 0.0, dE = i < nx - 1 ? hat[(i + 1) * hs + j] : 0.0;
-          const double ax = dinv_i * z[m] + ((lp * dW + e_s[q] * dE) + (wS_g[q] * hat[i * hs + jS] + wN_g[q] * hat[i * hs + jN]));
-          mres = nmax(mres, fabs(rhs_g[q] - ax) / dinv_i);
+          const double tW = lp * dW, tE = e_s[q] * dE, tS = wS_g[q] * hat[i * hs + jS], tN = wN_g[q] * hat[i * hs + jN];
+          const double ax = dinv_i * z[m] + ((tW + tE) + (tS + tN));
+          const double ra = fabs(rhs_g[q] - ax);
+          mres = nmax(mres, ra / dinv_i);
+          mrel = nmax(mrel, ra / (dinv_i * (1.0 + fabs(z[m])) + ((fabs(tW) + fabs(tE)) + (fabs(tS) + fabs(tN)))));
         }
       }
-      double mm[1] = {mres};
-      cta_reduce_x<1>(mm, 0, red);
+      double mm[2] = {mres, mrel};
+      cta_reduce_x<2>(mm, 0, red);
       res_true = mm[0];
+      res_rel = mm[1];
     }
     if (state >= 2) break;   // the solve stopped without converging (maxit, breakdown, NaN): f and yprev stay those of t^n
     double fneg = 0.0, fmin_neg = -1.0e300;
@@ -502,7 +559,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
       cta_reduce_x<2>(mm, 1, red);
       if (tid == 0) {
         if (mm[0] > 0.0) atomicAdd(&a.stats->negatives, (unsigned long long)mm[0]);
-        if (!(mm[1] == mm[1]) || !(res_true == res_true)) atomicAdd(&a.stats->n_bad, 1);   // non-finite f or residual
+        if (!(mm[1] == mm[1]) || !(res_rel == res_rel)) atomicAdd(&a.stats->n_bad, 1);   // non-finite f or residual
         const double mn = -(mm[1] - 1.0e300);
         unsigned long long* addr = reinterpret_cast<unsigned long long*>(&a.stats->fmin);
         unsigned long long old = *addr;
@@ -517,6 +574,14 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
     steps_ok = step + 1;
   }
   __syncthreads();   // (the failure path leaves the step loop without the barrier above)
+  if (xa.hout && (state >= 2 || step_end == a.nsteps)) {   // the problem leaves the queue: its f goes to the host buffer
+    double* dst = xa.hout + base;
+    if ((N & 1) == 0) {
+      for (int n = tid; n < N / 2; n += NT) reinterpret_cast<double2*>(dst)[n] = reinterpret_cast<const double2*>(f)[n];
+    } else {
+      for (int n = tid; n < N; n += NT) dst[n] = f[n];
+    }
+  }
   if (tid == 0) {
     Scal* sc = a.scal + prob;
     const int cost = (a.cost ? a.cost[prob] : 0) + it_total;
@@ -524,7 +589,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
     sc->it = it;
     sc->state = state;
     sc->rmax = rmax;
-    atomicMax(&a.stats->it_max, it);
+    if (state >= 2 || step_end == a.nsteps) atomicMax(&a.stats->it_max, it);   // iterations of the problem's LAST step of the call
     atomicAdd(&a.stats->it_sum_all, (unsigned long long)it_total);
     xa.steps_done[prob] = steps_ok;
     if (state >= 2) {   // failed: nothing of the failing step was committed, the problem leaves the queue
@@ -540,6 +605,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
       atomicMin(&a.stats->steps_min, steps_ok);
       atomicMax(&a.stats->it_total_max, cost);
       atomicMax(reinterpret_cast<unsigned long long*>(&a.stats->resid_max), (unsigned long long)__double_as_longlong(res_true));
+      atomicMax(reinterpret_cast<unsigned long long*>(&a.stats->resid_rel_max), (unsigned long long)__double_as_longlong(res_rel));
     }
   }
  }

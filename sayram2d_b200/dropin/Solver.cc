@@ -3,7 +3,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <exception>
+#include <chrono>
 #include <future>
+#include <thread>
 #include <stdexcept>
 #include <string>
 
@@ -116,11 +118,15 @@ bool Solver::gather_boundaries(double tt, bool force) {
 // update_Lambda + update_vertex_f of the reference (Solver.cc:57-65, 292-422) for time tt: gather what changed and hand
 // it to the library - blocking (first staging) or asynchronously into the second buffer set (every later step).
 void Solver::stage(double tt, bool force, bool async) {
-  if (gather_coefficients(force)) {
+  upload(gather_coefficients(force), gather_boundaries(tt, force), async);
+}
+
+void Solver::upload(bool coeffs, bool boundaries, bool async) {
+  if (coeffs) {
     if (async) check(sy2d_set_coeffs_async(ctx_, G_.data(), Dxx_.data(), Dxy_.data(), Dyy_.data(), itau_.data()));
     else check(sy2d_set_coeffs(ctx_, G_.data(), Dxx_.data(), Dxy_.data(), Dyy_.data(), itau_.data()));
   }
-  if (gather_boundaries(tt, force)) {
+  if (boundaries) {
     const double* lines[4];
     for (int s = 0; s < 4; ++s) lines[s] = bc_lines_[s].empty() ? nullptr : bc_lines_[s].data();
     if (async) check(sy2d_set_bc_async(ctx_, bc_types_, lines[0], lines[1], lines[2], lines[3]));
@@ -152,12 +158,16 @@ void Solver::update() {
   // on a copy stream) run on this thread WHILE the GPU advances step n on a helper thread; the new set is swapped in at
   // the start of step n+1.  The reference's order of effects (Solver.cc:286-289) is kept for everything the Solver's
   // result depends on; the only visible difference: eq.update(t^{n+1}) has already run if step n throws.
+  const long long begun = sy2d_steps_begun(ctx_);
   std::future<int> step = std::async(std::launch::async, [&] { return sy2d_step(ctx_, 1, &st); });
   std::exception_ptr err;
   try {
     const double tnext = static_cast<double>(istep_ + 1) * m.dt();
     eq.update(tnext);
-    stage(tnext, false, true);
+    const bool coeffs = gather_coefficients(false), boundaries = gather_boundaries(tnext, false);
+    // step n must have taken ITS fields (swap-in at the start of sy2d_step) before those of step n+1 are staged
+    while (sy2d_steps_begun(ctx_) == begun && step.wait_for(std::chrono::seconds(0)) != std::future_status::ready) std::this_thread::yield();
+    upload(coeffs, boundaries, true);
   } catch (...) {
     err = std::current_exception();
   }

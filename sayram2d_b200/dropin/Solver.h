@@ -68,6 +68,7 @@ class Solver {
   bool gather_coefficients(bool force);   // false: the Equation's dirty counter says nothing changed
   bool gather_boundaries(double t, bool force);
   void stage(double t, bool force, bool async);
+  void upload(bool coeffs, bool boundaries, bool async);
   void account(const sy2d_stats& st);
   void check(int rc) const;
 };

@@ -73,6 +73,7 @@ def load_library():
         "sy2d_set_coeffs_async": (C.c_int, [vp, dp, dp, dp, dp, dp]),
         "sy2d_set_bc_async": (C.c_int, [vp, ip, dp, dp, dp, dp]),
         "sy2d_stage_swaps": (C.c_longlong, [vp]),
+        "sy2d_steps_begun": (C.c_longlong, [vp]),
         "sy2d_set_f": (C.c_int, [vp, dp]),
         "sy2d_set_f_dev": (C.c_int, [vp, vp]),
         "sy2d_put_f": (C.c_int, [vp, dp]),
@@ -84,6 +85,7 @@ def load_library():
         "sy2d_step_count": (C.c_longlong, [vp]),
         "sy2d_dump_operator": (C.c_int, [vp, dp, dp]),
         "sy2d_dump_vertex_f": (C.c_int, [vp, dp]),
+        "sy2d_dump_scaled_operator": (C.c_int, [vp, dp, dp, dp]),
         "sy2d_debug_vcycle": (C.c_int, [vp, dp, dp, dp, dp]),
         "sy2d_set_profiling": (C.c_int, [vp, C.c_int]),
         "sy2d_get_profile": (C.c_int, [vp, C.POINTER(Profile)]),
@@ -273,6 +275,35 @@ class Engine:
     def stage_swaps(self):
         return self.lib.sy2d_stage_swaps(self._ctx)
 
+    def steps_begun(self):
+        return self.lib.sy2d_steps_begun(self._ctx)
+
+    def step_overlapped(self, stage_next, nsteps=1):
+        """Runs step(nsteps) on a helper thread and calls stage_next() - which should use set_coeffs_async /
+        set_bc_async - on this thread once the step has taken its own fields (sy2d_steps_begun advanced)."""
+        import threading
+        import time as _t
+        res = {}
+
+        def work():
+            try:
+                res["st"] = self.step(nsteps)
+            except BaseException as ex:  # noqa: BLE001
+                res["err"] = ex
+
+        begun = self.steps_begun()
+        th = threading.Thread(target=work)
+        th.start()
+        while self.steps_begun() == begun and th.is_alive():
+            _t.sleep(0)
+        try:
+            stage_next()
+        finally:
+            th.join()
+        if "err" in res:
+            raise res["err"]
+        return res["st"]
+
     def set_f(self, f):
         self._check(self.lib.sy2d_set_f(self._ctx, _dp(_f64(f, self.shape, "f"))))
 
@@ -324,6 +355,14 @@ class Engine:
         rhs = np.empty(self.shape)
         self._check(self.lib.sy2d_dump_operator(self._ctx, _dp(diags), _dp(rhs)))
         return dict(diag=diags[0], W=diags[1], E=diags[2], S=diags[3], N=diags[4], R=rhs)
+
+    def dump_scaled_operator(self):
+        """Scaled system of the current f by the configured assembly kernel -> (w4, rhs, cs)."""
+        w4 = np.empty((4,) + self.shape)
+        rhs = np.empty(self.shape)
+        cs = np.empty(self.shape)
+        self._check(self.lib.sy2d_dump_scaled_operator(self._ctx, _dp(w4), _dp(rhs), _dp(cs)))
+        return w4, rhs, cs
 
     def dump_vertex_f(self):
         vf = np.empty((self.nbatch, self.nx + 1, self.ny + 1))

@@ -365,7 +365,6 @@ def test_time_dependent_fields_and_boundary_data(tmp_path):
         eng.close()
     # the asynchronous route: the fields of step n+1 are staged into the second buffer set while step n runs on another
     # host thread (sy2d_set_coeffs_async / sy2d_set_bc_async), and swapped in at the start of step n+1
-    import threading
     for engine, precond in ((1, 2), (2, 1)):
         eng = sy.Engine(g["x_edges"], g["y_edges"], 0.002)
         eng.set_options(engine=engine, precond=precond)
@@ -374,15 +373,12 @@ def test_time_dependent_fields_and_boundary_data(tmp_path):
         eng.set_coeffs_async(eq.G, eq.Dxx, eq.Dxy, eq.Dyy, eq.inv_tau)      # also the very first set may come this way
         eng.set_bc_async(eq.bc, *eq.dirichlet_lines(0.0))
         for step in range(60):
-            res = {}
-            th = threading.Thread(target=lambda: res.update(st=eng.step(1)))
-            th.start()
-            tn = (step + 1) * 0.002
-            eq.update(tn)
-            eng.set_coeffs_async(eq.G, eq.Dxx, eq.Dxy, eq.Dyy, eq.inv_tau)
-            eng.set_bc_async(eq.bc, *eq.dirichlet_lines(tn))
-            th.join()
-            assert res["st"]["negatives"] == 0
+            def stage_next(tn=(step + 1) * 0.002):
+                eq.update(tn)
+                eng.set_coeffs_async(eq.G, eq.Dxx, eq.Dxy, eq.Dyy, eq.inv_tau)
+                eng.set_bc_async(eq.bc, *eq.dirichlet_lines(tn))
+            st = eng.step_overlapped(stage_next)
+            assert st["negatives"] == 0
             if (step + 1) % 20 == 0:
                 assert max_rel(eng.get_f()[0], g[f"f_{(step + 1) // 20}"]) < PARITY, (engine, step)
         assert eng.stage_swaps() == 2 * 60
@@ -425,6 +421,55 @@ def test_tiled_assembly_equals_per_cell_assembly(tag):
         e.close()
 
 
+@pytest.mark.parametrize("tag,nx,ny,nbatch,bc", [("syn", 1024, 1024, 1, None), ("syn", 100, 70, 3, None), ("syn", 23, 34, 2, None),
+                                                 ("syn", 264, 96, 1, None), ("syn", 61, 91, 2, (1, 0, 1, 0)), ("syn", 160, 64, 1, (1, 1, 1, 1)),
+                                                 ("nu48x40", 0, 0, 1, None), ("lc80", 0, 0, 2, None)])
+def test_assembly_kernels_agree(tag, nx, ny, nbatch, bc):
+    """The three fast engine-1 assembly kernels - shared-memory tiles with plain loads (2), warp-marching strips (3),
+    TMA-staged tiles (4) - evaluate every face ONCE with the same expression and sum a row in the same order: the scaled
+    operator, the right-hand side and the column scale of (2) and (4) must be IDENTICAL, those of (3) equal to the last
+    bits (full-size, ragged, odd-ny, batched, non-uniform and zero-flux grids; odd ny has no TMA variant).  The
+    one-thread-per-cell kernel (1) evaluates a face from both of its cells and agrees to round-off."""
+    if tag == "syn":
+        xe, ye = fields.uniform_edges(nx, ny)
+        Dxx, Dxy, Dyy, inv_tau = fields.synthetic_tensor(xe, ye)
+        G = fields.ay_G(xe, ye)
+        f0, bct, lines = fields.ay_init_and_bc(xe, ye)
+        if bc is not None:   # other boundary types: every side gets a Dirichlet line (unused on the zero-flux sides)
+            bct = list(bc)
+            rng = np.random.default_rng(5)
+            lines = [rng.uniform(0.0, 1e-3, ny + 1), rng.uniform(0.0, 1e-3, ny + 1), rng.uniform(0.0, 1e-3, nx + 1), rng.uniform(0.0, 1e-3, nx + 1)]
+    else:
+        g = load_golden(tag)
+        xe, ye, G, Dxx, Dxy, Dyy, inv_tau, f0 = (g[k] for k in ("x_edges", "y_edges", "G", "Dxx", "Dxy", "Dyy", "inv_tau", "f_0"))
+        bct, lines = bc_for(CASE_OF[tag], xe, ye)
+    rep = lambda a: np.broadcast_to(a, (nbatch,) + a.shape).copy()
+    scale = (1.0 + 0.25 * np.arange(nbatch))[:, None, None]
+    eng = sy.Engine(xe, ye, 0.002, nbatch=nbatch)
+    eng.set_options(engine=1, precond=0)
+    eng.set_coeffs(rep(G), rep(Dxx) * scale, rep(Dxy) * scale, rep(Dyy) * scale, rep(inv_tau))
+    eng.set_bc(bct, *lines)
+    eng.set_f(rep(f0))
+    eng.step(2)                       # a predictor state (yprev != 1) and an f that is not the initial one
+    ref = None
+    variants = (2, 3, 4, 1) if (len(ye) - 1) % 2 == 0 else (2, 3, 1)
+    for variant in variants:
+        _force_assembly(eng, variant)
+        got = eng.dump_scaled_operator()
+        if ref is None:
+            ref = got
+            continue
+        for name, a, b in zip(("w4", "rhs", "cs"), got, ref):
+            if variant == 4:   # TMA staging changes where the operands come from, not the instruction stream
+                assert np.array_equal(a, b), (variant, name, float(np.max(np.abs(a - b))))
+            else:
+                # 3: the same expressions, but the compiler contracts a * b + c * d into FMAs differently in a different kernel
+                # body (last-bit differences); 1: the per-cell kernel also evaluates a face from both of its cells
+                tol = 1e-14 if variant == 3 else 1e-12
+                assert np.max(np.abs(a - b)) <= tol * max(1.0, np.max(np.abs(b))), (variant, name, float(np.max(np.abs(a - b))))
+    eng.close()
+
+
 @pytest.mark.parametrize("nx,ny,nbatch", [(1024, 1024, 1), (100, 70, 3), (23, 34, 2), (264, 96, 1)])
 def test_tma_assembly_equals_the_tiled_kernel(nx, ny, nbatch):
     """TMA-staged halo tiles (zero-filled outside the domain, two-stage ring, several tiles per CTA)
@@ -437,7 +482,7 @@ def test_tma_assembly_equals_the_tiled_kernel(nx, ny, nbatch):
     rep = lambda a: np.broadcast_to(a, (nbatch,) + a.shape).copy()
     scale = (1.0 + 0.25 * np.arange(nbatch))[:, None, None]
     out = []
-    for variant in (0, 2):
+    for variant in (4, 2, 3):
         eng = sy.Engine(xe, ye, 0.002, nbatch=nbatch)
         eng.set_options(engine=1)
         _force_assembly(eng, variant)
@@ -448,7 +493,7 @@ def test_tma_assembly_equals_the_tiled_kernel(nx, ny, nbatch):
         assert st["negatives"] == 0
         out.append(eng.get_f())
         eng.close()
-    assert max_rel(out[0], out[1]) < 1e-11
+    assert max_rel(out[0], out[1]) < 1e-11 and max_rel(out[2], out[1]) < 1e-11
 
 
 def test_step_host_pipelined_matches_resident_stepping():
@@ -476,3 +521,45 @@ def test_step_host_pipelined_matches_resident_stepping():
     assert st["kernel_launches"] >= 2 and piped.step_count() == 3
     assert max_rel(h_in, f_ref) < 1e-11 and max_rel(piped.get_f(), f_ref) < 1e-11
     ref.close(); piped.close()
+
+
+@pytest.mark.parametrize("mode", ["direct", "copy"])
+def test_step_host_with_pinned_buffers(mode):
+    """sy2d_step_host with pinned (device-accessible) host buffers: the pipelined copy-engine route (default) and the
+    opt-in route where the x-line kernel pulls every problem's f from the host buffer when it starts the problem and
+    pushes the result back when it finishes it (SY2D_HOST_IO=direct; measured slower: an SM's loads from system memory
+    run at ~1 GB/s); both must equal device-resident stepping bit for bit."""
+    import os
+    import torch
+    lc = load_golden("lc80")
+    nb = 700
+    a, b = fields.ensemble_scales(np.arange(nb) * 5 % 4096)
+    sc = lambda arr, s: np.ascontiguousarray(arr[None] * s[:, None, None])
+    one = np.ones(nb)
+    bct, lines = bc_for("LC", lc["x_edges"], lc["y_edges"])
+    os.environ["SY2D_HOST_IO"] = mode
+    try:
+        engs = []
+        for _ in range(2):
+            e = sy.Engine(lc["x_edges"], lc["y_edges"], lc["meta"]["dt"], nbatch=nb)
+            e.set_coeffs(sc(lc["G"], one), sc(lc["Dxx"], a), sc(lc["Dxy"], a), sc(lc["Dyy"], a), sc(lc["inv_tau"], b))
+            e.set_bc(bct, *lines)
+            e.set_f(sc(lc["f_0"], one))
+            engs.append(e)
+    finally:
+        del os.environ["SY2D_HOST_IO"]
+    ref, host = engs
+    ref.step(5)
+    f_ref = ref.get_f()
+    pin = [torch.empty((nb, 80, 80), dtype=torch.float64).pin_memory() for _ in range(2)]
+    pin[0].numpy()[...] = sc(lc["f_0"], one)
+    h_in, h_out = pin[0].numpy(), pin[1].numpy()
+    st = host.step_host(h_in, h_out, 2)
+    h_in, h_out = h_out, h_in
+    for _ in range(3):
+        st = host.step_host(h_in, h_out, 1)
+        h_in, h_out = h_out, h_in
+    assert host.step_count() == 5 and st["negatives"] == 0
+    assert np.array_equal(h_in, f_ref) and np.array_equal(host.get_f(), f_ref)
+    assert st["kernel_launches"] == (2 if mode == "direct" else st["kernel_launches"]) and (mode == "direct" or st["kernel_launches"] > 2)
+    ref.close(); host.close()
