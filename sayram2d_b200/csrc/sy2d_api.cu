@@ -45,7 +45,7 @@ struct sy2d_ctx {
   // grid caps of the grid-stride kernels (tuning: SY2D_CTAS_PER_SM, SY2D_ASM_CTAS_PER_SM).  6 = the CTAs of 256 threads x 40
   // registers that are resident on an SM at once: one full wave, no tail (profiles/sweep_caps_steps.py: 1024^2 4.98 -> 4.81 ms
   // per step against 16, 2048^2 15.2 -> 14.9, 4096^2 equal; 8 is worse everywhere - a partial second wave)
-  int ctas_per_sm = 6, asm_ctas_per_sm = 4, march_ctas_per_sm = 4;
+  int ctas_per_sm = 6, asm_ctas_per_sm = 4, march_ctas_per_sm = 5;
   int asm_kernel = 0;   // default fast assembly: 0 TMA-staged tiles, 1 warp-marching (SY2D_ASM_KERNEL)
   int pipe_max = 32, pipe_forced = 0;   // sy2d_step_host: at most pipe_max pipelined sub-batches (SY2D_PIPE_CHUNKS forces a count)
   std::string err;
@@ -290,7 +290,7 @@ void launch_iteration_xline(sy2d_ctx* c) {
 
 
 // Tensor maps for the TMA-staged assembly: [nbatch][local rows][ny] fp64 arrays seen as 3-D tensors (ny fastest),
-// halo boxes of 36 x 10 cells, out-of-bounds elements zero-filled.
+// halo boxes of 36 x 10 cells and interior boxes of 32 x 8 cells, out-of-bounds elements zero-filled.
 // cuTensorMapEncodeTiled is a driver entry point; it is resolved through the runtime, so the library
 // keeps linking against libcudart only.
 bool tma_encode_maps(sy2d_ctx* c, AsmMaps* host_maps, double* tx, double* ty, double* cxy, double* U, double* Ud);
@@ -319,13 +319,12 @@ bool tma_encode_maps(sy2d_ctx* c, AsmMaps* host_maps, double* tx, double* ty, do
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
   EncodeFn encode = reinterpret_cast<EncodeFn>(fn);
-  (void)U; (void)Ud;   // no halo, used once per cell: loaded directly by the kernel
-  double* arrs[5] = {c->f, c->yprev, tx, ty, cxy};
+  double* arrs[7] = {c->f, c->yprev, tx, ty, cxy, U, Ud};
   const cuuint64_t dims[3] = {(cuuint64_t)c->ny, (cuuint64_t)c->nx, (cuuint64_t)c->nbatch};
   const cuuint64_t strides[2] = {(cuuint64_t)c->ny * sizeof(double), (cuuint64_t)c->N * sizeof(double)};
   const cuuint32_t estr[3] = {1, 1, 1};
-  for (int k = 0; k < 5; ++k) {
-    const cuuint32_t box[3] = {(cuuint32_t)kTmaHaloJ, (cuuint32_t)kTmaHaloI, 1};
+  for (int k = 0; k < 7; ++k) {
+    const cuuint32_t box[3] = {(cuuint32_t)(k < 5 ? kTmaHaloJ : kTJ), (cuuint32_t)(k < 5 ? kTmaHaloI : kTI), 1};
     const CUresult r = encode(&host_maps->m[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, arrs[k], dims, strides, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,  // (L2 promotion raises an illegal-instruction fault with these boxes on B200 / driver 580: profiles/tma_probe.cu)
                              
@@ -350,12 +349,15 @@ void launch_march(sy2d_ctx* c, const Geometry& geo, const AssembleOut& o, int gi
 void launch_assembly(sy2d_ctx* c, const Geometry& geo, const AssembleOut& o, int variant) {
   const int tiles_i = (c->nx + kTI - 1) / kTI, tiles_j = (c->ny + kTJ - 1) / kTJ;
   const bool tiled = c->nx >= 2 * kTI && c->ny >= kTJ && variant != 1;
-  if (tiled && (variant == 3 || (variant == 0 && c->asm_kernel == 1))) {
+  // default: TMA-staged tiles (the fastest of the three at every size measured: 34 / 101 / 364 us at 1024^2 / 2048^2 /
+  // 4096^2 against 37 / 104 / 410 us for the marching kernel and 55 / 196 / 767 us for the plain-load tiles); where no
+  // tensor map exists (odd ny) the marching kernel, which has no alignment requirement
+  if (tiled && (variant == 3 || (variant == 0 && (c->asm_kernel == 1 || !c->have_tma)))) {
     launch_march(c, geo, o, 0, 0, c->nx, 0);
   } else if (tiled && c->have_tma && (variant == 0 || variant == 4)) {
     const int ntiles = tiles_i * tiles_j;
     const unsigned ctas = (unsigned)std::min<size_t>((size_t)ntiles, std::max<size_t>(1, (size_t)c->sm_count * c->asm_ctas_per_sm / (size_t)c->nbatch));
-    k_assemble_tma<<<dim3(ctas, (unsigned)c->nbatch, 1), kTI * kTJ, kTmaSmemBytes, c->stream>>>(c->d_tma_maps, c->U, c->Ud, geo, o, tiles_j, ntiles, 0, 0, c->nx, 0);
+    k_assemble_tma<<<dim3(ctas, (unsigned)c->nbatch, 1), kTI * kTJ, kTmaSmemBytes, c->stream>>>(c->d_tma_maps, geo, o, tiles_j, ntiles, 0, 0, c->nx, 0);
   } else if (tiled) {
     k_assemble_tiled<<<dim3(capped_blocks(c, (size_t)tiles_i * tiles_j, 1), (unsigned)c->nbatch, 1), kTI * kTJ, 0, c->stream>>>(
         c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud, geo, o, tiles_j, 0, 0, c->nx, 0);
@@ -927,12 +929,12 @@ int step_slab_impl(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
     o.wW = c->wW; o.wE = c->wE; o.wS = c->wS; o.wN = c->wN; o.rhs = c->rhs; o.cs = c->cs;
     o.scal = c->scal; o.n_active = c->d_nactive; o.tol = c->opt.tol; o.local_rows = c->nx;
     if (mg) o.om = c->mg_om0;
-    if (c->opt.reserved[0] == 3 || (c->opt.reserved[0] == 0 && c->asm_kernel == 1)) {
+    if (c->opt.reserved[0] == 3 || (c->opt.reserved[0] == 0 && (c->asm_kernel == 1 || !c->have_tma))) {
       launch_march(c, geo, o, c->i_lo - 1, 1, rows + 1, 1);
     } else if (c->have_tma && (c->opt.reserved[0] == 0 || c->opt.reserved[0] == 4)) {
       const int ntiles = tiles_i * tiles_j;
       const unsigned ctas = (unsigned)std::min<size_t>((size_t)ntiles, (size_t)c->sm_count * c->asm_ctas_per_sm);
-      k_assemble_tma<<<dim3(ctas, 1, 1), kTI * kTJ, kTmaSmemBytes, c->stream>>>(c->d_tma_maps, c->U, c->Ud, geo, o, tiles_j, ntiles, c->i_lo - 1, 1, rows + 1, 1);
+      k_assemble_tma<<<dim3(ctas, 1, 1), kTI * kTJ, kTmaSmemBytes, c->stream>>>(c->d_tma_maps, geo, o, tiles_j, ntiles, c->i_lo - 1, 1, rows + 1, 1);
     } else {
       k_assemble_tiled<<<dim3(capped_blocks(c, (size_t)tiles_i * tiles_j, 1), 1, 1), kTI * kTJ, 0, c->stream>>>(
           c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud, geo, o, tiles_j, c->i_lo - 1, 1, rows + 1, 1);

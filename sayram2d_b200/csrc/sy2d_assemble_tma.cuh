@@ -2,20 +2,20 @@
 //
 // Same tile decomposition and the same per-vertex / per-face / per-row arithmetic as k_assemble_tiled
 // (bit-identical rows), but the staging is done by the TMA engine instead of ~25 % of the kernel's
-// instructions: one thread issues five cp.async.bulk.tensor loads per tile - the 10 x 36 halo boxes of
-// f, yprev, tx, ty, cxy - into a three-stage shared-memory ring, so the loads of tiles k+1 and k+2 are in
-// flight while the CTA computes tile k (mbarrier complete_tx signalling).  U and Ud have no halo and are
-// used once per cell: every thread loads its own two values straight into registers before it waits for the
-// tile, which keeps the ring at 14.7 KB per stage (three stages and four CTAs per SM fit in 227 KB).
+// instructions: one thread issues seven cp.async.bulk.tensor loads per tile - the 10 x 36 halo boxes of
+// f, yprev, tx, ty, cxy and the 8 x 32 interior boxes of U, Ud - into a two-stage shared-memory ring, and
+// the loads of tile k+1 are in flight while the CTA computes tile k (mbarrier complete_tx signalling).
 // Out-of-domain halo cells are zero-filled by the TMA unit; they only ever meet zero weights, exactly
 // like the clamped reads of the other kernels.
 //
-// Row-slab contexts use the same kernel on their LOCAL arrays (one halo row on each side, filled by the
-// halo exchange): memory and TMA coordinates are local rows, geometry and boundary logic use global rows
-// i = gi0 + li, and only the owned rows [li_begin, li_end) are written.
+// Row-slab contexts use the same kernel on their LOCAL arrays (one halo row on each side, filled by the halo
+// exchange): memory and TMA coordinates are local rows, geometry and boundary logic use global rows i = gi0 + li,
+// and only the owned rows [li_begin, li_end) are written.
 //
-// Requirements: ny even (global strides of a tensor map are multiples of 16 bytes).  Algorithmic HBM bytes:
-// 104 per cell (112 with the multigrid row weights), halo re-reads come from L2.
+// Requirements: ny even (global strides of a tensor map are multiples of 16 bytes).  Algorithmic HBM bytes: 104 per
+// cell (112 with the multigrid row weights), halo re-reads come from L2.  Tried in round 2 and reverted: a three-stage
+// ring with U and Ud loaded straight into registers (14.7 KB per stage, still four CTAs per SM): 362 -> 398 us at
+// 4096^2 - the two direct loads per cell sit exposed on the long scoreboard (3.7 against 1.7 stall cycles per issue).
 #pragma once
 #include <cuda.h>
 
@@ -29,12 +29,13 @@ namespace sy2d {
 constexpr int kTmaHaloI = kTI + 2, kTmaHaloJ = kTJ + 4;
 constexpr int kTmaHaloElems = kTmaHaloI * kTmaHaloJ;                  // 360 doubles = 2880 B
 constexpr int kTmaHaloPad = (kTmaHaloElems * 8 + 127) / 128 * 16;     // doubles per halo buffer, 128-B multiple (368)
-constexpr int kTmaStageDoubles = 5 * kTmaHaloPad;
-constexpr unsigned kTmaStageBytes = 5u * kTmaHaloElems * 8u;          // bytes the TMA engine delivers per tile
-constexpr int kTmaStages = 3;
+constexpr int kTmaInnerElems = kTI * kTJ;                             // 256 doubles = 2048 B
+constexpr int kTmaStageDoubles = 5 * kTmaHaloPad + 2 * kTmaInnerElems;
+constexpr unsigned kTmaStageBytes = 5u * kTmaHaloElems * 8u + 2u * kTmaInnerElems * 8u;  // bytes the TMA engine delivers per tile
+constexpr int kTmaStages = 2;
 
-struct AsmMaps {   // f, yprev, tx, ty, cxy: box (36, 10, 1); dims (ny, rows of the local array, nbatch)
-  CUtensorMap m[5];
+struct AsmMaps {   // f, yprev, tx, ty, cxy: box (36, 10, 1); U, Ud: box (32, 8, 1); dims (ny, rows of the local array, nbatch)
+  CUtensorMap m[7];
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -75,12 +76,11 @@ struct TmaSmem {
 };
 constexpr size_t kTmaSmemBytes = sizeof(TmaSmem);
 
-// The five tensor maps live in global memory (written once by the host at context creation).
+// The seven tensor maps live in global memory (written once by the host at context creation).
 // Rows: li = local row of the arrays (tensor-map coordinate), i = gi0 + li the global row; the kernel assembles local
 // rows [li_begin, li_end).  Single-GPU: gi0 = 0, li_begin = 0, li_end = nx, defer = 0.
-__global__ void __launch_bounds__(kTI * kTJ, 4) k_assemble_tma(const AsmMaps* __restrict__ maps_ptr, const double* __restrict__ U,
-                                                               const double* __restrict__ Ud, Geometry g, AssembleOut o, int tiles_j,
-                                                               int ntiles, int gi0, int li_begin, int li_end, int defer) {
+__global__ void __launch_bounds__(kTI * kTJ, 4) k_assemble_tma(const AsmMaps* __restrict__ maps_ptr, Geometry g, AssembleOut o, int tiles_j, int ntiles,
+                                                               int gi0, int li_begin, int li_end, int defer) {
   const AsmMaps& maps = *maps_ptr;
   extern __shared__ __align__(128) unsigned char tma_raw[];   // the only shared memory of the kernel: starts at a 128-B boundary
   TmaSmem& sm = *reinterpret_cast<TmaSmem*>(tma_raw);
@@ -93,26 +93,24 @@ __global__ void __launch_bounds__(kTI * kTJ, 4) k_assemble_tma(const AsmMaps* __
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  auto issue = [&](int tile, int s) {   // one thread: arm the barrier, launch the five box loads of a tile
+  auto issue = [&](int tile, int s) {   // one thread: arm the barrier, launch the seven box loads of a tile
     const int tile_i = tile / tiles_j, tile_j = tile - tile_i * tiles_j;
-    const int L0 = li_begin + tile_i * kTI, J0 = tile_j * kTJ;
+    const int L0 = li_begin + tile_i * kTI, J0 = tile_j * kTJ;   // local row / column of the tile origin
     double* d = sm.stage[s];
     mbar_expect_tx(&sm.full[s], kTmaStageBytes);
 #pragma unroll
     for (int k = 0; k < 5; ++k) tma_load_3d(d + k * kTmaHaloPad, &maps.m[k], J0 - 2, L0 - 1, (int)blockIdx.y, &sm.full[s]);
+    tma_load_3d(d + 5 * kTmaHaloPad, &maps.m[5], J0, L0, (int)blockIdx.y, &sm.full[s]);
+    tma_load_3d(d + 5 * kTmaHaloPad + kTmaInnerElems, &maps.m[6], J0, L0, (int)blockIdx.y, &sm.full[s]);
   };
-  if (tid == 0) {
-#pragma unroll
-    for (int d = 0; d < kTmaStages - 1; ++d)
-      if ((int)blockIdx.x + d * (int)gridDim.x < ntiles) issue(blockIdx.x + d * gridDim.x, d);
-  }
+  if (tid == 0 && (int)blockIdx.x < ntiles) issue(blockIdx.x, 0);
   double rr = 0.0, rabs = 0.0;
   int it = 0;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-    const int s = it % kTmaStages;
-    const unsigned parity = (unsigned)(it / kTmaStages) & 1u;
-    // the stage refilled here was fully consumed in the previous iteration (trailing __syncthreads)
-    if (tid == 0 && tile + (kTmaStages - 1) * (int)gridDim.x < ntiles) issue(tile + (kTmaStages - 1) * gridDim.x, (it + kTmaStages - 1) % kTmaStages);
+    const int s = it & 1;
+    const unsigned parity = (unsigned)(it >> 1) & 1u;
+    // the other stage was fully consumed in the previous iteration (trailing __syncthreads)
+    if (tid == 0 && tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x, s ^ 1);
     const int tile_i = tile / tiles_j, tile_j = tile - tile_i * tiles_j;
     const int L0 = li_begin + tile_i * kTI;          // local row of the tile origin
     const int I0 = gi0 + L0, J0 = tile_j * kTJ;      // global row / column of the tile origin
@@ -121,14 +119,13 @@ __global__ void __launch_bounds__(kTI * kTJ, 4) k_assemble_tma(const AsmMaps* __
     const double* txs = ys + kTmaHaloPad;
     const double* tys = txs + kTmaHaloPad;
     const double* cxs = tys + kTmaHaloPad;
+    const double* Us = cxs + kTmaHaloPad;            // [8][32] interior tiles
+    const double* Uds = Us + kTmaInnerElems;
 #define H(arr, aa, bb) arr[(aa) * kTmaHaloJ + (bb) + 1]
     const bool edge_tile = I0 == 0 || I0 + kTI >= nx || J0 == 0 || J0 + kTJ >= ny || L0 + kTI > li_end;
-    // vertex weights of the thread's own vertex and the cell's U, Ud: fetched before the wait so that their latency overlaps it
-    double wl = 0.0, wr = 0.0, wb = 0.0, wt = 0.0, Uc = 0.0, Udc = 0.0;
+    // vertex weights of the thread's own vertex: fetched before the wait so that their latency overlaps it
+    double wl = 0.0, wr = 0.0, wb = 0.0, wt = 0.0;
     if (!edge_tile) { wl = g.wxL[I0 + a]; wr = g.wxR[I0 + a]; wb = g.wyB[J0 + b]; wt = g.wyT[J0 + b]; }
-    const bool own_cell = !edge_tile || (I0 + a < nx && L0 + a < li_end && J0 + b < ny);
-    const size_t c0 = base + (size_t)(L0 + a) * ny + (J0 + b);
-    if (own_cell) { Uc = U[c0]; Udc = Ud[c0]; }
     mbar_wait(&sm.full[s], parity);
     // 2. vertices (I0 + a', J0 + b').  The extra row / column of every stage goes to a different warp
     // (1 .. 4), so that no warp does more than one extra pass between two barriers.
@@ -182,7 +179,8 @@ __global__ void __launch_bounds__(kTI * kTJ, 4) k_assemble_tma(const AsmMaps* __
     __syncthreads();
     // 4. rows
     const int i = I0 + a, j = J0 + b;
-    if (own_cell) {
+    if (!edge_tile || (i < nx && L0 + a < li_end && j < ny)) {
+      const size_t c0 = base + (size_t)(L0 + a) * ny + j;
       const double f00 = H(fs, a + 1, b + 1);
       double diag = 0.0, R = 0.0, oW = 0.0, oE = 0.0, oS = 0.0, oN = 0.0;
       if (!edge_tile) {
@@ -204,8 +202,8 @@ __global__ void __launch_bounds__(kTI * kTJ, 4) k_assemble_tma(const AsmMaps* __
           if (j == ny - 1 && g.bc[3] == 0) diag += dirichlet_face((tyP + cP) * vNE + (tyP - cP) * vNW, (tyP + cP) + (tyP - cP), f00, R);
         }
       }
-      diag += Udc;
-      R += Uc * f00;
+      diag += Uds[a * kTJ + b];
+      R += Us[a * kTJ + b] * f00;
       const double cs0 = f00 * H(ys, a + 1, b + 1);
       const double om = diag * cs0;
       const double dscale = sy2d_div(1.0, om);
