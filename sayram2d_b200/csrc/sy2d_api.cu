@@ -71,6 +71,11 @@ struct sy2d_ctx {
   MgLevels mg;
   double* mg_rc[kMgMaxLevels] = {};   // writable right-hand sides of the coarse levels
   double *mg_om0 = nullptr, *mg_shat = nullptr;
+  unsigned* mg_tail_ctr = nullptr;      // [nbatch] barrier counters of the fused coarse-tail kernel (zero between launches)
+  int mg_tail_ny = 0;                   // SY2D_MG_TAIL_NY = n: levels with at most n columns run inside the fused k_mg_tail kernel.  Off by
+                                        // default: at 1024^2 it halves the launches of a step (2878 -> 1558 in 5 steps) and changes nothing
+                                        // (4.62 -> 4.68 ms per step) - a stage costs its dependent chain (loads, sweep, scan, sweep, scan,
+                                        // store: ~7 us), not its launch, whether it is a kernel or a stage behind a barrier
   // row-slab mode, exact lines across ranks (spike correction, sy2d_mg.cuh): per level the damped spikes of the
   // own rows and the gathered spike tips [nranks][4][ny_l]; per solve the tips [2][ny] / gathered [nranks][2][ny] / coefficients
   double* mg_spW[kMgMaxLevels] = {};
@@ -135,6 +140,8 @@ struct sy2d_ctx {
   // iteration-chunk graph
   cudaGraphExec_t chunk_exec = nullptr;
   cudaGraphExec_t one_exec = nullptr;   // multigrid: a single iteration + the convergence poll
+  cudaGraphExec_t slab_exec = nullptr;  // slab mode over NCCL: one multigrid-preconditioned iteration (kernels AND collectives) + the poll
+  int slab_graph = 1;                   // SY2D_SLAB_GRAPH=0: issue the slab iteration call by call
   int mg_last_iters = 0;                // iterations of the previous time step (issue plan of the next one)
   bool mg_off = false;                  // multigrid failed on the current step: it is being redone with the x-line iteration
   int chunk_iters = 0;
@@ -422,8 +429,33 @@ int mg_alloc(sy2d_ctx* c) {
         (rc = grab((size_t)2 * c->ny, &c->mg_coef)))
       return rc;
   }
+  if (!c->mg_tail_ctr) {
+    CU(cudaMalloc(reinterpret_cast<void**>(&c->mg_tail_ctr), c->nbatch * sizeof(unsigned)));
+    CU(cudaMemsetAsync(c->mg_tail_ctr, 0, c->nbatch * sizeof(unsigned), c->stream));
+  }
   c->mg_nlev = nlev;
   return SY2D_OK;
+}
+
+// First level of the V-cycle that runs inside the fused coarse-tail kernel (sy2d_mg.cuh, k_mg_tail), or mg_nlev when the
+// cycle is not fused: single-GPU contexts only (slab ranks exchange halos and spike tips between the stages), all fused
+// levels must have the predicate-free shape, and the CTAs of all problems must be resident at once (one per SM).
+int mg_tail_cols(const sy2d_ctx* c) {   // columns per CTA inside the tail: 4 while the CTA stays within its thread limit
+  const int rows = mg_rows(c), seg = c->mg_seg, nseg = (rows + seg - 1) / seg;
+  return nseg * 4 <= 512 ? 4 : 2;
+}
+int mg_tail_first_level(const sy2d_ctx* c) {
+  const int L = c->mg_nlev;
+  if (c->slab || c->mg_tail_ny <= 0 || c->profiling || c->nbatch > c->sm_count) return L;
+  const int rows = mg_rows(c), seg = c->mg_seg, nseg = (rows + seg - 1) / seg, cols = mg_tail_cols(c);
+  if (rows % seg != 0 || (nseg * cols) % 32 != 0 || nseg * cols > 512) return L;
+  int k0 = L;
+  for (int k = L - 1; k >= 0; --k) {
+    const int ny = c->mg.lv[k].ny;
+    if (ny > c->mg_tail_ny || ny % cols != 0 || ny % 2 != 0) break;
+    k0 = k;
+  }
+  return k0;
 }
 
 // coarse operators (level by level) and the line LU of every level (one launch) for this step's operator
@@ -553,6 +585,40 @@ int mg_vcycle(sy2d_ctx* c, const double* r, double* z) {
   };
   int rc = SY2D_OK;
   const double scale0 = c->cur_cells;
+  const int k0 = mg_tail_first_level(c);
+  if (k0 < L) {
+    // levels 0 .. k0-1 as separate launches, levels k0 .. L-1 (down, coarsest sweeps, up) inside ONE kernel
+    for (int k = 0; k < k0; ++k) {
+      if ((rc = mg_line<0>(c, level(k), nullptr, k))) return rc;
+      mg_resid<1>(c, level(k), nullptr, c->mg.lv[k + 1].om, c->mg_rc[k + 1]);
+    }
+    {
+      Prof p(c, SY2D_K_MG_LINE);
+      MgTailArgs t;
+      t.L = c->mg;
+      t.L.lv[0] = lv0;
+      t.a = MgArgs{c->scal, mg_rows(c), 0, nullptr};
+      t.barrier = c->mg_tail_ctr;
+      t.k0 = k0;
+      t.coarse_sweeps = mg_coarse_sweeps(c);
+      const int cols = mg_tail_cols(c), seg = c->mg_seg, nseg = mg_rows(c) / seg;
+      const int groups = level(k0).ny / cols;
+      const unsigned ctas = (unsigned)std::max(1, std::min(groups, c->sm_count / c->nbatch));
+      const dim3 g(ctas, (unsigned)c->nbatch, 1);
+      const int threads = nseg * cols;
+      const size_t smem = (size_t)3 * cols * (nseg + 1) * sizeof(double);
+      if (seg == 8 && cols == 4) k_mg_tail<8, 4><<<g, threads, smem, c->stream>>>(t);
+      else if (seg == 8) k_mg_tail<8, 2><<<g, threads, smem, c->stream>>>(t);
+      else if (cols == 4) k_mg_tail<16, 4><<<g, threads, smem, c->stream>>>(t);
+      else k_mg_tail<16, 2><<<g, threads, smem, c->stream>>>(t);
+    }
+    for (int k = k0 - 1; k >= 0; --k) {
+      mg_resid<2>(c, level(k), c->mg.lv[k + 1].z, nullptr, nullptr);
+      if ((rc = mg_line<1>(c, level(k), c->mg.lv[k + 1].z, k))) return rc;
+    }
+    c->cur_cells = scale0;
+    return SY2D_OK;
+  }
   for (int k = 0; k + 1 < L; ++k) {
     c->cur_cells = scale0 / (double)(1 << k);
     if ((rc = mg_line<0>(c, level(k), nullptr, k))) return rc;
@@ -575,7 +641,11 @@ int mg_vcycle(sy2d_ctx* c, const double* r, double* z) {
   c->cur_cells = scale0;
   return SY2D_OK;
 }
-int mg_kernels_per_vcycle(const sy2d_ctx* c) { return 4 * (c->mg_nlev - 1) + 1 + 2 * (mg_coarse_sweeps(c) - 1); }
+int mg_kernels_per_vcycle(const sy2d_ctx* c) {
+  const int k0 = mg_tail_first_level(c);
+  if (k0 < c->mg_nlev) return 4 * k0 + 1;
+  return 4 * (c->mg_nlev - 1) + 1 + 2 * (mg_coarse_sweeps(c) - 1);
+}
 
 int launch_iteration_mg(sy2d_ctx* c) {
   int rc = SY2D_OK;
@@ -744,6 +814,7 @@ struct SlabTransport {
   virtual int gather(sy2d_ctx* c, const double* src, double* dst, size_t count) = 0;
   virtual void abort(sy2d_ctx* c) = 0;
   virtual const char* name() const = 0;
+  virtual bool capturable() const { return false; }   // the calls are plain stream work that a CUDA graph can record
 };
 
 // NCCL over NVLink / NVSwitch: one process (or thread) per GPU.
@@ -773,6 +844,7 @@ struct NcclTransport : SlabTransport {
     if (comm && nccl().CommAbort) { nccl().CommAbort(comm); comm = nullptr; }   // frees this rank's resources without a collective teardown
   }
   const char* name() const override { return "nccl"; }
+  bool capturable() const override { return true; }
 };
 }  // namespace
 
@@ -876,6 +948,7 @@ int slab_gather(sy2d_ctx* c, const double* src, double* dst, size_t count) { ret
 
 // accumulators of every rank -> scalars on every rank (identical summation order everywhere)
 int slab_reduce(sy2d_ctx* c, int phase, const KrylovVecs& k) {
+  Prof p(c, SY2D_K_OTHER);
   int rc = slab_gather(c, &c->scal->acc_rv, c->d_gather, 5);
   if (rc) return rc;
   k_slab_scalars<<<1, 32, 0, c->stream>>>(phase, c->scal, c->d_gather, c->nranks, k);
@@ -952,27 +1025,57 @@ int step_slab_impl(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
     CU(cudaMemcpyAsync(c->h_nactive, c->d_nactive, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     int done_its = 0;
-    while (*c->h_nactive > 0 && done_its < c->opt.maxit + check_every) {
-      for (int it = 0; it < check_every && mg; ++it) {
-        // right-preconditioned BiCGSTAB, one V-cycle per preconditioner application; the smoother's line solves are made
-        // exact across the ranks by mg_spike_fix, every residual uses the neighbours' rows (halo exchange)
-        double* phat = c->xl_hat;
-        double* shat = c->mg_shat;
-        k_p_update2<<<g2, kBlock, 0, c->stream>>>(k, c->N);
-        if ((rc = mg_vcycle(c, c->p, phat))) return rc;
-        if ((rc = slab_halo_exchange(c, phat))) return rc;
-        KrylovVecs kv = k;
-        kv.p = phat;
-        k_spmv_v2<<<g2, kBlock, 0, c->stream>>>(kv, c->N, c->ny);
-        if ((rc = slab_reduce(c, 1, k))) return rc;
-        k_s_update2<<<g2, kBlock, 0, c->stream>>>(k, c->N);
-        if ((rc = mg_vcycle(c, c->s, shat))) return rc;
-        if ((rc = slab_halo_exchange(c, shat))) return rc;
-        k_mg_spmv_t<<<g2, kBlock, 0, c->stream>>>(k, shat, c->N, c->ny);
-        if ((rc = slab_reduce(c, 2, k))) return rc;
-        k_mg_xr<<<g2, kBlock, 0, c->stream>>>(k, phat, shat, c->N);
-        if ((rc = slab_reduce(c, 3, k))) return rc;
+    // right-preconditioned BiCGSTAB, one V-cycle per preconditioner application; the smoother's line solves are made
+    // exact across the ranks by mg_spike_fix, every residual uses the neighbours' rows (halo exchange)
+    auto mg_iteration = [&]() -> int {
+      double* phat = c->xl_hat;
+      double* shat = c->mg_shat;
+      int r = SY2D_OK;
+      k_p_update2<<<g2, kBlock, 0, c->stream>>>(k, c->N);
+      if ((r = mg_vcycle(c, c->p, phat))) return r;
+      if ((r = slab_halo_exchange(c, phat))) return r;
+      KrylovVecs kv = k;
+      kv.p = phat;
+      k_spmv_v2<<<g2, kBlock, 0, c->stream>>>(kv, c->N, c->ny);
+      if ((r = slab_reduce(c, 1, k))) return r;
+      k_s_update2<<<g2, kBlock, 0, c->stream>>>(k, c->N);
+      if ((r = mg_vcycle(c, c->s, shat))) return r;
+      if ((r = slab_halo_exchange(c, shat))) return r;
+      k_mg_spmv_t<<<g2, kBlock, 0, c->stream>>>(k, shat, c->N, c->ny);
+      if ((r = slab_reduce(c, 2, k))) return r;
+      k_mg_xr<<<g2, kBlock, 0, c->stream>>>(k, phat, shat, c->N);
+      return slab_reduce(c, 3, k);
+    };
+    if (mg && c->slab_graph && !c->profiling && c->tp->capturable() && *c->h_nactive > 0) {
+      // Over NCCL the iteration - ~90 kernels and ~45 collectives (halo lines, spike tips, scalar gathers) - is recorded once
+      // into a CUDA graph (NCCL's calls are capturable stream work) and replayed: without it the step is bound by the
+      // host-side cost of enqueueing the collectives (4096^2 on 2 GPUs: 11 ms per iteration against 2.3 ms of kernels).
+      // Every rank replays the same number of times: the polled counters derive from all-gathered scalars.
+      if (!c->slab_exec) {
+        cudaGraph_t graph = nullptr;
+        CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+        const int rci = mg_iteration();
+        cudaMemcpyAsync(c->h_nactive, c->d_nactive, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+        const cudaError_t ec = cudaStreamEndCapture(c->stream, &graph);
+        if (rci) { if (graph) cudaGraphDestroy(graph); return rci; }
+        if (ec != cudaSuccess) return fail(c, SY2D_ERR_CUDA, "capturing the slab iteration failed: %s (SY2D_SLAB_GRAPH=0 issues it call by call)", cudaGetErrorString(ec));
+        CU(cudaGraphInstantiate(&c->slab_exec, graph, 0));
+        cudaGraphDestroy(graph);
       }
+      // iteration counts barely change from step to step: last step's count minus one without polling, then one by one
+      int planned = std::min(c->mg_last_iters - 1, c->opt.maxit);
+      for (; planned > 0; --planned, ++done_its) CU(cudaGraphLaunch(c->slab_exec, c->stream));
+      if (done_its > 0) CU(cudaStreamSynchronize(c->stream));
+      while (*c->h_nactive > 0 && done_its < c->opt.maxit + 1) {
+        CU(cudaGraphLaunch(c->slab_exec, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        done_its += 1;
+      }
+      c->launches += (long long)done_its * kernels_per_iteration(c);
+    }
+    while (*c->h_nactive > 0 && done_its < c->opt.maxit + check_every) {
+      for (int it = 0; it < check_every && mg; ++it)
+        if ((rc = mg_iteration())) return rc;
       for (int it = 0; it < check_every && xl; ++it) {
         k_xl_sweep<0><<<gs, kSweepThreads, 0, c->stream>>>(xv, c->N);
         if ((rc = slab_halo_exchange(c, c->xl_hat))) return rc;
@@ -1034,6 +1137,7 @@ int step_slab_impl(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
     st.iters_total += c->h_stats->it_max;
     st.iters_sum_all += c->h_stats->it_max;
     st.iters_last = c->h_stats->it_max;
+    if (!bad) c->mg_last_iters = c->h_stats->it_max;
     st.fmin = c->h_stats->fmin;                      // of this rank's rows
     st.negatives = (long long)c->h_stats->negatives;  // of this rank's rows
     st.kernel_launches = c->launches;
@@ -1050,7 +1154,7 @@ int step_slab_impl(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
   CU(cudaEventElapsedTime(&ms, c->ev_call0, c->ev_call1));
   st.seconds_device = ms * 1e-3;
   if (stats) *stats = st;
-  return SY2D_OK;
+  return collect_profile(c);
 }
 }  // namespace
 
@@ -1132,6 +1236,8 @@ static int create_impl(sy2d_ctx** out, int device, int nx, int ny, int nbatch, c
   if (const char* e = std::getenv("SY2D_PIPE_CHUNKS")) ctx->pipe_forced = std::max(1, std::min(64, std::atoi(e)));
   if (const char* e = std::getenv("SY2D_ASM_CTAS_PER_SM")) ctx->asm_ctas_per_sm = std::max(1, std::min(4, std::atoi(e)));
   if (const char* e = std::getenv("SY2D_XLINE_CHUNK")) ctx->xl_chunk = std::max(0, std::atoi(e));
+  if (const char* e = std::getenv("SY2D_MG_TAIL_NY")) ctx->mg_tail_ny = std::max(0, std::atoi(e));
+  if (const char* e = std::getenv("SY2D_SLAB_GRAPH")) ctx->slab_graph = std::atoi(e) != 0;
   if (const char* e = std::getenv("SY2D_HOST_IO")) ctx->host_io_direct = std::string(e) == "direct" ? 1 : 0;
   if (const char* e = std::getenv("SY2D_ASM_KERNEL")) ctx->asm_kernel = std::string(e) == "march" ? 1 : 0;
   if (const char* e = std::getenv("SY2D_MARCH_CTAS_PER_SM")) ctx->march_ctas_per_sm = std::max(1, std::min(16, std::atoi(e)));
@@ -1180,12 +1286,14 @@ void sy2d_destroy(sy2d_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->chunk_exec) cudaGraphExecDestroy(c->chunk_exec);
   if (c->one_exec) cudaGraphExecDestroy(c->one_exec);
+  if (c->slab_exec) cudaGraphExecDestroy(c->slab_exec);
   double* bufs[] = {c->d_wxL, c->d_wxR, c->d_wyB, c->d_wyT, c->d_dx, c->d_dy, c->d_bc[0], c->d_bc[1], c->d_bc[2], c->d_bc[3],
                     c->tx, c->ty, c->cxy, c->U, c->Ud, c->f, c->yprev, c->cs, c->wW, c->wE, c->wS, c->wN, c->rhs,
                     c->x, c->r, c->p, c->v, c->s, c->t, c->xl_scratch, c->xl_l, c->xl_dinv, c->xl_e, c->xl_hat};
   for (double* b : bufs) if (b) cudaFree(b);
   if (c->scal) cudaFree(c->scal);
   for (double* b : c->mg_bufs) cudaFree(b);
+  if (c->mg_tail_ctr) cudaFree(c->mg_tail_ctr);
   if (c->d_tma_maps) cudaFree(c->d_tma_maps);
   if (c->d_tma_maps2) cudaFree(c->d_tma_maps2);
   if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
@@ -1229,6 +1337,11 @@ int sy2d_set_options(sy2d_ctx* c, const sy2d_options* o) {
   if (o->tol != c->opt.tol || o->maxit != c->opt.maxit) {
     if (c->chunk_exec) { cudaGraphExecDestroy(c->chunk_exec); c->chunk_exec = nullptr; }
     if (c->one_exec) { cudaGraphExecDestroy(c->one_exec); c->one_exec = nullptr; }
+    if (c->slab_exec) { cudaGraphExecDestroy(c->slab_exec); c->slab_exec = nullptr; }
+  }
+  if (o->precond != c->opt.precond || o->mg_levels != c->opt.mg_levels || o->mg_coarse_sweeps != c->opt.mg_coarse_sweeps ||
+      o->reserved[2] != c->opt.reserved[2]) {
+    if (c->slab_exec) { cudaGraphExecDestroy(c->slab_exec); c->slab_exec = nullptr; }
   }
   c->opt = *o;
   if (c->slab) c->opt.use_graph = 0;

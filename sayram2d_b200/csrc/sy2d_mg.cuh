@@ -29,6 +29,8 @@
 // scan over the segments of the column, and a correction pass adds carry * (prefix product).  A CTA
 // covers all segments of kMgCols adjacent columns, so neighbouring threads touch adjacent addresses.
 #pragma once
+#include <type_traits>
+
 #include "sy2d_kernels.cuh"
 
 namespace sy2d {
@@ -172,10 +174,10 @@ __device__ __forceinline__ void mg_carry_scan(const double* sA, const double* sP
 // The kernel is latency bound (a CTA is one dependent chain of load - sweep - scan - sweep - scan - store
 // and a level has at most ny / COLS CTAs), so the instruction count per thread is what matters: short
 // segments, running pointers instead of index products, all loads of a phase issued before their use.
+// `group` = which COLS adjacent columns, `batch` = which problem (the stand-alone kernel passes blockIdx.x / .y; the fused
+// coarse-level kernel below loops over groups).  `state` != 0: the problem has converged, nothing to do.
 template <int SEG, int COLS, int MODE, bool FULL>
-__global__ void __launch_bounds__(SEG <= 8 ? 1024 : 512, 1) k_mg_line(MgLevel lv, const double* __restrict__ zc, MgArgs a) {
-  extern __shared__ double mg_smem[];
-  const int state = a.scal[blockIdx.y].state;   // used after the first loads are in flight
+__device__ __forceinline__ void mg_line_body(const MgLevel& lv, const double* zc, const MgArgs& a, int group, int batch, int state, double* mg_smem) {
   const int nx = a.nx, ny = lv.ny;
   const int nseg = (nx + SEG - 1) / SEG;
   const int stride = nseg + 1;
@@ -183,12 +185,12 @@ __global__ void __launch_bounds__(SEG <= 8 ? 1024 : 512, 1) k_mg_line(MgLevel lv
   double* sP = sA + COLS * stride;
   double* sC = sP + COLS * stride;
   const int col = threadIdx.x % COLS, seg = threadIdx.x / COLS;
-  const int j = blockIdx.x * COLS + col;
+  const int j = group * COLS + col;
   const bool in_cta = FULL || seg < nseg;
   const bool live = FULL || (in_cta && j < ny);
   const int r0 = seg * SEG;
   const int cnt = FULL ? SEG : (live ? min(SEG, nx - r0) : 0);
-  const size_t n0 = live ? (size_t)blockIdx.y * lv.N + (size_t)r0 * ny + j : 0;
+  const size_t n0 = live ? (size_t)batch * lv.N + (size_t)r0 * ny + j : 0;
   double y[SEG], c[SEG];
   // forward sweep y_m = b_m - l_m y_{m-1} with carry-in 0; P = product of (-l) over the segment
   {
@@ -273,7 +275,7 @@ __global__ void __launch_bounds__(SEG <= 8 ? 1024 : 512, 1) k_mg_line(MgLevel lv
   double* pz = lv.z + n0;
   if (MODE != 0) {
     const double* pq = pz;
-    const double* pc = MODE == 1 ? zc + ((size_t)blockIdx.y * (lv.N >> 1) + (size_t)r0 * (ny >> 1) + (j >> 1)) : nullptr;
+    const double* pc = MODE == 1 ? zc + ((size_t)batch * (lv.N >> 1) + (size_t)r0 * (ny >> 1) + (j >> 1)) : nullptr;
 #pragma unroll
     for (int m = 0; m < SEG; ++m) {
       c[m] = 0.0;
@@ -290,6 +292,12 @@ __global__ void __launch_bounds__(SEG <= 8 ? 1024 : 512, 1) k_mg_line(MgLevel lv
     if (FULL || m < cnt) *pz = MODE == 0 ? kMgOmega * y[m] : c[m] + kMgOmega * y[m];
     pz += ny;
   }
+}
+
+template <int SEG, int COLS, int MODE, bool FULL>
+__global__ void __launch_bounds__(SEG <= 8 ? 1024 : 512, 1) k_mg_line(MgLevel lv, const double* __restrict__ zc, MgArgs a) {
+  extern __shared__ double mg_smem[];
+  mg_line_body<SEG, COLS, MODE, FULL>(lv, zc, a, (int)blockIdx.x, (int)blockIdx.y, a.scal[blockIdx.y].state, mg_smem);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -371,15 +379,14 @@ __global__ void __launch_bounds__(kBlock) k_mg_spike_apply(double* __restrict__ 
 // Out-of-range neighbours are clamped: their weights are exactly zero.
 // ---------------------------------------------------------------------------------------------
 template <int KIND>
-__global__ void __launch_bounds__(kBlock) k_mg_resid(MgLevel lv, const double* __restrict__ zc, const double* __restrict__ omc,
-                                                     double* __restrict__ rc, MgArgs a) {
-  if (a.scal[blockIdx.y].state != 0) return;
+__device__ __forceinline__ void mg_resid_body(const MgLevel& lv, const double* zc, const double* omc, double* rc, const MgArgs& a, int batch,
+                                              size_t first, size_t stride) {
   const int nx = a.nx, ny = lv.ny, nyc = ny >> 1;
   const size_t Nc = (size_t)nx * nyc;
-  const size_t bf = (size_t)blockIdx.y * lv.N, bc = (size_t)blockIdx.y * Nc;
-  const double* __restrict__ z = lv.z + bf;
-  const double* __restrict__ zcp = KIND == 2 ? zc + bc : nullptr;
-  for (size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < Nc; n += (size_t)gridDim.x * blockDim.x) {
+  const size_t bf = (size_t)batch * lv.N, bc = (size_t)batch * Nc;
+  const double* z = lv.z + bf;
+  const double* zcp = KIND == 2 ? zc + bc : nullptr;
+  for (size_t n = first; n < Nc; n += stride) {
     const int i = (int)(n / nyc), J = (int)(n - (size_t)i * nyc);
     const ptrdiff_t p = (ptrdiff_t)i * ny + 2 * J;    // in-problem index of cell a
     const ptrdiff_t pW = (i > 0 || a.halo) ? p - ny : p, pE = (i < nx - 1 || a.halo) ? p + ny : p;
@@ -406,6 +413,90 @@ __global__ void __launch_bounds__(kBlock) k_mg_resid(MgLevel lv, const double* _
     } else {
       st2(lv.t + bf + p, ra, rb);
     }
+  }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kBlock) k_mg_resid(MgLevel lv, const double* __restrict__ zc, const double* __restrict__ omc,
+                                                     double* __restrict__ rc, MgArgs a) {
+  if (a.scal[blockIdx.y].state != 0) return;
+  mg_resid_body<KIND>(lv, zc, omc, rc, a, (int)blockIdx.y, (size_t)blockIdx.x * blockDim.x + threadIdx.x, (size_t)gridDim.x * blockDim.x);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The coarse tail of the V-cycle in ONE launch.  On the levels with few columns every kernel above is a latency-bound
+// launch of 5-10 us whatever its size (a level has at most ny_l / COLS line CTAs, each one dependent chain), and a
+// V-cycle spends 11 of its 19 launches on the three coarsest levels, which hold 7 / 16 of the fine grid's cells.
+// k_mg_tail runs levels k0 .. L-1 - down sweep, coarsest-level sweeps, up sweep - as the stages of one kernel separated
+// by a barrier over the CTAs of a problem (an atomic counter per problem; the grid is at most one CTA per SM, so all CTAs
+// are resident).  A CTA has SEG x COLS-shaped work like the stand-alone line kernel (nseg x COLS threads) and loops over
+// the column groups of a level; the residual stages are grid-stride over the same threads.  Plain loads only: arrays
+// written in one stage are read in the next (no ld.global.nc), and the barrier's acquire invalidates the SM's L1.
+// ---------------------------------------------------------------------------------------------
+struct MgTailArgs {
+  MgLevels L;
+  MgArgs a;
+  unsigned* barrier;   // [nbatch] arrival counters, zero between launches
+  int k0;              // first fused level; its right-hand side lv[k0].r is ready, its iterate lv[k0].z is the result
+  int coarse_sweeps;
+};
+
+__device__ __forceinline__ void mg_problem_barrier(unsigned* ctr, unsigned nblocks, unsigned& target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += nblocks;
+    __threadfence();
+    atomicAdd(ctr, 1u);
+    unsigned seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+    } while (seen < target);
+  }
+  __syncthreads();
+}
+
+template <int SEG, int COLS>
+__global__ void __launch_bounds__(512, 1) k_mg_tail(MgTailArgs t) {   // nseg x COLS <= 512 threads (the host picks COLS)
+  extern __shared__ double mg_smem[];
+  const int batch = blockIdx.y;
+  if (t.a.scal[batch].state != 0) return;   // the whole problem is skipped by all of its CTAs alike
+  unsigned* ctr = t.barrier + batch;
+  unsigned target = 0;
+  const unsigned nblk = gridDim.x;
+  const int Lc = t.L.nlev;
+  const size_t first = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  auto line = [&](auto mode, const MgLevel& lv, const double* zc) {
+    constexpr int MODE = decltype(mode)::value;
+    const int groups = lv.ny / COLS;
+    for (int g = blockIdx.x; g < groups; g += gridDim.x) {
+      mg_line_body<SEG, COLS, MODE, true>(lv, zc, t.a, g, batch, 0, mg_smem);
+      __syncthreads();   // the scan buffers are reused by the next group
+    }
+  };
+  for (int k = t.k0; k + 1 < Lc; ++k) {
+    line(std::integral_constant<int, 0>{}, t.L.lv[k], nullptr);
+    mg_problem_barrier(ctr, nblk, target);
+    mg_resid_body<1>(t.L.lv[k], nullptr, t.L.lv[k + 1].om, const_cast<double*>(t.L.lv[k + 1].r), t.a, batch, first, stride);
+    mg_problem_barrier(ctr, nblk, target);
+  }
+  line(std::integral_constant<int, 0>{}, t.L.lv[Lc - 1], nullptr);
+  for (int sweep = 1; sweep < t.coarse_sweeps; ++sweep) {
+    mg_problem_barrier(ctr, nblk, target);
+    mg_resid_body<0>(t.L.lv[Lc - 1], nullptr, nullptr, nullptr, t.a, batch, first, stride);
+    mg_problem_barrier(ctr, nblk, target);
+    line(std::integral_constant<int, 2>{}, t.L.lv[Lc - 1], nullptr);
+  }
+  for (int k = Lc - 2; k >= t.k0; --k) {
+    mg_problem_barrier(ctr, nblk, target);
+    mg_resid_body<2>(t.L.lv[k], t.L.lv[k + 1].z, nullptr, nullptr, t.a, batch, first, stride);
+    mg_problem_barrier(ctr, nblk, target);
+    line(std::integral_constant<int, 1>{}, t.L.lv[k], t.L.lv[k + 1].z);
+  }
+  // exit arrival: the last CTA of the problem to get here leaves the counter at zero for the next launch
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned old = atomicAdd(ctr, 1u);
+    if (old == target + nblk - 1) *ctr = 0u;
   }
 }
 

@@ -121,3 +121,25 @@ def test_failed_multigrid_step_is_redone_with_the_xline_iteration():
     sc = b.step(1)                            # back to multigrid on the next call
     assert sc["precond"] == 2 and sc["restarts_total"] == 0 and sc["iters_last"] <= sa["iters_last"] + 3
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("n,batch", [(256, 1), (1024, 1), (512, 3)])
+def test_fused_coarse_tail_equals_the_separate_launches(n, batch):
+    """SY2D_MG_TAIL_NY: the coarse levels of the V-cycle as the stages of ONE kernel (k_mg_tail, a barrier over the CTAs of a
+    problem between the stages) - same arithmetic as the separate launches: the same f and the same iteration counts."""
+    import os
+    out = []
+    for tail in ("0", "256"):
+        os.environ["SY2D_MG_TAIL_NY"] = tail
+        try:
+            eng = synthetic_engine(n, n, nbatch=batch)
+        finally:
+            del os.environ["SY2D_MG_TAIL_NY"]
+        eng.set_options(engine=1, precond=2)
+        st = eng.step(3)
+        out.append((eng.get_f(), st["iters_total"], st["kernel_launches"]))
+        assert st["negatives"] == 0 and st["precond"] == 2
+        eng.close()
+    # (the fine-level dot products are summed with atomics: two runs agree to round-off, not bit for bit)
+    assert max_rel(out[1][0], out[0][0]) < 1e-11 and abs(out[0][1] - out[1][1]) <= 2
+    assert out[1][2] < out[0][2]      # fewer launches with the fused tail
