@@ -72,6 +72,7 @@ struct sy2d_ctx {
   double* mg_rc[kMgMaxLevels] = {};   // writable right-hand sides of the coarse levels
   double *mg_om0 = nullptr, *mg_shat = nullptr;
   unsigned* mg_tail_ctr = nullptr;      // [nbatch] barrier counters of the fused coarse-tail kernel (zero between launches)
+  int mg_cluster = 1;                   // SY2D_MG_CLUSTER=0: long columns in one CTA (fewer columns per CTA) instead of a CTA cluster
   int mg_tail_ny = 0;                   // SY2D_MG_TAIL_NY = n: levels with at most n columns run inside the fused k_mg_tail kernel.  Off by
                                         // default: at 1024^2 it halves the launches of a step (2878 -> 1558 in 5 steps) and changes nothing
                                         // (4.62 -> 4.68 ms per step) - a stage costs its dependent chain (loads, sweep, scan, sweep, scan,
@@ -502,8 +503,54 @@ int mg_line_cols(const sy2d_ctx* c, const MgLevel& lv) {
   return cols;
 }
 
+// Long columns (16-row segments, i.e. more than 1024 rows): one group of 8 columns per thread-block cluster whose CTAs split
+// the segments (k_mg_line_cluster); returns false when the shape does not fit (the stand-alone kernel runs then).
+int mg_cluster_size(const sy2d_ctx* c, const MgLevel& lv) {
+  if (!c->mg_cluster || c->mg_seg != 16 || lv.ny % 8 != 0) return 0;
+  const int rows = mg_rows(c);
+  if (rows % 16 != 0) return 0;
+  const int nseg = rows / 16;
+  for (int cl : {2, 4, 8}) {
+    if (nseg % cl) continue;
+    const int threads = nseg / cl * 8;
+    if (threads <= 512 && threads % 32 == 0) return cl;
+  }
+  return 0;
+}
+
+template <int MODE, int CL>
+cudaError_t mg_line_cluster_launch(sy2d_ctx* c, const MgLevel& lv, const double* zc) {
+  const int rows = mg_rows(c), nseg_c = rows / (16 * CL);
+  const MgArgs a{c->scal, rows, c->slab ? 1 : 0, c->slab ? c->mg_tips : nullptr};
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(lv.ny / 8 * CL), (unsigned)c->nbatch, 1);
+  cfg.blockDim = dim3((unsigned)(nseg_c * 8), 1, 1);
+  cfg.dynamicSmemBytes = (size_t)(4 * 8 * (nseg_c + 1) + 4 * 8) * sizeof(double);
+  cfg.stream = c->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, k_mg_line_cluster<16, 8, MODE, CL>, lv, zc, a);
+}
+
+template <int MODE>
+bool mg_line_cluster(sy2d_ctx* c, const MgLevel& lv, const double* zc) {
+  cudaError_t e = cudaErrorInvalidValue;
+  switch (mg_cluster_size(c, lv)) {
+    case 2: e = mg_line_cluster_launch<MODE, 2>(c, lv, zc); break;
+    case 4: e = mg_line_cluster_launch<MODE, 4>(c, lv, zc); break;
+    case 8: e = mg_line_cluster_launch<MODE, 8>(c, lv, zc); break;
+    default: return false;
+  }
+  if (e != cudaSuccess) { cudaGetLastError(); return false; }   // e.g. the cluster cannot be scheduled: stand-alone kernel
+  return true;
+}
+
 template <int SEG, int MODE>
 void mg_line_seg(sy2d_ctx* c, const MgLevel& lv, const double* zc) {
+  if (SEG == 16 && mg_line_cluster<MODE>(c, lv, zc)) return;
   switch (mg_line_cols<SEG>(c, lv)) {
     case 8: mg_line_shape<SEG, 8, MODE>(c, lv, zc); break;
     case 4: mg_line_shape<SEG, 4, MODE>(c, lv, zc); break;
@@ -1236,6 +1283,7 @@ static int create_impl(sy2d_ctx** out, int device, int nx, int ny, int nbatch, c
   if (const char* e = std::getenv("SY2D_PIPE_CHUNKS")) ctx->pipe_forced = std::max(1, std::min(64, std::atoi(e)));
   if (const char* e = std::getenv("SY2D_ASM_CTAS_PER_SM")) ctx->asm_ctas_per_sm = std::max(1, std::min(4, std::atoi(e)));
   if (const char* e = std::getenv("SY2D_XLINE_CHUNK")) ctx->xl_chunk = std::max(0, std::atoi(e));
+  if (const char* e = std::getenv("SY2D_MG_CLUSTER")) ctx->mg_cluster = std::atoi(e) != 0;
   if (const char* e = std::getenv("SY2D_MG_TAIL_NY")) ctx->mg_tail_ny = std::max(0, std::atoi(e));
   if (const char* e = std::getenv("SY2D_SLAB_GRAPH")) ctx->slab_graph = std::atoi(e) != 0;
   if (const char* e = std::getenv("SY2D_HOST_IO")) ctx->host_io_direct = std::string(e) == "direct" ? 1 : 0;

@@ -301,6 +301,157 @@ __global__ void __launch_bounds__(SEG <= 8 ? 1024 : 512, 1) k_mg_line(MgLevel lv
 }
 
 // ---------------------------------------------------------------------------------------------
+// Long columns: one column group per thread-block CLUSTER (sm_90+ clusters, distributed shared memory).
+//
+// A thread's registers limit a CTA to 512 threads of 16 rows: beyond 2048 rows the stand-alone kernel above can only
+// keep the whole column in one CTA by taking fewer columns (4096 rows: 2, 8192 rows: 1), and with one column per CTA
+// a row access is 8 bytes of a 32-byte sector - the line solves of a 16384^2 grid on 2 GPUs moved 4x their bytes.
+// Here the CL CTAs of a cluster split the SEGMENTS of the same 8 columns (64-byte row accesses for any column length up
+// to 8192 rows): every CTA scans the affine maps of its own segments as before, publishes the composed map of its
+// whole part per column in its shared memory, and after a cluster barrier reads the parts below (forward sweep) or
+// above (backward sweep) through DSMEM to get its carry-in: three cluster barriers per solve, one pass over memory.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ double ld_dsmem(const double* local_smem_ptr, unsigned rank) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(local_smem_ptr);
+  unsigned ra;
+  double v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
+  return v;
+}
+
+// Like mg_carry_scan, for the segments of ONE CTA of the cluster: sC = carry-in of a segment if the carry into the CTA's
+// first segment were 0, sQ = the factor a non-zero carry into the CTA is multiplied by on its way to the segment, and
+// (totA, totP)[col] = the composed map of the CTA's whole part.
+template <int COLS>
+__device__ __forceinline__ void mg_carry_scan_part(const double* sA, const double* sP, double* sC, double* sQ, double* totA, double* totP,
+                                                   int nseg, int stride) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int col = w; col < COLS; col += nw) {
+    double cb = 0.0, pb = 1.0;
+    for (int s0 = 0; s0 < nseg; s0 += 32) {
+      const int s = s0 + lane;
+      double A = 0.0, P = 1.0;
+      if (s < nseg) { A = sA[col * stride + s]; P = sP[col * stride + s]; }
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double Ao = __shfl_up_sync(0xffffffffu, A, o), Po = __shfl_up_sync(0xffffffffu, P, o);
+        if (lane >= o) { A = A + P * Ao; P = P * Po; }
+      }
+      double Ae = __shfl_up_sync(0xffffffffu, A, 1), Pe = __shfl_up_sync(0xffffffffu, P, 1);
+      if (lane == 0) { Ae = 0.0; Pe = 1.0; }
+      if (s < nseg) { sC[col * stride + s] = Ae + Pe * cb; sQ[col * stride + s] = Pe * pb; }
+      const double At = __shfl_sync(0xffffffffu, A, 31), Pt = __shfl_sync(0xffffffffu, P, 31);
+      cb = At + Pt * cb;
+      pb = Pt * pb;
+    }
+    if (lane == 0) { totA[col] = cb; totP[col] = pb; }
+  }
+}
+
+// grid: (groups * CL, nbatch) with cluster dimension (CL, 1, 1); block: (nseg / CL) * COLS threads.
+// Requires nx % (SEG * CL) == 0, ny % COLS == 0, ((nseg / CL) * COLS) % 32 == 0 (the host falls back to k_mg_line otherwise).
+template <int SEG, int COLS, int MODE, int CL>
+__global__ void __launch_bounds__(512, 1) k_mg_line_cluster(MgLevel lv, const double* zc, MgArgs a) {
+  extern __shared__ double mg_smem[];
+  const int state = a.scal[blockIdx.y].state;
+  const int nx = a.nx, ny = lv.ny;
+  const int nseg_c = nx / (SEG * CL);          // segments of this CTA
+  const int stride = nseg_c + 1;
+  double* sA = mg_smem;
+  double* sP = sA + COLS * stride;
+  double* sC = sP + COLS * stride;
+  double* sQ = sC + COLS * stride;
+  double* tot = sQ + COLS * stride;            // [2 sweeps][A, P][COLS]: read by the other CTAs of the cluster
+  const unsigned q = cluster_ctarank();
+  const int group = blockIdx.x / CL;
+  const int col = threadIdx.x % COLS, seg = threadIdx.x / COLS;
+  const int j = group * COLS + col;
+  const int r0 = ((int)q * nseg_c + seg) * SEG;
+  const size_t n0 = (size_t)blockIdx.y * lv.N + (size_t)r0 * ny + j;
+  double y[SEG], c[SEG];
+  {
+    const double* ps = (MODE == 0 ? lv.r : lv.t) + n0;
+    const double* pl = lv.l + n0;
+#pragma unroll
+    for (int m = 0; m < SEG; ++m) { y[m] = *ps; c[m] = *pl; ps += ny; pl += ny; }
+  }
+  if (state != 0) return;   // uniform over the cluster (one problem per cluster): nobody reaches a cluster barrier
+  double carry = 0.0, P = 1.0;
+#pragma unroll
+  for (int m = 0; m < SEG; ++m) { carry = y[m] - c[m] * carry; y[m] = carry; P = -c[m] * P; }
+  sA[col * stride + seg] = carry;
+  sP[col * stride + seg] = P;
+  __syncthreads();
+  mg_carry_scan_part<COLS>(sA, sP, sC, sQ, tot, tot + COLS, nseg_c, stride);
+  cluster_sync_all();                          // every part's map is published (and this CTA's scan is complete)
+  {
+    double cb = 0.0;                           // carry into this CTA: the parts below, in order
+    for (unsigned r = 0; r < q; ++r) cb = ld_dsmem(tot + col, r) + ld_dsmem(tot + COLS + col, r) * cb;
+    double qv = sC[col * stride + seg] + sQ[col * stride + seg] * cb;
+#pragma unroll
+    for (int m = 0; m < SEG; ++m) { qv = -c[m] * qv; y[m] += qv; }
+  }
+  {
+    const double* pd = lv.dinv + n0;
+    const double* pe = lv.e + n0;
+    double dv[SEG];
+#pragma unroll
+    for (int m = 0; m < SEG; ++m) { dv[m] = *pd; c[m] = *pe; pd += ny; pe += ny; }
+#pragma unroll
+    for (int m = 0; m < SEG; ++m) y[m] *= dv[m];
+  }
+  carry = 0.0; P = 1.0;
+#pragma unroll
+  for (int m = SEG - 1; m >= 0; --m) { carry = y[m] - c[m] * carry; y[m] = carry; P = -c[m] * P; }
+  __syncthreads();                             // sA .. sQ are reused (tot of the forward sweep stays: separate slots below)
+  sA[col * stride + (nseg_c - 1 - seg)] = y[0];
+  sP[col * stride + (nseg_c - 1 - seg)] = P;
+  __syncthreads();
+  mg_carry_scan_part<COLS>(sA, sP, sC, sQ, tot + 2 * COLS, tot + 3 * COLS, nseg_c, stride);
+  cluster_sync_all();
+  {
+    double cb = 0.0;                           // carry into this CTA from the parts above, nearest last
+    for (int r = CL - 1; r > (int)q; --r) cb = ld_dsmem(tot + 2 * COLS + col, (unsigned)r) + ld_dsmem(tot + 3 * COLS + col, (unsigned)r) * cb;
+    double qv = sC[col * stride + (nseg_c - 1 - seg)] + sQ[col * stride + (nseg_c - 1 - seg)] * cb;
+#pragma unroll
+    for (int m = SEG - 1; m >= 0; --m) { qv = -c[m] * qv; y[m] += qv; }
+  }
+  if (a.tips) {   // interface values of the local solution (spike correction, row-slab mode)
+    if (r0 == 0) a.tips[j] = y[0];
+    if (r0 + SEG == nx) a.tips[ny + j] = y[SEG - 1];
+  }
+  {
+    double* pz = lv.z + n0;
+    if (MODE != 0) {
+      const double* pq = pz;
+      const double* pc = MODE == 1 ? zc + ((size_t)blockIdx.y * (lv.N >> 1) + (size_t)r0 * (ny >> 1) + (j >> 1)) : nullptr;
+#pragma unroll
+      for (int m = 0; m < SEG; ++m) {
+        c[m] = *pq;
+        if (MODE == 1) c[m] += *pc;
+        pq += ny;
+        if (MODE == 1) pc += ny >> 1;
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < SEG; ++m) {
+      *pz = MODE == 0 ? kMgOmega * y[m] : c[m] + kMgOmega * y[m];
+      pz += ny;
+    }
+  }
+  cluster_sync_all();                          // no CTA may exit while its shared memory can still be read
+}
+
+// ---------------------------------------------------------------------------------------------
 // Row-slab mode: exact x-lines across ranks (SPIKE).  Rank r owns rows [0, n) of every global line; with
 // T_r its own tridiagonal block, bot_{r-1} the line's value on the last row of rank r-1 and top_{r+1} the one on
 // the first row of rank r+1,

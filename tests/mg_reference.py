@@ -11,7 +11,7 @@ OMEGA, THETA, COARSE_SWEEPS = 0.7, 0.5, 2
 
 def level_count(nx, ny, want=0):
     """The engine's rule: coarsen to <= 64 columns (at least two levels); want > 0 caps the count instead."""
-    if nx > 4096 or nx < 8 or ny % 4 or ny < 16:
+    if nx > 8192 or nx < 8 or ny % 4 or ny < 16:
         return 0
     nlev, cap = 1, (want if want > 0 else 8)
     while nlev < cap and ny % 4 == 0 and ny >= 16 and (want > 0 or ny > 64 or nlev < 2):

@@ -29,7 +29,7 @@ def synthetic_engine(nx, ny, nbatch=1, **opts):
     return eng
 
 
-@pytest.mark.parametrize("nx,ny,nbatch", [(128, 64, 1), (100, 48, 2), (37, 16, 1), (1024, 128, 1), (1100, 32, 1), (2048, 32, 1), (520, 24, 1), (4096, 16, 1), (2500, 16, 1)])
+@pytest.mark.parametrize("nx,ny,nbatch", [(128, 64, 1), (100, 48, 2), (37, 16, 1), (1024, 128, 1), (1100, 32, 1), (2048, 32, 1), (520, 24, 1), (4096, 16, 1), (2500, 16, 1), (8192, 32, 1), (2048, 64, 2)])
 def test_vcycle_matches_numpy_restatement(nx, ny, nbatch):
     eng = synthetic_engine(nx, ny, nbatch)
     eng.step(2)      # a developed f (predictor column scale active)
