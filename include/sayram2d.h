@@ -62,7 +62,9 @@ typedef struct {
   double tol;        /* stop when max_K |r_K| <= tol on the scaled system (unknown ~ O(1)); default 1e-14 */
   int maxit;         /* per linear solve; default 20000 */
   int precond;       /* SY2D_PRECOND_*; default AUTO */
-  int predictor;     /* 1: column-scale by f^n * (f^n/f^{n-1}) instead of f^n; default 1 */
+  int predictor;     /* column scale (initial guess) of a step: 0 f^n; 1 f^n y_n with y_n = f^n / f^{n-1} the last per-cell ratio;
+                        2 f^n y_n (y_n / y_{n-1}), its geometric extrapolation (one more state array).  Ratios are clamped
+                        to [0.5, 2]; the solution does not depend on the choice beyond the tolerance; default 2 */
   int check_every;   /* iterations between host convergence polls; default 16 */
   int use_graph;     /* 1: replay the iteration chunk as a CUDA graph; default 1 */
   int engine;        /* 0 auto (2 when nx*ny <= 16384, else 1), 1 lockstep multi-kernel,

@@ -20,6 +20,7 @@
 #include "sy2d_kernels.cuh"
 #include "sy2d_problem_kernel.cuh"
 #include "sy2d_xline_kernel.cuh"
+#include "sy2d_xline_cluster.cuh"
 #include "sy2d_xline_lockstep.cuh"
 #include "sy2d_mg.cuh"
 #include "sy2d_assemble_tma.cuh"
@@ -60,7 +61,7 @@ struct sy2d_ctx {
   // coefficients
   double *tx = nullptr, *ty = nullptr, *cxy = nullptr, *U = nullptr, *Ud = nullptr;
   // state
-  double *f = nullptr, *yprev = nullptr, *cs = nullptr;
+  double *f = nullptr, *yprev = nullptr, *ylast = nullptr, *cs = nullptr;
   // operator + Krylov vectors
   double *wW = nullptr, *wE = nullptr, *wS = nullptr, *wN = nullptr, *rhs = nullptr;
   double *x = nullptr, *r = nullptr, *p = nullptr, *v = nullptr, *s = nullptr, *t = nullptr;
@@ -131,6 +132,7 @@ struct sy2d_ctx {
   int host_io_direct = 0;        // sy2d_step_host, SY2D_HOST_IO=direct: the x-line kernel reads / writes pinned host buffers itself instead of
                                  // the copy engines (measured SLOWER on B200 / PCIe: 9.9 against 8.5 ms per end-to-end step at 4096
                                  // members - the loads an SM issues to system memory run at ~1 GB/s per SM; kept as an experiment)
+  int xl_cluster = 0;            // SY2D_XLINE_CLUSTER=1: 80 x 80 problems on pairs of CTAs (sy2d_xline_cluster.cuh), all iteration state on chip
   int xl_chunk = 1;              // time steps per work item (SY2D_XLINE_CHUNK; 0 = all steps of a call: one CTA per problem)
   std::vector<cudaStream_t> pipe_streams;   // sy2d_step_host: one stream per sub-batch
   std::vector<cudaEvent_t> pipe_events;
@@ -1170,7 +1172,7 @@ int step_slab_impl(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
       if ((rc = slab_gather(c, &c->d_stats->resid_max, c->d_gather, 2))) return rc;   // resid_max, resid_rel_max are adjacent
       k_slab_max<<<1, 32, 0, c->stream>>>(c->d_gather, c->nranks, &c->d_stats->resid_max);
       const dim3 gf((unsigned)((own + kBlock - 1) / kBlock), 1, 1);
-      k_finish<<<gf, kBlock, 0, c->stream>>>(c->x + c->ny, c->cs + c->ny, c->f + c->ny, c->yprev + c->ny, c->scal, own, c->opt.predictor, c->d_stats,
+      k_finish<<<gf, kBlock, 0, c->stream>>>(c->x + c->ny, c->cs + c->ny, c->f + c->ny, c->yprev + c->ny, c->ylast + c->ny, c->scal, own, c->opt.predictor, c->d_stats,
                                              budget ? 1.0e300 : 1000.0 * c->opt.tol);
     }
     CU(cudaGetLastError());
@@ -1229,7 +1231,7 @@ int sy2d_default_options(sy2d_options* o) {
   o->tol = 1e-14;
   o->maxit = 20000;
   o->precond = SY2D_PRECOND_AUTO;
-  o->predictor = 1;
+  o->predictor = 2;
   o->check_every = 16;
   o->use_graph = 1;
   o->engine = 0;
@@ -1283,6 +1285,7 @@ static int create_impl(sy2d_ctx** out, int device, int nx, int ny, int nbatch, c
   if (const char* e = std::getenv("SY2D_PIPE_CHUNKS")) ctx->pipe_forced = std::max(1, std::min(64, std::atoi(e)));
   if (const char* e = std::getenv("SY2D_ASM_CTAS_PER_SM")) ctx->asm_ctas_per_sm = std::max(1, std::min(4, std::atoi(e)));
   if (const char* e = std::getenv("SY2D_XLINE_CHUNK")) ctx->xl_chunk = std::max(0, std::atoi(e));
+  if (const char* e = std::getenv("SY2D_XLINE_CLUSTER")) ctx->xl_cluster = std::max(0, std::min(2, std::atoi(e)));
   if (const char* e = std::getenv("SY2D_MG_CLUSTER")) ctx->mg_cluster = std::atoi(e) != 0;
   if (const char* e = std::getenv("SY2D_MG_TAIL_NY")) ctx->mg_tail_ny = std::max(0, std::atoi(e));
   if (const char* e = std::getenv("SY2D_SLAB_GRAPH")) ctx->slab_graph = std::atoi(e) != 0;
@@ -1302,7 +1305,7 @@ static int create_impl(sy2d_ctx** out, int device, int nx, int ny, int nbatch, c
     CUB(cudaMalloc(reinterpret_cast<void**>(&ctx->d_bc[k]), n * sizeof(double)));
     CUB(cudaMemset(ctx->d_bc[k], 0, n * sizeof(double)));
   }
-  double** fields[] = {&ctx->tx, &ctx->ty, &ctx->cxy, &ctx->U, &ctx->Ud, &ctx->f, &ctx->yprev, &ctx->cs, &ctx->wW, &ctx->wE,
+  double** fields[] = {&ctx->tx, &ctx->ty, &ctx->cxy, &ctx->U, &ctx->Ud, &ctx->f, &ctx->yprev, &ctx->ylast, &ctx->cs, &ctx->wW, &ctx->wE,
                        &ctx->wS, &ctx->wN, &ctx->rhs, &ctx->x, &ctx->r, &ctx->p, &ctx->v, &ctx->s, &ctx->t};
   for (double** fp : fields) {
     CUB(cudaMalloc(reinterpret_cast<void**>(fp), ctx->total * sizeof(double)));
@@ -1336,7 +1339,7 @@ void sy2d_destroy(sy2d_ctx* c) {
   if (c->one_exec) cudaGraphExecDestroy(c->one_exec);
   if (c->slab_exec) cudaGraphExecDestroy(c->slab_exec);
   double* bufs[] = {c->d_wxL, c->d_wxR, c->d_wyB, c->d_wyT, c->d_dx, c->d_dy, c->d_bc[0], c->d_bc[1], c->d_bc[2], c->d_bc[3],
-                    c->tx, c->ty, c->cxy, c->U, c->Ud, c->f, c->yprev, c->cs, c->wW, c->wE, c->wS, c->wN, c->rhs,
+                    c->tx, c->ty, c->cxy, c->U, c->Ud, c->f, c->yprev, c->ylast, c->cs, c->wW, c->wE, c->wS, c->wN, c->rhs,
                     c->x, c->r, c->p, c->v, c->s, c->t, c->xl_scratch, c->xl_l, c->xl_dinv, c->xl_e, c->xl_hat};
   for (double* b : bufs) if (b) cudaFree(b);
   if (c->scal) cudaFree(c->scal);
@@ -1589,6 +1592,7 @@ static int check_f_input(sy2d_ctx* c, const char* who) {
 static int reset_state(sy2d_ctx* c) {
   // yprev = 1: the first step column-scales by f^n alone
   k_fill<<<grid_of(c), kBlock, 0, c->stream>>>(c->yprev, c->N, 1.0);
+  k_fill<<<grid_of(c), kBlock, 0, c->stream>>>(c->ylast, c->N, 1.0);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(c->stream));
   c->istep = 0;
@@ -1695,6 +1699,16 @@ static cudaError_t launch_xline(const XlineArgs& xa, int nctas, size_t smem, cud
   return cudaGetLastError();
 }
 
+// The pair kernel: two CTAs (one cluster) per problem; the cluster shape is a compile-time attribute of the kernel.
+template <int R, int NCH, int NT, int HS>
+static cudaError_t launch_xline_cl(const XlineArgs& xa, int nclusters, cudaStream_t stream) {
+  constexpr size_t smem = ((size_t)NCH * R * HS + 6 * (size_t)R * NT + 384 + 8) * sizeof(double);
+  cudaError_t e = cudaFuncSetAttribute(k_problem_xline_cl<R, NCH, NT, HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_problem_xline_cl<R, NCH, NT, HS><<<2 * nclusters, NT, smem, stream>>>(xa);
+  return cudaGetLastError();
+}
+
 // slots[0 .. nprob) = the problems of the launch in issue order, the rest "not yet pushed"; control words
 __global__ void k_xline_queue_init(XlineQueue* q, int* __restrict__ slots, const int* __restrict__ order, int nprob, int nchunks) {
   const int total = nprob * nchunks;
@@ -1778,7 +1792,7 @@ static int step_per_problem(sy2d_ctx* c, int nsteps, sy2d_stats* stats, const do
   CU(cudaMemcpyAsync(c->d_stats, c->h_stats, sizeof(StepStats), cudaMemcpyHostToDevice, c->stream));
   ProblemArgs a;
   a.tx = c->tx; a.ty = c->ty; a.cxy = c->cxy; a.U = c->U; a.Ud = c->Ud;
-  a.f = c->f; a.yprev = c->yprev; a.cs = c->cs;
+  a.f = c->f; a.yprev = c->yprev; a.ylast = c->ylast; a.cs = c->cs;
   a.wW = c->wW; a.wE = c->wE; a.wS = c->wS; a.wN = c->wN; a.rhs = c->rhs;
   a.x = c->x; a.r = c->r; a.p = c->p; a.v = c->v; a.s = c->s; a.t = c->t;
   a.scal = c->scal; a.stats = c->d_stats; a.g = geometry(c);
@@ -1843,6 +1857,9 @@ static int step_per_problem(sy2d_ctx* c, int nsteps, sy2d_stats* stats, const do
       xa.chunk = chunk; xa.nchunks = nchunks;
       xa.hin = d_hin; xa.hout = d_hout;
       k_xline_queue_init<<<std::max(1, std::min(64, (nprob * nchunks + 255) / 256)), 256, 0, stream>>>(xa.q, xa.slots, c->d_order + b0, nprob, nchunks);
+      if (c->xl_cluster && c->nx == 80 && c->ny == 80)
+        return c->xl_cluster == 2 ? launch_xline_cl<5, 16, 640, 43>(xa, std::min(nprob, c->sm_count / 2), stream)
+                                  : launch_xline_cl<10, 8, 320, 45>(xa, std::min(nprob, c->sm_count / 2), stream);
       return dispatch_xline(xa, R, nctas, smem, stream);
     }
     aa.order = c->d_order + b0;   // CTA b of this launch works on problem order[b0 + b]
@@ -2045,7 +2062,7 @@ int sy2d_step(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
       }
       {
         Prof p(c, SY2D_K_FINISH);
-        k_finish<<<g, kBlock, 0, c->stream>>>(c->x, c->cs, c->f, c->yprev, c->scal, c->N, c->opt.predictor, c->d_stats, 1000.0 * c->opt.tol);
+        k_finish<<<g, kBlock, 0, c->stream>>>(c->x, c->cs, c->f, c->yprev, c->ylast, c->scal, c->N, c->opt.predictor, c->d_stats, 1000.0 * c->opt.tol);
       }
       c->launches += 2;
     }

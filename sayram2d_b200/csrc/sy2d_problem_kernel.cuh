@@ -18,7 +18,7 @@ namespace sy2d {
 
 struct ProblemArgs {
   const double *tx, *ty, *cxy, *U, *Ud;  // read-only coefficients [nbatch][N]
-  double *f, *yprev, *cs;
+  double *f, *yprev, *ylast, *cs;          // ylast: the last per-cell ratio (predictor 2 only)
   double *wW, *wE, *wS, *wN, *rhs;       // scaled operator (scratch, rewritten every step)
   double *x, *r, *p, *v, *s, *t;         // Krylov vectors (scratch)
   Scal* scal;                            // per-problem outcome
@@ -172,11 +172,7 @@ __global__ void __launch_bounds__(kProblemThreads, 1) k_problem_steps(ProblemArg
       const double fold = f[n];
       const double fnew = cs[n] * (1.0 + (it > 0 ? x[n] : 0.0));
       f[n] = fnew;
-      if (a.predictor) {
-        double y = fnew / fold;
-        y = ::fmin(::fmax(y, kPredMin), kPredMax);
-        yprev[n] = (y == y) ? y : 1.0;
-      }
+      if (a.predictor) predictor_update(a.predictor, fnew, fold, yprev + n, a.ylast + base + n);
       fmin_l = ::fmin(fmin_l, fnew);
       neg += fnew < 0.0;
     }

@@ -544,11 +544,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
         const double d = z[m];
         const double fnew = (fold * yp) * (1.0 + d);
         f[n] = fnew;
-        if (a.predictor) {
-          double y = fnew / fold;
-          y = ::fmin(::fmax(y, kPredMin), kPredMax);
-          yprev[n] = (y == y) ? y : 1.0;
-        }
+        if (a.predictor) predictor_update(a.predictor, fnew, fold, yprev + n, a.ylast + base + n);
         fneg += fnew < 0.0 ? 1.0 : 0.0;
         fmin_neg = nmax(fmin_neg, -fnew);
       }

@@ -26,7 +26,7 @@ def scaled_system(n_alpha, n_E):
 
 def test_level_count_rule():
     assert MG.level_count(1024, 1024) == 5 and MG.level_count(2048, 2048) == 6 and MG.level_count(80, 80) == 2
-    assert MG.level_count(64, 48) == 2 and MG.level_count(64, 50) == 0 and MG.level_count(8192, 64) == 0
+    assert MG.level_count(64, 48) == 2 and MG.level_count(64, 50) == 0 and MG.level_count(8192, 64) == 2 and MG.level_count(16384, 64) == 0
     assert MG.level_count(64, 16) == 2 and MG.level_count(1024, 1024, 3) == 3 and MG.level_count(256, 256) == 3
 
 
