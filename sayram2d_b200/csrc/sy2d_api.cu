@@ -1718,7 +1718,7 @@ __global__ void k_xline_queue_init(XlineQueue* q, int* __restrict__ slots, const
 
 static cudaError_t dispatch_xline(const XlineArgs& xa, int R, int nbatch, size_t smem, cudaStream_t stream) {
   if (R == 10 && xa.NT == 640 && xa.hs == 85 && xa.a.g.nx == 80 && xa.a.g.ny == 80)
-    return launch_xline<10, 640, 640, 85>(xa, nbatch, smem, stream);   // 80 x 80: the production shape, everything compile-time
+    return launch_xline<10, 640, 640, 85>(xa, nbatch, xline_full_smem_doubles<10, 640, 85>() * sizeof(double), stream);   // 80 x 80: the production shape, everything compile-time
   if (R == 10 && xa.NT == 640) return launch_xline<10, 640, 640>(xa, nbatch, smem, stream);
   const bool small = xa.NT <= 640;
   switch (R) {
@@ -1828,7 +1828,7 @@ static int step_per_problem(sy2d_ctx* c, int nsteps, sy2d_stats* stats, const do
     if (!c->xl_scratch || c->xl_S != S || c->xl_scratch_slots < scratch_slots) {
       if (c->xl_scratch) cudaFree(c->xl_scratch);
       c->xl_scratch = nullptr;
-      CU(cudaMalloc(reinterpret_cast<void**>(&c->xl_scratch), scratch_slots * 5 * S * sizeof(double)));
+      CU(cudaMalloc(reinterpret_cast<void**>(&c->xl_scratch), scratch_slots * kXlineScratchArrays * S * sizeof(double)));
       c->xl_S = S;
       c->xl_scratch_slots = scratch_slots;
     }
@@ -1849,7 +1849,7 @@ static int step_per_problem(sy2d_ctx* c, int nsteps, sy2d_stats* stats, const do
       const int nctas = std::min(nprob, c->sm_count * ctas_per_sm);
       XlineArgs xa;
       xa.a = aa; xa.NT = NT; xa.S = S; xa.hs = HS;
-      xa.scratch = c->xl_scratch + (size_t)scratch_next * 5 * S;
+      xa.scratch = c->xl_scratch + (size_t)scratch_next * kXlineScratchArrays * S;
       scratch_next += nctas;
       xa.q = c->d_qctl + k;
       xa.slots = c->d_slots + (size_t)b0 * nchunks;

@@ -34,12 +34,14 @@
 // Traffic per cell and iteration: 10 L2 accesses (80 B: v r/w, wS wN twice, rhat twice, y r/w) + 18 shared
 // accesses (two Thomas solves of 4, two publishes, four neighbour reads, p written once and read three times).
 #pragma once
+#include "sy2d_assemble_tma.cuh"   // smem_u32, mbar_init / mbar_expect_tx / mbar_wait
 #include "sy2d_problem_kernel.cuh"
 
 namespace sy2d {
 
 constexpr int kXlineNCH = 8;          // lanes per column
 constexpr int kXlineCPW = 32 / kXlineNCH;
+constexpr int kXlineScratchArrays = 6;   // per CTA: wS, wN, v, y, rhs (thread-private layout) + one staging array of the block assembly
 
 // Work queue of one launch.  An item is "the next `chunk` time steps of problem p"; the persistent CTAs (one per SM)
 // pop tickets from `head`, wait until the ticket's slot holds a problem, run the chunk and - when the problem has steps
@@ -155,6 +157,171 @@ __device__ __noinline__ Scaled assemble_scaled_cell(const double* f, const doubl
   return sc;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Assembly of a FULL tile (nx = 8 R rows, ny = NT / 8 columns) by the whole CTA, block by block.
+//
+// The marching assembly (a thread walks up the R rows it owns, loading what each row needs when it gets there) spends
+// ~20 cycles per cell waiting for L2: ten-odd dependent round trips per row with one row in flight per thread.  Here
+// the CTA works through the grid in blocks of BR = 8 rows x ny columns - exactly one cell per thread - whose inputs
+// (f, yprev, tx, cxy with one halo row on each side; ty, U, Ud) one thread fetches with seven bulk copies
+// (cp.async.bulk global -> shared, mbarrier complete_tx) into a two-stage ring, so the loads of the next block are in
+// flight while this one is computed from shared memory:
+//   1. vertex values of the block's 9 x (ny+1) vertices                      -> V
+//   2. per cell its west and south face (A_K, A_L), each face evaluated once  -> XK/XL, YK/YL
+//   3. per cell the row: its four faces, boundary faces, U, the scaling       -> wW, wE (shared), wS, wN, rhs (scratch)
+// Blocks run from the top of the grid down, so the east faces of a block's last row are the west faces of the block
+// done just before (kept as row BR of XK/XL).  The ring, V and the face tiles live in the hat + p regions (unused during
+// the assembly); outputs go to NATURAL (i, j) layouts: wW, wE with row stride LS (LS * R = 10 (mod 16): the 16 lanes of
+// a half-warp of the solver - eight row chunks x two columns - hit 16 distinct banks), wS, wN, rhs with row stride ny
+// (consecutive lanes of a row write consecutive doubles).  Same per-face expressions, operand and accumulation order as
+// assemble_row.
+template <int NX, int NY>
+struct XlAsm {
+  static constexpr int BR = 8;
+  static constexpr int NBLK = NX / BR;
+  static constexpr int HROWS = BR + 2;                                   // f, yprev, tx, cxy: with halo rows
+  static constexpr int STAGE = 4 * HROWS * NY + 3 * BR * NY;             // doubles per ring stage
+  static constexpr int oF = 0, oY = HROWS * NY, oTX = 2 * HROWS * NY, oCX = 3 * HROWS * NY, oTY = 4 * HROWS * NY,
+                       oU = 4 * HROWS * NY + BR * NY, oUD = 4 * HROWS * NY + 2 * BR * NY;
+  static constexpr int VW = NY + 1;                                      // vertex tile row length
+  static constexpr int oV = 2 * STAGE;
+  static constexpr int oXK = oV + (((BR + 1) * VW + 1) & ~1);
+  static constexpr int oXL = oXK + (BR + 1) * NY;
+  static constexpr int oYK = oXL + (BR + 1) * NY;
+  static constexpr int oYL = oYK + BR * NY;
+  static constexpr int END = oYL + BR * NY;                              // doubles of shared memory the assembly needs
+  static_assert(NX % BR == 0, "full tiles only");
+};
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// `area`: >= XlAsm::END doubles of shared memory (16-byte aligned), `full`: two initialised mbarriers (count 1), `ph`: their
+// phase parities (bits 0, 1; kept by the caller across calls).  All NT = BR * NY threads call it; ends with a CTA barrier.
+template <int NX, int NY, int LS>
+__device__ __forceinline__ void xline_assemble_blocks(double* area, unsigned long long* full, unsigned& ph, const double* f,
+                                                      const double* yprev, const double* __restrict__ tx,
+                                                      const double* __restrict__ ty, const double* __restrict__ cxy,
+                                                      const double* __restrict__ U, const double* __restrict__ Ud, const Geometry& g,
+                                                      double* l_s, double* e_s, double* wS_g, double* wN_g, double* rhs_g) {
+  using A = XlAsm<NX, NY>;
+  constexpr int BR = A::BR, NBLK = A::NBLK, VW = A::VW;
+  const int tid = threadIdx.x;
+  const int li = tid / NY, jc = tid - li * NY;
+  double* V = area + A::oV;
+  double* XK = area + A::oXK;
+  double* XL = area + A::oXL;
+  double* YK = area + A::oYK;
+  double* YL = area + A::oYL;
+  auto issue = [&](int b, int s) {   // one thread: arm the stage's barrier, launch the seven copies of block b
+    const int r0 = b * BR;
+    const int lo = r0 > 0 ? r0 - 1 : 0, hi = r0 + BR < NX ? r0 + BR : NX - 1;
+    const int nrow = hi - lo + 1, drow = lo - (r0 - 1);
+    double* st = area + s * A::STAGE;
+    mbar_expect_tx(&full[s], (unsigned)((4 * nrow + 3 * BR) * NY * sizeof(double)));
+    const unsigned hb = (unsigned)(nrow * NY * sizeof(double)), cb = (unsigned)(BR * NY * sizeof(double));
+    bulk_g2s(st + A::oF + drow * NY, f + lo * NY, hb, &full[s]);
+    bulk_g2s(st + A::oY + drow * NY, yprev + lo * NY, hb, &full[s]);
+    bulk_g2s(st + A::oTX + drow * NY, tx + lo * NY, hb, &full[s]);
+    bulk_g2s(st + A::oCX + drow * NY, cxy + lo * NY, hb, &full[s]);
+    bulk_g2s(st + A::oTY, ty + r0 * NY, cb, &full[s]);
+    bulk_g2s(st + A::oU, U + r0 * NY, cb, &full[s]);
+    bulk_g2s(st + A::oUD, Ud + r0 * NY, cb, &full[s]);
+  };
+  if (tid == 0) {
+    // the ring overwrites shared memory the generic proxy wrote (hat, p) and reads global memory the generic proxy
+    // wrote (f, yprev of the last step): order both against the async proxy
+    asm volatile("fence.proxy.async;" ::: "memory");
+    issue(NBLK - 1, 0);
+    if (NBLK > 1) issue(NBLK - 2, 1);
+  }
+#pragma unroll 1
+  for (int n = 0; n < NBLK; ++n) {
+    const int b = NBLK - 1 - n, s = n & 1;
+    const int r0 = b * BR, i = r0 + li;
+    const double* st = area + s * A::STAGE;
+    // row i of a staged array with halo rows sits at slot i - (r0 - 1)
+    const double* F = st + A::oF - (r0 - 1) * NY;
+    const double* Y = st + A::oY - (r0 - 1) * NY;
+    const double* TX = st + A::oTX - (r0 - 1) * NY;
+    const double* CX = st + A::oCX - (r0 - 1) * NY;
+    mbar_wait(&full[s], (ph >> s) & 1u);
+    ph ^= 1u << s;
+    // 1. vertices (r0 + lv, vj), lv = 0 .. BR, vj = 0 .. NY
+    auto vtx = [&](int lv, int vj) {
+      const int vi = r0 + lv;
+      const int il = vi > 0 ? vi - 1 : 0, ih = vi < NX ? vi : NX - 1;
+      const int jb = vj > 0 ? vj - 1 : 0, jh = vj < NY ? vj : NY - 1;
+      return vertex_value(g, vi, vj, F[il * NY + jb], F[ih * NY + jb], F[il * NY + jh], F[ih * NY + jh]);
+    };
+    V[li * VW + jc] = vtx(li, jc);
+    if (tid < NY) V[BR * VW + tid] = vtx(BR, tid);
+    else if (tid < NY + BR + 1) V[(tid - NY) * VW + NY] = vtx(tid - NY, NY);
+    __syncthreads();
+    // 2. west and south face of the cell
+    const double f00 = F[i * NY + jc], txP = TX[i * NY + jc], cP = CX[i * NY + jc], tyP = st[A::oTY + li * NY + jc];
+    const double vSW = V[li * VW + jc], vSE = V[(li + 1) * VW + jc], vNW = V[li * VW + jc + 1], vNE = V[(li + 1) * VW + jc + 1];
+    {
+      if (li == 0 && n > 0) {   // the block above left its first row of west faces in row 0: they are this block's row BR
+        XK[BR * NY + jc] = XK[jc];
+        XL[BR * NY + jc] = XL[jc];
+      }
+      double AKw = 0.0, ALw = 0.0;
+      if (i > 0) {   // K = (i, j), L = (i-1, j)
+        const double t = TX[(i - 1) * NY + jc], c = CX[(i - 1) * NY + jc];
+        const double aW_A = txP - cP, aW_B = txP + cP, lA = t - c, lB = t + c;
+        face_pair(aW_A * vNW + aW_B * vSW, aW_A + aW_B, f00, lA * vSW + lB * vNW, lA + lB, F[(i - 1) * NY + jc], AKw, ALw);
+      }
+      double AKs = 0.0, ALs = 0.0;
+      if (jc > 0) {   // K = (i, j), L = (i, j-1)
+        const double t = st[A::oTY + li * NY + jc - 1], c = CX[i * NY + jc - 1];
+        const double aS_A = tyP + cP, aS_B = tyP - cP, lA = t + c, lB = t - c;
+        face_pair(aS_A * vSW + aS_B * vSE, aS_A + aS_B, f00, lA * vSE + lB * vSW, lA + lB, F[i * NY + jc - 1], AKs, ALs);
+      }
+      XK[li * NY + jc] = AKw; XL[li * NY + jc] = ALw;
+      YK[li * NY + jc] = AKs; YL[li * NY + jc] = ALs;
+    }
+    __syncthreads();
+    // 3. the row
+    {
+      Row row;
+      double diag = 0.0, Rr = 0.0;
+      row.oW = 0.0; row.oE = 0.0; row.oS = 0.0; row.oN = 0.0;
+      if (i > 0) { diag += XK[li * NY + jc]; row.oW = -XL[li * NY + jc]; }
+      else if (g.bc[0] == 0) diag += dirichlet_face((txP - cP) * vNW + (txP + cP) * vSW, (txP - cP) + (txP + cP), f00, Rr);
+      if (i < NX - 1) { diag += XL[(li + 1) * NY + jc]; row.oE = -XK[(li + 1) * NY + jc]; }
+      else if (g.bc[1] == 0) diag += dirichlet_face((txP - cP) * vSE + (txP + cP) * vNE, (txP - cP) + (txP + cP), f00, Rr);
+      if (jc > 0) { diag += YK[li * NY + jc]; row.oS = -YL[li * NY + jc]; }
+      else if (g.bc[2] == 0) diag += dirichlet_face((tyP + cP) * vSW + (tyP - cP) * vSE, (tyP + cP) + (tyP - cP), f00, Rr);
+      if (jc < NY - 1) { diag += YL[li * NY + jc + 1]; row.oN = -YK[li * NY + jc + 1]; }
+      else if (g.bc[3] == 0) diag += dirichlet_face((tyP + cP) * vNE + (tyP - cP) * vNW, (tyP + cP) + (tyP - cP), f00, Rr);
+      diag += st[A::oUD + li * NY + jc];
+      Rr += st[A::oU + li * NY + jc] * f00;
+      row.diag = diag; row.R = Rr; row.f00 = f00;
+      const int iW = i > 0 ? i - 1 : i, iE = i < NX - 1 ? i + 1 : i, jS = jc > 0 ? jc - 1 : jc, jN = jc < NY - 1 ? jc + 1 : jc;
+      row.fW = F[iW * NY + jc]; row.fE = F[iE * NY + jc]; row.fS = F[i * NY + jS]; row.fN = F[i * NY + jN];
+      Scaled sc;
+      scale_row(row, Y[i * NY + jc], Y[iW * NY + jc], Y[iE * NY + jc], Y[i * NY + jS], Y[i * NY + jN], sc);
+      l_s[i * LS + jc] = sc.wW;   // raw wW, wE until the factorisation
+      e_s[i * LS + jc] = sc.wE;
+      wS_g[i * NY + jc] = sc.wS; wN_g[i * NY + jc] = sc.wN; rhs_g[i * NY + jc] = sc.rhs;
+    }
+    __syncthreads();   // the stage, V and the face tiles are free
+    if (tid == 0 && n + 2 < NBLK) issue(NBLK - 3 - n, s);
+  }
+}
+
+// shared memory (doubles) of the full-tile instance: assembly area (>= hat + p) | wW/l' | wE/e | reduction buffers, work item, mbarriers
+template <int R, int NT, int HS>
+constexpr size_t xline_full_smem_doubles() {
+  constexpr int NX = kXlineNCH * R, NY = NT / kXlineNCH, LS = NY + 1;
+  constexpr size_t area = (size_t)(XlAsm<NX, NY>::END > NX * HS + R * NT ? XlAsm<NX, NY>::END : NX * HS + R * NT);
+  return area + 2 * (size_t)NX * LS + 192 + 2 + 2;
+}
+
 // NTC > 0 fixes the CTA size at compile time (the 80-column production shape: 640 threads), so
 // that every thread-private slot m*NT + tid is base + immediate and costs no address registers.
 // HSC > 0 fixes the hat row stride too and promises a FULL tile (nx = NCH*R rows, ny = NT/NCH columns:
@@ -174,14 +341,33 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
   const bool col_ok = FULL || j < ny;
   const int i0 = k * R;
   const int hs = HSC > 0 ? HSC : xa.hs;   // hat row stride, chosen on the host so that the NCH lanes of a column hit distinct banks
+  // Full tile: l', e in the natural (i, j) layout with row stride LS (written by the block assembly), the scaled wS', wN',
+  // rhs' of the scratch in the natural layout with row stride ny; otherwise thread-private slots m * NT + tid.
+  constexpr int NXC = NCH * R, NYC = (NTC > 0 ? NTC : NCH) / NCH, LS = NYC + 1;
+  constexpr int AREA = FULL ? (XlAsm<NXC, NYC>::END > NXC * HSC + R * NTC ? XlAsm<NXC, NYC>::END : NXC * HSC + R * NTC) : 0;
   double* hat = sm;
-  double* l_s = hat + nx * hs;
-  double* p_s = l_s + S;     // the search direction p; during the assembly: face exchange, then 1/d of the factorisation
-  double* e_s = p_s + S;
-  double* red = e_s + S;
+  double* p_s = hat + nx * hs;   // the search direction p; during the assembly: 1/d of the factorisation
+  double* l_s = FULL ? sm + AREA : p_s + S;
+  double* e_s = l_s + (FULL ? NXC * LS : S);
+  double* red = e_s + (FULL ? NXC * LS : S);
   int* s_item = reinterpret_cast<int*>(red + 192);
-  double* scr = xa.scratch + (size_t)blockIdx.x * 5 * S;
+  unsigned long long* asm_bar = reinterpret_cast<unsigned long long*>(red + 194);   // full tile: the two stage barriers of the assembly ring
+  unsigned asm_ph = 0;
+  const int lq0 = FULL ? i0 * LS + j : tid, lqs = FULL ? LS : NT;     // slot of owned row m in l_s / e_s: lq0 + m * lqs
+  const int gq0 = FULL ? i0 * ny + j : tid, gqs = FULL ? ny : NT;     // ... in wS_g / wN_g / rhs_g
+  if (FULL) {
+    if (tid == 0) {
+      mbar_init(&asm_bar[0], 1);
+      mbar_init(&asm_bar[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
+  double* scr = xa.scratch + (size_t)blockIdx.x * kXlineScratchArrays * S;
   double* wS_g = scr; double* wN_g = scr + S; double* v_g = scr + 2 * S; double* y_g = scr + 3 * S; double* rhs_g = scr + 4 * S;
+  // full tile: the block assembly leaves wS, wN, rhs in the natural (i, j) layout (coalesced stores) in v, y and a sixth
+  // array; the pivot-scaling pass moves them into the thread-private layout the iteration reads
+  double* wS_n = FULL ? v_g : wS_g; double* wN_n = FULL ? y_g : wN_g; double* rhs_n = FULL ? scr + 5 * S : rhs_g;
   const unsigned full = 0xffffffffu;
 
   double rs[R], z[R];
@@ -227,87 +413,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
     // ------------- assembly of the scaled rows owned by this thread -------------
     double acc[2] = {0.0, 0.0};
     if (FULL) {
-      // Full 80 x 80 tile: every interior face is evaluated ONCE per CTA instead of once per adjacent cell.
-      // A thread owns rows i0 .. i0+R-1 of column j: it marches up its column, so the W face of a row is the
-      // E face it computed for the row below (11 x-faces per 10 cells); the S faces of its cells go through
-      // shared memory (the hat and 1/d regions are free during the assembly) and come back as the N faces
-      // of column j-1.  Vertices: the vertical lines j and j+1, 2 x 11 evaluations per 10 cells instead of
-      // 40.  Same per-face expressions as assemble_row (K/L roles, operand order), same accumulation order.
-      const Geometry& g = a.g;
-      double* SK_s = hat;    // A_K, A_L of the south face of slot q
-      double* SL_s = p_s;
-      auto vertex_at = [&](int vi, int vj) {
-        const int il = vi > 0 ? vi - 1 : 0, ih = vi < nx ? vi : nx - 1;
-        const int jl = vj > 0 ? vj - 1 : 0, jh = vj < ny ? vj : ny - 1;
-        return vertex_value(g, vi, vj, f[il * ny + jl], f[ih * ny + jl], f[il * ny + jh], f[ih * ny + jh]);
-      };
-      // Both passes are rolled loops (small code, no spills); the vertices of line j are stashed in the l
-      // region (slot m holds V(i0 + m, j) until row m overwrites it with its wW), the top one in a register.
-      double vprev = vertex_at(i0, j);
-#pragma unroll 1
-      for (int m = 0; m < R; ++m) {
-        const int n = (i0 + m) * ny + j;
-        const double vnext = vertex_at(i0 + m + 1, j);
-        double AK = 0.0, AL = 0.0;
-        if (j > 0) {   // south face: K = (i, j), L = (i, j-1)
-          const double tyP = ty[n], cP = cxy[n], t = ty[n - 1], c = cxy[n - 1];
-          const double aS_A = tyP + cP, aS_B = tyP - cP, lA = t + c, lB = t - c;
-          face_pair(aS_A * vprev + aS_B * vnext, aS_A + aS_B, f[n], lA * vnext + lB * vprev, lA + lB, f[n - 1], AK, AL);
-        }
-        SK_s[m * NT + tid] = AK;
-        SL_s[m * NT + tid] = AL;
-        l_s[m * NT + tid] = vprev;
-        vprev = vnext;
-      }
-      const double vtop = vprev;   // V(i0 + R, j)
-      __syncthreads();
-      const int jn = j + 1;
-      const int tidN = jn < ny ? (jn / kXlineCPW) * 32 + (jn % kXlineCPW) * NCH + k : tid;   // same rows, column j+1
-      double vNW = vertex_at(i0, jn);
-      double AKw = 0.0, ALw = 0.0;   // west face of the current row: K = current cell, L = the row below
-      if (i0 > 0) {
-        const int n = i0 * ny + j;
-        const double v0 = l_s[tid];
-        const double txP = tx[n], cP = cxy[n], t = tx[n - ny], c = cxy[n - ny];
-        const double aW_A = txP - cP, aW_B = txP + cP, lA = t - c, lB = t + c;
-        face_pair(aW_A * vNW + aW_B * v0, aW_A + aW_B, f[n], lA * v0 + lB * vNW, lA + lB, f[n - ny], AKw, ALw);
-      }
-#pragma unroll 1
-      for (int m = 0; m < R; ++m) {
-        const int i = i0 + m, n = i * ny + j, q = m * NT + tid;
-        const double vSW = l_s[q], vSE = m + 1 < R ? l_s[q + NT] : vtop, vNE = vertex_at(i + 1, jn);
-        const double txP = tx[n], tyP = ty[n], cP = cxy[n], f00 = f[n];
-        Row row;
-        double diag = 0.0, Rr = 0.0;
-        row.oW = 0.0; row.oE = 0.0; row.oS = 0.0; row.oN = 0.0;
-        if (i > 0) { diag += AKw; row.oW = -ALw; }
-        else if (g.bc[0] == 0) diag += dirichlet_face((txP - cP) * vNW + (txP + cP) * vSW, (txP - cP) + (txP + cP), f00, Rr);
-        double AKe = 0.0, ALe = 0.0;
-        if (i < nx - 1) {   // east face: K = (i+1, j), L = this cell
-          const double t = tx[n + ny], c = cxy[n + ny];
-          const double kA = t - c, kB = t + c, aE_A = txP - cP, aE_B = txP + cP;
-          face_pair(kA * vNE + kB * vSE, kA + kB, f[n + ny], aE_A * vSE + aE_B * vNE, aE_A + aE_B, f00, AKe, ALe);
-          diag += ALe;
-          row.oE = -AKe;
-        } else if (g.bc[1] == 0) {
-          diag += dirichlet_face((txP - cP) * vSE + (txP + cP) * vNE, (txP - cP) + (txP + cP), f00, Rr);
-        }
-        if (j > 0) { diag += SK_s[q]; row.oS = -SL_s[q]; }
-        else if (g.bc[2] == 0) diag += dirichlet_face((tyP + cP) * vSW + (tyP - cP) * vSE, (tyP + cP) + (tyP - cP), f00, Rr);
-        if (j < ny - 1) { diag += SL_s[m * NT + tidN]; row.oN = -SK_s[m * NT + tidN]; }
-        else if (g.bc[3] == 0) diag += dirichlet_face((tyP + cP) * vNE + (tyP - cP) * vNW, (tyP + cP) + (tyP - cP), f00, Rr);
-        diag += Ud[n];
-        Rr += U[n] * f00;
-        row.diag = diag; row.R = Rr; row.f00 = f00;
-        const int nW = i > 0 ? n - ny : n, nE = i < nx - 1 ? n + ny : n, nS = j > 0 ? n - 1 : n, nN = j < ny - 1 ? n + 1 : n;
-        row.fW = f[nW]; row.fE = f[nE]; row.fS = f[nS]; row.fN = f[nN];
-        Scaled sc;
-        scale_row(row, yprev[n], yprev[nW], yprev[nE], yprev[nS], yprev[nN], sc);
-        l_s[q] = sc.wW;   // raw wW, wE until the factorisation below turns them into l and wE/d
-        e_s[q] = sc.wE;
-        wS_g[q] = sc.wS; wN_g[q] = sc.wN; rhs_g[q] = sc.rhs;
-        AKw = AKe; ALw = ALe; vNW = vNE;
-      }
+      xline_assemble_blocks<NXC, NYC, LS>(sm, asm_bar, asm_ph, f, yprev, tx, ty, cxy, U, Ud, a.g, l_s, e_s, wS_n, wN_n, rhs_n);
     } else {
 #pragma unroll
       for (int m = 0; m < R; ++m) {
@@ -322,7 +428,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
         wS_g[q] = wS; wN_g[q] = wN; rhs_g[q] = rh;
       }
     }
-    __syncthreads();   // the face exchange through the p region is over: the factorisation writes 1/d there
+    if (!FULL) __syncthreads();   // (the block assembly ends with a barrier)
     // LU of T down each column: chain over the NCH lanes of the column.  d_i = 1 - wW_i e_{i-1} (e = wE / d), so only
     // e is handed from row to row and from lane to lane; l' = wW / d, e = wE / d, 1/d parked in the p region.
     {
@@ -334,11 +440,11 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
           double eprev = k == 0 ? 0.0 : ein;   // wW of the first row of a column is 0
 #pragma unroll
           for (int m = 0; m < R; ++m) {
-            const int q = m * NT + tid;
-            const double wW = l_s[q], wE = e_s[q];
+            const int q = m * NT + tid, lq = lq0 + m * lqs;
+            const double wW = l_s[lq], wE = e_s[lq];
             const double dinv = sy2d_div(1.0, 1.0 - wW * eprev);
             eprev = wE * dinv;
-            l_s[q] = wW * dinv; p_s[q] = dinv; e_s[q] = eprev;
+            l_s[lq] = wW * dinv; p_s[q] = dinv; e_s[lq] = eprev;
           }
           elast = eprev;
         }
@@ -347,10 +453,10 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
     // pivot scaling of the rest of the row (thread-private slots: no barrier needed), r0 = rhs', rho0, max|r0|
 #pragma unroll
     for (int m = 0; m < R; ++m) {
-      const int q = m * NT + tid;
+      const int q = m * NT + tid, gq = gq0 + m * gqs;
       const double dinv = p_s[q];
-      wS_g[q] *= dinv; wN_g[q] *= dinv;
-      const double rh = rhs_g[q] * dinv;
+      wS_g[q] = wS_n[gq] * dinv; wN_g[q] = wN_n[gq] * dinv;
+      const double rh = rhs_n[gq] * dinv;
       rhs_g[q] = rh;
       rs[m] = rh;
       acc[0] += rh * rh;
@@ -373,7 +479,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
       double A = 0.0, B = 1.0;
 #pragma unroll
       for (int m = 0; m < R; ++m) {
-        const double lm = l_s[m * NT + tid];
+        const double lm = l_s[lq0 + m * lqs];
         A = bget(m) - lm * A;
         z[m] = A;
         B = -lm * B;
@@ -388,14 +494,14 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
       double P = 1.0;
 #pragma unroll
       for (int m = 0; m < R; ++m) {
-        P = -l_s[m * NT + tid] * P;
+        P = -l_s[lq0 + m * lqs] * P;
         z[m] += P * cin;
       }
       // backward (unit diagonal): x_m = z_m - e_m x_{m+1}
       A = 0.0; B = 1.0;
 #pragma unroll
       for (int m = R - 1; m >= 0; --m) {
-        const double em = e_s[m * NT + tid];
+        const double em = e_s[lq0 + m * lqs];
         A = z[m] - em * A;
         z[m] = A;
         B = -em * B;
@@ -410,7 +516,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
       P = 1.0;
 #pragma unroll
       for (int m = R - 1; m >= 0; --m) {
-        P = -e_s[m * NT + tid] * P;
+        P = -e_s[lq0 + m * lqs] * P;
         z[m] += P * cin;
       }
     };
@@ -510,17 +616,17 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
       double mres = 0.0, mrel = 0.0;   // absolute, and componentwise-relative (k_true_residual) true residual
 #pragma unroll
       for (int m = 0; m < R; ++m) {
-        const int i = i0 + m, q = m * NT + tid;
+        const int i = i0 + m, lq = lq0 + m * lqs, q = m * NT + tid;
         if (FULL || (col_ok && i < nx)) {
-          const double lp = l_s[q];
+          const double lp = l_s[lq];
           double dinv_i = 1.0;
           if (i > 0) {
             const int kp = (i - 1) / R, mp = (i - 1) - kp * R;
             const int tp = tid - (k - kp);
-            dinv_i = 1.0 + lp * e_s[mp * NT + tp];
+            dinv_i = 1.0 + lp * e_s[FULL ? (i - 1) * LS + j : mp * NT + tp];
           }
           const double dW = i > 0 ? hat[(i - 1) * hs + j] : 0.0, dE = i < nx - 1 ? hat[(i + 1) * hs + j] : 0.0;
-          const double tW = lp * dW, tE = e_s[q] * dE, tS = wS_g[q] * hat[i * hs + jS], tN = wN_g[q] * hat[i * hs + jN];
+          const double tW = lp * dW, tE = e_s[lq] * dE, tS = wS_g[q] * hat[i * hs + jS], tN = wN_g[q] * hat[i * hs + jN];
           const double ax = dinv_i * z[m] + ((tW + tE) + (tS + tN));
           const double ra = fabs(rhs_g[q] - ax);
           mres = nmax(mres, ra / dinv_i);
@@ -566,6 +672,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
         }
       }
     }
+    if (FULL) __threadfence();   // the next assembly reads f, yprev through the async proxy (bulk copies)
     __syncthreads();  // f and yprev complete before the next step's assembly reads neighbours
     steps_ok = step + 1;
   }
