@@ -319,7 +319,7 @@ template <int R, int NT, int HS>
 constexpr size_t xline_full_smem_doubles() {
   constexpr int NX = kXlineNCH * R, NY = NT / kXlineNCH, LS = NY + 1;
   constexpr size_t area = (size_t)(XlAsm<NX, NY>::END > NX * HS + R * NT ? XlAsm<NX, NY>::END : NX * HS + R * NT);
-  return area + 2 * (size_t)NX * LS + 192 + 2 + 2;
+  return area + 2 * (size_t)NX * LS + 192 + 2 + 2 + (size_t)R * NT / 4;   // ... and the 16-bit shadow residual
 }
 
 // NTC > 0 fixes the CTA size at compile time (the 80-column production shape: 640 threads), so
@@ -353,6 +353,12 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
   int* s_item = reinterpret_cast<int*>(red + 192);
   unsigned long long* asm_bar = reinterpret_cast<unsigned long long*>(red + 194);   // full tile: the two stage barriers of the assembly ring
   unsigned asm_ph = 0;
+  // Full tile: the shadow residual rhat of BiCGSTAB - any fixed vector with (rhat, r0) != 0 - is r0 TRUNCATED to the upper 16
+  // bits of its doubles (sign, exponent, 4 bits of mantissa: rhat_i = r0_i (1 - eps_i), 0 <= eps_i < 1/16, so (rhat, r0) >=
+  // 15/16 |r0|^2) and lives in 12.8 KB of shared memory instead of the L2 scratch: 16 B less L2 traffic per cell and iteration.
+  // The arithmetic stays fp64; only the choice of the shadow vector differs from rhat = r0.
+  constexpr bool RH16 = FULL;
+  unsigned short* rh16 = reinterpret_cast<unsigned short*>(asm_bar + 2);
   const int lq0 = FULL ? i0 * LS + j : tid, lqs = FULL ? LS : NT;     // slot of owned row m in l_s / e_s: lq0 + m * lqs
   const int gq0 = FULL ? i0 * ny + j : tid, gqs = FULL ? ny : NT;     // ... in wS_g / wN_g / rhs_g
   if (FULL) {
@@ -368,9 +374,14 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
   // full tile: the block assembly leaves wS, wN, rhs in the natural (i, j) layout (coalesced stores) in v, y and a sixth
   // array; the pivot-scaling pass moves them into the thread-private layout the iteration reads
   double* wS_n = FULL ? v_g : wS_g; double* wN_n = FULL ? y_g : wN_g; double* rhs_n = FULL ? scr + 5 * S : rhs_g;
+  auto rhat_of = [&](int q) { return RH16 ? __hiloint2double((int)((unsigned)rh16[q] << 16), 0) : rhs_g[q]; };
   const unsigned full = 0xffffffffu;
 
   double rs[R], z[R];
+  // VREG: v stays in registers from the v phase to the end of the iteration, where the p array takes p - omega v (the next
+  // search direction is then r + beta * that): no v array in the scratch, 16 B less L2 traffic per cell and iteration.
+  constexpr bool VREG = FULL;
+  double vr[VREG ? R : 1];
 
  for (;;) {   // work items: (problem, chunk of time steps)
   if (tid == 0) {
@@ -459,7 +470,12 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
       const double rh = rhs_n[gq] * dinv;
       rhs_g[q] = rh;
       rs[m] = rh;
-      acc[0] += rh * rh;
+      if (RH16) {
+        rh16[q] = (unsigned short)((unsigned)__double2hiint(rh) >> 16);
+        acc[0] += rhat_of(q) * rh;
+      } else {
+        acc[0] += rh * rh;
+      }
       acc[1] = nmax(acc[1], fabs(rh));
     }
     cta_reduce_x<2>(acc, 1, red);
@@ -535,7 +551,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
       // p = r + beta (p - omega v), formed row by row as the right-hand side of the first sweep
       tsolve([&](int m) {
         const int q = m * NT + tid;
-        const double pm = first ? rs[m] : rs[m] + beta * (p_s[q] - omega * v_g[q]);
+        const double pm = first ? rs[m] : (VREG ? rs[m] + beta * p_s[q] : rs[m] + beta * (p_s[q] - omega * v_g[q]));
         p_s[q] = pm;
         return pm;
       });
@@ -549,15 +565,15 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
         const int i = i0 + m, q = m * NT + tid;
         double val = 0.0;
         if (FULL || (col_ok && i < nx)) val = p_s[q] + (wS_g[q] * hat[i * hs + jS] + wN_g[q] * hat[i * hs + jN]);
-        vv[m] = val;
-        v_g[q] = val;
-        a1[0] += rhs_g[q] * val;
+        if (VREG) vr[VREG ? m : 0] = val;
+        else { vv[m] = val; v_g[q] = val; }
+        a1[0] += rhat_of(q) * val;
       }
       cta_reduce_x<1, false>(a1, 1, red);
       alpha = a1[0] != 0.0 ? rho / a1[0] : 0.0;
       // s = r - alpha v (in place)
 #pragma unroll
-      for (int m = 0; m < R; ++m) rs[m] -= alpha * vv[m];
+      for (int m = 0; m < R; ++m) rs[m] -= alpha * (VREG ? vr[VREG ? m : 0] : vv[m]);
       tsolve([&](int m) { return rs[m]; });
       publish();
       // t = s + wS shat_S + wN shat_N ; (t,s), (t,t)
@@ -579,9 +595,11 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
 #pragma unroll
       for (int m = 0; m < R; ++m) {
         const int q = m * NT + tid;
-        y_g[q] = (first ? 0.0 : y_g[q]) + (alpha * p_s[q] + omega * rs[m]);
+        const double pm = p_s[q];
+        y_g[q] = (first ? 0.0 : y_g[q]) + (alpha * pm + omega * rs[m]);
+        if (VREG) p_s[q] = pm - omega * vr[VREG ? m : 0];
         rs[m] -= omega * vv[m];
-        a3[0] += rhs_g[q] * rs[m];
+        a3[0] += rhat_of(q) * rs[m];
         a3[1] = nmax(a3[1], fabs(rs[m]));
       }
       cta_reduce_sum_max(a3[0], a3[1], red + 128);
@@ -596,6 +614,16 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
       rho = rho_new;
     }
     it_total += it;
+    // full tile: f^n and yprev of the owned cells are fetched now, into the registers of r and v (dead from here on), so
+    // that their L2 latency hides behind the last line solve
+    if (VREG) {
+#pragma unroll
+      for (int m = 0; m < R; ++m) {
+        const int n = (i0 + m) * ny + j;
+        rs[m] = f[n];
+        vr[VREG ? m : 0] = yprev[n];
+      }
+    }
     // x = T^-1 y  (left in z)
     if (it > 0) {
       tsolve([&](int m) { return y_g[m * NT + tid]; });
@@ -645,8 +673,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
       const int i = i0 + m;
       if (FULL || (col_ok && i < nx)) {
         const int n = i * ny + j;
-        const double fold = f[n];
-        const double yp = yprev[n];
+        const double fold = VREG ? rs[m] : f[n];
+        const double yp = VREG ? vr[VREG ? m : 0] : yprev[n];
         const double d = z[m];
         const double fnew = (fold * yp) * (1.0 + d);
         f[n] = fnew;
