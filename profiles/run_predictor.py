@@ -1,6 +1,6 @@
 """Column-scale predictor of the ensemble kernel (options.predictor = 0 / 1 / 2): iterations and ms per step, and
 the difference of the solutions (they must agree to the solver tolerance).
-    python profiles/run_predictor.py [members] [steps]"""
+    python profiles/run_predictor.py [members] [steps] [first member]"""
 import os
 import sys
 
@@ -11,11 +11,12 @@ import bench  # noqa: E402
 
 members = int(sys.argv[1]) if len(sys.argv) > 1 else 1184
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+lo = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 bench.NB_TOTAL = 4096
 stride = 4096 // members
 out = {}
 for pred in (0, 1, 2):
-    eng, _ = bench.make_ensemble(0, members, 0)
+    eng, _ = bench.make_ensemble(lo, lo + members, 0)
     eng.set_options(predictor=pred)
     eng.step(5)
     ms, its = [], []
