@@ -1592,7 +1592,7 @@ static int check_f_input(sy2d_ctx* c, const char* who) {
 static int reset_state(sy2d_ctx* c) {
   // yprev = 1: the first step column-scales by f^n alone
   k_fill<<<grid_of(c), kBlock, 0, c->stream>>>(c->yprev, c->N, 1.0);
-  k_fill<<<grid_of(c), kBlock, 0, c->stream>>>(c->ylast, c->N, 1.0);
+  k_fill<<<grid_of(c), kBlock, 0, c->stream>>>(c->ylast, c->N, 0.0);   // no ratio history yet (predictor 2 extrapolates from the second step on)
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(c->stream));
   c->istep = 0;

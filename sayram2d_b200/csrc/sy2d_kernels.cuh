@@ -37,7 +37,8 @@ __host__ __device__ __forceinline__ void predictor_update(int predictor, double 
   if (!(y == y)) y = 1.0;
   double pred = y;
   if (predictor >= 2) {
-    pred = y * (y / *ylast);
+    const double yl = *ylast;          // 0 until the first step after (re)setting f has been taken: nothing to extrapolate from
+    pred = yl > 0.0 ? y * (y / yl) : y;
     pred = pred < kPredMin ? kPredMin : (pred > kPredMax ? kPredMax : pred);
     if (!(pred == pred)) pred = y;
     *ylast = y;
