@@ -31,19 +31,22 @@ constexpr double kPredMin = 0.5, kPredMax = 2.0;
 // the coming ratio the closer the initial guess d = 0 is to the solution).  predictor 1: the last ratio y_n = f^{n+1} / f^n;
 // predictor 2: its geometric extrapolation y_n (y_n / y_{n-1}) - quasi-steady decay and growth curve a little, and the
 // extrapolated guess starts 10-20x closer (about one BiCGSTAB iteration per step).  Both clamped to [kPredMin, kPredMax].
-__host__ __device__ __forceinline__ void predictor_update(int predictor, double fnew, double fold, double* yprev, double* ylast) {
+// yl: the value of *ylast (0 until the first step after (re)setting f has been taken: nothing to extrapolate from)
+__host__ __device__ __forceinline__ void predictor_update(int predictor, double fnew, double fold, double* yprev, double* ylast, double yl) {
   double y = fnew / fold;
   y = y < kPredMin ? kPredMin : (y > kPredMax ? kPredMax : y);
   if (!(y == y)) y = 1.0;
   double pred = y;
   if (predictor >= 2) {
-    const double yl = *ylast;          // 0 until the first step after (re)setting f has been taken: nothing to extrapolate from
     pred = yl > 0.0 ? y * (y / yl) : y;
     pred = pred < kPredMin ? kPredMin : (pred > kPredMax ? kPredMax : pred);
     if (!(pred == pred)) pred = y;
     *ylast = y;
   }
   *yprev = pred;
+}
+__host__ __device__ __forceinline__ void predictor_update(int predictor, double fnew, double fold, double* yprev, double* ylast) {
+  predictor_update(predictor, fnew, fold, yprev, ylast, predictor >= 2 ? *ylast : 0.0);
 }
 
 // Per-problem Krylov scalars, written only by the last block of a kernel to

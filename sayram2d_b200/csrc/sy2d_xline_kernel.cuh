@@ -668,6 +668,13 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
     }
     if (state >= 2) break;   // the solve stopped without converging (maxit, breakdown, NaN): f and yprev stay those of t^n
     double fneg = 0.0, fmin_neg = -1.0e300;
+    // full tile: the last ratios are fetched as one batch (inside the loop each load would wait for the stores of the row
+    // before it - the compiler has to assume they alias)
+    double yl[VREG ? R : 1];
+    if (VREG && a.predictor >= 2) {
+#pragma unroll
+      for (int m = 0; m < R; ++m) yl[VREG ? m : 0] = a.ylast[base + (i0 + m) * ny + j];
+    }
 #pragma unroll
     for (int m = 0; m < R; ++m) {
       const int i = i0 + m;
@@ -678,7 +685,10 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
         const double d = z[m];
         const double fnew = (fold * yp) * (1.0 + d);
         f[n] = fnew;
-        if (a.predictor) predictor_update(a.predictor, fnew, fold, yprev + n, a.ylast + base + n);
+        if (a.predictor) {
+          if (VREG) predictor_update(a.predictor, fnew, fold, yprev + n, a.ylast + base + n, yl[VREG ? m : 0]);
+          else predictor_update(a.predictor, fnew, fold, yprev + n, a.ylast + base + n);
+        }
         fneg += fnew < 0.0 ? 1.0 : 0.0;
         fmin_neg = nmax(fmin_neg, -fnew);
       }
