@@ -36,6 +36,7 @@
 #pragma once
 #include "sy2d_assemble_tma.cuh"   // smem_u32, mbar_init / mbar_expect_tx / mbar_wait
 #include "sy2d_problem_kernel.cuh"
+#include "sy2d_tmem.cuh"
 
 namespace sy2d {
 
@@ -361,14 +362,42 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
   unsigned short* rh16 = reinterpret_cast<unsigned short*>(asm_bar + 2);
   const int lq0 = FULL ? i0 * LS + j : tid, lqs = FULL ? LS : NT;     // slot of owned row m in l_s / e_s: lq0 + m * lqs
   const int gq0 = FULL ? i0 * ny + j : tid, gqs = FULL ? ny : NT;     // ... in wS_g / wN_g / rhs_g
+  // Full tile: wS', wN' and y of the owned rows live in TENSOR MEMORY (sy2d_tmem.cuh) instead of the L2 scratch: the thread's
+  // TMEM lane, 6 R columns of the warp's range - (wS'_m, wN'_m) row by row in [0, 4R), y_m in [4R, 6R).  The five warps that share
+  // a lane quarter (w % 4) take column ranges 96 apart.
+  constexpr bool TMW = FULL;
+  static_assert(!TMW || (R == 10 && MAXT <= 640), "TMEM layout: 10 rows per thread, at most five warps per lane quarter");
+  unsigned tcol = 0;
   if (FULL) {
     if (tid == 0) {
       mbar_init(&asm_bar[0], 1);
       mbar_init(&asm_bar[1], 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (TMW) {
+      if (w == 0) tmem_alloc_all(reinterpret_cast<unsigned*>(s_item + 1));
+      tmem_fence_before_sync();
+    }
     __syncthreads();
+    if (TMW) {
+      tmem_fence_after_sync();
+      tcol = reinterpret_cast<volatile unsigned*>(s_item + 1)[0] + ((unsigned)(32 * (w & 3)) << 16) + (unsigned)((w >> 2) * 96);
+    }
   }
+  // rows m0 .. m0+3 / m0 .. m0+1 of (wS', wN') from tensor memory; fn(m, wS'_m, wN'_m) per row
+  auto tm_rows = [&](auto fn) {
+#pragma unroll
+    for (int m0 = 0; m0 < 8; m0 += 4) {
+      double t[8];
+      tmem_ld<8>(t, tcol + 4 * m0);
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) fn(m0 + k4, t[2 * k4], t[2 * k4 + 1]);
+    }
+    double t[4];
+    tmem_ld<4>(t, tcol + 32);
+#pragma unroll
+    for (int k2 = 0; k2 < 2; ++k2) fn(8 + k2, t[2 * k2], t[2 * k2 + 1]);
+  };
   double* scr = xa.scratch + (size_t)blockIdx.x * kXlineScratchArrays * S;
   double* wS_g = scr; double* wN_g = scr + S; double* v_g = scr + 2 * S; double* y_g = scr + 3 * S; double* rhs_g = scr + 4 * S;
   // full tile: the block assembly leaves wS, wN, rhs in the natural (i, j) layout (coalesced stores) in v, y and a sixth
@@ -466,7 +495,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
     for (int m = 0; m < R; ++m) {
       const int q = m * NT + tid, gq = gq0 + m * gqs;
       const double dinv = p_s[q];
-      wS_g[q] = wS_n[gq] * dinv; wN_g[q] = wN_n[gq] * dinv;
+      if (TMW) { z[m] = wS_n[gq] * dinv; vr[VREG ? m : 0] = wN_n[gq] * dinv; }   // (z and v are free here) -> tensor memory below
+      else { wS_g[q] = wS_n[gq] * dinv; wN_g[q] = wN_n[gq] * dinv; }
       const double rh = rhs_n[gq] * dinv;
       rhs_g[q] = rh;
       rs[m] = rh;
@@ -477,6 +507,16 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
         acc[0] += rh * rh;
       }
       acc[1] = nmax(acc[1], fabs(rh));
+    }
+    if (TMW) {
+#pragma unroll
+      for (int m0 = 0; m0 < 8; m0 += 4) {
+        const double t[8] = {z[m0], vr[VREG ? m0 : 0], z[m0 + 1], vr[VREG ? m0 + 1 : 0], z[m0 + 2], vr[VREG ? m0 + 2 : 0], z[m0 + 3], vr[VREG ? m0 + 3 : 0]};
+        tmem_st<8>(tcol + 4 * m0, t);
+      }
+      const double t[4] = {z[8], vr[VREG ? 8 : 0], z[9], vr[VREG ? 9 : 0]};
+      tmem_st<4>(tcol + 32, t);
+      tmem_wait_st();
     }
     cta_reduce_x<2>(acc, 1, red);
     double rho = acc[0];
@@ -560,14 +600,23 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
       // phat from hat), so v and later t reuse its registers: peak live arrays are rs, p and one more.
       double (&vv)[R] = z;
       double a1[1] = {0.0};
+      if (TMW) {
+        tm_rows([&](int m, double ws, double wn) {
+          const int i = i0 + m, q = m * NT + tid;
+          const double val = p_s[q] + (ws * hat[i * hs + jS] + wn * hat[i * hs + jN]);
+          vr[VREG ? m : 0] = val;
+          a1[0] += rhat_of(q) * val;
+        });
+      } else {
 #pragma unroll
-      for (int m = 0; m < R; ++m) {
-        const int i = i0 + m, q = m * NT + tid;
-        double val = 0.0;
-        if (FULL || (col_ok && i < nx)) val = p_s[q] + (wS_g[q] * hat[i * hs + jS] + wN_g[q] * hat[i * hs + jN]);
-        if (VREG) vr[VREG ? m : 0] = val;
-        else { vv[m] = val; v_g[q] = val; }
-        a1[0] += rhat_of(q) * val;
+        for (int m = 0; m < R; ++m) {
+          const int i = i0 + m, q = m * NT + tid;
+          double val = 0.0;
+          if (FULL || (col_ok && i < nx)) val = p_s[q] + (wS_g[q] * hat[i * hs + jS] + wN_g[q] * hat[i * hs + jN]);
+          if (VREG) vr[VREG ? m : 0] = val;
+          else { vv[m] = val; v_g[q] = val; }
+          a1[0] += rhat_of(q) * val;
+        }
       }
       cta_reduce_x<1, false>(a1, 1, red);
       alpha = a1[0] != 0.0 ? rho / a1[0] : 0.0;
@@ -578,29 +627,56 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
       publish();
       // t = s + wS shat_S + wN shat_N ; (t,s), (t,t)
       double a2[2] = {0.0, 0.0};
+      if (TMW) {
+        tm_rows([&](int m, double ws, double wn) {
+          const int i = i0 + m;
+          const double val = rs[m] + (ws * hat[i * hs + jS] + wn * hat[i * hs + jN]);
+          vv[m] = val;  // t
+          a2[0] += val * rs[m];
+          a2[1] += val * val;
+        });
+      } else {
 #pragma unroll
-      for (int m = 0; m < R; ++m) {
-        const int i = i0 + m, q = m * NT + tid;
-        double val = 0.0;
-        if (FULL || (col_ok && i < nx)) val = rs[m] + (wS_g[q] * hat[i * hs + jS] + wN_g[q] * hat[i * hs + jN]);
-        vv[m] = val;  // t
-        a2[0] += val * rs[m];
-        a2[1] += val * val;
+        for (int m = 0; m < R; ++m) {
+          const int i = i0 + m, q = m * NT + tid;
+          double val = 0.0;
+          if (FULL || (col_ok && i < nx)) val = rs[m] + (wS_g[q] * hat[i * hs + jS] + wN_g[q] * hat[i * hs + jN]);
+          vv[m] = val;  // t
+          a2[0] += val * rs[m];
+          a2[1] += val * val;
+        }
       }
       cta_reduce_pair(a2[0], a2[1], red + 64);
       omega = a2[1] > 0.0 ? a2[0] / a2[1] : 0.0;
       // y += alpha p + omega s (x = T^-1 y is formed once, after the loop: x = sum alpha phat + omega shat and
       // T^-1 is linear) ; r = s - omega t ; (rhat, r), max|r|
       double a3[2] = {0.0, 0.0};
-#pragma unroll
-      for (int m = 0; m < R; ++m) {
+      auto yrow = [&](int m, double yold) {   // returns the new y_m
         const int q = m * NT + tid;
         const double pm = p_s[q];
-        y_g[q] = (first ? 0.0 : y_g[q]) + (alpha * pm + omega * rs[m]);
+        const double ynew = yold + (alpha * pm + omega * rs[m]);
         if (VREG) p_s[q] = pm - omega * vr[VREG ? m : 0];
         rs[m] -= omega * vv[m];
         a3[0] += rhat_of(q) * rs[m];
         a3[1] = nmax(a3[1], fabs(rs[m]));
+        return ynew;
+      };
+      if (TMW) {
+        double y8[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, y2[2] = {0.0, 0.0};
+        if (!first) { tmem_ld<8>(y8, tcol + 4 * R); tmem_ld<2>(y2, tcol + 4 * R + 16); }
+#pragma unroll
+        for (int m = 0; m < 8; ++m) y8[m] = yrow(m, y8[m]);
+        tmem_st<8>(tcol + 4 * R, y8);
+#pragma unroll
+        for (int m = 0; m < 2; ++m) y2[m] = yrow(8 + m, y2[m]);
+        tmem_st<2>(tcol + 4 * R + 16, y2);
+        tmem_wait_st();
+      } else {
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+          const int q = m * NT + tid;
+          y_g[q] = yrow(m, first ? 0.0 : y_g[q]);
+        }
       }
       cta_reduce_sum_max(a3[0], a3[1], red + 128);
       const double rho_new = a3[0];
@@ -626,7 +702,17 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
     }
     // x = T^-1 y  (left in z)
     if (it > 0) {
-      tsolve([&](int m) { return y_g[m * NT + tid]; });
+      if (TMW) {   // y into z (the solve reads row m before it writes it)
+        double y8[8], y2[2];
+        tmem_ld<8>(y8, tcol + 4 * R);
+        tmem_ld<2>(y2, tcol + 4 * R + 16);
+#pragma unroll
+        for (int m = 0; m < 8; ++m) z[m] = y8[m];
+        z[8] = y2[0]; z[9] = y2[1];
+        tsolve([&](int m) { return z[m]; });
+      } else {
+        tsolve([&](int m) { return y_g[m * NT + tid]; });
+      }
     } else {
 #pragma unroll
       for (int m = 0; m < R; ++m) z[m] = 0.0;
@@ -642,8 +728,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
       __syncthreads();   // every thread is past its last read of shat
       publish();
       double mres = 0.0, mrel = 0.0;   // absolute, and componentwise-relative (k_true_residual) true residual
-#pragma unroll
-      for (int m = 0; m < R; ++m) {
+      auto resrow = [&](int m, double wS_m, double wN_m) {
         const int i = i0 + m, lq = lq0 + m * lqs, q = m * NT + tid;
         if (FULL || (col_ok && i < nx)) {
           const double lp = l_s[lq];
@@ -654,12 +739,18 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
             dinv_i = 1.0 + lp * e_s[FULL ? (i - 1) * LS + j : mp * NT + tp];
           }
           const double dW = i > 0 ? hat[(i - 1) * hs + j] : 0.0, dE = i < nx - 1 ? hat[(i + 1) * hs + j] : 0.0;
-          const double tW = lp * dW, tE = e_s[lq] * dE, tS = wS_g[q] * hat[i * hs + jS], tN = wN_g[q] * hat[i * hs + jN];
+          const double tW = lp * dW, tE = e_s[lq] * dE, tS = wS_m * hat[i * hs + jS], tN = wN_m * hat[i * hs + jN];
           const double ax = dinv_i * z[m] + ((tW + tE) + (tS + tN));
           const double ra = fabs(rhs_g[q] - ax);
           mres = nmax(mres, ra / dinv_i);
           mrel = nmax(mrel, ra / (dinv_i * (1.0 + fabs(z[m])) + ((fabs(tW) + fabs(tE)) + (fabs(tS) + fabs(tN)))));
         }
+      };
+      if (TMW) {
+        tm_rows(resrow);
+      } else {
+#pragma unroll
+        for (int m = 0; m < R; ++m) resrow(m, wS_g[m * NT + tid], wN_g[m * NT + tid]);
       }
       double mm[2] = {mres, mrel};
       cta_reduce_x<2>(mm, 0, red);
@@ -750,6 +841,11 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
     }
   }
  }
+  if (TMW) {
+    tmem_fence_before_sync();
+    __syncthreads();
+    if (w == 0) tmem_dealloc_all(reinterpret_cast<volatile unsigned*>(s_item + 1)[0]);
+  }
 }
 
 }  // namespace sy2d
