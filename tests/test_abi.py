@@ -53,7 +53,7 @@ def test_argument_validation_messages_follow_reference():
     assert e.value.code == -1
     o = sy.Options()
     assert lib.sy2d_default_options(ctypes.byref(o)) == 0
-    assert o.tol == 1e-14 and o.maxit >= 1000 and o.predictor == 1
+    assert o.tol == 1e-14 and o.maxit >= 1000 and o.predictor == 2
 
 
 def test_no_cpu_fallback():
