@@ -190,12 +190,14 @@ BYTES_PER_CELL_XLINE = {"p_update": 64, "spmv_v": 48, "s_update": 80, "spmv_t": 
 
 
 # The engine-2 x-line kernel (k_problem_xline) keeps a problem's state on chip: what it moves goes through the L1TEX data
-# pipe of its SM (shared memory + the L2-backed thread-private scratch), not through HBM.  Algorithmic bytes, counted
+# pipe of its SM (shared memory), not through HBM.  Algorithmic bytes, counted
 # from the kernel source ("engine 2"): per cell and BiCGSTAB iteration 19 shared-memory accesses of
 # 8 bytes (two Thomas solves of 4, two publishes, four neighbour reads, p written twice and read three times) + two 2-byte
-# reads of the 16-bit shadow residual + 6 L2-backed accesses (wS and wN twice, y r/w) = 204 B; per cell and time step
-# (block assembly from the staged inputs, factorisation, pivot scaling, final solve and update) 76 accesses = 608 B.
-XLINE_L1_BYTES_PER_CELL_ITER = 204
+# reads of the 16-bit shadow residual = 156 B; the six further accesses of an iteration (wS' and wN' twice, y read and written)
+# go to TENSOR MEMORY (tcgen05.ld / st, sy2d_tmem.cuh) and do not pass through the L1TEX data pipe, so they are not counted;
+# per cell and time step (block assembly from the staged inputs, factorisation, pivot scaling, final solve and update)
+# 76 accesses = 608 B.
+XLINE_L1_BYTES_PER_CELL_ITER = 156
 XLINE_L1_BYTES_PER_CELL_STEP = 608
 HBM_COMPULSORY_BYTES_PER_CELL_STEP = 88   # tx, ty, cxy, U, Ud, f, yprev, ylast in; f, yprev, ylast out
 
@@ -479,7 +481,7 @@ def ours(args):
                                 "unit": "GB/s", "frac": r["frac"], "traffic": traffic, "traffic_source": traffic_src,
                                 "bytes_per_launch": r["bytes_total"] / r["launches"], "ms_per_launch": r["ms_total"] / r["launches"],
                                 "model": f"{XLINE_L1_BYTES_PER_CELL_STEP} B per cell-step + {XLINE_L1_BYTES_PER_CELL_ITER} B per cell-iteration through "
-                                         "the L1TEX data pipe (19 shared + 6 L2-backed 8-byte accesses and two 2-byte reads per cell and iteration)",
+                                         "the L1TEX data pipe (19 shared-memory 8-byte accesses and two 2-byte reads per cell and iteration; 6 more 8-byte accesses go to tensor memory, not counted)",
                                 "peak_source": "measured: sy2d_measure_peaks shared-memory copy (8-byte accesses, loads + stores, all SMs)",
                                 "hbm_compulsory": r["hbm_compulsory"], "measured_peaks": peaks, "kernels": {"ensemble_xline": r}}
         else:

@@ -18,8 +18,7 @@ BIN = os.path.join(PKG, "bin", "sayram2d")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CUDA_SOURCES = [os.path.join(PKG, "csrc", "sy2d_api.cu")]
-CUDA_HEADERS = [os.path.join(PKG, "csrc", h) for h in ("sy2d_kernels.cuh", "sy2d_geometry.h", "sy2d_problem_kernel.cuh",
-                                                        "sy2d_xline_kernel.cuh", "sy2d_xline_lockstep.cuh", "sy2d_mg.cuh", "sy2d_assemble_tma.cuh", "sy2d_assemble_march.cuh", "sy2d_peaks.cuh")] + [
+CUDA_HEADERS = sorted(os.path.join(PKG, "csrc", h) for h in os.listdir(os.path.join(PKG, "csrc")) if h.endswith((".cuh", ".h"))) + [
     os.path.join(ROOT, "include", "sayram2d.h")]
 
 

@@ -25,6 +25,7 @@
 #include "sy2d_mg.cuh"
 #include "sy2d_assemble_tma.cuh"
 #include "sy2d_assemble_march.cuh"
+#include "sy2d_assemble_col.cuh"
 #include "sy2d_peaks.cuh"
 
 using namespace sy2d;
@@ -47,7 +48,10 @@ struct sy2d_ctx {
   // registers that are resident on an SM at once: one full wave, no tail (profiles/sweep_caps_steps.py: 1024^2 4.98 -> 4.81 ms
   // per step against 16, 2048^2 15.2 -> 14.9, 4096^2 equal; 8 is worse everywhere - a partial second wave)
   int ctas_per_sm = 6, asm_ctas_per_sm = 4, march_ctas_per_sm = 5;
-  int asm_kernel = 0;   // default fast assembly: 0 TMA-staged tiles, 1 warp-marching (SY2D_ASM_KERNEL)
+  int asm_kernel = 0;   // default fast assembly: 0 TMA-staged tiles (strided tile order), 1 warp-marching, 2 TMA-staged column runs (experiment, slower); SY2D_ASM_KERNEL = tma | march | col
+  double col_edge_weight = 1.5;   // cost of a boundary tile relative to an interior one when the column runs are cut (SY2D_COL_EDGE_WEIGHT)
+  int* d_col_runs = nullptr;      // k_assemble_col: first tile of every CTA's run (strip-major order)
+  int col_runs_key[3] = {0, 0, 0};   // tiles_i, tiles_j, CTAs the device array was built for
   int pipe_max = 32, pipe_forced = 0;   // sy2d_step_host: at most pipe_max pipelined sub-batches (SY2D_PIPE_CHUNKS forces a count)
   std::string err;
   sy2d_options opt;
@@ -309,6 +313,7 @@ bool tma_build_maps(sy2d_ctx* c) {
   if (c->ny % 2 != 0 || mg_rows(c) < 2 * kTI || c->ny < kTJ) return false;
   if (!tma_encode_maps(c, &c->tma_maps, c->tx, c->ty, c->cxy, c->U, c->Ud)) return false;
   if (cudaFuncSetAttribute(k_assemble_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes) != cudaSuccess ||
+      cudaFuncSetAttribute(k_assemble_col, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kColSmemBytes) != cudaSuccess ||
       cudaMalloc(reinterpret_cast<void**>(&c->d_tma_maps), sizeof(AsmMaps)) != cudaSuccess ||
       cudaMemcpy(c->d_tma_maps, &c->tma_maps, sizeof(AsmMaps), cudaMemcpyHostToDevice) != cudaSuccess) {
     cudaGetLastError();
@@ -354,6 +359,45 @@ void launch_march(sy2d_ctx* c, const Geometry& geo, const AssembleOut& o, int gi
       c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud, geo, o, strips_j, nstrips, gi0, li_begin, li_end, defer);
 }
 
+// Column-run assembly (sy2d_assemble_col.cuh): the tiles in strip-major order are cut into one contiguous run per CTA so that
+// every run has the same COST; a tile on the boundary of the grid (predicated path, Dirichlet faces) counts col_edge_weight.
+bool col_runs(sy2d_ctx* c, int tiles_i, int tiles_j, int ctas) {
+  if (c->d_col_runs && c->col_runs_key[0] == tiles_i && c->col_runs_key[1] == tiles_j && c->col_runs_key[2] == ctas) return true;
+  const int ntiles = tiles_i * tiles_j;
+  std::vector<double> cost((size_t)ntiles + 1, 0.0);
+  for (int t = 0; t < ntiles; ++t) {
+    const int tj = t / tiles_i, ti = t - tj * tiles_i;
+    const bool edge = ti == 0 || ti == tiles_i - 1 || tj == 0 || tj == tiles_j - 1;
+    cost[(size_t)t + 1] = cost[t] + (edge ? c->col_edge_weight : 1.0);
+  }
+  std::vector<int> start((size_t)ctas + 1, ntiles);
+  start[0] = 0;
+  int t = 0;
+  for (int k = 1; k < ctas; ++k) {
+    const double target = cost[ntiles] * k / ctas;
+    while (t < ntiles && cost[(size_t)t + 1] <= target + 1e-9) ++t;   // the tile that crosses the target goes to the later run
+    if (t < ntiles && cost[(size_t)t + 1] - target < target - cost[t]) ++t;   // ... unless most of it lies before the target
+    start[k] = std::max(t, start[(size_t)k - 1]);
+  }
+  if (c->d_col_runs) { cudaFree(c->d_col_runs); c->d_col_runs = nullptr; }
+  if (cudaMalloc(reinterpret_cast<void**>(&c->d_col_runs), start.size() * sizeof(int)) != cudaSuccess ||
+      cudaMemcpy(c->d_col_runs, start.data(), start.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaGetLastError();
+    c->d_col_runs = nullptr;
+    return false;
+  }
+  c->col_runs_key[0] = tiles_i; c->col_runs_key[1] = tiles_j; c->col_runs_key[2] = ctas;
+  return true;
+}
+
+bool launch_col(sy2d_ctx* c, const Geometry& geo, const AssembleOut& o, int tiles_i, int tiles_j, int gi0, int li_begin, int li_end, int defer) {
+  const int ntiles = tiles_i * tiles_j;   // per problem; every problem of a batch is cut into the same runs (blockIdx.y = problem)
+  const int ctas = (int)std::min<size_t>((size_t)ntiles, std::max<size_t>(1, (size_t)c->sm_count * c->asm_ctas_per_sm / (size_t)c->nbatch));
+  if (!col_runs(c, tiles_i, tiles_j, ctas)) return false;
+  k_assemble_col<<<dim3((unsigned)ctas, (unsigned)c->nbatch, 1), kColThreads, kColSmemBytes, c->stream>>>(c->d_tma_maps, geo, o, c->d_col_runs, tiles_i, gi0, li_begin, li_end, defer);
+  return true;
+}
+
 // Engine-1 assembly of the whole batch.  variant: 0 auto (SY2D_ASM_KERNEL = march | tma picks the default fast kernel),
 // 1 per-cell kernel, 2 tiled kernel without TMA, 3 warp-marching kernel, 4 TMA-staged tiles (tests compare them).
 void launch_assembly(sy2d_ctx* c, const Geometry& geo, const AssembleOut& o, int variant) {
@@ -364,7 +408,8 @@ void launch_assembly(sy2d_ctx* c, const Geometry& geo, const AssembleOut& o, int
   // tensor map exists (odd ny) the marching kernel, which has no alignment requirement
   if (tiled && (variant == 3 || (variant == 0 && (c->asm_kernel == 1 || !c->have_tma)))) {
     launch_march(c, geo, o, 0, 0, c->nx, 0);
-  } else if (tiled && c->have_tma && (variant == 0 || variant == 4)) {
+  } else if (tiled && c->have_tma && (variant == 5 || (variant == 0 && c->asm_kernel == 2)) && launch_col(c, geo, o, tiles_i, tiles_j, 0, 0, c->nx, 0)) {
+  } else if (tiled && c->have_tma && (variant == 0 || variant == 4 || variant == 5)) {
     const int ntiles = tiles_i * tiles_j;
     const unsigned ctas = (unsigned)std::min<size_t>((size_t)ntiles, std::max<size_t>(1, (size_t)c->sm_count * c->asm_ctas_per_sm / (size_t)c->nbatch));
     k_assemble_tma<<<dim3(ctas, (unsigned)c->nbatch, 1), kTI * kTJ, kTmaSmemBytes, c->stream>>>(c->d_tma_maps, geo, o, tiles_j, ntiles, 0, 0, c->nx, 0);
@@ -1053,7 +1098,9 @@ int step_slab_impl(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
     if (mg) o.om = c->mg_om0;
     if (c->opt.reserved[0] == 3 || (c->opt.reserved[0] == 0 && (c->asm_kernel == 1 || !c->have_tma))) {
       launch_march(c, geo, o, c->i_lo - 1, 1, rows + 1, 1);
-    } else if (c->have_tma && (c->opt.reserved[0] == 0 || c->opt.reserved[0] == 4)) {
+    } else if (c->have_tma && (c->opt.reserved[0] == 5 || (c->opt.reserved[0] == 0 && c->asm_kernel == 2)) &&
+               launch_col(c, geo, o, tiles_i, tiles_j, c->i_lo - 1, 1, rows + 1, 1)) {
+    } else if (c->have_tma && (c->opt.reserved[0] == 0 || c->opt.reserved[0] == 4 || c->opt.reserved[0] == 5)) {
       const int ntiles = tiles_i * tiles_j;
       const unsigned ctas = (unsigned)std::min<size_t>((size_t)ntiles, (size_t)c->sm_count * c->asm_ctas_per_sm);
       k_assemble_tma<<<dim3(ctas, 1, 1), kTI * kTJ, kTmaSmemBytes, c->stream>>>(c->d_tma_maps, geo, o, tiles_j, ntiles, c->i_lo - 1, 1, rows + 1, 1);
@@ -1290,7 +1337,8 @@ static int create_impl(sy2d_ctx** out, int device, int nx, int ny, int nbatch, c
   if (const char* e = std::getenv("SY2D_MG_TAIL_NY")) ctx->mg_tail_ny = std::max(0, std::atoi(e));
   if (const char* e = std::getenv("SY2D_SLAB_GRAPH")) ctx->slab_graph = std::atoi(e) != 0;
   if (const char* e = std::getenv("SY2D_HOST_IO")) ctx->host_io_direct = std::string(e) == "direct" ? 1 : 0;
-  if (const char* e = std::getenv("SY2D_ASM_KERNEL")) ctx->asm_kernel = std::string(e) == "march" ? 1 : 0;
+  if (const char* e = std::getenv("SY2D_ASM_KERNEL")) ctx->asm_kernel = std::string(e) == "march" ? 1 : std::string(e) == "col" ? 2 : 0;
+  if (const char* e = std::getenv("SY2D_COL_EDGE_WEIGHT")) ctx->col_edge_weight = std::max(0.25, std::min(8.0, std::atof(e)));
   if (const char* e = std::getenv("SY2D_MARCH_CTAS_PER_SM")) ctx->march_ctas_per_sm = std::max(1, std::min(16, std::atoi(e)));
   const HostGeometry hg = make_host_geometry(nx, ny, xe, ye);
   const std::vector<double>&wxL = hg.wxL, &wxR = hg.wxR, &wyB = hg.wyB, &wyT = hg.wyT, &dx = hg.dx, &dy = hg.dy;
@@ -1346,6 +1394,7 @@ void sy2d_destroy(sy2d_ctx* c) {
   for (double* b : c->mg_bufs) cudaFree(b);
   if (c->mg_tail_ctr) cudaFree(c->mg_tail_ctr);
   if (c->d_tma_maps) cudaFree(c->d_tma_maps);
+  if (c->d_col_runs) cudaFree(c->d_col_runs);
   if (c->d_tma_maps2) cudaFree(c->d_tma_maps2);
   if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
   if (c->coeffs_ready) cudaEventDestroy(c->coeffs_ready);
