@@ -781,6 +781,12 @@ def slab_parity(n, steps, rank, world, local_rank, dist, torch):
 
 def main():
     global NB_TOTAL
+    # stdout carries ONE JSON line: native code that writes to file descriptor 1 (NCCL's version banner, whatever its debug
+    # level says) is sent to stderr; Python's own stdout keeps the real descriptor
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
         # NCCL prints its version banner on stdout, where the JSON line goes (the level may also come from an nccl.conf,
         # which an explicit environment value overrides); a level the user set explicitly is left alone

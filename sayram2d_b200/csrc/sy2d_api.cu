@@ -48,6 +48,7 @@ struct sy2d_ctx {
   // registers that are resident on an SM at once: one full wave, no tail (profiles/sweep_caps_steps.py: 1024^2 4.98 -> 4.81 ms
   // per step against 16, 2048^2 15.2 -> 14.9, 4096^2 equal; 8 is worse everywhere - a partial second wave)
   int ctas_per_sm = 6, asm_ctas_per_sm = 4, march_ctas_per_sm = 5;
+  int mg_line_pre = 1;   // line kernel with prefetched backward factors / old iterate and block-parallel scans (SY2D_MG_LINE_PRE=0: the three-phase kernel)
   int asm_kernel = 0;   // default fast assembly: 0 TMA-staged tiles (strided tile order), 1 warp-marching, 2 TMA-staged column runs (experiment, slower); SY2D_ASM_KERNEL = tma | march | col
   double col_edge_weight = 1.5;   // cost of a boundary tile relative to an interior one when the column runs are cut (SY2D_COL_EDGE_WEIGHT)
   int* d_col_runs = nullptr;      // k_assemble_col: first tile of every CTA's run (strip-major order)
@@ -535,6 +536,18 @@ void mg_line_shape(sy2d_ctx* c, const MgLevel& lv, const double* zc) {
   const size_t smem = (size_t)3 * COLS * (nseg + 1) * sizeof(double);
   const dim3 g((unsigned)((lv.ny + COLS - 1) / COLS), (unsigned)c->nbatch, 1);
   const bool full = rows % SEG == 0 && lv.ny % COLS == 0 && nseg * COLS == threads;
+  if (full && nseg % 32 == 0 && c->mg_line_pre) {   // one exposed memory latency per solve, scans on all warps (sy2d_mg.cuh, PRE)
+    const size_t smem_pre = ((size_t)4 * COLS * (nseg + 1) + (size_t)2 * COLS * (nseg / 32) + (size_t)2 * SEG * threads) * sizeof(double);
+    static bool attr_set = false;   // per instantiation
+    if (!attr_set) {
+      attr_set = cudaFuncSetAttribute(k_mg_line<SEG, COLS, MODE, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess;
+      cudaGetLastError();
+    }
+    if (attr_set && smem_pre <= 200 * 1024) {
+      k_mg_line<SEG, COLS, MODE, true, true><<<g, threads, smem_pre, c->stream>>>(lv, zc, a);
+      return;
+    }
+  }
   if (full) k_mg_line<SEG, COLS, MODE, true><<<g, threads, smem, c->stream>>>(lv, zc, a);
   else k_mg_line<SEG, COLS, MODE, false><<<g, threads, smem, c->stream>>>(lv, zc, a);
 }
@@ -1338,6 +1351,7 @@ static int create_impl(sy2d_ctx** out, int device, int nx, int ny, int nbatch, c
   if (const char* e = std::getenv("SY2D_SLAB_GRAPH")) ctx->slab_graph = std::atoi(e) != 0;
   if (const char* e = std::getenv("SY2D_HOST_IO")) ctx->host_io_direct = std::string(e) == "direct" ? 1 : 0;
   if (const char* e = std::getenv("SY2D_ASM_KERNEL")) ctx->asm_kernel = std::string(e) == "march" ? 1 : std::string(e) == "col" ? 2 : 0;
+  if (const char* e = std::getenv("SY2D_MG_LINE_PRE")) ctx->mg_line_pre = std::atoi(e) != 0;
   if (const char* e = std::getenv("SY2D_COL_EDGE_WEIGHT")) ctx->col_edge_weight = std::max(0.25, std::min(8.0, std::atof(e)));
   if (const char* e = std::getenv("SY2D_MARCH_CTAS_PER_SM")) ctx->march_ctas_per_sm = std::max(1, std::min(16, std::atoi(e)));
   const HostGeometry hg = make_host_geometry(nx, ny, xe, ye);

@@ -166,6 +166,41 @@ __device__ __forceinline__ void mg_carry_scan(const double* sA, const double* sP
   }
 }
 
+// The same scan with ONE (column, block of 32 segments) per warp - all warps of the CTA busy for one shuffle scan instead of
+// COLS warps for nseg / 32 of them in a row (the chain a latency-bound launch waits for).  Needs nseg % 32 == 0 and
+// COLS * nseg / 32 warps.  (sC, sQ)[col][s] = the map from the carry into the BLOCK to the carry into segment s,
+// (tA, tP)[col][blk] = the composed map of a whole block; mg_block_carry chains the blocks before the reader's own.
+template <int COLS>
+__device__ __forceinline__ void mg_carry_scan_blocks(const double* sA, const double* sP, double* sC, double* sQ, double* tA, double* tP,
+                                                     int stride, int nblk) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int col = w % COLS, blk = w / COLS;
+  const int s = blk * 32 + lane;
+  double A = sA[col * stride + s], P = sP[col * stride + s];
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double Ao = __shfl_up_sync(0xffffffffu, A, o), Po = __shfl_up_sync(0xffffffffu, P, o);
+    if (lane >= o) { A = A + P * Ao; P = P * Po; }
+  }
+  double Ae = __shfl_up_sync(0xffffffffu, A, 1), Pe = __shfl_up_sync(0xffffffffu, P, 1);
+  if (lane == 0) { Ae = 0.0; Pe = 1.0; }
+  sC[col * stride + s] = Ae;
+  sQ[col * stride + s] = Pe;
+  if (lane == 31) { tA[col * nblk + blk] = A; tP[col * nblk + blk] = P; }
+}
+__device__ __forceinline__ double mg_block_carry(const double* sC, const double* sQ, const double* tA, const double* tP, int col, int s,
+                                                 int stride, int nblk) {
+  const int blk = s >> 5;
+  double cb = 0.0;
+  for (int b2 = 0; b2 < blk; ++b2) cb = tA[col * nblk + b2] + tP[col * nblk + b2] * cb;
+  return sC[col * stride + s] + sQ[col * stride + s] * cb;
+}
+
+__device__ __forceinline__ void mg_cp_async8(double* smem_dst, const double* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void mg_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // MODE 0: z = omega T^-1 r
 // MODE 1: z = z + P zc + omega T^-1 t      (zc: solution of the next coarser level)
 // MODE 2: z = z + omega T^-1 t
@@ -176,14 +211,25 @@ __device__ __forceinline__ void mg_carry_scan(const double* sA, const double* sP
 // segments, running pointers instead of index products, all loads of a phase issued before their use.
 // `group` = which COLS adjacent columns, `batch` = which problem (the stand-alone kernel passes blockIdx.x / .y; the fused
 // coarse-level kernel below loops over groups).  `state` != 0: the problem has converged, nothing to do.
-template <int SEG, int COLS, int MODE, bool FULL>
+// PRE (FULL shapes with nseg % 32 == 0; the host adds the shared memory): the solve as ONE exposed memory latency instead of
+// three - the factors of the backward sweep (dinv, e) travel by cp.async into thread-private shared-memory slots while the forward
+// sweep runs, the old iterate (and the coarse correction) follow into the same slots during the backward sweep - and the scans run one block of 32
+// segments per warp (mg_carry_scan_blocks).
+template <int SEG, int COLS, int MODE, bool FULL, bool PRE = false>
 __device__ __forceinline__ void mg_line_body(const MgLevel& lv, const double* zc, const MgArgs& a, int group, int batch, int state, double* mg_smem) {
+  static_assert(!PRE || FULL, "PRE needs a shape without predicates");
   const int nx = a.nx, ny = lv.ny;
   const int nseg = (nx + SEG - 1) / SEG;
   const int stride = nseg + 1;
+  const int nblk = nseg >> 5;
   double* sA = mg_smem;
   double* sP = sA + COLS * stride;
   double* sC = sP + COLS * stride;
+  double* sQ = sC + COLS * stride;            // PRE only from here on
+  double* tA = sQ + COLS * stride;
+  double* tP = tA + COLS * nblk;
+  double* sD = tP + COLS * nblk;              // [SEG][threads]: dinv, then e
+  double* sE = sD + SEG * (int)blockDim.x;
   const int col = threadIdx.x % COLS, seg = threadIdx.x / COLS;
   const int j = group * COLS + col;
   const bool in_cta = FULL || seg < nseg;
@@ -204,6 +250,16 @@ __device__ __forceinline__ void mg_line_body(const MgLevel& lv, const double* zc
     }
   }
   if (state != 0) return;   // uniform over the CTA
+  if (PRE) {
+    const double* pd = lv.dinv + n0;
+    const double* pe = lv.e + n0;
+#pragma unroll
+    for (int m = 0; m < SEG; ++m) {
+      mg_cp_async8(sD + m * (int)blockDim.x + threadIdx.x, pd);
+      mg_cp_async8(sE + m * (int)blockDim.x + threadIdx.x, pe);
+      pd += ny; pe += ny;
+    }
+  }
   double carry = 0.0, P = 1.0, last = 0.0;
 #pragma unroll
   for (int m = 0; m < SEG; ++m) {
@@ -219,15 +275,34 @@ __device__ __forceinline__ void mg_line_body(const MgLevel& lv, const double* zc
     sP[col * stride + seg] = (FULL || cnt > 0) ? P : 0.0;
   }
   __syncthreads();
-  mg_carry_scan<COLS>(sA, sP, sC, nseg, stride);
+  if (PRE) mg_carry_scan_blocks<COLS>(sA, sP, sC, sQ, tA, tP, stride, nblk);
+  else mg_carry_scan<COLS>(sA, sP, sC, nseg, stride);
   __syncthreads();
   {
-    double q = in_cta ? sC[col * stride + seg] : 0.0;
+    double q = PRE ? mg_block_carry(sC, sQ, tA, tP, col, seg, stride, nblk) : (in_cta ? sC[col * stride + seg] : 0.0);
 #pragma unroll
     for (int m = 0; m < SEG; ++m) { q = -c[m] * q; y[m] += q; }   // rows past cnt have c = 0
   }
   // backward sweep z_m = y_m / d_m - e_m z_{m+1} with carry-in 0; P = product of (-e)
-  {
+  if (PRE) {
+    mg_cp_async_wait_all();   // the thread's own copies: no barrier needed
+#pragma unroll
+    for (int m = 0; m < SEG; ++m) {
+      y[m] *= sD[m * (int)blockDim.x + threadIdx.x];
+      c[m] = sE[m * (int)blockDim.x + threadIdx.x];
+    }
+    if (MODE != 0) {   // the slots are free again: the old iterate (and the coarse correction) of the update travel next
+      const double* pq = lv.z + n0;
+      const double* pc = MODE == 1 ? zc + ((size_t)batch * (lv.N >> 1) + (size_t)r0 * (ny >> 1) + (j >> 1)) : nullptr;
+#pragma unroll
+      for (int m = 0; m < SEG; ++m) {
+        mg_cp_async8(sD + m * (int)blockDim.x + threadIdx.x, pq);
+        if (MODE == 1) mg_cp_async8(sE + m * (int)blockDim.x + threadIdx.x, pc);
+        pq += ny;
+        if (MODE == 1) pc += ny >> 1;
+      }
+    }
+  } else {
     const double* pd = lv.dinv + n0;
     const double* pe = lv.e + n0;
     double dv[SEG];
@@ -255,10 +330,11 @@ __device__ __forceinline__ void mg_line_body(const MgLevel& lv, const double* zc
     sP[col * stride + (nseg - 1 - seg)] = (FULL || cnt > 0) ? P : 0.0;
   }
   __syncthreads();
-  mg_carry_scan<COLS>(sA, sP, sC, nseg, stride);
+  if (PRE) mg_carry_scan_blocks<COLS>(sA, sP, sC, sQ, tA, tP, stride, nblk);
+  else mg_carry_scan<COLS>(sA, sP, sC, nseg, stride);
   __syncthreads();
   {
-    double q = in_cta ? sC[col * stride + (nseg - 1 - seg)] : 0.0;
+    double q = PRE ? mg_block_carry(sC, sQ, tA, tP, col, nseg - 1 - seg, stride, nblk) : (in_cta ? sC[col * stride + (nseg - 1 - seg)] : 0.0);
 #pragma unroll
     for (int m = SEG - 1; m >= 0; --m) { q = -c[m] * q; y[m] += q; }
   }
@@ -273,7 +349,14 @@ __device__ __forceinline__ void mg_line_body(const MgLevel& lv, const double* zc
   }
   // all loads of the update before the first store (z is read and written through the same pointer)
   double* pz = lv.z + n0;
-  if (MODE != 0) {
+  if (PRE && MODE != 0) {
+    mg_cp_async_wait_all();
+#pragma unroll
+    for (int m = 0; m < SEG; ++m) {
+      c[m] = sD[m * (int)blockDim.x + threadIdx.x];
+      if (MODE == 1) c[m] += sE[m * (int)blockDim.x + threadIdx.x];
+    }
+  } else if (MODE != 0) {
     const double* pq = pz;
     const double* pc = MODE == 1 ? zc + ((size_t)batch * (lv.N >> 1) + (size_t)r0 * (ny >> 1) + (j >> 1)) : nullptr;
 #pragma unroll
@@ -294,10 +377,10 @@ __device__ __forceinline__ void mg_line_body(const MgLevel& lv, const double* zc
   }
 }
 
-template <int SEG, int COLS, int MODE, bool FULL>
+template <int SEG, int COLS, int MODE, bool FULL, bool PRE = false>
 __global__ void __launch_bounds__(SEG <= 8 ? 1024 : 512, 1) k_mg_line(MgLevel lv, const double* __restrict__ zc, MgArgs a) {
   extern __shared__ double mg_smem[];
-  mg_line_body<SEG, COLS, MODE, FULL>(lv, zc, a, (int)blockIdx.x, (int)blockIdx.y, a.scal[blockIdx.y].state, mg_smem);
+  mg_line_body<SEG, COLS, MODE, FULL, PRE>(lv, zc, a, (int)blockIdx.x, (int)blockIdx.y, a.scal[blockIdx.y].state, mg_smem);
 }
 
 // ---------------------------------------------------------------------------------------------
