@@ -190,15 +190,15 @@ BYTES_PER_CELL_XLINE = {"p_update": 64, "spmv_v": 48, "s_update": 80, "spmv_t": 
 
 
 # The engine-2 x-line kernel (k_problem_xline) keeps a problem's state on chip: what it moves goes through the L1TEX data
-# pipe of its SM (shared memory), not through HBM.  Algorithmic bytes, counted
-# from the kernel source ("engine 2"): per cell and BiCGSTAB iteration 19 shared-memory accesses of
-# 8 bytes (two Thomas solves of 4, two publishes, four neighbour reads, p written twice and read three times) + two 2-byte
-# reads of the 16-bit shadow residual = 156 B; the six further accesses of an iteration (wS' and wN' twice, y read and written)
-# go to TENSOR MEMORY (tcgen05.ld / st, sy2d_tmem.cuh) and do not pass through the L1TEX data pipe, so they are not counted;
-# per cell and time step (block assembly from the staged inputs, factorisation, pivot scaling, final solve and update)
-# 76 accesses = 608 B.
-XLINE_L1_BYTES_PER_CELL_ITER = 156
-XLINE_L1_BYTES_PER_CELL_STEP = 608
+# pipe of its SM (shared memory), not through HBM.  Algorithmic bytes, counted from the kernel source (DESIGN.md section 4,
+# "engine 2"): per cell and BiCGSTAB iteration 11 shared-memory accesses of 8 bytes (two publishes of the line solutions, four
+# neighbour reads, p written twice and read three times) + two 2-byte reads of the 16-bit shadow residual = 92 B; the other
+# 14 accesses of an iteration (wS' and wN' twice, y read and written, the sweep factors l' and e twice per line solve) go to
+# TENSOR MEMORY (tcgen05.ld / st, sy2d_tmem.cuh) and do not pass through the L1TEX data pipe, so they are not counted; per cell
+# and time step (block assembly from the staged inputs, factorisation, pivot scaling, factors into tensor memory, final solve
+# and update) 78 accesses = 624 B.
+XLINE_L1_BYTES_PER_CELL_ITER = 92
+XLINE_L1_BYTES_PER_CELL_STEP = 624
 HBM_COMPULSORY_BYTES_PER_CELL_STEP = 88   # tx, ty, cxy, U, Ud, f, yprev, ylast in; f, yprev, ylast out
 
 
@@ -475,13 +475,15 @@ def ours(args):
                 tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))["k_problem_xline"]
                 traffic = tj["l1tex_bytes_per_cell_iteration"] * r["cell_iterations"] / r["launches"]
                 traffic_src = tj["source"]
+                unit_busy = tj.get("ncu_l1tex_throughput_pct")
             except Exception:
-                pass
+                unit_busy = None
             line["roofline"] = {"bound": "l1tex", "kernel": "k_problem_xline", "achieved": r["achieved"], "peak": r["peak"],
                                 "unit": "GB/s", "frac": r["frac"], "traffic": traffic, "traffic_source": traffic_src,
+                                "ncu_unit_busy_pct": unit_busy,   # l1tex__throughput of the committed capture: what the unit itself reports (wavefront granularity: a 2-byte read costs a wavefront like an 8-byte one)
                                 "bytes_per_launch": r["bytes_total"] / r["launches"], "ms_per_launch": r["ms_total"] / r["launches"],
                                 "model": f"{XLINE_L1_BYTES_PER_CELL_STEP} B per cell-step + {XLINE_L1_BYTES_PER_CELL_ITER} B per cell-iteration through "
-                                         "the L1TEX data pipe (19 shared-memory 8-byte accesses and two 2-byte reads per cell and iteration; 6 more 8-byte accesses go to tensor memory, not counted)",
+                                         "the L1TEX data pipe (11 shared-memory 8-byte accesses and two 2-byte reads per cell and iteration; 14 more 8-byte accesses go to tensor memory, not counted)",
                                 "peak_source": "measured: sy2d_measure_peaks shared-memory copy (8-byte accesses, loads + stores, all SMs)",
                                 "hbm_compulsory": r["hbm_compulsory"], "measured_peaks": peaks, "kernels": {"ensemble_xline": r}}
         else:

@@ -61,6 +61,24 @@ __device__ __forceinline__ void tmem_ld<8>(double (&d)[8], unsigned taddr) {
   for (int k = 0; k < 8; ++k) d[k] = __hiloint2double((int)r[2 * k + 1], (int)r[2 * k]);
 }
 
+// Ten doubles in two loads (8 at `ta`, 2 at `tb`) and ONE wait.
+__device__ __forceinline__ void tmem_ld2(double (&a)[8], unsigned ta, double (&b)[2], unsigned tb) {
+  unsigned r[16], q[4];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(ta)
+      : "memory");
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]) : "r"(tb) : "memory");
+  tmem_wait_ld();
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = __hiloint2double((int)r[2 * k + 1], (int)r[2 * k]);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) b[k] = __hiloint2double((int)q[2 * k + 1], (int)q[2 * k]);
+}
+__device__ __forceinline__ void tmem_ld2(double (&a)[1], unsigned, double (&b)[1], unsigned) { a[0] = 0.0; b[0] = 0.0; }   // (never called: keeps the non-TMEM instantiations compiling)
+
 // The store is complete (visible to a later tmem_ld of the same warp) after tmem_wait_st().
 template <int ND>
 __device__ __forceinline__ void tmem_st(unsigned taddr, const double (&d)[ND]);
@@ -87,5 +105,10 @@ __device__ __forceinline__ void tmem_st<8>(unsigned taddr, const double (&d)[8])
       "r"(__double2hiint(d[7]))
       : "memory");
 }
+
+// size-generic wrappers (the one-element overloads only keep the non-TMEM instantiations of the ensemble kernel compiling)
+__device__ __forceinline__ void tmem_st_any(unsigned taddr, const double (&d)[8]) { tmem_st<8>(taddr, d); }
+__device__ __forceinline__ void tmem_st_any(unsigned taddr, const double (&d)[2]) { tmem_st<2>(taddr, d); }
+__device__ __forceinline__ void tmem_st_any(unsigned, const double (&)[1]) {}
 
 }  // namespace sy2d

@@ -363,9 +363,19 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
   const int lq0 = FULL ? i0 * LS + j : tid, lqs = FULL ? LS : NT;     // slot of owned row m in l_s / e_s: lq0 + m * lqs
   const int gq0 = FULL ? i0 * ny + j : tid, gqs = FULL ? ny : NT;     // ... in wS_g / wN_g / rhs_g
   // Full tile: wS', wN' and y of the owned rows live in TENSOR MEMORY (sy2d_tmem.cuh) instead of the L2 scratch: the thread's
-  // TMEM lane, 6 R columns of the warp's range - (wS'_m, wN'_m) row by row in [0, 4R), y_m in [4R, 6R).  The five warps that share
-  // a lane quarter (w % 4) take column ranges 96 apart.
+  // TMEM lane, 10 R columns of the warp's range - (wS'_m, wN'_m) row by row in [0, 4R), y_m in [4R, 6R), the sweep factors l'_m in
+  // [6R, 8R) and e_m in [8R, 10R) (TML: a line solve reads its factors four times per row; from tensor memory those 8 reads per
+  // cell and iteration no longer go through the shared-memory pipe, the unit ncu shows the kernel is bound by).  The five warps
+  // that share a lane quarter (w % 4) take column ranges 102 apart (5 x 102 <= 512; tcgen05.ld / st need no column alignment,
+  // profiles/tmem_probe.cu).
   constexpr bool TMW = FULL;
+  constexpr bool TML = TMW;
+  // PTM (experiment, off): the search direction p (read three times and written twice per cell and iteration) takes y's place in
+  // tensor memory and y (one read-modify-write) takes p's thread-private slots in shared memory - three shared-memory accesses
+  // less, but every phase then waits for a tensor-memory round trip before it can start and the p batches cost registers
+  // (spills 356 -> 512 bytes): 5.06 -> 5.73 ms per step at 4096 members.
+  constexpr bool PTM = false;
+  constexpr int kTmWarpCols = 102;
   static_assert(!TMW || (R == 10 && MAXT <= 640), "TMEM layout: 10 rows per thread, at most five warps per lane quarter");
   unsigned tcol = 0;
   if (FULL) {
@@ -381,7 +391,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
     __syncthreads();
     if (TMW) {
       tmem_fence_after_sync();
-      tcol = reinterpret_cast<volatile unsigned*>(s_item + 1)[0] + ((unsigned)(32 * (w & 3)) << 16) + (unsigned)((w >> 2) * 96);
+      tcol = reinterpret_cast<volatile unsigned*>(s_item + 1)[0] + ((unsigned)(32 * (w & 3)) << 16) + (unsigned)((w >> 2) * kTmWarpCols);
     }
   }
   // rows m0 .. m0+3 / m0 .. m0+1 of (wS', wN') from tensor memory; fn(m, wS'_m, wN'_m) per row
@@ -397,6 +407,22 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
     tmem_ld<4>(t, tcol + 32);
 #pragma unroll
     for (int k2 = 0; k2 < 2; ++k2) fn(8 + k2, t[2 * k2], t[2 * k2 + 1]);
+  };
+  // the same with p_m (PTM): fn(m, wS'_m, wN'_m, p_m)
+  auto tm_rows_p = [&](auto fn) {
+#pragma unroll
+    for (int m0 = 0; m0 < 8; m0 += 4) {
+      double t[8], pp[4];
+      tmem_ld<8>(t, tcol + 4 * m0);
+      tmem_ld<4>(pp, tcol + 4 * R + 2 * m0);
+#pragma unroll
+      for (int k4 = 0; k4 < 4; ++k4) fn(m0 + k4, t[2 * k4], t[2 * k4 + 1], pp[k4]);
+    }
+    double t[4], pp[2];
+    tmem_ld<4>(t, tcol + 32);
+    tmem_ld<2>(pp, tcol + 4 * R + 16);
+#pragma unroll
+    for (int k2 = 0; k2 < 2; ++k2) fn(8 + k2, t[2 * k2], t[2 * k2 + 1], pp[k2]);
   };
   double* scr = xa.scratch + (size_t)blockIdx.x * kXlineScratchArrays * S;
   double* wS_g = scr; double* wN_g = scr + S; double* v_g = scr + 2 * S; double* y_g = scr + 3 * S; double* rhs_g = scr + 4 * S;
@@ -490,6 +516,19 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
         }
       }
     }
+    if (TML) {   // the thread's own factors (its own slots of l_s / e_s: no barrier needed) into tensor memory
+      double t8[8], t2[2];
+#pragma unroll
+      for (int m = 0; m < 8; ++m) t8[m] = l_s[lq0 + m * lqs];
+      t2[0] = l_s[lq0 + 8 * lqs]; t2[1] = l_s[lq0 + 9 * lqs];
+      tmem_st<8>(tcol + 6 * R, t8);
+      tmem_st<2>(tcol + 6 * R + 16, t2);
+#pragma unroll
+      for (int m = 0; m < 8; ++m) t8[m] = e_s[lq0 + m * lqs];
+      t2[0] = e_s[lq0 + 8 * lqs]; t2[1] = e_s[lq0 + 9 * lqs];
+      tmem_st<8>(tcol + 8 * R, t8);
+      tmem_st<2>(tcol + 8 * R + 16, t2);
+    }
     // pivot scaling of the rest of the row (thread-private slots: no barrier needed), r0 = rhs', rho0, max|r0|
 #pragma unroll
     for (int m = 0; m < R; ++m) {
@@ -531,15 +570,20 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
     // the multipliers, i.e. its chunk as an affine map  carry_out = A + B * carry_in.  The maps
     // of the NCH lanes of a column are composed with a 3-step shuffle scan, and a second pass adds
     // (product up to row m) * carry_in.  All lanes work concurrently - no serial hand-off.
-    auto tsolve = [&](auto bget) {   // bget(m): right-hand side of owned row m (called once per row, in order)
+    auto tsolve = [&](auto bget, auto after_forward) {   // bget(m): right-hand side of owned row m (called once per row, in order); after_forward(): once all rows were fetched
       double A = 0.0, B = 1.0;
+      double fa[TML ? 8 : 1], fb[TML ? 2 : 1];   // the factors of the sweep in flight (TML)
+      if (TML) tmem_ld2(fa, tcol + 6 * R, fb, tcol + 6 * R + 16);
+      auto lfac = [&](int m) { return TML ? (m < 8 ? fa[TML ? m : 0] : fb[TML ? m - 8 : 0]) : l_s[lq0 + m * lqs]; };
+      auto efac = [&](int m) { return TML ? (m < 8 ? fa[TML ? m : 0] : fb[TML ? m - 8 : 0]) : e_s[lq0 + m * lqs]; };
 #pragma unroll
       for (int m = 0; m < R; ++m) {
-        const double lm = l_s[lq0 + m * lqs];
+        const double lm = lfac(m);
         A = bget(m) - lm * A;
         z[m] = A;
         B = -lm * B;
       }
+      after_forward();
 #pragma unroll
       for (int d = 1; d < NCH; d <<= 1) {
         const double Au = __shfl_up_sync(full, A, d, NCH), Bu = __shfl_up_sync(full, B, d, NCH);
@@ -550,14 +594,15 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
       double P = 1.0;
 #pragma unroll
       for (int m = 0; m < R; ++m) {
-        P = -l_s[lq0 + m * lqs] * P;
+        P = -lfac(m) * P;
         z[m] += P * cin;
       }
       // backward (unit diagonal): x_m = z_m - e_m x_{m+1}
+      if (TML) tmem_ld2(fa, tcol + 8 * R, fb, tcol + 8 * R + 16);
       A = 0.0; B = 1.0;
 #pragma unroll
       for (int m = R - 1; m >= 0; --m) {
-        const double em = e_s[lq0 + m * lqs];
+        const double em = efac(m);
         A = z[m] - em * A;
         z[m] = A;
         B = -em * B;
@@ -572,7 +617,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
       P = 1.0;
 #pragma unroll
       for (int m = R - 1; m >= 0; --m) {
-        P = -e_s[lq0 + m * lqs] * P;
+        P = -efac(m) * P;
         z[m] += P * cin;
       }
     };
@@ -589,18 +634,39 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
 
     while (state == 0) {
       // p = r + beta (p - omega v), formed row by row as the right-hand side of the first sweep
-      tsolve([&](int m) {
-        const int q = m * NT + tid;
-        const double pm = first ? rs[m] : (VREG ? rs[m] + beta * p_s[q] : rs[m] + beta * (p_s[q] - omega * v_g[q]));
-        p_s[q] = pm;
-        return pm;
-      });
+      if (PTM) {
+        double p8[PTM ? 8 : 1], p2[PTM ? 2 : 1];
+        if (!first) tmem_ld2(p8, tcol + 4 * R, p2, tcol + 4 * R + 16);
+        tsolve([&](int m) {
+          double& pm = m < 8 ? p8[PTM ? m : 0] : p2[PTM ? m - 8 : 0];
+          pm = first ? rs[m] : rs[m] + beta * pm;
+          return pm;
+        }, [&]() {
+          tmem_st_any(tcol + 4 * R, p8);
+          tmem_st_any(tcol + 4 * R + 16, p2);
+          tmem_wait_st();
+        });
+      } else {
+        tsolve([&](int m) {
+          const int q = m * NT + tid;
+          const double pm = first ? rs[m] : (VREG ? rs[m] + beta * p_s[q] : rs[m] + beta * (p_s[q] - omega * v_g[q]));
+          p_s[q] = pm;
+          return pm;
+        }, [] {});
+      }
       publish();
       // v = p + wS phat_S + wN phat_N ; (rhat, v).  z is dead from here on (the thread re-reads its own
       // phat from hat), so v and later t reuse its registers: peak live arrays are rs, p and one more.
       double (&vv)[R] = z;
       double a1[1] = {0.0};
-      if (TMW) {
+      if (PTM) {
+        tm_rows_p([&](int m, double ws, double wn, double pm) {
+          const int i = i0 + m, q = m * NT + tid;
+          const double val = pm + (ws * hat[i * hs + jS] + wn * hat[i * hs + jN]);
+          vr[VREG ? m : 0] = val;
+          a1[0] += rhat_of(q) * val;
+        });
+      } else if (TMW) {
         tm_rows([&](int m, double ws, double wn) {
           const int i = i0 + m, q = m * NT + tid;
           const double val = p_s[q] + (ws * hat[i * hs + jS] + wn * hat[i * hs + jN]);
@@ -623,7 +689,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
       // s = r - alpha v (in place)
 #pragma unroll
       for (int m = 0; m < R; ++m) rs[m] -= alpha * (VREG ? vr[VREG ? m : 0] : vv[m]);
-      tsolve([&](int m) { return rs[m]; });
+      tsolve([&](int m) { return rs[m]; }, [] {});
       publish();
       // t = s + wS shat_S + wN shat_N ; (t,s), (t,t)
       double a2[2] = {0.0, 0.0};
@@ -661,7 +727,23 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
         a3[1] = nmax(a3[1], fabs(rs[m]));
         return ynew;
       };
-      if (TMW) {
+      if (PTM) {   // p from / to tensor memory, y in the thread-private shared-memory slots
+        double p8[PTM ? 8 : 1], p2[PTM ? 2 : 1];
+        tmem_ld2(p8, tcol + 4 * R, p2, tcol + 4 * R + 16);
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+          const int q = m * NT + tid;
+          double& pm = m < 8 ? p8[PTM ? m : 0] : p2[PTM ? m - 8 : 0];
+          p_s[q] = (first ? 0.0 : p_s[q]) + (alpha * pm + omega * rs[m]);   // y
+          pm -= omega * vr[VREG ? m : 0];
+          rs[m] -= omega * vv[m];
+          a3[0] += rhat_of(q) * rs[m];
+          a3[1] = nmax(a3[1], fabs(rs[m]));
+        }
+        tmem_st_any(tcol + 4 * R, p8);
+        tmem_st_any(tcol + 4 * R + 16, p2);
+        tmem_wait_st();
+      } else if (TMW) {
         double y8[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0}, y2[2] = {0.0, 0.0};
         if (!first) { tmem_ld<8>(y8, tcol + 4 * R); tmem_ld<2>(y2, tcol + 4 * R + 16); }
 #pragma unroll
@@ -702,16 +784,18 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
     }
     // x = T^-1 y  (left in z)
     if (it > 0) {
-      if (TMW) {   // y into z (the solve reads row m before it writes it)
+      if (PTM) {
+        tsolve([&](int m) { return p_s[m * NT + tid]; }, [] {});   // y sits in the p slots
+      } else if (TMW) {   // y into z (the solve reads row m before it writes it)
         double y8[8], y2[2];
         tmem_ld<8>(y8, tcol + 4 * R);
         tmem_ld<2>(y2, tcol + 4 * R + 16);
 #pragma unroll
         for (int m = 0; m < 8; ++m) z[m] = y8[m];
         z[8] = y2[0]; z[9] = y2[1];
-        tsolve([&](int m) { return z[m]; });
+        tsolve([&](int m) { return z[m]; }, [] {});
       } else {
-        tsolve([&](int m) { return y_g[m * NT + tid]; });
+        tsolve([&](int m) { return y_g[m * NT + tid]; }, [] {});
       }
     } else {
 #pragma unroll
