@@ -776,6 +776,7 @@ def slab_parity(n, steps, rank, world, local_rank, dist, torch):
         out = {"grid": n, "steps": steps, "parity_max_rel": float(np.max(np.abs(f - fr) / np.abs(fr))),
                "iters_slab": st["iters_total"], "iters_single": rs["iters_total"], "resid_slab": st["resid_last"], "resid_single": rs["resid_last"],
                "ms_per_step_slab": 1e3 * st["seconds_device"] / steps, "ms_per_step_single": 1e3 * rs["seconds_device"] / steps,
+               "timing_note": "both runs poll the host after EVERY iteration (check_every = 1, so that the iteration counts can be compared exactly) and include the first-use graph captures: the ms figures are not throughput numbers, slab.solved is",
                "what": f"{steps} time steps of {n}x{n} as {world} NCCL row slabs against one context on rank 0 (multigrid-preconditioned BiCGSTAB on both)"}
     dist.barrier()
     return out
