@@ -38,6 +38,10 @@
 #include "sy2d_problem_kernel.cuh"
 #include "sy2d_tmem.cuh"
 
+#ifndef SY2D_XLINE_RHREG
+#define SY2D_XLINE_RHREG 0   // experiment, slower (see RHREG below)
+#endif
+
 namespace sy2d {
 
 constexpr int kXlineNCH = 8;          // lanes per column
@@ -429,7 +433,15 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
   // full tile: the block assembly leaves wS, wN, rhs in the natural (i, j) layout (coalesced stores) in v, y and a sixth
   // array; the pivot-scaling pass moves them into the thread-private layout the iteration reads
   double* wS_n = FULL ? v_g : wS_g; double* wN_n = FULL ? y_g : wN_g; double* rhs_n = FULL ? scr + 5 * S : rhs_g;
-  auto rhat_of = [&](int q) { return RH16 ? __hiloint2double((int)((unsigned)rh16[q] << 16), 0) : rhs_g[q]; };
+  // RHREG (experiment, off): the ten 16-bit shadow-residual values of the owned rows packed into five registers instead of shared
+  // memory (a warp's 2-byte reads cost a shared-memory wavefront each: 10 % of the kernel's wavefronts, ncu capture xu).  The
+  // kernel sits at its 96-register limit: five more live registers raise the spills from 356 to 476 bytes, 4.75 -> 5.20 ms per step.
+  constexpr bool RHREG = RH16 && SY2D_XLINE_RHREG;
+  unsigned rhp[RHREG ? R / 2 : 1] = {};
+  auto rhat_of = [&](int q, int m) {
+    if (RHREG) return __hiloint2double((int)((m & 1) ? (rhp[RHREG ? m >> 1 : 0] & 0xffff0000u) : (rhp[RHREG ? m >> 1 : 0] << 16)), 0);
+    return RH16 ? __hiloint2double((int)((unsigned)rh16[q] << 16), 0) : rhs_g[q];
+  };
   const unsigned full = 0xffffffffu;
 
   double rs[R], z[R];
@@ -540,8 +552,10 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
       rhs_g[q] = rh;
       rs[m] = rh;
       if (RH16) {
-        rh16[q] = (unsigned short)((unsigned)__double2hiint(rh) >> 16);
-        acc[0] += rhat_of(q) * rh;
+        const unsigned h16 = (unsigned)__double2hiint(rh) >> 16;
+        if (RHREG) rhp[RHREG ? m >> 1 : 0] = (m & 1) ? (rhp[RHREG ? m >> 1 : 0] | (h16 << 16)) : h16;
+        else rh16[q] = (unsigned short)h16;
+        acc[0] += rhat_of(q, m) * rh;
       } else {
         acc[0] += rh * rh;
       }
@@ -664,14 +678,14 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
           const int i = i0 + m, q = m * NT + tid;
           const double val = pm + (ws * hat[i * hs + jS] + wn * hat[i * hs + jN]);
           vr[VREG ? m : 0] = val;
-          a1[0] += rhat_of(q) * val;
+          a1[0] += rhat_of(q, m) * val;
         });
       } else if (TMW) {
         tm_rows([&](int m, double ws, double wn) {
           const int i = i0 + m, q = m * NT + tid;
           const double val = p_s[q] + (ws * hat[i * hs + jS] + wn * hat[i * hs + jN]);
           vr[VREG ? m : 0] = val;
-          a1[0] += rhat_of(q) * val;
+          a1[0] += rhat_of(q, m) * val;
         });
       } else {
 #pragma unroll
@@ -681,7 +695,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
           if (FULL || (col_ok && i < nx)) val = p_s[q] + (wS_g[q] * hat[i * hs + jS] + wN_g[q] * hat[i * hs + jN]);
           if (VREG) vr[VREG ? m : 0] = val;
           else { vv[m] = val; v_g[q] = val; }
-          a1[0] += rhat_of(q) * val;
+          a1[0] += rhat_of(q, m) * val;
         }
       }
       cta_reduce_x<1, false>(a1, 1, red);
@@ -723,7 +737,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
         const double ynew = yold + (alpha * pm + omega * rs[m]);
         if (VREG) p_s[q] = pm - omega * vr[VREG ? m : 0];
         rs[m] -= omega * vv[m];
-        a3[0] += rhat_of(q) * rs[m];
+        a3[0] += rhat_of(q, m) * rs[m];
         a3[1] = nmax(a3[1], fabs(rs[m]));
         return ynew;
       };
@@ -737,7 +751,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
           p_s[q] = (first ? 0.0 : p_s[q]) + (alpha * pm + omega * rs[m]);   // y
           pm -= omega * vr[VREG ? m : 0];
           rs[m] -= omega * vv[m];
-          a3[0] += rhat_of(q) * rs[m];
+          a3[0] += rhat_of(q, m) * rs[m];
           a3[1] = nmax(a3[1], fabs(rs[m]));
         }
         tmem_st_any(tcol + 4 * R, p8);
