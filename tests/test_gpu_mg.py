@@ -143,3 +143,24 @@ def test_fused_coarse_tail_equals_the_separate_launches(n, batch):
     # (the fine-level dot products are summed with atomics: two runs agree to round-off, not bit for bit)
     assert max_rel(out[1][0], out[0][0]) < 1e-11 and abs(out[0][1] - out[1][1]) <= 2
     assert out[1][2] < out[0][2]      # fewer launches with the fused tail
+
+
+@pytest.mark.parametrize("n,batch", [(256, 1), (1024, 1), (512, 2)])
+def test_prefetching_line_kernel_equals_the_three_phase_kernel(n, batch):
+    """SY2D_MG_LINE_PRE: the line kernel that stages the backward factors and the old iterate by cp.async into shared memory and
+    scans the carries on all warps does the same arithmetic per row; only the association of the carry composition across blocks of
+    32 segments differs (round-off): the same f and the same iteration counts as the kernel with three exposed load phases."""
+    import os
+    out = []
+    for pre in ("0", "1"):
+        os.environ["SY2D_MG_LINE_PRE"] = pre
+        try:
+            eng = synthetic_engine(n, n, nbatch=batch)
+        finally:
+            del os.environ["SY2D_MG_LINE_PRE"]
+        eng.set_options(engine=1, precond=2)
+        st = eng.step(3)
+        out.append((eng.get_f(), st["iters_total"]))
+        assert st["negatives"] == 0 and st["precond"] == 2
+        eng.close()
+    assert max_rel(out[1][0], out[0][0]) < 1e-11 and abs(out[0][1] - out[1][1]) <= 2
