@@ -1,4 +1,4 @@
-"""Sustained launches of the engine-1 assembly kernels (variant 4 = TMA tiles in strided order, 5 = column runs) on n x n
+"""Sustained launches of the engine-1 assembly kernels (variant 4 = TMA tiles in strided order, 5 = column runs, 6 = two cells per thread on 8 x 64 tiles) on n x n
 synthetic grids, and the column-run kernel with several boundary-tile weights:  python profiles/run_asm_cmp.py [reps]"""
 import os
 import subprocess
@@ -14,10 +14,9 @@ if len(sys.argv) > 2 and sys.argv[1] == "one":
     eng._check(eng.lib.sy2d_set_options(eng._ctx, o))
     eng.bench_kernel("assembly", 20)
     t = min(eng.bench_kernel("assembly", 200 if n <= 2048 else 50) for _ in range(3))
-    print(n, variant, os.environ.get("SY2D_COL_EDGE_WEIGHT", "-"), os.environ.get("SY2D_ASM_CTAS_PER_SM", "-"), round(1e3 * t, 2), "us", flush=True)
+    print(n, variant, os.environ.get("SY2D_COL_EDGE_WEIGHT", "-"), os.environ.get("SY2D_WIDE_CTAS_PER_SM", "-"), round(1e3 * t, 2), "us", flush=True)
     eng.close()
 else:
     for n in (1024, 2048, 4096):
-        for variant, env in ((4, {}), (5, {}), (5, {"SY2D_COL_EDGE_WEIGHT": "1.0"}), (5, {"SY2D_COL_EDGE_WEIGHT": "1.25"}), (5, {"SY2D_COL_EDGE_WEIGHT": "2.0"}),
-                             (5, {"SY2D_ASM_CTAS_PER_SM": "3"})):
+        for variant, env in ((4, {}), (5, {}), (6, {}), (6, {"SY2D_WIDE_CTAS_PER_SM": "1"})):
             subprocess.run([sys.executable, __file__, "one", str(n), str(variant)], env={**os.environ, **env})

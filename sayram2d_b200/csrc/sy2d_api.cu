@@ -26,6 +26,7 @@
 #include "sy2d_assemble_tma.cuh"
 #include "sy2d_assemble_march.cuh"
 #include "sy2d_assemble_col.cuh"
+#include "sy2d_assemble_wide.cuh"
 #include "sy2d_peaks.cuh"
 
 using namespace sy2d;
@@ -47,7 +48,7 @@ struct sy2d_ctx {
   // grid caps of the grid-stride kernels (tuning: SY2D_CTAS_PER_SM, SY2D_ASM_CTAS_PER_SM).  6 = the CTAs of 256 threads x 40
   // registers that are resident on an SM at once: one full wave, no tail (profiles/sweep_caps_steps.py: 1024^2 4.98 -> 4.81 ms
   // per step against 16, 2048^2 15.2 -> 14.9, 4096^2 equal; 8 is worse everywhere - a partial second wave)
-  int ctas_per_sm = 6, asm_ctas_per_sm = 4, march_ctas_per_sm = 5;
+  int ctas_per_sm = 6, asm_ctas_per_sm = 4, march_ctas_per_sm = 5, wide_ctas_per_sm = 2;
   int mg_line_pre = 1;   // line kernel with prefetched backward factors / old iterate and block-parallel scans (SY2D_MG_LINE_PRE=0: the three-phase kernel)
   int asm_kernel = 0;   // default fast assembly: 0 TMA-staged tiles (strided tile order), 1 warp-marching, 2 TMA-staged column runs (experiment, slower); SY2D_ASM_KERNEL = tma | march | col
   double col_edge_weight = 1.5;   // cost of a boundary tile relative to an interior one when the column runs are cut (SY2D_COL_EDGE_WEIGHT)
@@ -315,6 +316,7 @@ bool tma_build_maps(sy2d_ctx* c) {
   if (!tma_encode_maps(c, &c->tma_maps, c->tx, c->ty, c->cxy, c->U, c->Ud)) return false;
   if (cudaFuncSetAttribute(k_assemble_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes) != cudaSuccess ||
       cudaFuncSetAttribute(k_assemble_col, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kColSmemBytes) != cudaSuccess ||
+      cudaFuncSetAttribute(k_assemble_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWideSmemBytes) != cudaSuccess ||
       cudaMalloc(reinterpret_cast<void**>(&c->d_tma_maps), sizeof(AsmMaps)) != cudaSuccess ||
       cudaMemcpy(c->d_tma_maps, &c->tma_maps, sizeof(AsmMaps), cudaMemcpyHostToDevice) != cudaSuccess) {
     cudaGetLastError();
@@ -339,9 +341,10 @@ bool tma_encode_maps(sy2d_ctx* c, AsmMaps* host_maps, double* tx, double* ty, do
   const cuuint64_t dims[3] = {(cuuint64_t)c->ny, (cuuint64_t)c->nx, (cuuint64_t)c->nbatch};
   const cuuint64_t strides[2] = {(cuuint64_t)c->ny * sizeof(double), (cuuint64_t)c->N * sizeof(double)};
   const cuuint32_t estr[3] = {1, 1, 1};
-  for (int k = 0; k < 7; ++k) {
-    const cuuint32_t box[3] = {(cuuint32_t)(k < 5 ? kTmaHaloJ : kTJ), (cuuint32_t)(k < 5 ? kTmaHaloI : kTI), 1};
-    const CUresult r = encode(&host_maps->m[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, arrs[k], dims, strides, box, estr,
+  for (int k = 0; k < 14; ++k) {
+    const bool wide = k >= 7, halo = k % 7 < 5;
+    const cuuint32_t box[3] = {(cuuint32_t)(halo ? (wide ? kWHaloJ : kTmaHaloJ) : (wide ? kWJ : kTJ)), (cuuint32_t)(halo ? kTmaHaloI : kTI), 1};
+    const CUresult r = encode(&host_maps->m[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, arrs[k % 7], dims, strides, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,  // (L2 promotion raises an illegal-instruction fault with these boxes on B200 / driver 580: profiles/tma_probe.cu)
                              
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -399,6 +402,15 @@ bool launch_col(sy2d_ctx* c, const Geometry& geo, const AssembleOut& o, int tile
   return true;
 }
 
+// Two cells per thread on 8 x 64 tiles (sy2d_assemble_wide.cuh); two CTAs per SM.
+bool launch_wide(sy2d_ctx* c, const Geometry& geo, const AssembleOut& o, int tiles_i, int gi0, int li_begin, int li_end, int defer) {
+  if (c->ny < kWJ) return false;
+  const int tiles_j = (c->ny + kWJ - 1) / kWJ, ntiles = tiles_i * tiles_j;
+  const unsigned ctas = (unsigned)std::min<size_t>((size_t)ntiles, std::max<size_t>(1, (size_t)c->sm_count * c->wide_ctas_per_sm / (size_t)c->nbatch));
+  k_assemble_wide<<<dim3(ctas, (unsigned)c->nbatch, 1), kTI * kTJ, kWideSmemBytes, c->stream>>>(c->d_tma_maps, geo, o, tiles_j, ntiles, gi0, li_begin, li_end, defer);
+  return true;
+}
+
 // Engine-1 assembly of the whole batch.  variant: 0 auto (SY2D_ASM_KERNEL = march | tma picks the default fast kernel),
 // 1 per-cell kernel, 2 tiled kernel without TMA, 3 warp-marching kernel, 4 TMA-staged tiles (tests compare them).
 void launch_assembly(sy2d_ctx* c, const Geometry& geo, const AssembleOut& o, int variant) {
@@ -409,8 +421,9 @@ void launch_assembly(sy2d_ctx* c, const Geometry& geo, const AssembleOut& o, int
   // tensor map exists (odd ny) the marching kernel, which has no alignment requirement
   if (tiled && (variant == 3 || (variant == 0 && (c->asm_kernel == 1 || !c->have_tma)))) {
     launch_march(c, geo, o, 0, 0, c->nx, 0);
+  } else if (tiled && c->have_tma && (variant == 6 || (variant == 0 && c->asm_kernel == 3)) && launch_wide(c, geo, o, tiles_i, 0, 0, c->nx, 0)) {
   } else if (tiled && c->have_tma && (variant == 5 || (variant == 0 && c->asm_kernel == 2)) && launch_col(c, geo, o, tiles_i, tiles_j, 0, 0, c->nx, 0)) {
-  } else if (tiled && c->have_tma && (variant == 0 || variant == 4 || variant == 5)) {
+  } else if (tiled && c->have_tma && (variant == 0 || variant == 4 || variant == 5 || variant == 6)) {
     const int ntiles = tiles_i * tiles_j;
     const unsigned ctas = (unsigned)std::min<size_t>((size_t)ntiles, std::max<size_t>(1, (size_t)c->sm_count * c->asm_ctas_per_sm / (size_t)c->nbatch));
     k_assemble_tma<<<dim3(ctas, (unsigned)c->nbatch, 1), kTI * kTJ, kTmaSmemBytes, c->stream>>>(c->d_tma_maps, geo, o, tiles_j, ntiles, 0, 0, c->nx, 0);
@@ -1111,9 +1124,11 @@ int step_slab_impl(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
     if (mg) o.om = c->mg_om0;
     if (c->opt.reserved[0] == 3 || (c->opt.reserved[0] == 0 && (c->asm_kernel == 1 || !c->have_tma))) {
       launch_march(c, geo, o, c->i_lo - 1, 1, rows + 1, 1);
+    } else if (c->have_tma && (c->opt.reserved[0] == 6 || (c->opt.reserved[0] == 0 && c->asm_kernel == 3)) &&
+               launch_wide(c, geo, o, tiles_i, c->i_lo - 1, 1, rows + 1, 1)) {
     } else if (c->have_tma && (c->opt.reserved[0] == 5 || (c->opt.reserved[0] == 0 && c->asm_kernel == 2)) &&
                launch_col(c, geo, o, tiles_i, tiles_j, c->i_lo - 1, 1, rows + 1, 1)) {
-    } else if (c->have_tma && (c->opt.reserved[0] == 0 || c->opt.reserved[0] == 4 || c->opt.reserved[0] == 5)) {
+    } else if (c->have_tma && (c->opt.reserved[0] == 0 || c->opt.reserved[0] == 4 || c->opt.reserved[0] == 5 || c->opt.reserved[0] == 6)) {
       const int ntiles = tiles_i * tiles_j;
       const unsigned ctas = (unsigned)std::min<size_t>((size_t)ntiles, (size_t)c->sm_count * c->asm_ctas_per_sm);
       k_assemble_tma<<<dim3(ctas, 1, 1), kTI * kTJ, kTmaSmemBytes, c->stream>>>(c->d_tma_maps, geo, o, tiles_j, ntiles, c->i_lo - 1, 1, rows + 1, 1);
@@ -1350,7 +1365,8 @@ static int create_impl(sy2d_ctx** out, int device, int nx, int ny, int nbatch, c
   if (const char* e = std::getenv("SY2D_MG_TAIL_NY")) ctx->mg_tail_ny = std::max(0, std::atoi(e));
   if (const char* e = std::getenv("SY2D_SLAB_GRAPH")) ctx->slab_graph = std::atoi(e) != 0;
   if (const char* e = std::getenv("SY2D_HOST_IO")) ctx->host_io_direct = std::string(e) == "direct" ? 1 : 0;
-  if (const char* e = std::getenv("SY2D_ASM_KERNEL")) ctx->asm_kernel = std::string(e) == "march" ? 1 : std::string(e) == "col" ? 2 : 0;
+  if (const char* e = std::getenv("SY2D_ASM_KERNEL")) ctx->asm_kernel = std::string(e) == "march" ? 1 : std::string(e) == "col" ? 2 : std::string(e) == "wide" ? 3 : 0;
+  if (const char* e = std::getenv("SY2D_WIDE_CTAS_PER_SM")) ctx->wide_ctas_per_sm = std::max(1, std::min(2, std::atoi(e)));
   if (const char* e = std::getenv("SY2D_MG_LINE_PRE")) ctx->mg_line_pre = std::atoi(e) != 0;
   if (const char* e = std::getenv("SY2D_COL_EDGE_WEIGHT")) ctx->col_edge_weight = std::max(0.25, std::min(8.0, std::atof(e)));
   if (const char* e = std::getenv("SY2D_MARCH_CTAS_PER_SM")) ctx->march_ctas_per_sm = std::max(1, std::min(16, std::atoi(e)));

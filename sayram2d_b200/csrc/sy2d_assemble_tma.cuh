@@ -35,7 +35,7 @@ constexpr unsigned kTmaStageBytes = 5u * kTmaHaloElems * 8u + 2u * kTmaInnerElem
 constexpr int kTmaStages = 2;
 
 struct AsmMaps {   // f, yprev, tx, ty, cxy: box (36, 10, 1); U, Ud: box (32, 8, 1); dims (ny, rows of the local array, nbatch)
-  CUtensorMap m[7];
+  CUtensorMap m[14];   // [7 .. 13]: the same arrays with the boxes of the two-cells-per-thread kernel, (68, 10, 1) and (64, 8, 1)
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }

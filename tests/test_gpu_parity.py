@@ -426,8 +426,8 @@ def test_tiled_assembly_equals_per_cell_assembly(tag):
                                                  ("nu48x40", 0, 0, 1, None), ("lc80", 0, 0, 2, None)])
 def test_assembly_kernels_agree(tag, nx, ny, nbatch, bc):
     """The fast engine-1 assembly kernels - shared-memory tiles with plain loads (2), warp-marching strips (3),
-    TMA-staged tiles in strided order (4) and in column runs with carried rows (5, the default) - evaluate every face ONCE with the same expression and sum a row in the same order: the scaled
-    operator, the right-hand side and the column scale of (2), (4) and (5) must be IDENTICAL, those of (3) equal to the last
+    TMA-staged tiles in strided order (4), in column runs with carried rows (5) and with two cells per thread on 8 x 64 tiles (6) - evaluate every face ONCE with the same expression and sum a row in the same order: the scaled
+    operator, the right-hand side and the column scale of (2), (4), (5) and (6) must be IDENTICAL, those of (3) equal to the last
     bits (full-size, ragged, odd-ny, batched, non-uniform and zero-flux grids; odd ny has no TMA variant).  The
     one-thread-per-cell kernel (1) evaluates a face from both of its cells and agrees to round-off."""
     if tag == "syn":
@@ -452,7 +452,7 @@ def test_assembly_kernels_agree(tag, nx, ny, nbatch, bc):
     eng.set_f(rep(f0))
     eng.step(2)                       # a predictor state (yprev != 1) and an f that is not the initial one
     ref = None
-    variants = (2, 3, 4, 5, 1) if (len(ye) - 1) % 2 == 0 else (2, 3, 1)
+    variants = (2, 3, 4, 5, 6, 1) if (len(ye) - 1) % 2 == 0 else (2, 3, 1)
     for variant in variants:
         _force_assembly(eng, variant)
         got = eng.dump_scaled_operator()
@@ -460,7 +460,7 @@ def test_assembly_kernels_agree(tag, nx, ny, nbatch, bc):
             ref = got
             continue
         for name, a, b in zip(("w4", "rhs", "cs"), got, ref):
-            if variant in (4, 5):   # TMA staging / the column-run tile order change where the operands come from, not the arithmetic
+            if variant in (4, 5, 6):   # TMA staging / the tile order / two cells per thread change where the operands come from, not the arithmetic
                 assert np.array_equal(a, b), (variant, name, float(np.max(np.abs(a - b))))
             else:
                 # 3: the same expressions, but the compiler contracts a * b + c * d into FMAs differently in a different kernel
