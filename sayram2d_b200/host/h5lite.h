@@ -1,8 +1,9 @@
 // Minimal HDF5 access for the files at the edge of the hot path (libhdf5 / HighFive /
 // xtensor-io are not available in this image).
-//  read : the subset D/AlbertYoung_chorus.h5 uses - superblock v0, v1 group B-tree +
-//         local heap + symbol-table nodes (walked, not hard-coded offsets), v1 object
-//         headers, contiguous (layout v3) little-endian f64 datasets without filters.
+//  read : what D tables are written with in practice (h5py / libhdf5 / MATLAB defaults and `libver="latest"`): superblock
+//         v0 - v3, old-style groups (v1 B-tree + local heap + symbol-table nodes, walked, not hard-coded offsets) and
+//         new-style groups with compact links, v1 and v2 object headers, compact / contiguous / chunked (v1 B-tree)
+//         layouts, deflate / shuffle / fletcher32 filters, little-endian f64, f32 and integer data (see `File`).
 //  write: the same HDF5 subset (h5lite::Writer: /alpha0, /logEN, /f/<k>, /t of main.cc:58-89, readable
 //         by libhdf5 / h5py / plot/cmp_ay.py) and NumPy .npy copies of the snapshots.
 #ifndef SY2D_HOST_H5LITE_H_
@@ -20,11 +21,152 @@
 
 namespace h5lite {
 
-struct Dataset {
-  std::vector<std::size_t> shape;
-  std::uint64_t addr = 0, bytes = 0;
+struct Filter {
+  unsigned id = 0;                    // 1 deflate, 2 shuffle, 3 fletcher32
+  std::vector<std::uint32_t> cd;      // client data
 };
 
+struct Dataset {
+  std::vector<std::size_t> shape;
+  std::uint64_t addr = 0, bytes = 0;  // contiguous: address (relative to the base address) and size; compact: absolute offset of the inline data
+  int layout = 1;                     // 0 compact, 1 contiguous, 2 chunked (B-tree v1 index)
+  int type_class = 1, type_size = 8;  // 0 fixed point, 1 IEEE floating point (little endian)
+  bool type_signed = true;
+  std::vector<std::size_t> chunk;     // chunked: chunk dimensions in elements
+  std::uint64_t btree = 0;            // chunked: address of the chunk B-tree
+  std::vector<Filter> filters;        // in the order they were applied when the chunk was written
+};
+
+// RFC 1950 / 1951 decoder for the deflate filter (zlib-wrapped chunks); small, bit-by-bit canonical Huffman decoding.
+class Inflate {
+ public:
+  static std::vector<unsigned char> zlib(const unsigned char* in, std::size_t n) {
+    if (n < 6 || (in[0] & 0x0f) != 8 || ((in[0] << 8) | in[1]) % 31 != 0 || (in[1] & 0x20)) throw std::runtime_error("h5lite: bad zlib header");
+    Inflate z(in + 2, n - 2);
+    z.run();
+    return std::move(z.out_);
+  }
+
+ private:
+  const unsigned char* in_;
+  std::size_t n_, pos_ = 0;
+  std::uint32_t bitbuf_ = 0;
+  int bitcnt_ = 0;
+  std::vector<unsigned char> out_;
+  struct Huff { std::uint16_t count[16]; std::uint16_t symbol[288]; };
+
+  Inflate(const unsigned char* in, std::size_t n) : in_(in), n_(n) {}
+  [[noreturn]] static void bad() { throw std::runtime_error("h5lite: corrupt deflate stream"); }
+  unsigned bits(int need) {
+    std::uint32_t v = bitbuf_;
+    while (bitcnt_ < need) {
+      if (pos_ >= n_) bad();
+      v |= (std::uint32_t)in_[pos_++] << bitcnt_;
+      bitcnt_ += 8;
+    }
+    bitbuf_ = need < 32 ? v >> need : 0;
+    bitcnt_ -= need;
+    return need < 32 ? v & ((1u << need) - 1u) : v;
+  }
+  static void build(Huff& h, const std::uint16_t* len, int n) {
+    std::fill(h.count, h.count + 16, 0);
+    for (int k = 0; k < n; ++k) ++h.count[len[k]];
+    std::uint16_t offs[16];
+    offs[1] = 0;
+    for (int l = 1; l < 15; ++l) offs[l + 1] = offs[l] + h.count[l];
+    for (int k = 0; k < n; ++k) if (len[k]) h.symbol[offs[len[k]]++] = (std::uint16_t)k;
+  }
+  int decode(const Huff& h) {
+    int code = 0, first = 0, index = 0;
+    for (int l = 1; l <= 15; ++l) {
+      code |= (int)bits(1);
+      const int count = h.count[l];
+      if (code - count < first) return h.symbol[index + (code - first)];
+      index += count; first += count; first <<= 1; code <<= 1;
+    }
+    bad();
+  }
+  void codes(const Huff& lc, const Huff& dc) {
+    static const std::uint16_t lbase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+    static const std::uint16_t lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+    static const std::uint16_t dbase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+    static const std::uint16_t dext[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+    for (;;) {
+      int sym = decode(lc);
+      if (sym < 256) { out_.push_back((unsigned char)sym); continue; }
+      if (sym == 256) return;
+      sym -= 257;
+      if (sym >= 29) bad();
+      const std::size_t len = lbase[sym] + bits(lext[sym]);
+      const int ds = decode(dc);
+      if (ds >= 30) bad();
+      const std::size_t dist = dbase[ds] + bits(dext[ds]);
+      if (dist > out_.size()) bad();
+      for (std::size_t k = 0; k < len; ++k) out_.push_back(out_[out_.size() - dist]);
+    }
+  }
+  void run() {
+    for (bool last = false; !last;) {
+      last = bits(1) != 0;
+      const unsigned type = bits(2);
+      if (type == 0) {   // stored
+        bitbuf_ = 0; bitcnt_ = 0;
+        if (pos_ + 4 > n_) bad();
+        const unsigned len = in_[pos_] | (in_[pos_ + 1] << 8), nlen = in_[pos_ + 2] | (in_[pos_ + 3] << 8);
+        pos_ += 4;
+        if ((len ^ 0xffffu) != nlen || pos_ + len > n_) bad();
+        out_.insert(out_.end(), in_ + pos_, in_ + pos_ + len);
+        pos_ += len;
+      } else if (type == 1) {   // fixed codes
+        std::uint16_t len[320];
+        int k = 0;
+        for (; k < 144; ++k) len[k] = 8;
+        for (; k < 256; ++k) len[k] = 9;
+        for (; k < 280; ++k) len[k] = 7;
+        for (; k < 288; ++k) len[k] = 8;
+        Huff lc, dc;
+        build(lc, len, 288);
+        for (k = 0; k < 30; ++k) len[k] = 5;
+        build(dc, len, 30);
+        codes(lc, dc);
+      } else if (type == 2) {   // dynamic codes
+        static const int order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+        const int nlen = (int)bits(5) + 257, ndist = (int)bits(5) + 1, ncode = (int)bits(4) + 4;
+        if (nlen > 286 || ndist > 30) bad();
+        std::uint16_t len[320];
+        std::fill(len, len + 19, 0);
+        for (int k = 0; k < ncode; ++k) len[order[k]] = (std::uint16_t)bits(3);
+        Huff cc;
+        build(cc, len, 19);
+        for (int k = 0; k < nlen + ndist;) {
+          int sym = decode(cc);
+          if (sym < 16) { len[k++] = (std::uint16_t)sym; continue; }
+          int rep, val = 0;
+          if (sym == 16) { if (k == 0) bad(); val = len[k - 1]; rep = 3 + (int)bits(2); }
+          else if (sym == 17) rep = 3 + (int)bits(3);
+          else rep = 11 + (int)bits(7);
+          if (k + rep > nlen + ndist) bad();
+          while (rep--) len[k++] = (std::uint16_t)val;
+        }
+        Huff lc, dc;
+        build(lc, len, nlen);
+        build(dc, len + nlen, ndist);
+        codes(lc, dc);
+      } else {
+        bad();
+      }
+    }
+  }
+};
+
+// Reader.  Walks the whole file into a name -> Dataset map and converts on read().
+//   superblock v0 / v1 (root symbol-table entry) and v2 / v3 (root object header);
+//   groups: v1 B-tree + local heap + symbol-table nodes, or compact link messages of new-style groups (dense link
+//   storage - fractal heap + v2 B-tree, used above 8 links - is not read);
+//   object headers v1 and v2 (continuation blocks of both);
+//   datatypes: little-endian IEEE f64 / f32 and fixed point of 1, 2, 4, 8 bytes, all returned as double;
+//   layouts (message v3, and the contiguous / compact classes of v4): compact, contiguous, chunked with the v1 chunk
+//   B-tree; filters: deflate, shuffle, fletcher32 (checksum skipped).
 class File {
  public:
   explicit File(const std::string& path) : path_(path) {
@@ -32,13 +174,23 @@ class File {
     if (!in) throw std::runtime_error("h5lite: cannot open " + path);
     buf_.assign(std::istreambuf_iterator<char>(in), std::istreambuf_iterator<char>());
     static const unsigned char magic[8] = {0x89, 'H', 'D', 'F', '\r', '\n', 0x1a, '\n'};
-    if (buf_.size() < 96 || std::memcmp(buf_.data(), magic, 8) != 0) fail("not an HDF5 file");
-    if (at8(8) != 0) fail("only superblock version 0 is supported");
-    if (at8(13) != 8 || at8(14) != 8) fail("only 8-byte offsets and lengths are supported");
-    base_ = rd<std::uint64_t>(24);
-    // root symbol-table entry at byte 56: name offset, header address, cache type, scratch
-    if (rd<std::uint32_t>(56 + 16) != 1) fail("root group without cached B-tree/heap addresses");
-    walk_group(rd<std::uint64_t>(56 + 24), rd<std::uint64_t>(56 + 32), "");
+    if (buf_.size() < 48 || std::memcmp(buf_.data(), magic, 8) != 0) fail("not an HDF5 file");
+    const unsigned ver = at8(8);
+    if (ver <= 1) {
+      if (at8(13) != 8 || at8(14) != 8) fail("only 8-byte offsets and lengths are supported");
+      const std::size_t o = ver == 0 ? 24 : 28;     // v1 adds the indexed-storage K and two reserved bytes
+      base_ = rd<std::uint64_t>(o);
+      // root symbol-table entry: name offset, header address, cache type, reserved, scratch
+      const std::size_t root = o + 32;
+      if (rd<std::uint32_t>(root + 16) == 1) walk_group(rd<std::uint64_t>(root + 24), rd<std::uint64_t>(root + 32), "");
+      else walk_object(rd<std::uint64_t>(root + 8), "");
+    } else if (ver <= 3) {
+      if (at8(9) != 8 || at8(10) != 8) fail("only 8-byte offsets and lengths are supported");
+      base_ = rd<std::uint64_t>(12);
+      walk_object(rd<std::uint64_t>(36), "");
+    } else {
+      fail("unknown superblock version");
+    }
   }
 
   bool has(const std::string& name) const { return sets_.count(name) != 0; }
@@ -50,9 +202,15 @@ class File {
     const Dataset& d = it->second;
     std::size_t n = 1;
     for (auto s : d.shape) n *= s;
-    if (d.bytes != n * 8 || base_ + d.addr + d.bytes > buf_.size()) fail("bad extent of " + name);
-    std::vector<double> out(n);
-    std::memcpy(out.data(), buf_.data() + base_ + d.addr, n * 8);
+    std::vector<double> out(n, 0.0);
+    const std::size_t es = (std::size_t)d.type_size;
+    if (d.layout == 0 || d.layout == 1) {
+      const std::size_t at = d.layout == 0 ? (std::size_t)d.addr : (std::size_t)(base_ + d.addr);
+      if (d.bytes != n * es || at + d.bytes > buf_.size()) fail("bad extent of " + name);
+      for (std::size_t k = 0; k < n; ++k) out[k] = element(d, &buf_[at + k * es]);
+    } else {
+      read_chunks(d, d.btree, name, out);
+    }
     if (shape) *shape = d.shape;
     return out;
   }
@@ -62,23 +220,43 @@ class File {
   std::vector<unsigned char> buf_;
   std::uint64_t base_ = 0;
   std::map<std::string, Dataset> sets_;
+  int depth_ = 0;
 
   [[noreturn]] void fail(const std::string& why) const { throw std::runtime_error("h5lite: " + path_ + ": " + why); }
   unsigned at8(std::size_t o) const { need(o, 1); return buf_[o]; }
-  void need(std::size_t o, std::size_t n) const { if (o + n > buf_.size()) fail("truncated file"); }
+  void need(std::size_t o, std::size_t n) const { if (o + n > buf_.size() || o + n < o) fail("truncated file"); }
   template <class T>
   T rd(std::size_t o) const { need(o, sizeof(T)); T v; std::memcpy(&v, &buf_[o], sizeof(T)); return v; }
   bool tag(std::size_t o, const char* t) const { need(o, 4); return std::memcmp(&buf_[o], t, 4) == 0; }
+  std::uint64_t rdn(std::size_t o, unsigned width) const {   // little-endian integer of 1, 2, 4 or 8 bytes
+    need(o, width);
+    std::uint64_t v = 0;
+    for (unsigned k = 0; k < width; ++k) v |= (std::uint64_t)buf_[o + k] << (8 * k);
+    return v;
+  }
 
+  static double element(const Dataset& d, const unsigned char* p) {
+    if (d.type_class == 1) {
+      if (d.type_size == 8) { double v; std::memcpy(&v, p, 8); return v; }
+      float v; std::memcpy(&v, p, 4); return (double)v;
+    }
+    std::uint64_t u = 0;
+    for (int k = 0; k < d.type_size; ++k) u |= (std::uint64_t)p[k] << (8 * k);
+    if (d.type_signed && d.type_size < 8 && (u >> (8 * d.type_size - 1))) u |= ~std::uint64_t(0) << (8 * d.type_size);
+    return d.type_signed ? (double)(std::int64_t)u : (double)u;
+  }
+
+  // ---- groups ----
   void walk_group(std::uint64_t btree, std::uint64_t heap, const std::string& prefix) {
+    heap += base_; btree += base_;
     if (!tag(heap, "HEAP")) fail("bad local heap");
-    walk_tree(btree, rd<std::uint64_t>(heap + 24), prefix);
+    walk_tree(btree, base_ + rd<std::uint64_t>(heap + 24), prefix);
   }
   void walk_tree(std::uint64_t a, std::uint64_t heap_data, const std::string& prefix) {
     if (!tag(a, "TREE") || at8(a + 4) != 0) fail("bad group B-tree node");
     const unsigned level = at8(a + 5), n = rd<std::uint16_t>(a + 6);
     for (unsigned k = 0; k < n; ++k) {
-      const std::uint64_t child = rd<std::uint64_t>(a + 24 + 8 + 16 * k);  // key0, child0, key1, child1, ...
+      const std::uint64_t child = base_ + rd<std::uint64_t>(a + 24 + 8 + 16 * k);  // key0, child0, key1, child1, ...
       if (level > 0) walk_tree(child, heap_data, prefix); else walk_snod(child, heap_data, prefix);
     }
   }
@@ -88,58 +266,215 @@ class File {
     for (unsigned k = 0; k < n; ++k) {
       const std::size_t e = a + 8 + 40 * k;
       const std::size_t name_at = heap_data + rd<std::uint64_t>(e);
-      need(name_at, 1);
-      const std::string name = prefix + "/" + reinterpret_cast<const char*>(&buf_[name_at]);
+      const std::string name = prefix + "/" + cstring(name_at);
       if (rd<std::uint32_t>(e + 16) == 1) {  // group with cached addresses
         walk_group(rd<std::uint64_t>(e + 24), rd<std::uint64_t>(e + 32), name);
         continue;
       }
-      Dataset d;
-      std::uint64_t stab[2] = {0, 0};
-      if (parse_header(rd<std::uint64_t>(e + 8), &d, stab)) sets_[name] = d;
-      else if (stab[0]) walk_group(stab[0], stab[1], name);
+      walk_object(rd<std::uint64_t>(e + 8), name);
     }
   }
-  bool parse_header(std::uint64_t a, Dataset* d, std::uint64_t* stab) const {
-    if (at8(a) != 1) fail("only version-1 object headers are supported");
+  std::string cstring(std::size_t at) const {
+    std::size_t e = at;
+    while (at8(e) != 0) ++e;
+    return std::string(reinterpret_cast<const char*>(&buf_[at]), e - at);
+  }
+
+  // ---- objects ----
+  struct Link { std::string name; std::uint64_t addr; };
+  void walk_object(std::uint64_t addr, const std::string& name) {
+    if (++depth_ > 64) fail("group nesting too deep (a cycle of hard links?)");
+    Dataset d;
+    std::uint64_t stab[2] = {0, 0};
+    std::vector<Link> links;
+    const bool is_data = parse_header(base_ + addr, &d, stab, &links);
+    if (is_data) sets_[name] = d;
+    else if (stab[0] || stab[1]) walk_group(stab[0], stab[1], name);
+    for (const Link& l : links) walk_object(l.addr, name + "/" + l.name);
+    --depth_;
+  }
+  // one header message; returns true for the layout message (= the object is a dataset)
+  bool message(unsigned type, std::uint64_t body, std::uint64_t size, Dataset* d, std::uint64_t* stab, std::vector<Link>* links,
+               std::vector<std::pair<std::uint64_t, std::uint64_t>>* blocks) const {
+    need(body, size);
+    switch (type) {
+      case 0x0001: {  // dataspace
+        const unsigned ver = at8(body), rank = at8(body + 1);
+        if (ver != 1 && ver != 2) fail("dataspace version");
+        const std::uint64_t dims = body + (ver == 1 ? 8 : 4);
+        d->shape.clear();
+        for (unsigned r = 0; r < rank; ++r) d->shape.push_back(rd<std::uint64_t>(dims + 8 * r));
+        return false;
+      }
+      case 0x0002:  // link info: dense storage when the fractal-heap address is defined
+        if (rd<std::uint64_t>(body + 2 + ((at8(body + 1) & 1) ? 8 : 0)) != ~std::uint64_t(0)) fail("dense link storage (more than 8 links in a new-style group) is not supported");
+        return false;
+      case 0x0003: {  // datatype
+        d->type_class = at8(body) & 0x0f;
+        d->type_size = (int)rd<std::uint32_t>(body + 4);
+        const unsigned bits0 = at8(body + 1);
+        if (bits0 & 1) fail("big-endian data");
+        if (d->type_class == 1) { if (d->type_size != 8 && d->type_size != 4) fail("floating-point type of unsupported size"); }
+        else if (d->type_class == 0) {
+          d->type_signed = (bits0 & 0x08) != 0;
+          if (d->type_size != 1 && d->type_size != 2 && d->type_size != 4 && d->type_size != 8) fail("fixed-point type of unsupported size");
+        } else fail("only floating-point and fixed-point data");
+        return false;
+      }
+      case 0x0006: {  // link (new-style group, compact storage)
+        const unsigned flags = at8(body + 1);
+        std::uint64_t p = body + 2;
+        unsigned ltype = 0;
+        if (flags & 0x08) ltype = at8(p++);
+        if (flags & 0x04) p += 8;
+        if (flags & 0x10) p += 1;
+        const unsigned w = 1u << (flags & 3);
+        const std::uint64_t len = rdn(p, w);
+        p += w;
+        need(p, len);
+        const std::string lname(reinterpret_cast<const char*>(&buf_[p]), (std::size_t)len);
+        p += len;
+        if (ltype == 0) links->push_back(Link{lname, rd<std::uint64_t>(p)});   // soft / external links are ignored
+        return false;
+      }
+      case 0x0008: {  // layout
+        const unsigned ver = at8(body), cls = at8(body + 1);
+        if (ver != 3 && ver != 4) fail("data layout message version " + std::to_string(ver));
+        d->layout = (int)cls;
+        if (cls == 0) { d->bytes = rd<std::uint16_t>(body + 2); d->addr = body + 4; }
+        else if (cls == 1) { d->addr = rd<std::uint64_t>(body + 2); d->bytes = rd<std::uint64_t>(body + 10); }
+        else if (cls == 2 && ver == 3) {
+          const unsigned nd = at8(body + 2);
+          if (nd < 2 || nd > 9) fail("chunk dimensionality");
+          d->btree = rd<std::uint64_t>(body + 3);
+          d->chunk.clear();
+          for (unsigned r = 0; r + 1 < nd; ++r) d->chunk.push_back(rd<std::uint32_t>(body + 11 + 4 * r));
+        } else fail("unsupported data layout (class " + std::to_string(cls) + ", message v" + std::to_string(ver) + ")");
+        return true;
+      }
+      case 0x000B: {  // filter pipeline
+        const unsigned ver = at8(body), nf = at8(body + 1);
+        std::uint64_t p = body + (ver == 1 ? 8 : 2);
+        if (ver != 1 && ver != 2) fail("filter pipeline version");
+        d->filters.clear();
+        for (unsigned k = 0; k < nf; ++k) {
+          Filter f;
+          f.id = rd<std::uint16_t>(p); p += 2;
+          unsigned nlen = 0;
+          if (ver == 1 || f.id >= 256) { nlen = rd<std::uint16_t>(p); p += 2; }
+          p += 2;   // flags
+          const unsigned ncd = rd<std::uint16_t>(p); p += 2;
+          p += ver == 1 ? (nlen + 7) / 8 * 8 : nlen;
+          for (unsigned c = 0; c < ncd; ++c) { f.cd.push_back(rd<std::uint32_t>(p)); p += 4; }
+          if (ver == 1 && (ncd & 1)) p += 4;
+          if (f.id != 1 && f.id != 2 && f.id != 3) fail("filter " + std::to_string(f.id) + " is not supported (deflate, shuffle, fletcher32 are)");
+          d->filters.push_back(f);
+        }
+        return false;
+      }
+      case 0x0010: blocks->emplace_back(base_ + rd<std::uint64_t>(body), rd<std::uint64_t>(body + 8)); return false;
+      case 0x0011: stab[0] = rd<std::uint64_t>(body); stab[1] = rd<std::uint64_t>(body + 8); return false;
+      default: return false;
+    }
+  }
+  bool parse_header(std::uint64_t a, Dataset* d, std::uint64_t* stab, std::vector<Link>* links) const {
+    bool has_data = false;
+    std::vector<std::pair<std::uint64_t, std::uint64_t>> blocks;
+    if (tag(a, "OHDR")) {   // version 2
+      if (at8(a + 4) != 2) fail("object header version");
+      const unsigned flags = at8(a + 5);
+      std::uint64_t p = a + 6;
+      if (flags & 0x20) p += 16;
+      if (flags & 0x10) p += 4;
+      const unsigned w = 1u << (flags & 3);
+      const std::uint64_t size0 = rdn(p, w);
+      p += w;
+      blocks.emplace_back(p, size0);
+      const unsigned mh = 4 + ((flags & 0x04) ? 2 : 0);
+      for (std::size_t b = 0; b < blocks.size(); ++b) {
+        std::uint64_t q = blocks[b].first, end = q + blocks[b].second;
+        if (b > 0) {   // continuation block: "OCHK" + messages + checksum
+          if (!tag(q, "OCHK")) fail("bad object header continuation block");
+          q += 4; end -= 4;
+        }
+        need(q, end - q);
+        while (q + mh <= end) {
+          const unsigned type = at8(q);
+          const std::uint64_t size = rd<std::uint16_t>(q + 1);
+          const std::uint64_t body = q + mh;
+          if (body + size > end) break;   // gap at the end of a block
+          if (message(type, body, size, d, stab, links, &blocks)) has_data = true;
+          q = body + size;
+        }
+      }
+      return has_data;
+    }
+    if (at8(a) != 1) fail("object header version");
     const unsigned nmsg = rd<std::uint16_t>(a + 2);
     unsigned seen = 0;
-    bool has_data = false;
-    std::vector<std::pair<std::uint64_t, std::uint64_t>> blocks{{a + 16, rd<std::uint32_t>(a + 8)}};
+    blocks.emplace_back(a + 16, rd<std::uint32_t>(a + 8));
     for (std::size_t b = 0; b < blocks.size() && seen < nmsg; ++b) {
       std::uint64_t p = blocks[b].first;
       const std::uint64_t end = p + blocks[b].second;
       while (p + 8 <= end && seen < nmsg) {
         const unsigned type = rd<std::uint16_t>(p), size = rd<std::uint16_t>(p + 2);
-        const std::uint64_t body = p + 8;
         ++seen;
-        switch (type) {
-          case 0x0001: {  // dataspace
-            const unsigned ver = at8(body), rank = at8(body + 1);
-            if (ver != 1 && ver != 2) fail("dataspace version");
-            const std::uint64_t dims = body + (ver == 1 ? 8 : 4);
-            d->shape.clear();
-            for (unsigned r = 0; r < rank; ++r) d->shape.push_back(rd<std::uint64_t>(dims + 8 * r));
-            break;
-          }
-          case 0x0003:  // datatype: class 1 (floating point), little endian, 8 bytes
-            if ((at8(body) & 0x0f) != 1 || (at8(body + 1) & 1) || rd<std::uint32_t>(body + 4) != 8) fail("only little-endian f64 data");
-            break;
-          case 0x0008:  // layout
-            if (at8(body) != 3 || at8(body + 1) != 1) fail("only contiguous layout (message v3)");
-            d->addr = rd<std::uint64_t>(body + 2);
-            d->bytes = rd<std::uint64_t>(body + 10);
-            has_data = true;
-            break;
-          case 0x000B: fail("filtered datasets are not supported");
-          case 0x0010: blocks.emplace_back(rd<std::uint64_t>(body), rd<std::uint64_t>(body + 8)); break;
-          case 0x0011: stab[0] = rd<std::uint64_t>(body); stab[1] = rd<std::uint64_t>(body + 8); break;
-          default: break;
-        }
-        p = body + size;
+        if (message(type, p + 8, size, d, stab, links, &blocks)) has_data = true;
+        p += 8 + size;
       }
     }
     return has_data;
+  }
+
+  // ---- chunked storage ----
+  void read_chunks(const Dataset& d, std::uint64_t node, const std::string& name, std::vector<double>& out) const {
+    const std::size_t rank = d.shape.size();
+    if (d.chunk.size() != rank || rank == 0) fail("chunk rank of " + name);
+    if (node == ~std::uint64_t(0)) return;   // no chunk was ever written: fill value 0
+    const std::uint64_t a = base_ + node;
+    if (!tag(a, "TREE") || at8(a + 4) != 1) fail("bad chunk B-tree node of " + name);
+    const unsigned level = at8(a + 5), n = rd<std::uint16_t>(a + 6);
+    const std::size_t key = 8 + 8 * (rank + 1);
+    for (unsigned k = 0; k < n; ++k) {
+      const std::size_t e = a + 24 + k * (key + 8);
+      const std::uint64_t child = rd<std::uint64_t>(e + key);
+      if (level > 0) { read_chunks(d, child, name, out); continue; }
+      const std::uint32_t csize = rd<std::uint32_t>(e), mask = rd<std::uint32_t>(e + 4);
+      std::vector<std::size_t> off(rank);
+      for (std::size_t r = 0; r < rank; ++r) off[r] = (std::size_t)rd<std::uint64_t>(e + 8 + 8 * r);
+      need(base_ + child, csize);
+      std::vector<unsigned char> raw(buf_.begin() + (std::size_t)(base_ + child), buf_.begin() + (std::size_t)(base_ + child) + csize);
+      for (std::size_t fk = d.filters.size(); fk-- > 0;) {   // undo the pipeline, last filter first
+        if (mask & (1u << fk)) continue;
+        const Filter& f = d.filters[fk];
+        if (f.id == 3) { if (raw.size() < 4) fail("fletcher32 chunk of " + name); raw.resize(raw.size() - 4); }
+        else if (f.id == 1) raw = Inflate::zlib(raw.data(), raw.size());
+        else if (f.id == 2) {
+          const std::size_t es = f.cd.empty() ? (std::size_t)d.type_size : f.cd[0], ne = es ? raw.size() / es : 0;
+          std::vector<unsigned char> un(raw.size());
+          for (std::size_t b = 0; b < es; ++b)
+            for (std::size_t i = 0; i < ne; ++i) un[i * es + b] = raw[b * ne + i];
+          for (std::size_t i = ne * es; i < raw.size(); ++i) un[i] = raw[i];
+          raw.swap(un);
+        }
+      }
+      std::size_t celems = 1;
+      for (auto c : d.chunk) celems *= c;
+      if (raw.size() != celems * (std::size_t)d.type_size) fail("chunk size of " + name);
+      // scatter the chunk (row-major) into the array, clipped at the array's edges
+      std::vector<std::size_t> idx(rank, 0);
+      for (std::size_t c = 0; c < celems; ++c) {
+        bool inside = true;
+        std::size_t flat = 0;
+        for (std::size_t r = 0; r < rank; ++r) {
+          const std::size_t g = off[r] + idx[r];
+          if (g >= d.shape[r]) { inside = false; break; }
+          flat = flat * d.shape[r] + g;
+        }
+        if (inside) out[flat] = element(d, &raw[c * (std::size_t)d.type_size]);
+        for (std::size_t r = rank; r-- > 0;) { if (++idx[r] < d.chunk[r]) break; idx[r] = 0; }
+      }
+    }
   }
 };
 

@@ -10,6 +10,7 @@
 #include "Ini_reader.h"
 #include "Mesh.h"
 #include "Parameters.h"
+#include <algorithm>
 #include "h5lite.h"
 
 static Grid2D make_uniform(const Parameters& p) {
@@ -88,6 +89,24 @@ int main(int argc, char** argv) {
     w.save(argv[2]);
     h5lite::File back(argv[2]);                      // this repo's C++ reader walks what the writer wrote
     std::cout << "datasets " << back.datasets().size() << " f/12[23] " << (back.datasets().count("/f/12") ? back.read("/f/12")[23] : -1.0) << std::endl;
+    return 0;
+  }
+  if (argc >= 4 && !std::strcmp(argv[1], "h5read")) {
+    // h5read <file> <outdir>: every dataset of the file as <outdir>/<path with '/' -> '_'>.npy; errors as "error: <what>", exit 3
+    try {
+      h5lite::File h(argv[2]);
+      for (const auto& kv : h.datasets()) {
+        std::vector<std::size_t> shape;
+        const std::vector<double> v = h.read(kv.first, &shape);
+        std::string leaf = kv.first;
+        std::replace(leaf.begin(), leaf.end(), '/', '_');
+        h5lite::write_npy(std::string(argv[3]) + "/" + leaf + ".npy", v.data(), shape);
+        std::cout << kv.first << std::endl;
+      }
+    } catch (const std::exception& e) {
+      std::cout << "error: " << e.what() << std::endl;
+      return 3;
+    }
     return 0;
   }
   if (argc < 5 || std::strcmp(argv[1], "dump")) { std::cerr << "usage: host_check dump <AY|LC> <ini> <outdir> | errors | ini <file>" << std::endl; return 2; }

@@ -122,3 +122,59 @@ def test_hdf5_writer_round_trip_and_structures(host_check, tmp_path):
         assert hdr_a[lay + 8:lay + 16] == hdr_b[lay + 8:lay + 16]            # same dataset size
         hdr_a[lay:lay + 8] = hdr_b[lay:lay + 8] = b"\0" * 8                  # the raw-data address is the only difference
         assert hdr_a == hdr_b, k
+
+
+def test_hdf5_reader_reads_other_table_formats(host_check, tmp_path):
+    """h5lite::File on D tables that are NOT laid out like data/D/AlbertYoung_chorus.h5 (Albert_Young_IO.cc:17-36 takes any
+    D/<dID>.h5): files hand-packed by tests/h5craft.py - an independent writer of the HDF5 on-disk structures - with chunked
+    storage (two-level chunk B-tree, ragged edge chunks) and the shuffle + deflate (+ fletcher32) filters as h5py writes them
+    with compression="gzip", f32 and integer data, compact datasets, and the new-style format (superblock v2 / v3, version-2
+    object headers with a continuation block, compact link messages, nested groups)."""
+    import h5craft
+    rng = np.random.default_rng(11)
+    Daa = rng.uniform(0.0, 3e-4, (91, 49))
+    Dap = rng.normal(0.0, 1e-5, (91, 49))
+    E = np.linspace(0.1, 5.0, 49)
+    old = {"alpha0": dict(data=np.arange(91.0), code="f4", layout="contiguous"),
+           "E": dict(data=E, code="f8", layout="compact"),
+           "Daa": dict(data=Daa, code="f8", layout="chunked", chunk=(32, 20), filters=[(2, [8]), (1, [4])]),
+           "Dap": dict(data=Dap, code="f8", layout="chunked", chunk=(91, 49), filters=[(1, [9]), (3, [])], pipeline_version=2),
+           "Dpp": dict(data=Daa.T.copy(), code="f8", layout="chunked", chunk=(7, 91)),
+           "n": dict(data=np.array([[-3, 70000], [5, -2]]), code="i4", layout="contiguous"),
+           "m": dict(data=np.array([1, 65535, 17]), code="u2", layout="chunked", chunk=(2,), filters=[(2, [2])])}
+    f_old = tmp_path / "old.h5"
+    h5craft.write_old_style(str(f_old), old)
+    new = {"alpha0": dict(data=np.arange(91.0), code="f8", layout="contiguous"),
+           "tables": {"Daa": dict(data=Daa, code="f8", layout="chunked", chunk=(16, 49), filters=[(2, [8]), (1, [6])]),
+                      "Dap": dict(data=Dap, code="f4", layout="contiguous"),
+                      "deep": {"E": dict(data=E, code="f8", layout="compact")}},
+           "count": dict(data=np.array([2 ** 40, -7]), code="i8", layout="compact")}
+    cases = [(f_old, {("/" + k): v for k, v in old.items()})]
+    for ver, order in ((2, False), (3, True)):
+        f_new = tmp_path / f"new{ver}.h5"
+        h5craft.write_new_style(str(f_new), new, superblock_version=ver, track_order=order)
+        flat = {"/alpha0": new["alpha0"], "/tables/Daa": new["tables"]["Daa"], "/tables/Dap": new["tables"]["Dap"],
+                "/tables/deep/E": new["tables"]["deep"]["E"], "/count": new["count"]}
+        cases.append((f_new, flat))
+    for path, expect in cases:
+        out = tmp_path / (path.name + ".d")
+        out.mkdir()
+        res = subprocess.run([host_check, "h5read", str(path), str(out)], capture_output=True, text=True)
+        assert res.returncode == 0, res.stdout + res.stderr
+        assert sorted(res.stdout.split()) == sorted(expect), res.stdout
+        for name, d in expect.items():
+            got = np.load(out / (name.replace("/", "_") + ".npy"))
+            want = np.asarray(d["data"]).astype("<" + d["code"]).astype(np.float64)
+            assert got.shape == want.shape and np.array_equal(got, want), name
+    # the shipped libhdf5-written table still reads, and unsupported structures are reported, not misread
+    out = tmp_path / "ay.d"
+    out.mkdir()
+    res = subprocess.run([host_check, "h5read", os.path.join(ROOT, "data", "D", "AlbertYoung_chorus.h5"), str(out)], capture_output=True, text=True)
+    assert res.returncode == 0 and sorted(res.stdout.split()) == ["/Daa", "/Dap", "/Dpp", "/E", "/alpha0"]
+    assert np.load(out / "_Daa.npy").shape == (91, 49) and abs(np.load(out / "_E.npy")[48] - 5.0) < 1e-12
+    bad = dict(old)
+    bad["Daa"] = dict(data=Daa, code="f8", layout="chunked", chunk=(32, 20), filters=[(32000, [1])])   # lzf
+    f_bad = tmp_path / "bad.h5"
+    h5craft.write_old_style(str(f_bad), bad)
+    res = subprocess.run([host_check, "h5read", str(f_bad), str(out)], capture_output=True, text=True)
+    assert res.returncode == 3 and "filter 32000 is not supported" in res.stdout
