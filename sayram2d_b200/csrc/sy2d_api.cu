@@ -55,6 +55,9 @@ struct sy2d_ctx {
   int* d_col_runs = nullptr;      // k_assemble_col: first tile of every CTA's run (strip-major order)
   int col_runs_key[3] = {0, 0, 0};   // tiles_i, tiles_j, CTAs the device array was built for
   int pipe_max = 32, pipe_forced = 0;   // sy2d_step_host: at most pipe_max pipelined sub-batches (SY2D_PIPE_CHUNKS forces a count)
+  int deterministic = 0;     // SY2D_DETERMINISTIC=1: cross-CTA sums in slot order instead of floating-point atomics (bitwise reproducible runs)
+  double* part = nullptr;    // slots of the deterministic cross-CTA sums (sy2d_kernels.cuh, cta_totals)
+  size_t part_stride = 0;
   std::string err;
   sy2d_options opt;
   bool have_coeffs = false, have_bc = false, have_f = false;
@@ -199,7 +202,7 @@ KrylovVecs krylov(const sy2d_ctx* c) {
   KrylovVecs k;
   k.wW = c->wW; k.wE = c->wE; k.wS = c->wS; k.wN = c->wN; k.rhs = c->rhs;
   k.x = c->x; k.r = c->r; k.p = c->p; k.v = c->v; k.s = c->s; k.t = c->t;
-  k.scal = c->scal; k.n_active = c->d_nactive; k.tol = c->opt.tol; k.maxit = c->opt.maxit;
+  k.scal = c->scal; k.part = c->deterministic ? c->part : nullptr; k.part_stride = c->part_stride; k.n_active = c->d_nactive; k.tol = c->opt.tol; k.maxit = c->opt.maxit;
   k.freeze_state = 0;
   k.n_begin = 0; k.n_end = c->N; k.defer = 0;
   if (c->slab) { k.n_begin = (size_t)c->ny; k.n_end = (size_t)(c->nx - 1) * c->ny; k.defer = 1; }
@@ -1120,7 +1123,7 @@ int step_slab_impl(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
     AssembleOut o;
     std::memset(&o, 0, sizeof o);
     o.wW = c->wW; o.wE = c->wE; o.wS = c->wS; o.wN = c->wN; o.rhs = c->rhs; o.cs = c->cs;
-    o.scal = c->scal; o.n_active = c->d_nactive; o.tol = c->opt.tol; o.local_rows = c->nx;
+    o.scal = c->scal; o.part = c->deterministic ? c->part : nullptr; o.part_stride = c->part_stride; o.n_active = c->d_nactive; o.tol = c->opt.tol; o.local_rows = c->nx;
     if (mg) o.om = c->mg_om0;
     if (c->opt.reserved[0] == 3 || (c->opt.reserved[0] == 0 && (c->asm_kernel == 1 || !c->have_tma))) {
       launch_march(c, geo, o, c->i_lo - 1, 1, rows + 1, 1);
@@ -1367,6 +1370,7 @@ static int create_impl(sy2d_ctx** out, int device, int nx, int ny, int nbatch, c
   if (const char* e = std::getenv("SY2D_HOST_IO")) ctx->host_io_direct = std::string(e) == "direct" ? 1 : 0;
   if (const char* e = std::getenv("SY2D_ASM_KERNEL")) ctx->asm_kernel = std::string(e) == "march" ? 1 : std::string(e) == "col" ? 2 : std::string(e) == "wide" ? 3 : 0;
   if (const char* e = std::getenv("SY2D_WIDE_CTAS_PER_SM")) ctx->wide_ctas_per_sm = std::max(1, std::min(2, std::atoi(e)));
+  if (const char* e = std::getenv("SY2D_DETERMINISTIC")) ctx->deterministic = std::atoi(e) != 0;
   if (const char* e = std::getenv("SY2D_MG_LINE_PRE")) ctx->mg_line_pre = std::atoi(e) != 0;
   if (const char* e = std::getenv("SY2D_COL_EDGE_WEIGHT")) ctx->col_edge_weight = std::max(0.25, std::min(8.0, std::atof(e)));
   if (const char* e = std::getenv("SY2D_MARCH_CTAS_PER_SM")) ctx->march_ctas_per_sm = std::max(1, std::min(16, std::atoi(e)));
@@ -1391,6 +1395,11 @@ static int create_impl(sy2d_ctx** out, int device, int nx, int ny, int nbatch, c
   }
   CUB(cudaMalloc(reinterpret_cast<void**>(&ctx->scal), nbatch * sizeof(Scal)));
   CUB(cudaMemset(ctx->scal, 0, nbatch * sizeof(Scal)));
+  // slots of the deterministic cross-CTA sums: one per CTA a kernel can launch for a problem - ceil(N / 256) for the
+  // one-thread-per-cell kernels, the per-problem share of the capped grids (at most 32 CTAs per SM) for the others
+  ctx->part_stride = (size_t)kPartSlot * (std::max<size_t>((ctx->N + kBlock - 1) / kBlock, ((size_t)ctx->sm_count * 32 + nbatch - 1) / nbatch) + 8);
+  CUB(cudaMalloc(reinterpret_cast<void**>(&ctx->part), (size_t)nbatch * ctx->part_stride * sizeof(double)));
+  CUB(cudaMemset(ctx->part, 0, (size_t)nbatch * ctx->part_stride * sizeof(double)));
   CUB(cudaMalloc(reinterpret_cast<void**>(&ctx->d_nactive), 2 * sizeof(int)));
   CUB(cudaMallocHost(reinterpret_cast<void**>(&ctx->h_nactive), 2 * sizeof(int)));
   CUB(cudaMalloc(reinterpret_cast<void**>(&ctx->d_stats), sizeof(StepStats)));
@@ -1421,6 +1430,7 @@ void sy2d_destroy(sy2d_ctx* c) {
                     c->x, c->r, c->p, c->v, c->s, c->t, c->xl_scratch, c->xl_l, c->xl_dinv, c->xl_e, c->xl_hat};
   for (double* b : bufs) if (b) cudaFree(b);
   if (c->scal) cudaFree(c->scal);
+  if (c->part) cudaFree(c->part);
   for (double* b : c->mg_bufs) cudaFree(b);
   if (c->mg_tail_ctr) cudaFree(c->mg_tail_ctr);
   if (c->d_tma_maps) cudaFree(c->d_tma_maps);
@@ -2059,7 +2069,7 @@ int sy2d_step(sy2d_ctx* c, int nsteps, sy2d_stats* stats) {
       AssembleOut o;
       std::memset(&o, 0, sizeof o);
       o.wW = c->wW; o.wE = c->wE; o.wS = c->wS; o.wN = c->wN; o.rhs = c->rhs; o.cs = c->cs;
-      o.scal = c->scal; o.n_active = c->d_nactive; o.tol = c->opt.tol; o.local_rows = c->nx;
+      o.scal = c->scal; o.part = c->deterministic ? c->part : nullptr; o.part_stride = c->part_stride; o.n_active = c->d_nactive; o.tol = c->opt.tol; o.local_rows = c->nx;
       if (mg) o.om = c->mg_om0;
       launch_assembly(c, geo, o, c->opt.reserved[0]);  // reserved[0]: 1 forces the per-cell kernel, 2 the tiled kernel without TMA (tests)
     }
@@ -2232,7 +2242,7 @@ int sy2d_dump_scaled_operator(sy2d_ctx* c, double* w4, double* rhs, double* cs) 
   AssembleOut o;
   std::memset(&o, 0, sizeof o);
   o.wW = c->wW; o.wE = c->wE; o.wS = c->wS; o.wN = c->wN; o.rhs = c->rhs; o.cs = c->cs;
-  o.scal = c->scal; o.n_active = c->d_nactive; o.tol = -1.0;
+  o.scal = c->scal; o.part = c->deterministic ? c->part : nullptr; o.part_stride = c->part_stride; o.n_active = c->d_nactive; o.tol = -1.0;
   o.local_rows = c->nx;
   launch_assembly(c, geometry(c), o, c->opt.reserved[0]);
   CU(cudaGetLastError());
@@ -2288,7 +2298,7 @@ int sy2d_debug_vcycle(sy2d_ctx* c, const double* r, double* z, double* w4, doubl
   AssembleOut o;
   std::memset(&o, 0, sizeof o);
   o.wW = c->wW; o.wE = c->wE; o.wS = c->wS; o.wN = c->wN; o.rhs = c->rhs; o.cs = c->cs; o.om = c->mg_om0;
-  o.scal = c->scal; o.n_active = c->d_nactive; o.tol = -1.0;   // every problem stays active
+  o.scal = c->scal; o.part = c->deterministic ? c->part : nullptr; o.part_stride = c->part_stride; o.n_active = c->d_nactive; o.tol = -1.0;   // every problem stays active
   o.local_rows = c->nx;
   k_assemble<0><<<grid_of(c), kBlock, 0, c->stream>>>(c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud, geometry(c), o);
   CU(cudaGetLastError());
@@ -2326,7 +2336,7 @@ int sy2d_bench_kernel(sy2d_ctx* c, int which, int reps, double* ms_per_launch) {
   AssembleOut o;
   std::memset(&o, 0, sizeof o);
   o.wW = c->wW; o.wE = c->wE; o.wS = c->wS; o.wN = c->wN; o.rhs = c->rhs; o.cs = c->cs;
-  o.scal = c->scal; o.n_active = c->d_nactive; o.tol = -1.0;  // tol < 0: every problem stays active
+  o.scal = c->scal; o.part = c->deterministic ? c->part : nullptr; o.part_stride = c->part_stride; o.n_active = c->d_nactive; o.tol = -1.0;  // tol < 0: every problem stays active
   o.local_rows = c->nx;
   auto assemble = [&]() { launch_assembly(c, geo, o, c->opt.reserved[0]); };
   auto launch = [&](int w) {

@@ -224,10 +224,10 @@ __global__ void __launch_bounds__(kColThreads, 4) k_assemble_col(const AsmMaps* 
   block_sums<1>(sums, sm.red);
   const double bmax = block_max(rabs, sm.red);
   Scal* sc = o.scal + blockIdx.y;
-  if (threadIdx.x == 0) {
-    atomicAdd(&sc->acc_rho, sums[0]);
-    atomicMax(&sc->acc_rmax, (unsigned long long)__double_as_longlong(bmax));
-    if (last_block_done(sc, gridDim.x) && !defer) {
+  {
+    __shared__ int last_flag;
+    double* const dst[1] = {&sc->acc_rho};
+    if (cta_totals<1>(sc, o.part + (size_t)blockIdx.y * o.part_stride, sums, dst, &sc->acc_rmax, bmax, &last_flag) && !defer) {
       const double rmax = __longlong_as_double((long long)sc->acc_rmax);
       sc->rho = sc->acc_rho;
       sc->rmax = rmax;

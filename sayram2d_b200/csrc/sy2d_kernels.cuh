@@ -142,6 +142,77 @@ __device__ __forceinline__ double block_max(double v, double* smem /* >= 32 */) 
   return v;
 }
 
+// Cross-CTA sums of the lockstep engine.  `part` == NULL (default): one atomicAdd(double) per CTA and sum, the last CTA to arrive
+// (atomic ticket) finishes - the sums are formed in arrival order, so two runs agree to round-off and their iteration counts can
+// differ by one or two at tol = 1e-14.  `part` != NULL (SY2D_DETERMINISTIC=1 at context creation): WITHOUT floating-point atomics,
+// i.e. deterministic: CTA b of a problem leaves its partial sums (and its partial
+// maximum) in slot b of the problem's slot array `part`; the last CTA to arrive (atomic ticket) adds the slots IN SLOT ORDER with
+// its first warp (lane l takes slots l, l + 32, ...; then the fixed shuffle tree) and adds the totals to *dst / maxes them into
+// *dst_max, where the finishing code of the kernels - and, in row-slab mode, the all-gather over the ranks - reads them.  The
+// result does not depend on the order in which the CTAs finished: two runs of the same problem give the same bits, iteration
+// counts included.  Called by EVERY thread of the CTA (one barrier); true in thread 0 of the last CTA only.
+constexpr int kPartSlot = 4;   // doubles per slot: up to three partial sums, one partial maximum
+__device__ __forceinline__ bool last_block_done(Scal* sc, unsigned int nblocks);
+template <int NS>
+__device__ __forceinline__ bool cta_totals(Scal* sc, double* part, const double (&sums)[NS], double* const (&dst)[NS],
+                                           unsigned long long* dst_max, double bmax, int* flag) {
+  static_assert(NS <= 3, "three sums per slot");
+  if (part == nullptr) {   // default: floating-point atomics, the last CTA to arrive finishes (5 % faster per 1024^2 time step, sums in arrival order)
+    if (threadIdx.x != 0) return false;
+#pragma unroll
+    for (int k = 0; k < NS; ++k) atomicAdd(dst[k], sums[k]);
+    if (dst_max) atomicMax(dst_max, (unsigned long long)__double_as_longlong(bmax));
+    return last_block_done(sc, gridDim.x);
+  }
+  if (threadIdx.x == 0) {
+    double* mine = part + (size_t)blockIdx.x * kPartSlot;
+#pragma unroll
+    for (int k = 0; k < NS; ++k) mine[k] = sums[k];
+    if (dst_max) mine[3] = bmax;
+    __threadfence();
+    *flag = atomicAdd(&sc->counter, 1u) == gridDim.x - 1 ? 1 : 0;
+  }
+  __syncthreads();
+  if (*flag == 0 || threadIdx.x >= 32) return false;
+  __threadfence();
+  double acc[NS], m = 0.0;
+#pragma unroll
+  for (int k = 0; k < NS; ++k) acc[k] = 0.0;
+  // eight slots per lane in flight at a time (one L2 round trip per batch instead of one per slot); the order of the additions is
+  // fixed by the code, not by the arrival of the loads
+  for (unsigned b0 = threadIdx.x; b0 < gridDim.x; b0 += 32 * 8) {
+    double v[8][NS + 1];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const unsigned b = b0 + 32 * u;
+      const bool in = b < gridDim.x;
+      const double* s = part + (size_t)(in ? b : 0) * kPartSlot;
+#pragma unroll
+      for (int k = 0; k < NS; ++k) v[u][k] = in ? __ldcg(s + k) : 0.0;
+      v[u][NS] = (dst_max && in) ? __ldcg(s + 3) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+#pragma unroll
+      for (int k = 0; k < NS; ++k) acc[k] += v[u][k];
+      if (dst_max) m = nmax(m, v[u][NS]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NS; ++k) acc[k] = warp_sum(acc[k]);
+  if (dst_max) m = warp_max(m);
+  if (threadIdx.x != 0) return false;
+#pragma unroll
+  for (int k = 0; k < NS; ++k) *dst[k] += acc[k];
+  if (dst_max) {   // raw bits: non-negative doubles order like integers, NaN wins
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(m);
+    if (bits > *dst_max) *dst_max = bits;
+  }
+  sc->counter = 0;
+  __threadfence();
+  return true;
+}
+
 // true in exactly one thread (thread 0 of the last block of this problem to get here)
 __device__ __forceinline__ bool last_block_done(Scal* sc, unsigned int nblocks) {
   __threadfence();
@@ -357,6 +428,8 @@ struct AssembleOut {
   double *wW, *wE, *wS, *wN, *rhs, *cs;
   double* om;   // optional: row weight M_KK c_K = 1 / (row scale), the multigrid restriction weight (may be NULL)
   Scal* scal;
+  double* part;         // slots of the deterministic cross-CTA sums (cta_totals): [nbatch][part_stride]
+  size_t part_stride;
   int* n_active;
   double tol;
   // MODE 1 (dump): the reference's unscaled M as 5 diagonals + R
@@ -415,10 +488,10 @@ __global__ void __launch_bounds__(kBlock) k_assemble(const double* __restrict__ 
   block_sums<1>(sums, red);
   const double bmax = block_max(rabs, red);
   Scal* sc = o.scal + blockIdx.y;
-  if (threadIdx.x == 0) {
-    atomicAdd(&sc->acc_rho, sums[0]);
-    atomicMax(&sc->acc_rmax, (unsigned long long)__double_as_longlong(bmax));
-    if (last_block_done(sc, gridDim.x)) {
+  {
+    __shared__ int last_flag;
+    double* const dst[1] = {&sc->acc_rho};
+    if (cta_totals<1>(sc, o.part + (size_t)blockIdx.y * o.part_stride, sums, dst, &sc->acc_rmax, bmax, &last_flag)) {
       const double rmax = __longlong_as_double((long long)sc->acc_rmax);
       sc->rho = sc->acc_rho;
       sc->rmax = rmax;
@@ -585,10 +658,10 @@ __global__ void __launch_bounds__(kTI * kTJ, 4) k_assemble_tiled(const double* _
   block_sums<1>(sums, red);
   const double bmax = block_max(rabs, red);
   Scal* sc = o.scal + blockIdx.y;
-  if (threadIdx.x == 0) {
-    atomicAdd(&sc->acc_rho, sums[0]);
-    atomicMax(&sc->acc_rmax, (unsigned long long)__double_as_longlong(bmax));
-    if (last_block_done(sc, gridDim.x) && !defer) {
+  {
+    __shared__ int last_flag;
+    double* const dst[1] = {&sc->acc_rho};
+    if (cta_totals<1>(sc, o.part + (size_t)blockIdx.y * o.part_stride, sums, dst, &sc->acc_rmax, bmax, &last_flag) && !defer) {
       const double rmax = __longlong_as_double((long long)sc->acc_rmax);
       sc->rho = sc->acc_rho;
       sc->rmax = rmax;
@@ -618,6 +691,8 @@ struct KrylovVecs {
   const double *wW, *wE, *wS, *wN, *rhs;
   double *x, *r, *p, *v, *s, *t;
   Scal* scal;
+  double* part;         // slots of the deterministic cross-CTA sums (cta_totals): [nbatch][part_stride]
+  size_t part_stride;   // doubles per problem
   int* n_active;   // [0] problems still iterating, [1] problems that stopped without converging (maxit / breakdown)
   double tol;
   int maxit;
@@ -683,9 +758,10 @@ __global__ void __launch_bounds__(kBlock) k_spmv_v(KrylovVecs k, size_t N, int n
   }
   double sums[1] = {dot};
   block_sums<1>(sums, red);
-  if (threadIdx.x == 0) {
-    atomicAdd(&sc->acc_rv, sums[0]);
-    if (last_block_done(sc, gridDim.x)) {
+  {
+    __shared__ int last_flag;
+    double* const dst[1] = {&sc->acc_rv};
+    if (cta_totals<1>(sc, k.part + (size_t)blockIdx.y * k.part_stride, sums, dst, nullptr, 0.0, &last_flag)) {
       const double rv = sc->acc_rv;
       sc->acc_rv = 0.0;
       sc->alpha = rv != 0.0 ? sc->rho / rv : 0.0;
@@ -723,10 +799,10 @@ __global__ void __launch_bounds__(kBlock) k_spmv_t(KrylovVecs k, size_t N, int n
   }
   double sums[2] = {ts, tt};
   block_sums<2>(sums, red);
-  if (threadIdx.x == 0) {
-    atomicAdd(&sc->acc_ts, sums[0]);
-    atomicAdd(&sc->acc_tt, sums[1]);
-    if (last_block_done(sc, gridDim.x)) {
+  {
+    __shared__ int last_flag;
+    double* const dst[2] = {&sc->acc_ts, &sc->acc_tt};
+    if (cta_totals<2>(sc, k.part + (size_t)blockIdx.y * k.part_stride, sums, dst, nullptr, 0.0, &last_flag)) {
       const double a = sc->acc_ts, b = sc->acc_tt;
       sc->acc_ts = 0.0;
       sc->acc_tt = 0.0;
@@ -757,10 +833,10 @@ __global__ void __launch_bounds__(kBlock) k_xr_update(KrylovVecs k, size_t N) {
   double sums[1] = {dot};
   block_sums<1>(sums, red);
   const double bmax = block_max(rabs, red);
-  if (threadIdx.x == 0) {
-    atomicAdd(&sc->acc_rho, sums[0]);
-    atomicMax(&sc->acc_rmax, (unsigned long long)__double_as_longlong(bmax));
-    if (last_block_done(sc, gridDim.x)) xr_finish_iteration(sc, k);
+  {
+    __shared__ int last_flag;
+    double* const dst[1] = {&sc->acc_rho};
+    if (cta_totals<1>(sc, k.part + (size_t)blockIdx.y * k.part_stride, sums, dst, &sc->acc_rmax, bmax, &last_flag)) xr_finish_iteration(sc, k);
   }
 }
 
@@ -819,9 +895,10 @@ __global__ void __launch_bounds__(kBlock) k_spmv_v2(KrylovVecs k, size_t N, int 
   }
   double sums[1] = {dot};
   block_sums<1>(sums, red);
-  if (threadIdx.x == 0) {
-    atomicAdd(&sc->acc_rv, sums[0]);
-    if (last_block_done(sc, gridDim.x) && !k.defer) {
+  {
+    __shared__ int last_flag;
+    double* const dst[1] = {&sc->acc_rv};
+    if (cta_totals<1>(sc, k.part + (size_t)blockIdx.y * k.part_stride, sums, dst, nullptr, 0.0, &last_flag) && !k.defer) {
       const double rv = sc->acc_rv;
       sc->acc_rv = 0.0;
       sc->alpha = rv != 0.0 ? sc->rho / rv : 0.0;
@@ -861,10 +938,10 @@ __global__ void __launch_bounds__(kBlock) k_spmv_t2(KrylovVecs k, size_t N, int 
   }
   double sums[2] = {ts, tt};
   block_sums<2>(sums, red);
-  if (threadIdx.x == 0) {
-    atomicAdd(&sc->acc_ts, sums[0]);
-    atomicAdd(&sc->acc_tt, sums[1]);
-    if (last_block_done(sc, gridDim.x) && !k.defer) {
+  {
+    __shared__ int last_flag;
+    double* const dst[2] = {&sc->acc_ts, &sc->acc_tt};
+    if (cta_totals<2>(sc, k.part + (size_t)blockIdx.y * k.part_stride, sums, dst, nullptr, 0.0, &last_flag) && !k.defer) {
       const double a = sc->acc_ts, b = sc->acc_tt;
       sc->acc_ts = 0.0;
       sc->acc_tt = 0.0;
@@ -895,10 +972,10 @@ __global__ void __launch_bounds__(kBlock) k_xr_update2(KrylovVecs k, size_t N) {
   double sums[1] = {dot};
   block_sums<1>(sums, red);
   const double bmax = block_max(rabs, red);
-  if (threadIdx.x == 0) {
-    atomicAdd(&sc->acc_rho, sums[0]);
-    atomicMax(&sc->acc_rmax, (unsigned long long)__double_as_longlong(bmax));
-    if (last_block_done(sc, gridDim.x) && !k.defer) xr_finish_iteration(sc, k);
+  {
+    __shared__ int last_flag;
+    double* const dst[1] = {&sc->acc_rho};
+    if (cta_totals<1>(sc, k.part + (size_t)blockIdx.y * k.part_stride, sums, dst, &sc->acc_rmax, bmax, &last_flag) && !k.defer) xr_finish_iteration(sc, k);
   }
 }
 

@@ -761,10 +761,10 @@ __global__ void __launch_bounds__(kBlock) k_mg_spmv_t(KrylovVecs k, const double
   }
   double sums[2] = {ts, tt};
   block_sums<2>(sums, red);
-  if (threadIdx.x == 0) {
-    atomicAdd(&sc->acc_ts, sums[0]);
-    atomicAdd(&sc->acc_tt, sums[1]);
-    if (last_block_done(sc, gridDim.x) && !k.defer) {
+  {
+    __shared__ int last_flag;
+    double* const dst[2] = {&sc->acc_ts, &sc->acc_tt};
+    if (cta_totals<2>(sc, k.part + (size_t)blockIdx.y * k.part_stride, sums, dst, nullptr, 0.0, &last_flag) && !k.defer) {
       const double a = sc->acc_ts, b = sc->acc_tt;
       sc->acc_ts = 0.0;
       sc->acc_tt = 0.0;
@@ -797,10 +797,10 @@ __global__ void __launch_bounds__(kBlock) k_mg_xr(KrylovVecs k, const double* __
   double sums[1] = {dot};
   block_sums<1>(sums, red);
   const double bmax = block_max(rabs, red);
-  if (threadIdx.x == 0) {
-    atomicAdd(&sc->acc_rho, sums[0]);
-    atomicMax(&sc->acc_rmax, (unsigned long long)__double_as_longlong(bmax));
-    if (last_block_done(sc, gridDim.x) && !k.defer) xr_finish_iteration(sc, k);
+  {
+    __shared__ int last_flag;
+    double* const dst[1] = {&sc->acc_rho};
+    if (cta_totals<1>(sc, k.part + (size_t)blockIdx.y * k.part_stride, sums, dst, &sc->acc_rmax, bmax, &last_flag) && !k.defer) xr_finish_iteration(sc, k);
   }
 }
 

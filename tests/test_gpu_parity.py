@@ -5,6 +5,8 @@
 Tolerances: the reference solves with a direct LU, this engine with BiCGSTAB to
 max|r| <= 1e-14 on the scaled system; north_star asks for max relative difference
 in f <= 1e-8 after the full run and zero negative cells."""
+import os
+
 import numpy as np
 import pytest
 
@@ -563,3 +565,33 @@ def test_step_host_with_pinned_buffers(mode):
     assert np.array_equal(h_in, f_ref) and np.array_equal(host.get_f(), f_ref)
     assert st["kernel_launches"] == (2 if mode == "direct" else st["kernel_launches"]) and (mode == "direct" or st["kernel_launches"] > 2)
     ref.close(); host.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nx,ny,nbatch,precond", [(256, 256, 1, 2), (200, 120, 2, 1), (96, 61, 3, 0), (1024, 1024, 1, 2)])
+def test_lockstep_engine_is_bitwise_reproducible(nx, ny, nbatch, precond):
+    """SY2D_DETERMINISTIC=1: the cross-CTA sums of engine 1 (dot products, |rhs|^2) are added in slot order by the last CTA
+    (cta_totals), not with floating-point atomics: two runs of the same problem give the same BITS of f and the same iteration counts, whatever the
+    order the CTAs finished in (multigrid, x-line and unpreconditioned iterations; batched; odd ny = one cell per thread)."""
+    xe, ye = fields.uniform_edges(nx, ny)
+    Dxx, Dxy, Dyy, inv_tau = fields.synthetic_tensor(xe, ye)
+    G = fields.ay_G(xe, ye)
+    f0, bct, lines = fields.ay_init_and_bc(xe, ye)
+    rep = lambda a: np.broadcast_to(a, (nbatch,) + a.shape).copy()
+    scale = (1.0 + 0.25 * np.arange(nbatch))[:, None, None]
+    out = []
+    for _ in range(3):
+        os.environ["SY2D_DETERMINISTIC"] = "1"
+        try:
+            eng = sy.Engine(xe, ye, 0.002, nbatch=nbatch)
+        finally:
+            del os.environ["SY2D_DETERMINISTIC"]
+        eng.set_options(engine=1, precond=precond)
+        eng.set_coeffs(rep(G), rep(Dxx) * scale, rep(Dxy) * scale, rep(Dyy) * scale, rep(inv_tau))
+        eng.set_bc(bct, *lines)
+        eng.set_f(rep(f0))
+        st = eng.step(4)
+        out.append((eng.get_f(), st["iters_total"], st["resid_last"]))
+        eng.close()
+    for f, it, res in out[1:]:
+        assert np.array_equal(f, out[0][0]) and it == out[0][1] and res == out[0][2]
