@@ -742,7 +742,7 @@ __global__ void __launch_bounds__(kBlock) k_p_update(KrylovVecs k, size_t N) {
 }
 
 // KB: v = A p, acc (rhat, v); last block: alpha = rho / (rhat, v)            56 B/cell
-__global__ void __launch_bounds__(kBlock) k_spmv_v(KrylovVecs k, size_t N, int ny) {
+__global__ void __launch_bounds__(kBlock, 6) k_spmv_v(KrylovVecs k, size_t N, int ny) {
   __shared__ double red[32];
   Scal* sc = k.scal + blockIdx.y;
   if (sc->state != 0) return;
@@ -781,7 +781,7 @@ __global__ void __launch_bounds__(kBlock) k_s_update(KrylovVecs k, size_t N) {
 }
 
 // KD: t = A s, acc (t,s), (t,t); last block: omega = (t,s)/(t,t)             48 B/cell
-__global__ void __launch_bounds__(kBlock) k_spmv_t(KrylovVecs k, size_t N, int ny) {
+__global__ void __launch_bounds__(kBlock, 6) k_spmv_t(KrylovVecs k, size_t N, int ny) {
   __shared__ double red[2 * 32];
   Scal* sc = k.scal + blockIdx.y;
   if (sc->state != 0) return;
@@ -813,7 +813,7 @@ __global__ void __launch_bounds__(kBlock) k_spmv_t(KrylovVecs k, size_t N, int n
 
 // KE: x += alpha p + omega s; r = s - omega t; acc (rhat, r), max|r|;
 // last block: iteration bookkeeping, convergence, beta                        56 B/cell
-__global__ void __launch_bounds__(kBlock) k_xr_update(KrylovVecs k, size_t N) {
+__global__ void __launch_bounds__(kBlock, 6) k_xr_update(KrylovVecs k, size_t N) {
   __shared__ double red[32];
   Scal* sc = k.scal + blockIdx.y;
   if (sc->state != 0) return;
@@ -877,7 +877,7 @@ __device__ __forceinline__ void stencil_apply2(const double* __restrict__ x, siz
   y1 = xc.y + ((wW.y * xW.y + wE.y * xE.y) + (wS.y * xc.x + wN.y * xN));
 }
 
-__global__ void __launch_bounds__(kBlock) k_spmv_v2(KrylovVecs k, size_t N, int ny) {
+__global__ void __launch_bounds__(kBlock, 6) k_spmv_v2(KrylovVecs k, size_t N, int ny) {
   __shared__ double red[32];
   Scal* sc = k.scal + blockIdx.y;
   if (sc->state != 0) return;
@@ -919,7 +919,7 @@ __global__ void __launch_bounds__(kBlock) k_s_update2(KrylovVecs k, size_t N) {
   }
 }
 
-__global__ void __launch_bounds__(kBlock) k_spmv_t2(KrylovVecs k, size_t N, int ny) {
+__global__ void __launch_bounds__(kBlock, 6) k_spmv_t2(KrylovVecs k, size_t N, int ny) {
   __shared__ double red[2 * 32];
   Scal* sc = k.scal + blockIdx.y;
   if (sc->state != 0) return;
@@ -950,7 +950,7 @@ __global__ void __launch_bounds__(kBlock) k_spmv_t2(KrylovVecs k, size_t N, int 
   }
 }
 
-__global__ void __launch_bounds__(kBlock) k_xr_update2(KrylovVecs k, size_t N) {
+__global__ void __launch_bounds__(kBlock, 6) k_xr_update2(KrylovVecs k, size_t N) {
   __shared__ double red[32];
   Scal* sc = k.scal + blockIdx.y;
   if (sc->state != 0) return;

@@ -742,7 +742,7 @@ __global__ void __launch_bounds__(512, 1) k_mg_tail(MgTailArgs t) {   // nseg x 
 // ---------------------------------------------------------------------------------------------
 
 // t = A shat; (t, s), (t, t); last block: omega                        56 B/cell
-__global__ void __launch_bounds__(kBlock) k_mg_spmv_t(KrylovVecs k, const double* __restrict__ shat, size_t N, int ny) {
+__global__ void __launch_bounds__(kBlock, 6) k_mg_spmv_t(KrylovVecs k, const double* __restrict__ shat, size_t N, int ny) {
   __shared__ double red[2 * 32];
   Scal* sc = k.scal + blockIdx.y;
   if (sc->state != 0) return;
@@ -774,7 +774,7 @@ __global__ void __launch_bounds__(kBlock) k_mg_spmv_t(KrylovVecs k, const double
 }
 
 // x += alpha phat + omega shat; r = s - omega t; (rhat, r), max|r|; bookkeeping        72 B/cell
-__global__ void __launch_bounds__(kBlock) k_mg_xr(KrylovVecs k, const double* __restrict__ phat, const double* __restrict__ shat,
+__global__ void __launch_bounds__(kBlock, 6) k_mg_xr(KrylovVecs k, const double* __restrict__ phat, const double* __restrict__ shat,
                                                   size_t N) {
   __shared__ double red[32];
   Scal* sc = k.scal + blockIdx.y;

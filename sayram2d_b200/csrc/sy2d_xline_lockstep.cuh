@@ -158,7 +158,7 @@ __device__ __forceinline__ void xl_apply2(const XlVecs& x, const double* __restr
 }
 
 template <int V>
-__global__ void __launch_bounds__(kBlock) k_xl_spmv_v(XlVecs x, size_t N) {
+__global__ void __launch_bounds__(kBlock, 6) k_xl_spmv_v(XlVecs x, size_t N) {
   __shared__ double red[32];
   Scal* sc = x.k.scal + blockIdx.y;
   if (sc->state != 0) return;
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(kBlock) k_xl_spmv_v(XlVecs x, size_t N) {
 }
 
 template <int V>
-__global__ void __launch_bounds__(kBlock) k_xl_spmv_t(XlVecs x, size_t N) {
+__global__ void __launch_bounds__(kBlock, 6) k_xl_spmv_t(XlVecs x, size_t N) {
   __shared__ double red[2 * 32];
   Scal* sc = x.k.scal + blockIdx.y;
   if (sc->state != 0) return;
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(kBlock) k_xl_spmv_t(XlVecs x, size_t N) {
 }
 
 template <int V>
-__global__ void __launch_bounds__(kBlock) k_xl_xr(XlVecs x, size_t N) {
+__global__ void __launch_bounds__(kBlock, 6) k_xl_xr(XlVecs x, size_t N) {
   __shared__ double red[32];
   Scal* sc = x.k.scal + blockIdx.y;
   if (sc->state != 0) return;
