@@ -248,6 +248,13 @@ int sy2d_measure_peaks(int device, sy2d_peaks* out);
 
 /* Build/device facts: "sm_100a;cuda=12.9;..." */
 const char* sy2d_build_info(void);
+
+/* Which assembly kernel the last engine-1 assembly of this context (sy2d_step, sy2d_dump_scaled_operator) ran with:
+ * 1 one thread per cell, 2 shared-memory tiles with plain loads, 3 warp-marching strips, 4 TMA-staged tiles (the default
+ * where a tensor map exists: ny even, >= 32), 5 TMA column runs, 6 TMA tiles with two cells per thread; 0 = none yet.
+ * A forced kernel (options.reserved[0]) that the grid cannot use falls back to the next one in that list - this call says
+ * which.  No counterpart in the reference (diagnostic). */
+int sy2d_last_assembly_kernel(const sy2d_ctx* ctx);
 int sy2d_device_count(void);
 
 #ifdef __cplusplus

@@ -97,6 +97,8 @@ struct sy2d_ctx {
   std::vector<double*> mg_bufs;
   // TMA-staged assembly (sy2d_assemble_tma.cuh): tensor maps of f, yprev, tx, ty, cxy, U, Ud
   bool have_tma = false;
+  int last_asm_kernel = 0;   // which engine-1 assembly kernel the last launch_assembly used (sy2d_last_assembly_kernel; tests)
+  bool have_tma_wide = true;   // cleared when the 68 x 10 / 64 x 8 boxes cannot be encoded (ny < 64)
   AsmMaps tma_maps;
   AsmMaps* d_tma_maps = nullptr;   // device copy read by the TMA unit
   // Asynchronous staging (sy2d_set_coeffs_async / sy2d_set_bc_async): a second set of coefficient arrays and boundary
@@ -344,14 +346,19 @@ bool tma_encode_maps(sy2d_ctx* c, AsmMaps* host_maps, double* tx, double* ty, do
   const cuuint64_t dims[3] = {(cuuint64_t)c->ny, (cuuint64_t)c->nx, (cuuint64_t)c->nbatch};
   const cuuint64_t strides[2] = {(cuuint64_t)c->ny * sizeof(double), (cuuint64_t)c->N * sizeof(double)};
   const cuuint32_t estr[3] = {1, 1, 1};
-  for (int k = 0; k < 14; ++k) {
+  if (c->ny < kWJ) c->have_tma_wide = false;
+  for (int k = 0; k < (c->have_tma_wide ? 14 : 7); ++k) {
     const bool wide = k >= 7, halo = k % 7 < 5;
     const cuuint32_t box[3] = {(cuuint32_t)(halo ? (wide ? kWHaloJ : kTmaHaloJ) : (wide ? kWJ : kTJ)), (cuuint32_t)(halo ? kTmaHaloI : kTI), 1};
     const CUresult r = encode(&host_maps->m[k], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, arrs[k % 7], dims, strides, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,  // (L2 promotion raises an illegal-instruction fault with these boxes on B200 / driver 580: profiles/tma_probe.cu)
                              
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return false;
+    if (r != CUDA_SUCCESS) {
+      if (!wide) return false;
+      c->have_tma_wide = false;   // the wide boxes are only needed by the two-cells-per-thread experiment: the narrow maps stay usable
+      break;
+    }
   }
   return true;
 }
@@ -407,7 +414,7 @@ bool launch_col(sy2d_ctx* c, const Geometry& geo, const AssembleOut& o, int tile
 
 // Two cells per thread on 8 x 64 tiles (sy2d_assemble_wide.cuh); two CTAs per SM.
 bool launch_wide(sy2d_ctx* c, const Geometry& geo, const AssembleOut& o, int tiles_i, int gi0, int li_begin, int li_end, int defer) {
-  if (c->ny < kWJ) return false;
+  if (c->ny < kWJ || !c->have_tma_wide) return false;
   const int tiles_j = (c->ny + kWJ - 1) / kWJ, ntiles = tiles_i * tiles_j;
   const unsigned ctas = (unsigned)std::min<size_t>((size_t)ntiles, std::max<size_t>(1, (size_t)c->sm_count * c->wide_ctas_per_sm / (size_t)c->nbatch));
   k_assemble_wide<<<dim3(ctas, (unsigned)c->nbatch, 1), kTI * kTJ, kWideSmemBytes, c->stream>>>(c->d_tma_maps, geo, o, tiles_j, ntiles, gi0, li_begin, li_end, defer);
@@ -424,16 +431,22 @@ void launch_assembly(sy2d_ctx* c, const Geometry& geo, const AssembleOut& o, int
   // tensor map exists (odd ny) the marching kernel, which has no alignment requirement
   if (tiled && (variant == 3 || (variant == 0 && (c->asm_kernel == 1 || !c->have_tma)))) {
     launch_march(c, geo, o, 0, 0, c->nx, 0);
+    c->last_asm_kernel = 3;
   } else if (tiled && c->have_tma && (variant == 6 || (variant == 0 && c->asm_kernel == 3)) && launch_wide(c, geo, o, tiles_i, 0, 0, c->nx, 0)) {
+    c->last_asm_kernel = 6;
   } else if (tiled && c->have_tma && (variant == 5 || (variant == 0 && c->asm_kernel == 2)) && launch_col(c, geo, o, tiles_i, tiles_j, 0, 0, c->nx, 0)) {
+    c->last_asm_kernel = 5;
   } else if (tiled && c->have_tma && (variant == 0 || variant == 4 || variant == 5 || variant == 6)) {
+    c->last_asm_kernel = 4;
     const int ntiles = tiles_i * tiles_j;
     const unsigned ctas = (unsigned)std::min<size_t>((size_t)ntiles, std::max<size_t>(1, (size_t)c->sm_count * c->asm_ctas_per_sm / (size_t)c->nbatch));
     k_assemble_tma<<<dim3(ctas, (unsigned)c->nbatch, 1), kTI * kTJ, kTmaSmemBytes, c->stream>>>(c->d_tma_maps, geo, o, tiles_j, ntiles, 0, 0, c->nx, 0);
   } else if (tiled) {
+    c->last_asm_kernel = 2;
     k_assemble_tiled<<<dim3(capped_blocks(c, (size_t)tiles_i * tiles_j, 1), (unsigned)c->nbatch, 1), kTI * kTJ, 0, c->stream>>>(
         c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud, geo, o, tiles_j, 0, 0, c->nx, 0);
   } else {
+    c->last_asm_kernel = 1;
     k_assemble<0><<<grid_of(c), kBlock, 0, c->stream>>>(c->f, c->yprev, c->tx, c->ty, c->cxy, c->U, c->Ud, geo, o);
   }
 }
@@ -1289,6 +1302,8 @@ static int step_per_problem(sy2d_ctx* c, int nsteps, sy2d_stats* stats, const do
 static int engine_of(const sy2d_ctx* c);
 
 extern "C" {
+
+int sy2d_last_assembly_kernel(const sy2d_ctx* c) { return c ? c->last_asm_kernel : 0; }
 
 const char* sy2d_build_info(void) {
   return "sayram2d_b200;arch=sm_100a;cuda="

@@ -98,6 +98,7 @@ def load_library():
         "sy2d_bench_kernel": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_double)]),
         "sy2d_measure_peaks": (C.c_int, [C.c_int, C.POINTER(Peaks)]),
         "sy2d_build_info": (C.c_char_p, []),
+        "sy2d_last_assembly_kernel": (C.c_int, [C.c_void_p]),
         "sy2d_device_count": (C.c_int, []),
     }
     for name, (res, args) in sig.items():
@@ -392,6 +393,10 @@ class Engine:
         ms = C.c_double()
         self._check(self.lib.sy2d_bench_kernel(self._ctx, K_NAMES.index(name), int(reps), C.byref(ms)))
         return ms.value
+
+    def last_assembly_kernel(self):
+        """1 per cell, 2 plain-load tiles, 3 marching warps, 4 TMA tiles, 5 TMA column runs, 6 TMA tiles with two cells per thread."""
+        return int(self.lib.sy2d_last_assembly_kernel(self._ctx))
 
     def build_info(self):
         return self.lib.sy2d_build_info().decode()

@@ -458,6 +458,10 @@ def test_assembly_kernels_agree(tag, nx, ny, nbatch, bc):
     for variant in variants:
         _force_assembly(eng, variant)
         got = eng.dump_scaled_operator()
+        # the kernel asked for is the kernel that ran (no silent fall-back): TMA kernels need 32 columns, the two-cell one 64
+        nx_, ny_ = len(xe) - 1, len(ye) - 1
+        if nx_ >= 16 and ny_ >= (64 if variant == 6 else 32):
+            assert eng.last_assembly_kernel() == variant, (variant, eng.last_assembly_kernel())
         if ref is None:
             ref = got
             continue
