@@ -131,6 +131,25 @@ __global__ void __launch_bounds__(kTI * kTJ, 4) k_assemble_tma(const AsmMaps* __
 #define H(arr, aa, bb) arr[(aa) * kTmaHaloJ + (bb) + 1]
     const bool edge_tile = I0 == 0 || I0 + kTI >= nx || J0 == 0 || J0 + kTJ >= ny || L0 + kTI > li_end;
     mbar_wait(&sm.full[s], parity);
+#ifdef SY2D_ASM_NULL
+    {   // structure-only experiment (build with -DSY2D_ASM_NULL; never the product): the staged boxes straight to the outputs, no
+        // vertex / face / row arithmetic - what the TMA ring + stores cost by themselves: 21.3 / 88 / 343 us at 1024^2 / 2048^2 /
+        // 4096^2 against 33.6 / 100.7 / 348-365 us with the arithmetic
+      const int i = I0 + a, j = J0 + b;
+      if (!edge_tile || (i < nx && L0 + a < li_end && j < ny)) {
+        const size_t c0 = base + (size_t)(L0 + a) * ny + j;
+        const double f00 = H(fs, a + 1, b + 1), y0 = H(ys, a + 1, b + 1);
+        o.wW[c0] = H(txs, a + 1, b + 1) + H(fs, a, b + 1); o.wE[c0] = H(tys, a + 1, b + 1) + H(fs, a + 2, b + 1);
+        o.wS[c0] = H(cxs, a + 1, b + 1) + H(fs, a + 1, b); o.wN[c0] = Us[a * kTJ + b] + H(fs, a + 1, b + 2);
+        o.rhs[c0] = Uds[a * kTJ + b]; o.cs[c0] = f00 * y0;
+        if (o.om) o.om[c0] = y0;
+        rr += f00; rabs = nmax(rabs, fabs(y0));
+      }
+      tile_i = next_i; tile_j = next_j;
+      __syncthreads();
+      continue;
+    }
+#endif
     // 2. vertices (I0 + a', J0 + b').  The extra row / column of every stage goes to a different warp
     // (1 .. 4), so that no warp does more than one extra pass between two barriers.
     auto vertex = [&](int va, int vb, bool own) {
