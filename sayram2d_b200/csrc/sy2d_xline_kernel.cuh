@@ -856,7 +856,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
       res_rel = mm[1];
     }
     if (state >= 2) break;   // the solve stopped without converging (maxit, breakdown, NaN): f and yprev stay those of t^n
-    double fneg = 0.0, fmin_neg = -1.0e300;
+    double fneg = 0.0, fmin_neg = -1.0e300, fmin_l = 1.0e300;
     // full tile: the last ratios are fetched as one batch (inside the loop each load would wait for the stores of the row
     // before it - the compiler has to assume they alias)
     double yl[VREG ? R : 1];
@@ -880,16 +880,25 @@ __global__ void __launch_bounds__(MAXT, 1) k_problem_xline(XlineArgs xa) {
         }
         fneg += fnew < 0.0 ? 1.0 : 0.0;
         fmin_neg = nmax(fmin_neg, -fnew);
+        fmin_l = ::fmin(fmin_l, fnew);
       }
     }
     if (last) {
       // sum of negatives; max of (-f) shifted to be non-negative for the zero-padded reduction
-      double mm[2] = {fneg, fmin_neg + 1.0e300};
+      double mm[2] = {fneg, fmin_neg + 1.0e300};   // (the shifted maximum only carries a NaN through; min f itself is reduced below)
       cta_reduce_x<2>(mm, 1, red);
+      {   // min f of the problem: 1e300 + (-f) would round every |f| < 1e284 away
+        const int lane_ = tid & 31, w_ = tid >> 5, nw_ = NT >> 5;
+        double mn_ = warp_min(fmin_l);
+        if (lane_ == 0) red[w_] = mn_;
+        __syncthreads();
+        fmin_l = warp_min(lane_ < nw_ ? red[lane_] : 1.0e300);
+        __syncthreads();
+      }
       if (tid == 0) {
         if (mm[0] > 0.0) atomicAdd(&a.stats->negatives, (unsigned long long)mm[0]);
         if (!(mm[1] == mm[1]) || !(res_rel == res_rel)) atomicAdd(&a.stats->n_bad, 1);   // non-finite f or residual
-        const double mn = -(mm[1] - 1.0e300);
+        const double mn = fmin_l;
         unsigned long long* addr = reinterpret_cast<unsigned long long*>(&a.stats->fmin);
         unsigned long long old = *addr;
         while (mn < __longlong_as_double((long long)old)) {

@@ -147,3 +147,18 @@ def test_work_queue_is_bitwise_equal_to_one_cta_per_problem():
         e.close()
     assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
     assert its[0] == its[1] == its[2] and its[0][2] == 7
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precond", [1, 0])   # engine 2: x-line kernel, Jacobi kernel
+def test_ensemble_statistics_report_the_true_minimum(precond):
+    """stats.fmin of an ensemble call is the minimum of f after the call's last step, to the bit (the x-line kernel used to
+    reduce 1e300 - f, which rounds every |f| < 1e284 to zero and reported -0.0)."""
+    e = _ensemble(40, 1)
+    o = e.options(); o.precond = precond
+    e._check(e.lib.sy2d_set_options(e._ctx, o)); e._opt = o
+    st = e.step(3)
+    f = e.get_f()
+    assert st["engine"] == 2 and st["negatives"] == 0 and int((f < 0).sum()) == 0
+    assert st["fmin"] == float(f.min()) and st["fmin"] > 0.0
+    e.close()
