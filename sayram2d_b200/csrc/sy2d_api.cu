@@ -49,6 +49,8 @@ struct sy2d_ctx {
   // registers that are resident on an SM at once: one full wave, no tail (profiles/sweep_caps_steps.py: 1024^2 4.98 -> 4.81 ms
   // per step against 16, 2048^2 15.2 -> 14.9, 4096^2 equal; 8 is worse everywhere - a partial second wave)
   int ctas_per_sm = 6, asm_ctas_per_sm = 4, march_ctas_per_sm = 5, wide_ctas_per_sm = 2;
+  int mg_fuse = 1;            // p / s updates formed inside the first line solve of their V-cycle (SY2D_MG_FUSE=0: kernels of their own)
+  int mg_fuse_pending = 0;    // 1 / 2: the next MODE-0 line launch forms p / s (set by launch_iteration_mg, consumed by mg_line_shape)
   int mg_line_pre = 1;   // line kernel with prefetched backward factors / old iterate and block-parallel scans (SY2D_MG_LINE_PRE=0: the three-phase kernel)
   int asm_kernel = 0;   // default fast assembly: 0 TMA-staged tiles (strided tile order), 1 warp-marching, 2 TMA-staged column runs (experiment, slower); SY2D_ASM_KERNEL = tma | march | col
   double col_edge_weight = 1.5;   // cost of a boundary tile relative to an interior one when the column runs are cut (SY2D_COL_EDGE_WEIGHT)
@@ -559,7 +561,13 @@ void mg_setup(sy2d_ctx* c) {
 template <int SEG, int COLS, int MODE>
 void mg_line_shape(sy2d_ctx* c, const MgLevel& lv, const double* zc) {
   const int rows = mg_rows(c);
-  const MgArgs a{c->scal, rows, c->slab ? 1 : 0, c->slab ? c->mg_tips : nullptr};
+  MgArgs a{c->scal, rows, c->slab ? 1 : 0, c->slab ? c->mg_tips : nullptr};
+  if (MODE == 0 && c->mg_fuse_pending) {   // the Krylov update that feeds this V-cycle is formed inside its first line solve
+    a.fuse = c->mg_fuse_pending;
+    a.f_rhs = c->rhs; a.f_r = c->r; a.f_v = c->v;
+    a.f_dst = const_cast<double*>(lv.r);
+    c->mg_fuse_pending = 0;
+  }
   const int nseg = (rows + SEG - 1) / SEG;
   const int threads = (nseg * COLS + 31) / 32 * 32;
   const size_t smem = (size_t)3 * COLS * (nseg + 1) * sizeof(double);
@@ -783,13 +791,23 @@ int mg_kernels_per_vcycle(const sy2d_ctx* c) {
   return 4 * (c->mg_nlev - 1) + 1 + 2 * (mg_coarse_sweeps(c) - 1);
 }
 
+// The fused p / s updates need the first stage of the V-cycle to be a k_mg_line launch on level 0 (not the cluster kernel of long
+// columns, not the fused coarse tail) on a single-GPU context.
+bool mg_fuse_updates(sy2d_ctx* c) {
+  return c->mg_fuse && !c->slab && c->mg_nlev >= 2 && mg_cluster_size(c, c->mg.lv[0]) == 0 && mg_tail_first_level(c) > 0;
+}
+
 int launch_iteration_mg(sy2d_ctx* c) {
   int rc = SY2D_OK;
   KrylovVecs k = krylov(c);
   const dim3 g2(capped_blocks(c, c->N / 2, kBlock), (unsigned)c->nbatch, 1);
   double* phat = c->xl_hat;
   double* shat = c->mg_shat;
-  { Prof p(c, SY2D_K_P_UPDATE); k_p_update2<<<g2, kBlock, 0, c->stream>>>(k, c->N); }
+  // single GPU, level 0 solved by the stand-alone line kernel: the p and s updates are formed inside the first line solve of
+  // their V-cycle (one launch and one pass over p / s less per half-iteration)
+  const bool fuse = mg_fuse_updates(c);
+  if (fuse) c->mg_fuse_pending = 1;
+  else { Prof p(c, SY2D_K_P_UPDATE); k_p_update2<<<g2, kBlock, 0, c->stream>>>(k, c->N); }
   if ((rc = mg_vcycle(c, c->p, phat))) return rc;
   {
     Prof p(c, SY2D_K_SPMV_V);
@@ -797,7 +815,8 @@ int launch_iteration_mg(sy2d_ctx* c) {
     kv.p = phat;   // v = A phat, (rhat, v)
     k_spmv_v2<<<g2, kBlock, 0, c->stream>>>(kv, c->N, c->ny);
   }
-  { Prof p(c, SY2D_K_S_UPDATE); k_s_update2<<<g2, kBlock, 0, c->stream>>>(k, c->N); }
+  if (fuse) c->mg_fuse_pending = 2;
+  else { Prof p(c, SY2D_K_S_UPDATE); k_s_update2<<<g2, kBlock, 0, c->stream>>>(k, c->N); }
   if ((rc = mg_vcycle(c, c->s, shat))) return rc;
   { Prof p(c, SY2D_K_SPMV_T); k_mg_spmv_t<<<g2, kBlock, 0, c->stream>>>(k, shat, c->N, c->ny); }
   { Prof p(c, SY2D_K_XR_UPDATE); k_mg_xr<<<g2, kBlock, 0, c->stream>>>(k, phat, shat, c->N); }
@@ -825,7 +844,10 @@ int launch_iteration(sy2d_ctx* c) {
   { Prof p(c, SY2D_K_XR_UPDATE); k_xr_update<<<g, kBlock, 0, c->stream>>>(k, c->N); }
   return SY2D_OK;
 }
-int kernels_per_iteration(const sy2d_ctx* c) { return lockstep_mg(c) ? 5 + 2 * mg_kernels_per_vcycle(c) : 5; }
+int kernels_per_iteration(const sy2d_ctx* c) {
+  if (!lockstep_mg(c)) return 5;
+  return (mg_fuse_updates(const_cast<sy2d_ctx*>(c)) ? 3 : 5) + 2 * mg_kernels_per_vcycle(c);
+}
 // with multigrid an iteration is ~50 launches and a solve ~15 iterations: poll more often
 int effective_check_every(const sy2d_ctx* c) { return lockstep_mg(c) ? std::min(c->opt.check_every, 4) : c->opt.check_every; }
 
@@ -1386,6 +1408,7 @@ static int create_impl(sy2d_ctx** out, int device, int nx, int ny, int nbatch, c
   if (const char* e = std::getenv("SY2D_ASM_KERNEL")) ctx->asm_kernel = std::string(e) == "march" ? 1 : std::string(e) == "col" ? 2 : std::string(e) == "wide" ? 3 : 0;
   if (const char* e = std::getenv("SY2D_WIDE_CTAS_PER_SM")) ctx->wide_ctas_per_sm = std::max(1, std::min(2, std::atoi(e)));
   if (const char* e = std::getenv("SY2D_DETERMINISTIC")) ctx->deterministic = std::atoi(e) != 0;
+  if (const char* e = std::getenv("SY2D_MG_FUSE")) ctx->mg_fuse = std::atoi(e) != 0;
   if (const char* e = std::getenv("SY2D_MG_LINE_PRE")) ctx->mg_line_pre = std::atoi(e) != 0;
   if (const char* e = std::getenv("SY2D_COL_EDGE_WEIGHT")) ctx->col_edge_weight = std::max(0.25, std::min(8.0, std::atof(e)));
   if (const char* e = std::getenv("SY2D_MARCH_CTAS_PER_SM")) ctx->march_ctas_per_sm = std::max(1, std::min(16, std::atoi(e)));

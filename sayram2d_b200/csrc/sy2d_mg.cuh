@@ -59,6 +59,15 @@ struct MgArgs {
                       // The line kernel solves the rank's OWN rows; the coupling to the neighbour ranks' rows is
                       // restored afterwards by the spike correction below (exact global lines).
   double* tips;       // row-slab mode: [2][ny] - first and last value of every local line solution (before damping)
+  // Fused Krylov update (first line solve of a V-cycle, MODE 0 on level 0, single GPU): the right-hand side of the solve is FORMED
+  // here instead of by a kernel of its own and stored for the kernels that follow -
+  //   fuse = 1: p = first ? rhs : r + beta (p - omega v)     (k_p_update2)      fuse = 2: s = (first ? rhs : r) - alpha v     (k_s_update2)
+  // with the scalars of the problem's Scal; f_dst = the array the solve otherwise reads (lv.r).
+  int fuse = 0;
+  const double* f_rhs = nullptr;
+  const double* f_r = nullptr;
+  const double* f_v = nullptr;
+  double* f_dst = nullptr;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -239,7 +248,33 @@ __device__ __forceinline__ void mg_line_body(const MgLevel& lv, const double* zc
   const size_t n0 = live ? (size_t)batch * lv.N + (size_t)r0 * ny + j : 0;
   double y[SEG], c[SEG];
   // forward sweep y_m = b_m - l_m y_{m-1} with carry-in 0; P = product of (-l) over the segment
-  {
+  if (MODE == 0 && a.fuse != 0) {   // the right-hand side is the Krylov update itself (see MgArgs)
+    const Scal& sc = a.scal[batch];
+    const bool first = sc.first != 0;
+    const double alpha = sc.alpha, beta = sc.beta, omega = sc.omega;
+    const double* pr = (first ? a.f_rhs : a.f_r) + n0;
+    const double* pv = a.f_v + n0;
+    const double* pp = a.f_dst + n0;
+    const double* pl = lv.l + n0;
+#pragma unroll
+    for (int m = 0; m < SEG; ++m) {
+      y[m] = 0.0; c[m] = 0.0;
+      if (FULL || m < cnt) {
+        const double r = *pr;
+        if (a.fuse == 1) y[m] = first ? r : r + beta * (*pp - omega * *pv);
+        else y[m] = r - alpha * *pv;
+        c[m] = *pl;
+      }
+      pr += ny; pv += ny; pp += ny; pl += ny;
+    }
+    if (state != 0) return;
+    double* pd = a.f_dst + n0;
+#pragma unroll
+    for (int m = 0; m < SEG; ++m) {
+      if (FULL || m < cnt) *pd = y[m];
+      pd += ny;
+    }
+  } else {
     const double* ps = (MODE == 0 ? lv.r : lv.t) + n0;
     const double* pl = lv.l + n0;
 #pragma unroll
